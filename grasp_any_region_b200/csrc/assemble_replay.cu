@@ -1,0 +1,264 @@
+// Fused "assemble inputs_embeds + RoI-aligned feature replay" (SURVEY.md §2b K7+K8, rows R6+R7).
+//
+// Replaces, in the reference (hf_models/modeling_gar.py):
+//   :332      embed_tokens(input_ids)                                  (index_select)
+//   :341-346  get_placeholder_mask + masked_scatter of image_features  (bool mask S*D + scatter)
+//   :348-414  per crop token: `in` scan + 2 .item() syncs, _merge permute+contiguous, .float() of the
+//             whole map, torchvision.ops.roi_align, permute/cast, 3-way torch.cat
+// with two launches and no host synchronisation:
+//   plan_rows  : one block scans input_ids -> per-row source plan (text / image ordinal / crop offset),
+//                validates counts and run shapes into a status word
+//   assemble   : one warp per output row; text & image rows are 16-byte vector copies, crop rows
+//                evaluate roi_align for their (ph,pw) bin directly on the channel-contiguous
+//                (T,256,D) feature tensor (no merged map, no fp32 copy) in the operator's exact fp32
+//                operation order (oracle/roi_align_ref.py) and round once to bf16.
+// HBM-bound: ~2*S*D*2 bytes per request; no tensor cores on this path.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MAX_REGIONS = 8;
+constexpr int KIND_TEXT = 0, KIND_IMAGE = 1, KIND_CROP = 2;
+
+struct AssembleParams {
+  int n_regions;                 // number of crop token ids configured (prompt_numbers)
+  long long crop_ids[MAX_REGIONS];
+  float rois[MAX_REGIONS][5];    // [0, x1, y1, x2, y2] already in "feature coords" (reference quirk 1)
+  int has_roi[MAX_REGIONS];      // bbox supplied for this crop id
+  float spatial_scale;           // applied AGAIN inside roi_align, as the reference does
+  int ncw, nch, tpt;             // tile grid (w,h) and tokens per tile side (16)
+  long long image_token_id;
+};
+
+// plan word: kind in bits [30,32), payload in [0,30)
+__global__ void plan_rows_kernel(const long long* __restrict__ ids, int S, int n_image_feats, AssembleParams p,
+                                 int* __restrict__ plan, int* __restrict__ status) {
+  __shared__ int s_warp[32];
+  __shared__ int s_min[MAX_REGIONS], s_max[MAX_REGIONS], s_cnt[MAX_REGIONS];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  if (tid < MAX_REGIONS) { s_min[tid] = 0x7fffffff; s_max[tid] = -1; s_cnt[tid] = 0; }
+  __syncthreads();
+  const int per = (S + nthr - 1) / nthr;
+  const int lo = tid * per, hi = min(S, lo + per);
+  int cnt = 0;
+  for (int s = lo; s < hi; ++s) {
+    const long long id = ids[s];
+    if (id == p.image_token_id) ++cnt;
+    for (int k = 0; k < p.n_regions; ++k) {
+      if (id == p.crop_ids[k]) {
+        atomicMin(&s_min[k], s);
+        atomicMax(&s_max[k], s);
+        atomicAdd(&s_cnt[k], 1);
+      }
+    }
+  }
+  // block exclusive scan of cnt
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += v;
+  }
+  if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int w = tid < (nthr >> 5) ? s_warp[tid] : 0;
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (tid >= o) wi += v;
+    }
+    s_warp[tid] = wi - w;  // exclusive prefix of warp totals
+    if (tid == 31) s_total = wi;
+  }
+  __syncthreads();
+  int ord = s_warp[tid >> 5] + incl - cnt;
+  for (int s = lo; s < hi; ++s) {
+    const long long id = ids[s];
+    int word = KIND_TEXT << 30;
+    if (id == p.image_token_id) {
+      word = (KIND_IMAGE << 30) | ord;
+      ++ord;
+    } else {
+      for (int k = 0; k < p.n_regions; ++k) {
+        if (id == p.crop_ids[k] && p.has_roi[k]) {
+          word = (KIND_CROP << 30) | (k << 16) | ((s - s_min[k]) & 0xffff);
+        }
+      }
+    }
+    plan[s] = word;
+  }
+  if (tid == 0) {
+    int st = 0;
+    if (s_total != n_image_feats) st |= 1;  // reference: ValueError "Image features and image tokens do not match"
+    const int run = p.tpt * p.tpt;
+    for (int k = 0; k < p.n_regions; ++k) {
+      if (s_cnt[k] > 0) {
+        if (!p.has_roi[k]) st |= 4;                                          // reference: KeyError on bboxes[str(id)]
+        if (s_cnt[k] != run || s_max[k] - s_min[k] + 1 != run) st |= 2;      // replay would change the length
+      }
+    }
+    status[0] = st;
+    status[1] = s_total;
+  }
+}
+
+struct Sample {
+  int pos[4];
+  float w[4];
+  int valid;
+};
+
+// torchvision bilinear pre-calc for one sample point; explicit _rn intrinsics forbid FMA contraction
+__device__ __forceinline__ Sample make_sample(float y, float x, int H, int W) {
+  Sample sm;
+  sm.valid = !(y < -1.0f || y > static_cast<float>(H) || x < -1.0f || x > static_cast<float>(W));
+  if (y <= 0.f) y = 0.f;
+  if (x <= 0.f) x = 0.f;
+  int y_low = static_cast<int>(y), x_low = static_cast<int>(x);
+  int y_high, x_high;
+  if (y_low >= H - 1) { y_high = y_low = H - 1; y = static_cast<float>(y_low); } else { y_high = y_low + 1; }
+  if (x_low >= W - 1) { x_high = x_low = W - 1; x = static_cast<float>(x_low); } else { x_high = x_low + 1; }
+  const float ly = __fsub_rn(y, static_cast<float>(y_low));
+  const float lx = __fsub_rn(x, static_cast<float>(x_low));
+  const float hy = __fsub_rn(1.0f, ly), hx = __fsub_rn(1.0f, lx);
+  sm.w[0] = __fmul_rn(hy, hx);
+  sm.w[1] = __fmul_rn(hy, lx);
+  sm.w[2] = __fmul_rn(ly, hx);
+  sm.w[3] = __fmul_rn(ly, lx);
+  sm.pos[0] = y_low * W + x_low;
+  sm.pos[1] = y_low * W + x_high;
+  sm.pos[2] = y_high * W + x_low;
+  sm.pos[3] = y_high * W + x_high;
+  return sm;
+}
+
+__global__ void assemble_kernel(const long long* __restrict__ ids, const int* __restrict__ plan,
+                                const bf16* __restrict__ table, const bf16* __restrict__ feats,
+                                bf16* __restrict__ out, int S, int D, int vocab, AssembleParams p) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = D / 8;
+  for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < S; s += gridDim.x * wpb) {
+    const int word = plan[s];
+    const int kind = (word >> 30) & 3;
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(s) * D);
+    if (kind != KIND_CROP) {
+      const uint4* src;
+      if (kind == KIND_IMAGE) {
+        src = reinterpret_cast<const uint4*>(feats + static_cast<size_t>(word & 0x3fffffff) * D);
+      } else {
+        long long id = ids[s];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * D);
+      }
+      for (int v = lane; v < nvec; v += 32) dst[v] = __ldg(src + v);
+      continue;
+    }
+    // ---- RoI replay row: bin (ph, pw) of region k ----
+    const int k = (word >> 16) & 0x3fff;
+    const int off = word & 0xffff;
+    const int tpt = p.tpt;
+    const int ph = off / tpt, pw = off % tpt;
+    const int H = p.nch * tpt, W = p.ncw * tpt;
+    const float scale = p.spatial_scale;
+    const float start_w = __fsub_rn(__fmul_rn(p.rois[k][1], scale), 0.5f);
+    const float start_h = __fsub_rn(__fmul_rn(p.rois[k][2], scale), 0.5f);
+    const float end_w = __fsub_rn(__fmul_rn(p.rois[k][3], scale), 0.5f);
+    const float end_h = __fsub_rn(__fmul_rn(p.rois[k][4], scale), 0.5f);
+    const float bin_h = __fdiv_rn(__fsub_rn(end_h, start_h), static_cast<float>(tpt));
+    const float bin_w = __fdiv_rn(__fsub_rn(end_w, start_w), static_cast<float>(tpt));
+    Sample sm[4];
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy) {
+      const float yy = __fadd_rn(__fadd_rn(start_h, __fmul_rn(static_cast<float>(ph), bin_h)),
+                                 __fdiv_rn(__fmul_rn(iy + 0.5f, bin_h), 2.0f));
+#pragma unroll
+      for (int ix = 0; ix < 2; ++ix) {
+        const float xx = __fadd_rn(__fadd_rn(start_w, __fmul_rn(static_cast<float>(pw), bin_w)),
+                                   __fdiv_rn(__fmul_rn(ix + 0.5f, bin_w), 2.0f));
+        sm[iy * 2 + ix] = make_sample(yy, xx, H, W);
+      }
+    }
+    // feature cell (y,x) of the merged map lives at tile 1 + (y/tpt)*ncw + x/tpt, token (y%tpt)*tpt + x%tpt
+    const uint4* cell[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int lin = sm[q].pos[c];
+        const int y = lin / W, x = lin % W;
+        const size_t row = (static_cast<size_t>(1 + (y / tpt) * p.ncw + x / tpt) * tpt + (y % tpt)) * tpt + (x % tpt);
+        cell[q * 4 + c] = reinterpret_cast<const uint4*>(feats + row * D);
+      }
+    }
+    for (int v = lane; v < nvec; v += 32) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!sm[q].valid) continue;
+        float val[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 raw = __ldg(cell[q * 4 + c] + v);
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(rw[j]);
+            const float t0 = __fmul_rn(sm[q].w[c], f.x), t1 = __fmul_rn(sm[q].w[c], f.y);
+            val[2 * j] = c == 0 ? t0 : __fadd_rn(val[2 * j], t0);
+            val[2 * j + 1] = c == 0 ? t1 : __fadd_rn(val[2 * j + 1], t1);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], val[j]);
+      }
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        ow[j] = pack_bf16x2(__fdiv_rn(acc[2 * j], 4.0f), __fdiv_rn(acc[2 * j + 1], 4.0f));
+      dst[v] = o;
+    }
+  }
+}
+
+}  // namespace
+
+// rois: n_regions x 5 fp32 host array; has_roi: n_regions ints; crop_ids: n_regions int64 (host)
+extern "C" int gar_assemble_embeds(const long long* input_ids, int S, const void* embed_table, int vocab,
+                                   const void* image_features, int n_image_rows, int D, const long long* crop_ids,
+                                   const float* rois, const int* has_roi, int n_regions, float spatial_scale, int ncw,
+                                   int nch, int tpt, long long image_token_id, void* out, int* plan_ws,
+                                   int* status_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_regions > MAX_REGIONS || D % 8 || S <= 0 || tpt * tpt > 0xffff) {
+    gar_set_error("gar_assemble_embeds: bad args S=%d D=%d n_regions=%d", S, D, n_regions);
+    return GAR_ERR_ARG;
+  }
+  AssembleParams p;
+  p.n_regions = n_regions;
+  for (int k = 0; k < MAX_REGIONS; ++k) {
+    p.crop_ids[k] = k < n_regions ? crop_ids[k] : -1;
+    p.has_roi[k] = k < n_regions ? has_roi[k] : 0;
+    for (int j = 0; j < 5; ++j) p.rois[k][j] = k < n_regions ? rois[k * 5 + j] : 0.f;
+  }
+  p.spatial_scale = spatial_scale;
+  p.ncw = ncw;
+  p.nch = nch;
+  p.tpt = tpt;
+  p.image_token_id = image_token_id;
+  plan_rows_kernel<<<1, 1024, 0, stream>>>(input_ids, S, n_image_rows, p, plan_ws, status_dev);
+  GAR_CUDA_CHECK(cudaGetLastError());
+  const int wpb = 4;
+  int grid = (S + wpb - 1) / wpb;
+  assemble_kernel<<<grid, wpb * 32, 0, stream>>>(input_ids, plan_ws, static_cast<const bf16*>(embed_table),
+                                                  static_cast<const bf16*>(image_features), static_cast<bf16*>(out), S,
+                                                  D, vocab, p);
+  GAR_CUDA_CHECK(cudaGetLastError());
+  return GAR_OK;
+}

@@ -1,0 +1,314 @@
+// Fused softmax(Q K^T * scale) V for head_dim 64 on tcgen05 tensor cores with TMEM accumulators.
+//
+// Replaces F.scaled_dot_product_attention in timm's AttentionRope (PE ViT, non-causal, N=1025) and
+// flash-attn 2 `flash_attn_func` behind HF Llama (causal, GQA) on the prefill -- SURVEY.md §2b K5/K9.
+// Same numerics contract as those kernels: S and the online softmax in fp32, P rounded to bf16 for
+// the PV product, fp32 O accumulation, one bf16 rounding of O / l at the end.
+//
+// One CTA = one (sequence, head, 128-query block); two CTAs co-reside per SM so one CTA's softmax
+// overlaps the other's MMAs.  Roles (192 threads):
+//   warp 0     TMA producer: Q once, K double-buffered, V single-buffered (3-D tensor maps so rows
+//              past a sequence end are zero-filled on load and clipped on store)
+//   warp 1     MMA issuer : S = Q K^T  (128x128x64, both operands K-major, 128B swizzle)
+//                           O += P V   (128x64x128, P K-major from smem, V MN-major from smem)
+//   warps 2-5  softmax    : tcgen05.ld S row-per-thread -> online softmax -> P (bf16) into swizzled
+//                           smem, rescale O in TMEM, final O/l -> smem -> TMA store
+#include "common.cuh"
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int BQ = 128;
+constexpr int BKV = 128;
+constexpr int ATT_THREADS = 192;
+constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows of 128 B
+constexpr int SMEM_Q = 0;
+constexpr int SMEM_K = TILE_BYTES;                   // 2 stages
+constexpr int SMEM_V = SMEM_K + 2 * TILE_BYTES;      // 1 stage
+constexpr int SMEM_P = SMEM_V + TILE_BYTES;          // 2 sub-tiles [128 x 64]
+constexpr int SMEM_TOTAL = SMEM_P + 2 * TILE_BYTES;  // 96 KB
+constexpr int ATT_SMEM_BYTES = SMEM_TOTAL + 1024;
+constexpr int TMEM_COLS_ATT = 256;  // S: 128 cols, O: 64 cols (power-of-two allocation)
+constexpr uint32_t TM_S = 0, TM_O = 128;
+
+struct AttnParams {
+  int q_len, kv_len;       // per sequence
+  int causal;              // query i attends keys <= i + (kv_len - q_len)
+  int q_col0, k_col0, v_col0, o_col0;   // column (element) offsets of head 0 inside the row
+  int q_head_cols, kv_head_cols;        // column step per (kv) head
+  int group;               // q heads per kv head
+  int kv_batch_mul, kv_batch_head_mul;  // kv batch coordinate = b*kv_batch_mul + kvh*kv_batch_head_mul
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+                     AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[12];
+  __shared__ uint32_t tmem_ptr_sh;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t B_QFULL = bar0, B_KFULL0 = bar0 + 8, B_KEMPTY0 = bar0 + 24, B_VFULL = bar0 + 40,
+                 B_VEMPTY = bar0 + 48, B_SFULL = bar0 + 56, B_PFULL = bar0 + 64, B_OFULL = bar0 + 72;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_qb = (p.q_len + BQ - 1) / BQ;
+  const int qb = num_qb - 1 - blockIdx.x;  // heaviest (causal) blocks first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / p.group;
+  const int q0 = qb * BQ;
+  const int shift = p.kv_len - p.q_len;
+  int kv_end = p.kv_len;
+  if (p.causal) kv_end = min(p.kv_len, q0 + BQ + shift);
+  const int num_kvb = (kv_end + BKV - 1) / BKV;
+
+  if (threadIdx.x == 0) {
+    mbar_init(B_QFULL, 1);
+    mbar_init(B_KFULL0, 1);
+    mbar_init(B_KFULL0 + 8, 1);
+    mbar_init(B_KEMPTY0, 1);
+    mbar_init(B_KEMPTY0 + 8, 1);
+    mbar_init(B_VFULL, 1);
+    mbar_init(B_VEMPTY, 1);
+    mbar_init(B_SFULL, 1);
+    mbar_init(B_PFULL, 128);
+    mbar_init(B_OFULL, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_o);
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&tmem_ptr_sh), TMEM_COLS_ATT);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&tmem_ptr_sh);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int kb_coord = b * p.kv_batch_mul + kvh * p.kv_batch_head_mul;
+      mbar_expect_tx(B_QFULL, TILE_BYTES);
+      tma_load_3d(sbase + SMEM_Q, &tmap_q, p.q_col0 + h * p.q_head_cols, q0, b, B_QFULL);
+      for (int j = 0; j < num_kvb; ++j) {
+        const int st = j & 1;
+        mbar_wait(B_KEMPTY0 + 8 * st, ((j >> 1) & 1) ^ 1u);
+        mbar_expect_tx(B_KFULL0 + 8 * st, TILE_BYTES);
+        tma_load_3d(sbase + SMEM_K + st * TILE_BYTES, &tmap_k, p.k_col0 + kvh * p.kv_head_cols, j * BKV, kb_coord,
+                    B_KFULL0 + 8 * st);
+        mbar_wait(B_VEMPTY, (j & 1) ^ 1u);
+        mbar_expect_tx(B_VFULL, TILE_BYTES);
+        tma_load_3d(sbase + SMEM_V, &tmap_v, p.v_col0 + kvh * p.kv_head_cols, j * BKV, kb_coord, B_VFULL);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD, 0, 1);   // P K-major, V MN-major
+      mbar_wait(B_QFULL, 0);
+      const uint64_t qdesc = umma_desc_sw128(sbase + SMEM_Q, 0, 1024);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(B_KFULL0 + 8 * st, (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t kdesc = umma_desc_sw128(sbase + SMEM_K + st * TILE_BYTES, 0, 1024);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem + TM_S, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0);
+        umma_commit(B_KEMPTY0 + 8 * st);
+        umma_commit(B_SFULL);
+      };
+      issue_s(0);
+      for (int j = 0; j < num_kvb; ++j) {
+        mbar_wait(B_PFULL, j & 1);  // P(j) in smem, S consumed, O rescaled
+        mbar_wait(B_VFULL, j & 1);
+        tc_fence_after();
+        // V tile: [kv rows][64 hd] 128B rows => MN-major B operand; 16 kv rows per MMA = 2048 B
+        const uint64_t vdesc = umma_desc_sw128(sbase + SMEM_V, 0, 1024);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          const uint64_t pdesc = umma_desc_sw128(sbase + SMEM_P + (k >> 2) * TILE_BYTES, 0, 1024) + 2u * (k & 3);
+          umma_bf16_ss(tmem + TM_O, pdesc, vdesc + 128u * k, idesc_o, (j | k) != 0);
+        }
+        umma_commit(B_VEMPTY);
+        if (j + 1 < num_kvb) issue_s(j + 1);  // its s_full commit also covers PV(j)
+        else umma_commit(B_OFULL);
+      }
+    }
+  } else {
+    // ---------------- softmax warps: thread <-> query row ----------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const int q_pos = q0 + row + shift;  // last key this row may see (causal)
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < num_kvb; ++j) {
+      mbar_wait(B_SFULL, j & 1);
+      tc_fence_after();
+      uint32_t s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t(&sc)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
+        tmem_ld_32x32b_x32(tmem + lane_addr + TM_S + c * 32, sc);
+      }
+      tmem_ld_wait();
+      const int kv0 = j * BKV;
+      const bool need_mask = (kv0 + BKV > p.kv_len) || (p.causal && kv0 + BKV - 1 > q0 + shift);
+      float mx = -INFINITY;
+      if (need_mask) {
+        const int lim = p.causal ? min(p.kv_len - 1, q_pos) : p.kv_len - 1;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          float v = __uint_as_float(s[i]);
+          v = (kv0 + i <= lim) ? v : -INFINITY;
+          s[i] = __float_as_uint(v);
+          mx = fmaxf(mx, v);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = exp2f(m_run - m_use);
+      // rescale O (s_full(j) implies PV(j-1) retired, so O and the P buffer are quiescent)
+      if (j > 0) {
+        const bool any = __any_sync(0xffffffffu, alpha != 1.0f);
+        if (any) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // P = exp2(S*scale - m) -> bf16 -> smem, canonical K-major 128B-swizzled layout:
+      // row r, 16B chunk c at r*128 + ((c ^ (r&7))<<4); two [128 x 64] sub-tiles
+      float rs = 0.f;
+      {
+        const uint32_t rbase = sbase + SMEM_P + (row >> 3) * 1024 + (row & 7) * 128;
+        const uint32_t sw = row & 7;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float p0 = exp2f(__uint_as_float(s[c * 8 + 2 * i]) * p.scale_log2 - m_use);
+            const float p1 = exp2f(__uint_as_float(s[c * 8 + 2 * i + 1]) * p.scale_log2 - m_use);
+            rs += p0 + p1;
+            w[i] = pack_bf16x2(p0, p1);
+          }
+          const uint32_t addr = rbase + (c >> 3) * TILE_BYTES + (((c & 7) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                       : "memory");
+        }
+      }
+      l_run = l_run * alpha + rs;
+      m_run = m_new;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(B_PFULL);
+    }
+    // ---------------- finalize: O / l -> bf16 -> smem (reuse Q tile) -> TMA store ----------------
+    mbar_wait(B_OFULL, 0);
+    tc_fence_after();
+    const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+    const uint32_t rbase = sbase + SMEM_Q + (row >> 3) * 1024 + (row & 7) * 128;
+    const uint32_t sw = row & 7;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          w[i] = pack_bf16x2(__uint_as_float(o[q * 8 + 2 * i]) * inv_l, __uint_as_float(o[q * 8 + 2 * i + 1]) * inv_l);
+        const uint32_t addr = rbase + ((static_cast<uint32_t>(c * 4 + q) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                     : "memory");
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (warp == 2 && lane == 0) {
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                       reinterpret_cast<uint64_t>(&tmap_o)),
+                   "r"(sbase + SMEM_Q), "r"(p.o_col0 + h * p.q_head_cols), "r"(q0), "r"(b)
+                   : "memory");
+      tma_store_commit();
+      tma_store_wait<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS_ATT);
+  }
+}
+
+}  // namespace
+
+// Generic strided description (all in bf16 elements):
+//   Q/O: [batch][q_len rows][row width], K/V: [kv_batches][kv rows][row width]
+extern "C" int gar_attn_fwd(const void* q, long long q_row_stride, long long q_batch_stride, int q_col0,
+                            const void* k, const void* v, long long kv_row_stride, long long kv_batch_stride,
+                            int kv_batches, int k_col0, int v_col0, int kv_head_cols, int kv_batch_mul,
+                            int kv_batch_head_mul, void* o, long long o_row_stride, long long o_batch_stride,
+                            int o_col0, int batch, int heads, int kv_heads, int head_dim, int q_len, int kv_len,
+                            int kv_rows_alloc, int causal, float scale, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (head_dim != HD) {
+    gar_set_error("gar_attn_fwd: head_dim %d not built (this round: 64)", head_dim);
+    return GAR_ERR_SHAPE;
+  }
+  if (heads % kv_heads || q_len <= 0 || kv_len <= 0 || q_len > kv_len) return GAR_ERR_ARG;
+  CUtensorMap tq, tk, tv, to;
+  int rc;
+  const uint64_t qw = static_cast<uint64_t>(q_row_stride), kw = static_cast<uint64_t>(kv_row_stride),
+                 ow = static_cast<uint64_t>(o_row_stride);
+  if ((rc = gar_make_tmap_3d(&tq, q, qw, q_len, batch, q_row_stride, q_batch_stride, 64, BQ, 1, GAR_SW_128))) return rc;
+  if ((rc = gar_make_tmap_3d(&tk, k, kw, kv_rows_alloc, kv_batches, kv_row_stride, kv_batch_stride, 64, BKV, 1,
+                             GAR_SW_128)))
+    return rc;
+  if ((rc = gar_make_tmap_3d(&tv, v, kw, kv_rows_alloc, kv_batches, kv_row_stride, kv_batch_stride, 64, BKV, 1,
+                             GAR_SW_128)))
+    return rc;
+  if ((rc = gar_make_tmap_3d(&to, o, ow, q_len, batch, o_row_stride, o_batch_stride, 64, BQ, 1, GAR_SW_128))) return rc;
+  AttnParams p;
+  p.q_len = q_len;
+  p.kv_len = kv_len;
+  p.causal = causal;
+  p.q_col0 = q_col0;
+  p.k_col0 = k_col0;
+  p.v_col0 = v_col0;
+  p.o_col0 = o_col0;
+  p.q_head_cols = head_dim;
+  p.kv_head_cols = kv_head_cols;
+  p.group = heads / kv_heads;
+  p.kv_batch_mul = kv_batch_mul;
+  p.kv_batch_head_mul = kv_batch_head_mul;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GAR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_hd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        ATT_SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((q_len + BQ - 1) / BQ, heads, batch);
+  attn_fwd_hd64_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  GAR_CUDA_CHECK(cudaGetLastError());
+  return GAR_OK;
+}

@@ -1,0 +1,451 @@
+// Device-resident pipeline for GARModel.generate() (reference hf_models/modeling_gar.py:295-428):
+//   vit_encode  : R2-R5  mask-id decode, image+mask patch-embed GEMMs, PE-ViT blocks, projector, 2x2 pool
+//   assemble    : R6-R7  embed + image scatter + RoI feature replay (one fused kernel pair)
+//   prefill     : R8     causal Llama prefill into a pre-allocated KV-cache slot, last-position logits
+//   generate    : R9     batched greedy decode, one CUDA graph per step, no host sync in the loop
+// Requests are independent (the reference is batch-1): ViT + prefill run per request, decode is batched
+// across the slots so the weight stream is shared.  All math is in the per-kernel entry points of
+// gar_b200.h; this file only sequences them and owns the workspaces.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gar_b200.h"
+#include "common.cuh"
+
+#define TRY(x)                \
+  do {                        \
+    int _rc = (x);            \
+    if (_rc) return _rc;      \
+  } while (0)
+
+struct gar_engine {
+  gar_model_desc d;
+  std::map<std::string, const void*> w;
+  std::vector<void*> allocs;
+  // geometry
+  int grid, ntok, npt, hd_v, kpad, tpt, tokens_per_tile;
+  // ViT workspaces
+  bf16 *a_img, *a_mask, *pe, *x, *ln, *qkv_v, *att_v, *mlp_v, *p1, *p2, *feats;
+  // LLM workspaces
+  bf16 *emb, *h, *lnl, *qkv_l, *att_l, *gu, *act, *logits, *kcache, *vcache, *hdec, *lndec;
+  float *o_part, *ml_part;
+  int *plan, *status, *next_tok, *out_tokens, *pos, *finished, *step;
+  long long* ids_scratch;
+  int dec_splits;
+  // decode graph
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_batch = -1;
+  long long launches = 0;
+  int launches_per_step = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(gar_engine* e, T** p, size_t count, bool zero = false) {
+  void* q = nullptr;
+  GAR_CUDA_CHECK(cudaMalloc(&q, count * sizeof(T)));
+  if (zero) GAR_CUDA_CHECK(cudaMemset(q, 0, count * sizeof(T)));
+  e->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return GAR_OK;
+}
+
+const void* W(gar_engine* e, const std::string& name, bool required = true) {
+  auto it = e->w.find(name);
+  if (it == e->w.end()) {
+    if (required) gar_set_error("gar_engine: weight '%s' was never set", name.c_str());
+    return nullptr;
+  }
+  return it->second;
+}
+#define NEEDW(var, name)                 \
+  const void* var = W(e, name);          \
+  if (!var) return GAR_ERR_STATE
+
+std::string L(const char* prefix, int i, const char* suffix) {
+  return std::string(prefix) + "." + std::to_string(i) + "." + suffix;
+}
+
+int gemm(gar_engine* e, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K, int epi,
+         const void* bias, const void* gamma, const void* res, int ldres, void* s) {
+  e->launches += 1;
+  return gar_gemm_bf16(A, lda, B, ldb, C, ldc, M, N, K, epi, bias, gamma, res, ldres, 0, s);
+}
+
+// one Llama layer stack over `rows` rows of e->h (prefill: rows = S, one slot; decode: rows = batch)
+int llm_layers(gar_engine* e, bf16* h, bf16* ln, int rows, bool decode, int slot, void* s) {
+  const gar_model_desc& d = e->d;
+  const int D = d.llm_dim, hq = d.llm_heads, hkv = d.llm_kv_heads, hd = d.llm_head_dim, I = d.llm_inter;
+  const int qkv_w = (hq + 2 * hkv) * hd;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  NEEDW(cos_t, "llm.cos");
+  NEEDW(sin_t, "llm.sin");
+  for (int i = 0; i < d.llm_layers; ++i) {
+    NEEDW(ln1, L("llm", i, "ln1"));
+    NEEDW(wqkv, L("llm", i, "qkv.w"));
+    NEEDW(wo, L("llm", i, "o.w"));
+    NEEDW(ln2, L("llm", i, "ln2"));
+    NEEDW(wgu, L("llm", i, "gu.w"));
+    NEEDW(wdown, L("llm", i, "down.w"));
+    bf16* kc = e->kcache + static_cast<size_t>(i) * d.max_batch * hkv * d.max_seq * hd;
+    bf16* vc = e->vcache + static_cast<size_t>(i) * d.max_batch * hkv * d.max_seq * hd;
+    TRY(gar_rmsnorm(h, D, ln1, ln, D, rows, D, d.rms_eps, s));
+    TRY(gemm(e, ln, D, wqkv, D, e->qkv_l, qkv_w, rows, qkv_w, D, GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s));
+    if (decode) {
+      // decode: row b is sequence slot b, positions come from the device-side counters
+      TRY(gar_llama_rope_kv(e->qkv_l, rows, hq, hkv, hd, cos_t, sin_t, 0, e->pos, nullptr, -1, kc, vc, d.max_seq, s));
+    } else {
+      TRY(gar_llama_rope_kv(e->qkv_l, rows, hq, hkv, hd, cos_t, sin_t, 0, nullptr, nullptr, slot, kc, vc, d.max_seq, s));
+    }
+    e->launches += 2;
+    if (decode) {
+      TRY(gar_decode_attn(e->qkv_l, qkv_w, kc, vc, e->pos, nullptr, rows, hq, hkv, hd, d.max_seq, e->dec_splits, scale,
+                          e->o_part, e->ml_part, e->att_l, hq * hd, s));
+      e->launches += 2;
+    } else {
+      const bf16* kslot = kc + static_cast<size_t>(slot) * hkv * d.max_seq * hd;
+      const bf16* vslot = vc + static_cast<size_t>(slot) * hkv * d.max_seq * hd;
+      TRY(gar_attn_fwd(e->qkv_l, qkv_w, static_cast<long long>(rows) * qkv_w, 0, kslot, vslot, hd,
+                       static_cast<long long>(d.max_seq) * hd, hkv, 0, 0, 0, 0, 1, e->att_l, hq * hd,
+                       static_cast<long long>(rows) * hq * hd, 0, 1, hq, hkv, hd, rows, rows, d.max_seq, 1, scale, s));
+      e->launches += 1;
+    }
+    TRY(gemm(e, e->att_l, hq * hd, wo, hq * hd, h, D, rows, D, hq * hd, GAR_EPI_RES, nullptr, nullptr, h, D, s));
+    TRY(gar_rmsnorm(h, D, ln2, ln, D, rows, D, d.rms_eps, s));
+    TRY(gemm(e, ln, D, wgu, D, e->gu, 2 * I, rows, 2 * I, D, GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s));
+    TRY(gar_swiglu(e->gu, e->act, rows, I, s));
+    TRY(gemm(e, e->act, I, wdown, I, h, D, rows, D, I, GAR_EPI_RES, nullptr, nullptr, h, D, s));
+    e->launches += 1;
+  }
+  return GAR_OK;
+}
+
+int lm_head(gar_engine* e, const bf16* hrows, int ldh, int rows, bf16* logits, void* s) {
+  const gar_model_desc& d = e->d;
+  NEEDW(wn, "llm.norm");
+  NEEDW(wl, "llm.lm_head");
+  TRY(gar_rmsnorm(hrows, ldh, wn, e->lndec, d.llm_dim, rows, d.llm_dim, d.rms_eps, s));
+  e->launches += 1;
+  return gemm(e, e->lndec, d.llm_dim, wl, d.llm_dim, logits, d.vocab_padded, rows, d.vocab_padded, d.llm_dim,
+              GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s);
+}
+
+int decode_step(gar_engine* e, int batch, int eos, void* s) {
+  const gar_model_desc& d = e->d;
+  NEEDW(table, "llm.embed");
+  TRY(gar_embed_gather(table, nullptr, e->next_tok, e->hdec, batch, d.llm_dim, s));
+  e->launches += 1;
+  TRY(llm_layers(e, e->hdec, e->lndec, batch, true, 0, s));
+  TRY(lm_head(e, e->hdec, d.llm_dim, batch, e->logits, s));
+  TRY(gar_argmax_step(e->logits, d.vocab_padded, d.vocab, batch, e->next_tok, e->out_tokens, d.max_new_tokens, e->step,
+                      e->pos, e->finished, eos, 1, s));
+  TRY(gar_bump_step(e->step, s));
+  e->launches += 2;
+  return GAR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
+  if (!desc || !out) return GAR_ERR_ARG;
+  const gar_model_desc& d = *desc;
+  if (d.vit_dim % d.vit_heads || d.img_size % d.patch_size || d.vit_dim / d.vit_heads != 64 || d.llm_head_dim != 64) {
+    gar_set_error("gar_engine_create: this build supports head_dim 64 only (vit %d, llm %d)", d.vit_dim / d.vit_heads,
+                  d.llm_head_dim);
+    return GAR_ERR_SHAPE;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    gar_set_error("gar_engine_create: no CUDA device (this library has no CPU path)");
+    return GAR_ERR_CUDA;
+  }
+  gar_engine* e = new gar_engine();
+  e->d = d;
+  e->grid = d.img_size / d.patch_size;
+  e->npt = d.vit_use_cls ? 1 : 0;
+  e->ntok = e->grid * e->grid + e->npt;
+  e->hd_v = d.vit_dim / d.vit_heads;
+  e->kpad = ((3 * d.patch_size * d.patch_size + 63) / 64) * 64;
+  e->tpt = e->grid / d.pool_ratio;
+  e->tokens_per_tile = e->tpt * e->tpt;
+  e->dec_splits = 8;
+  const size_t T = d.max_tiles, NP = static_cast<size_t>(e->grid) * e->grid, NT = e->ntok;
+  const size_t dv = d.vit_dim, D = d.llm_dim, S = d.max_seq, B = d.max_batch;
+  const size_t qkv_w = static_cast<size_t>(d.llm_heads + 2 * d.llm_kv_heads) * d.llm_head_dim;
+  int rc = 0;
+  rc |= dev_alloc(e, &e->a_img, T * NP * e->kpad, true);
+  rc |= dev_alloc(e, &e->a_mask, T * NP * e->kpad, true);
+  rc |= dev_alloc(e, &e->pe, T * NP * dv);
+  rc |= dev_alloc(e, &e->x, T * NT * dv);
+  rc |= dev_alloc(e, &e->ln, T * NT * dv);
+  rc |= dev_alloc(e, &e->qkv_v, T * NT * 3 * dv);
+  rc |= dev_alloc(e, &e->att_v, T * NT * dv);
+  rc |= dev_alloc(e, &e->mlp_v, T * NT * d.vit_mlp);
+  rc |= dev_alloc(e, &e->p1, T * NT * D);
+  rc |= dev_alloc(e, &e->p2, T * NT * D);
+  rc |= dev_alloc(e, &e->feats, T * e->tokens_per_tile * D);
+  rc |= dev_alloc(e, &e->emb, S * D);
+  rc |= dev_alloc(e, &e->h, S * D);
+  rc |= dev_alloc(e, &e->lnl, S * D);
+  rc |= dev_alloc(e, &e->qkv_l, S * qkv_w);
+  rc |= dev_alloc(e, &e->att_l, S * d.llm_heads * d.llm_head_dim);
+  rc |= dev_alloc(e, &e->gu, S * 2 * d.llm_inter);
+  rc |= dev_alloc(e, &e->act, S * d.llm_inter);
+  rc |= dev_alloc(e, &e->logits, B * d.vocab_padded, true);
+  rc |= dev_alloc(e, &e->hdec, B * D);
+  rc |= dev_alloc(e, &e->lndec, (B > 1 ? B : 1) * D);
+  const size_t kv_elems = static_cast<size_t>(d.llm_layers) * B * d.llm_kv_heads * S * d.llm_head_dim;
+  rc |= dev_alloc(e, &e->kcache, kv_elems, true);  // zero-filled: TMA tiles past the live length must be finite
+  rc |= dev_alloc(e, &e->vcache, kv_elems, true);
+  rc |= dev_alloc(e, &e->o_part, B * d.llm_heads * e->dec_splits * d.llm_head_dim);
+  rc |= dev_alloc(e, &e->ml_part, B * d.llm_heads * e->dec_splits * 2);
+  rc |= dev_alloc(e, &e->plan, S);
+  rc |= dev_alloc(e, &e->status, 2 * B, true);
+  rc |= dev_alloc(e, &e->next_tok, B, true);
+  rc |= dev_alloc(e, &e->out_tokens, B * d.max_new_tokens, true);
+  rc |= dev_alloc(e, &e->pos, B, true);
+  rc |= dev_alloc(e, &e->finished, B, true);
+  rc |= dev_alloc(e, &e->step, 1, true);
+  rc |= dev_alloc(e, &e->ids_scratch, S);
+  if (rc) {
+    gar_engine_destroy(e);
+    return GAR_ERR_CUDA;
+  }
+  *out = e;
+  return GAR_OK;
+}
+
+int gar_engine_destroy(gar_engine* e) {
+  if (!e) return GAR_OK;
+  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  for (void* p : e->allocs) cudaFree(p);
+  delete e;
+  return GAR_OK;
+}
+
+int gar_engine_set_weight(gar_engine* e, const char* name, const void* dev_ptr) {
+  if (!e || !name) return GAR_ERR_ARG;
+  e->w[name] = dev_ptr;
+  return GAR_OK;
+}
+
+int gar_engine_get_buffer(gar_engine* e, const char* name, void** dev_ptr, long long* bytes) {
+  if (!e || !name || !dev_ptr) return GAR_ERR_ARG;
+  const gar_model_desc& d = e->d;
+  const std::string n(name);
+  const long long T = d.max_tiles;
+  long long b = 0;
+  void* p = nullptr;
+  if (n == "image_features") { p = e->feats; b = T * e->tokens_per_tile * d.llm_dim * 2; }
+  else if (n == "inputs_embeds") { p = e->emb; b = static_cast<long long>(d.max_seq) * d.llm_dim * 2; }
+  else if (n == "hidden") { p = e->h; b = static_cast<long long>(d.max_seq) * d.llm_dim * 2; }
+  else if (n == "logits") { p = e->logits; b = static_cast<long long>(d.max_batch) * d.vocab_padded * 2; }
+  else if (n == "patch_embed") { p = e->pe; b = T * e->grid * e->grid * d.vit_dim * 2; }
+  else if (n == "vit_x") { p = e->x; b = T * e->ntok * d.vit_dim * 2; }
+  else if (n == "kcache") { p = e->kcache; b = static_cast<long long>(d.llm_layers) * d.max_batch * d.llm_kv_heads * d.max_seq * d.llm_head_dim * 2; }
+  else if (n == "vcache") { p = e->vcache; b = static_cast<long long>(d.llm_layers) * d.max_batch * d.llm_kv_heads * d.max_seq * d.llm_head_dim * 2; }
+  else if (n == "out_tokens") { p = e->out_tokens; b = static_cast<long long>(d.max_batch) * d.max_new_tokens * 4; }
+  else {
+    gar_set_error("gar_engine_get_buffer: unknown buffer '%s'", name);
+    return GAR_ERR_ARG;
+  }
+  *dev_ptr = p;
+  if (bytes) *bytes = b;
+  return GAR_OK;
+}
+
+int gar_engine_vit_encode(gar_engine* e, const void* pixel_values, const void* mask_values, int T, void* s) {
+  if (!e || !pixel_values || T <= 0 || T > e->d.max_tiles) {
+    gar_set_error("gar_engine_vit_encode: T=%d outside [1,%d]", T, e ? e->d.max_tiles : 0);
+    return GAR_ERR_ARG;
+  }
+  const gar_model_desc& d = e->d;
+  const int dv = d.vit_dim, NP = e->grid * e->grid, NT = e->ntok, rows = T * NT, D = d.llm_dim;
+  NEEDW(wp, "vit.patch_w");
+  NEEDW(pos, "vit.pos");
+  NEEDW(npw, "vit.norm_pre.w");
+  NEEDW(npb, "vit.norm_pre.b");
+  NEEDW(rope, "vit.rope");
+  const void* cls = e->npt ? W(e, "vit.cls") : nullptr;
+  if (e->npt && !cls) return GAR_ERR_STATE;
+  // R2+R3 operand prep, then the two k=s=14 convs as GEMMs: x = bf16(conv(px)) ; x = bf16(x + bf16(conv(mask)))
+  TRY(gar_patchify(pixel_values, mask_values, e->a_img, e->a_mask, T, d.img_size, d.patch_size, e->kpad,
+                   d.prompt_numbers, s));
+  e->launches += 1;
+  TRY(gemm(e, e->a_img, e->kpad, wp, e->kpad, e->pe, dv, T * NP, dv, e->kpad, GAR_EPI_NONE, nullptr, nullptr, nullptr,
+           0, s));
+  if (mask_values) {
+    NEEDW(wm, "vit.mask_w");
+    TRY(gemm(e, e->a_mask, e->kpad, wm, e->kpad, e->pe, dv, T * NP, dv, e->kpad, GAR_EPI_RES, nullptr, nullptr, e->pe,
+             dv, s));
+  }
+  TRY(gar_vit_embed_ln(e->pe, cls, pos, npw, npb, e->x, T, NT, e->npt, dv, d.ln_eps, s));
+  e->launches += 1;
+  const float scale = 1.0f / sqrtf(static_cast<float>(e->hd_v));
+  for (int i = 0; i < d.vit_depth; ++i) {
+    NEEDW(l1w, L("vit", i, "ln1.w"));
+    NEEDW(l1b, L("vit", i, "ln1.b"));
+    NEEDW(wqkv, L("vit", i, "qkv.w"));
+    NEEDW(bqkv, L("vit", i, "qkv.b"));
+    NEEDW(wpr, L("vit", i, "proj.w"));
+    NEEDW(bpr, L("vit", i, "proj.b"));
+    NEEDW(g1, L("vit", i, "g1"));
+    NEEDW(l2w, L("vit", i, "ln2.w"));
+    NEEDW(l2b, L("vit", i, "ln2.b"));
+    NEEDW(w1, L("vit", i, "fc1.w"));
+    NEEDW(b1, L("vit", i, "fc1.b"));
+    NEEDW(w2, L("vit", i, "fc2.w"));
+    NEEDW(b2, L("vit", i, "fc2.b"));
+    NEEDW(g2, L("vit", i, "g2"));
+    TRY(gar_layernorm(e->x, dv, l1w, l1b, e->ln, dv, rows, dv, d.ln_eps, s));
+    TRY(gemm(e, e->ln, dv, wqkv, dv, e->qkv_v, 3 * dv, rows, 3 * dv, dv, GAR_EPI_BIAS, bqkv, nullptr, nullptr, 0, s));
+    TRY(gar_vit_rope(e->qkv_v, rope, rows, NT, e->npt, d.vit_heads, e->hd_v, s));
+    TRY(gar_attn_fwd(e->qkv_v, 3 * dv, static_cast<long long>(NT) * 3 * dv, 0, e->qkv_v, e->qkv_v, 3 * dv,
+                     static_cast<long long>(NT) * 3 * dv, T, dv, 2 * dv, e->hd_v, 1, 0, e->att_v, dv,
+                     static_cast<long long>(NT) * dv, 0, T, d.vit_heads, d.vit_heads, e->hd_v, NT, NT, NT, 0, scale, s));
+    TRY(gemm(e, e->att_v, dv, wpr, dv, e->x, dv, rows, dv, dv, GAR_EPI_BIAS_LS_RES, bpr, g1, e->x, dv, s));
+    TRY(gar_layernorm(e->x, dv, l2w, l2b, e->ln, dv, rows, dv, d.ln_eps, s));
+    TRY(gemm(e, e->ln, dv, w1, dv, e->mlp_v, d.vit_mlp, rows, d.vit_mlp, dv, GAR_EPI_BIAS_GELU, b1, nullptr, nullptr, 0,
+             s));
+    TRY(gemm(e, e->mlp_v, d.vit_mlp, w2, d.vit_mlp, e->x, dv, rows, dv, d.vit_mlp, GAR_EPI_BIAS_LS_RES, b2, g2, e->x, dv,
+             s));
+    e->launches += 4;
+  }
+  // projector on every token row (cls rows are computed and then skipped by the pool: 0.1% extra work)
+  NEEDW(pw1, "proj.l1.w");
+  NEEDW(pb1, "proj.l1.b");
+  NEEDW(pw2, "proj.l2.w");
+  NEEDW(pb2, "proj.l2.b");
+  TRY(gemm(e, e->x, dv, pw1, dv, e->p1, D, rows, D, dv, GAR_EPI_BIAS_GELU, pb1, nullptr, nullptr, 0, s));
+  TRY(gemm(e, e->p1, D, pw2, D, e->p2, D, rows, D, D, GAR_EPI_BIAS, pb2, nullptr, nullptr, 0, s));
+  if (d.pool_ratio == 2) {
+    TRY(gar_pool2x2(e->p2, e->feats, T, NT, e->npt, e->grid, D, s));
+  } else {
+    gar_set_error("gar_engine_vit_encode: projector_pooling_ratio %d not built (2 only)", d.pool_ratio);
+    return GAR_ERR_SHAPE;
+  }
+  e->launches += 1;
+  return GAR_OK;
+}
+
+int gar_engine_assemble(gar_engine* e, int slot, const long long* input_ids_dev, int S, int T, const float* rois,
+                        const int* has_roi, float spatial_scale, int ncw, int nch, void* s) {
+  if (!e || slot < 0 || slot >= e->d.max_batch || S <= 0 || S > e->d.max_seq) {
+    gar_set_error("gar_engine_assemble: slot=%d S=%d outside capacity (max_batch=%d max_seq=%d)", slot, S,
+                  e ? e->d.max_batch : 0, e ? e->d.max_seq : 0);
+    return GAR_ERR_ARG;
+  }
+  if (ncw * nch != T - 1) {  // reference assert in _merge, modeling_gar.py:250
+    gar_set_error("%d != %d", ncw * nch, T - 1);
+    return GAR_ERR_SHAPE;
+  }
+  const gar_model_desc& d = e->d;
+  NEEDW(table, "llm.embed");
+  e->launches += 2;
+  return gar_assemble_embeds(input_ids_dev, S, table, d.vocab, e->feats, T * e->tokens_per_tile, d.llm_dim,
+                             d.crop_token_ids, rois, has_roi, d.prompt_numbers, spatial_scale, ncw, nch, e->tpt,
+                             d.image_token_id, e->emb, e->plan, e->status + 2 * slot, s);
+}
+
+int gar_engine_prefill(gar_engine* e, int slot, int S, void* s) {
+  if (!e || slot < 0 || slot >= e->d.max_batch || S <= 0 || S + e->d.max_new_tokens > e->d.max_seq) {
+    gar_set_error("gar_engine_prefill: slot=%d S=%d (+%d new) exceeds max_seq=%d", slot, S,
+                  e ? e->d.max_new_tokens : 0, e ? e->d.max_seq : 0);
+    return GAR_ERR_ARG;
+  }
+  const gar_model_desc& d = e->d;
+  GAR_CUDA_CHECK(cudaMemcpyAsync(e->h, e->emb, static_cast<size_t>(S) * d.llm_dim * 2, cudaMemcpyDeviceToDevice,
+                                 static_cast<cudaStream_t>(s)));
+  TRY(llm_layers(e, e->h, e->lnl, S, false, slot, s));
+  // logits only for the last position (logits_to_keep=1 in HF generate's prefill)
+  TRY(lm_head(e, e->h + static_cast<size_t>(S - 1) * d.llm_dim, d.llm_dim, 1,
+              e->logits + static_cast<size_t>(slot) * d.vocab_padded, s));
+  const int pos = S;
+  GAR_CUDA_CHECK(cudaMemcpyAsync(e->pos + slot, &pos, sizeof(int), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(s)));
+  return GAR_OK;
+}
+
+int gar_engine_prefill_all_logits(gar_engine* e, int slot, int S, void* logits_out, void* s) {
+  if (!e || !logits_out || slot < 0 || slot >= e->d.max_batch || S <= 0 || S > e->d.max_seq) return GAR_ERR_ARG;
+  const gar_model_desc& d = e->d;
+  GAR_CUDA_CHECK(cudaMemcpyAsync(e->h, e->emb, static_cast<size_t>(S) * d.llm_dim * 2, cudaMemcpyDeviceToDevice,
+                                 static_cast<cudaStream_t>(s)));
+  TRY(llm_layers(e, e->h, e->lnl, S, false, slot, s));
+  NEEDW(wn, "llm.norm");
+  NEEDW(wl, "llm.lm_head");
+  TRY(gar_rmsnorm(e->h, d.llm_dim, wn, e->lnl, d.llm_dim, S, d.llm_dim, d.rms_eps, s));
+  e->launches += 1;
+  return gemm(e, e->lnl, d.llm_dim, wl, d.llm_dim, logits_out, d.vocab_padded, S, d.vocab_padded, d.llm_dim,
+              GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s);
+}
+
+int gar_engine_generate(gar_engine* e, int batch, int max_new_tokens, int eos, int* out_tokens_host, void* s_) {
+  cudaStream_t s = static_cast<cudaStream_t>(s_);
+  if (!e || batch <= 0 || batch > e->d.max_batch || max_new_tokens <= 0 || max_new_tokens > e->d.max_new_tokens ||
+      !out_tokens_host) {
+    gar_set_error("gar_engine_generate: batch=%d max_new_tokens=%d outside capacity", batch, max_new_tokens);
+    return GAR_ERR_ARG;
+  }
+  const gar_model_desc& d = e->d;
+  GAR_CUDA_CHECK(cudaMemsetAsync(e->step, 0, sizeof(int), s));
+  GAR_CUDA_CHECK(cudaMemsetAsync(e->finished, 0, sizeof(int) * batch, s));
+  GAR_CUDA_CHECK(cudaMemsetAsync(e->out_tokens, 0xff, sizeof(int) * d.max_batch * d.max_new_tokens, s));
+  // token 0 from the prefill logits (position bookkeeping already at S per slot)
+  TRY(gar_argmax_step(e->logits, d.vocab_padded, d.vocab, batch, e->next_tok, e->out_tokens, d.max_new_tokens, e->step,
+                      e->pos, e->finished, eos, 0, s));
+  TRY(gar_bump_step(e->step, s));
+  e->launches += 2;
+  const int steps = max_new_tokens - 1;
+  if (steps > 0) {
+    // step 1 eagerly (also the warm-up that sets every kernel attribute), the rest as graph replays
+    const long long before = e->launches;
+    TRY(decode_step(e, batch, eos, s));
+    e->launches_per_step = static_cast<int>(e->launches - before);
+    if (steps > 1) {
+      if (e->graph_exec == nullptr || e->graph_batch != batch) {
+        if (s == nullptr || s == cudaStreamLegacy) {
+          gar_set_error("gar_engine_generate: needs a non-default stream (CUDA graph capture)");
+          return GAR_ERR_ARG;
+        }
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        GAR_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const long long keep = e->launches;
+        int rc = decode_step(e, batch, eos, s);
+        e->launches = keep;
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc) return rc;
+        GAR_CUDA_CHECK(ce);
+        GAR_CUDA_CHECK(cudaGraphInstantiate(&e->graph_exec, graph, 0));
+        cudaGraphDestroy(graph);
+        e->graph_batch = batch;
+      }
+      // EOS is latched on the device; sequences that finished keep stepping (outputs masked to -1)
+      for (int i = 1; i < steps; ++i) GAR_CUDA_CHECK(cudaGraphLaunch(e->graph_exec, s));
+      e->launches += static_cast<long long>(e->launches_per_step) * (steps - 1);
+    }
+  }
+  std::vector<int> tmp(static_cast<size_t>(d.max_batch) * d.max_new_tokens);
+  GAR_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), e->out_tokens, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+  GAR_CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int b = 0; b < batch; ++b)
+    for (int t = 0; t < max_new_tokens; ++t)
+      out_tokens_host[b * max_new_tokens + t] = tmp[static_cast<size_t>(b) * d.max_new_tokens + t];
+  return GAR_OK;
+}
+
+int gar_engine_status(gar_engine* e, int slot, int* status_bits) {
+  if (!e || slot < 0 || slot >= e->d.max_batch || !status_bits) return GAR_ERR_ARG;
+  int st[2] = {0, 0};
+  GAR_CUDA_CHECK(cudaMemcpy(st, e->status + 2 * slot, sizeof(st), cudaMemcpyDeviceToHost));
+  *status_bits = st[0];
+  return GAR_OK;
+}
+
+long long gar_engine_launch_count(gar_engine* e) { return e ? e->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+// C[M,N] = epilogue(A[M,K] * B[N,K]^T)   bf16 in, fp32 accumulate in TMEM, bf16 out.
+//
+// Replaces the cuBLAS(Lt) GEMMs + ATen bias/GELU/mul/add launches behind the reference's
+// nn.Linear / nn.Conv2d(k=s) calls (timm EvaBlock qkv/proj/fc1/fc2, PerceptionLM projector
+// modeling_perception_lm.py:85-92, HF Llama q/k/v/o/gate/up/down -- SURVEY.md §2b K1,K2,K5,K6,K9).
+//
+// B200-native structure (no CUTLASS): persistent CTAs, one 128 x BLOCK_N output tile at a time.
+//   warp 0      TMA producer   : cp.async.bulk.tensor 128B-swizzled A/B k-slabs into a smem ring
+//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16)
+//   warp 2      TMEM allocator
+//   warps 4..11 epilogue       : tcgen05.ld accumulator -> registers -> fused epilogue with the
+//                                reference's bf16 rounding points -> swizzled smem -> TMA store
+// Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_THREADS = 256;
+constexpr int C_CHUNK = 32;                               // columns per TMA store box
+constexpr int C_STAGE_BYTES = BLOCK_M * C_CHUNK * 2;      // 8 KB, 64B-swizzled rows
+
+enum Epi { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_BIAS_LS_RES = 3, EPI_RES = 4 };
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (power of two >= 32)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * C_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct EpiArgs {
+  const bf16* bias;
+  const bf16* gamma;
+  const bf16* res;
+  int ldres;
+};
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, EpiArgs ea) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_ab = smem_base;
+  const uint32_t smem_c = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = smem_c + 4 * C_STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] ; then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * C::STAGES + 4);
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_ptr_smem - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = K / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), EPI_THREADS / 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          const uint32_t sa = smem_ab + stage * C::STAGE_BYTES;
+          tma_load_2d(sa, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M, full_bar(stage));
+          tma_load_2d(sa + C::A_BYTES, &tmap_b, kb * BLOCK_K, n_blk * BLOCK_N, full_bar(stage));
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_ab + stage * C::STAGE_BYTES;
+          const uint64_t adesc = umma_desc_sw128(sa, 0, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sa + C::A_BYTES, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the >>4 address field
+            umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ----------------------------------
+    const int ew = warp - 4;           // 0..7
+    const int quarter = warp & 3;      // TMEM lane quarter this warp may touch (warp id % 4)
+    const int half = ew >> 2;          // which half of the tile's columns
+    const int row = quarter * 32 + lane;
+    constexpr int COLS_PER_HALF = BLOCK_N / 2;
+    constexpr int CHUNKS = COLS_PER_HALF / C_CHUNK;
+    const uint32_t stage_c0 = smem_c + half * 2 * C_STAGE_BYTES;
+    const uint32_t bar_id = 1 + half;  // named barriers 1,2 (0 is __syncthreads)
+    const bool issuer = (quarter == 0 && lane == 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int cbuf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int gm = m_blk * BLOCK_M + row;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int col0 = half * COLS_PER_HALF + c * C_CHUNK;
+        const int gn = n_blk * BLOCK_N + col0;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + col0, r);
+        tmem_ld_wait();
+        if (c == CHUNKS - 1) {
+          // all of this warp's TMEM reads for the tile are done -> release the accumulator stage
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        const bool col_ok = gn < N;  // N % 32 == 0 is enforced on the host
+        uint32_t packed[16];
+        if (col_ok) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_LS_RES) {
+            const uint4* bp = reinterpret_cast<const uint4*>(ea.bias + gn);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 b = __ldg(bp + q);
+              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(bw[j]);
+                v[q * 8 + j * 2] += f.x;
+                v[q * 8 + j * 2 + 1] += f.y;
+              }
+            }
+          }
+          // first rounding point: the Linear's bf16 output
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = bf16r(v[i]);
+          if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          }
+          if (EPI == EPI_BIAS_LS_RES) {
+            const uint4* gp = reinterpret_cast<const uint4*>(ea.gamma + gn);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 g = __ldg(gp + q);
+              const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(gw[j]);
+                v[q * 8 + j * 2] = bf16r(v[q * 8 + j * 2] * f.x);
+                v[q * 8 + j * 2 + 1] = bf16r(v[q * 8 + j * 2 + 1] * f.y);
+              }
+            }
+          }
+          if (EPI == EPI_BIAS_LS_RES || EPI == EPI_RES) {
+            if (gm < M) {
+              const uint4* rp = reinterpret_cast<const uint4*>(ea.res + static_cast<size_t>(gm) * ea.ldres + gn);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 x = rp[q];
+                const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = unpack_bf16x2(xw[j]);
+                  v[q * 8 + j * 2] += f.x;
+                  v[q * 8 + j * 2 + 1] += f.y;
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        }
+        // staging buffer reuse: the TMA store issued two chunks ago must have finished reading smem
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(bar_id, 128);
+        if (col_ok) {
+          const uint32_t rbase = stage_c0 + cbuf * C_STAGE_BYTES + row * 64;
+          const uint32_t sw = (row >> 1) & 3;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t addr = rbase + ((static_cast<uint32_t>(q) ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[q * 4]),
+                         "r"(packed[q * 4 + 1]), "r"(packed[q * 4 + 2]), "r"(packed[q * 4 + 3])
+                         : "memory");
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (issuer && col_ok) {
+          tma_store_2d(&tmap_c, stage_c0 + cbuf * C_STAGE_BYTES, gn, m_blk * BLOCK_M);
+        }
+        if (issuer) tma_store_commit();
+        cbuf ^= 1;
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (issuer) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, int EPI>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
+                const EpiArgs& ea, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GAR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = num_tiles < gar_num_sms() ? num_tiles : gar_num_sms();
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tc, M, N, K, ea);
+  GAR_CUDA_CHECK(cudaGetLastError());
+  return GAR_OK;
+}
+
+template <int BLOCK_N>
+int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
+                 const EpiArgs& ea, cudaStream_t stream) {
+  switch (epi) {
+    case EPI_NONE: return launch_gemm<BLOCK_N, EPI_NONE>(ta, tb, tc, M, N, K, ea, stream);
+    case EPI_BIAS: return launch_gemm<BLOCK_N, EPI_BIAS>(ta, tb, tc, M, N, K, ea, stream);
+    case EPI_BIAS_GELU: return launch_gemm<BLOCK_N, EPI_BIAS_GELU>(ta, tb, tc, M, N, K, ea, stream);
+    case EPI_BIAS_LS_RES: return launch_gemm<BLOCK_N, EPI_BIAS_LS_RES>(ta, tb, tc, M, N, K, ea, stream);
+    case EPI_RES: return launch_gemm<BLOCK_N, EPI_RES>(ta, tb, tc, M, N, K, ea, stream);
+  }
+  gar_set_error("gar_gemm_bf16: unknown epilogue %d", epi);
+  return GAR_ERR_ARG;
+}
+
+}  // namespace
+
+extern "C" int gar_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* Cout, int ldc, int M, int N, int K,
+                             int epi, const void* bias, const void* gamma, const void* res, int ldres,
+                             int block_n_hint, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (M <= 0 || N <= 0 || K <= 0 || (K % BLOCK_K) != 0 || (N % 32) != 0 || (lda % 8) || (ldb % 8) || (ldc % 8)) {
+    gar_set_error("gar_gemm_bf16: unsupported shape M=%d N=%d K=%d lda=%d ldb=%d ldc=%d (need K%%64==0, N%%32==0, ld%%8==0)",
+                  M, N, K, lda, ldb, ldc);
+    return GAR_ERR_SHAPE;
+  }
+  if ((epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_LS_RES) && !bias) return GAR_ERR_ARG;
+  if (epi == EPI_BIAS_LS_RES && !gamma) return GAR_ERR_ARG;
+  if ((epi == EPI_BIAS_LS_RES || epi == EPI_RES) && (!res || (ldres % 8))) return GAR_ERR_ARG;
+  int bn = block_n_hint;
+  if (bn != 64 && bn != 128 && bn != 256) {
+    // widest tile that still gives every SM a tile; wide tiles halve A re-reads from L2
+    const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+    const int sms = gar_num_sms();
+    bn = 64;
+    const int cand[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      if (num_m * ((N + cand[i] - 1) / cand[i]) >= sms) { bn = cand[i]; break; }
+    }
+  }
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if ((rc = gar_make_tmap_2d(&ta, A, K, M, lda, BLOCK_K, BLOCK_M, GAR_SW_128))) return rc;
+  if ((rc = gar_make_tmap_2d(&tb, B, K, N, ldb, BLOCK_K, bn, GAR_SW_128))) return rc;
+  if ((rc = gar_make_tmap_2d(&tc, Cout, N, M, ldc, C_CHUNK, BLOCK_M, GAR_SW_64))) return rc;
+  EpiArgs ea{static_cast<const bf16*>(bias), static_cast<const bf16*>(gamma), static_cast<const bf16*>(res), ldres};
+  if (bn == 256) return dispatch_epi<256>(epi, ta, tb, tc, M, N, K, ea, stream);
+  if (bn == 128) return dispatch_epi<128>(epi, ta, tb, tc, M, N, K, ea, stream);
+  return dispatch_epi<64>(epi, ta, tb, tc, M, N, K, ea, stream);
+}

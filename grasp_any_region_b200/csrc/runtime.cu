@@ -1,0 +1,97 @@
+// Host-side runtime shared by every kernel file: error string, SM count, TMA descriptor encode.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void gar_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* gar_last_error(void) { return g_err; }
+extern "C" int gar_abi_version(void) { return 1; }
+
+int gar_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle to_cu_swizzle(GarSwizzle sw) {
+  switch (sw) {
+    case GAR_SW_32: return CU_TENSOR_MAP_SWIZZLE_32B;
+    case GAR_SW_64: return CU_TENSOR_MAP_SWIZZLE_64B;
+    case GAR_SW_128: return CU_TENSOR_MAP_SWIZZLE_128B;
+    default: return CU_TENSOR_MAP_SWIZZLE_NONE;
+  }
+}
+
+int gar_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                     uint32_t box_inner, uint32_t box_outer, GarSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    gar_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return GAR_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, to_cu_swizzle(sw), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    gar_set_error("cuTensorMapEncodeTiled(2d) failed: %d (base=%p dims=%llu,%llu pitch=%llu box=%u,%u)", (int)r, base,
+                  (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_elems, box_inner,
+                  box_outer);
+    return GAR_ERR_CUDA;
+  }
+  return GAR_OK;
+}
+
+int gar_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t p1,
+                     uint64_t p2, uint32_t b0, uint32_t b1, uint32_t b2, GarSwizzle sw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    gar_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return GAR_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {p1 * 2, p2 * 2};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, to_cu_swizzle(sw), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    gar_set_error("cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+    return GAR_ERR_CUDA;
+  }
+  return GAR_OK;
+}

@@ -1,0 +1,222 @@
+"""Python owner of one ``gar_engine`` (include/gar_b200.h): lays the reference's HF state dict out
+the way the kernels want it (fused qkv / gate-up, K-padded conv matrices, padded lm_head, RoPE
+tables), keeps those tensors alive, and drives the stage entry points.
+
+State-dict key layout follows the reference checkpoint (modeling_gar.py:47-60,
+convert_to_hf.py:126-135): ``mllm.model.vision_tower.timm_model.*``,
+``mllm.model.multi_modal_projector.linear_{1,2}.*``, ``mllm.model.language_model.*``,
+``mllm.lm_head.weight``, ``mask_patch_embedding.weight``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import GarModelDesc, check
+from .config import GARSpec
+from .rope import llama_cos_sin, vit_rope_table
+
+VT = "mllm.model.vision_tower.timm_model."
+PJ = "mllm.model.multi_modal_projector."
+LM = "mllm.model.language_model."
+
+
+def roi_boxes_f32(spec: GARSpec, bboxes: Dict[str, Sequence[float]], ncw: int, nch: int):
+    """Box arithmetic exactly as modeling_gar.py:366-387 does it on the host: python doubles, then one
+    rounding to fp32 (torch.tensor(..., dtype=float32)).  Returns (rois flat list, has list, scale)."""
+    tpt = int(math.isqrt(spec.tokens_per_tile))
+    feat_h, feat_w = nch * tpt, ncw * tpt
+    orig_h, orig_w = feat_h * 28, feat_w * 28
+    spatial_scale = feat_w / orig_w
+    rois, has = [], []
+    for cid in spec.crop_tokens_ids:
+        box = bboxes.get(str(cid)) if bboxes is not None else None
+        if box is None:
+            rois.append([0.0] * 5)
+            has.append(0)
+            continue
+        x1, y1, x2, y2 = [float(v) for v in box]
+        vals = [0.0, x1 * orig_w * spatial_scale, y1 * orig_h * spatial_scale, x2 * orig_w * spatial_scale,
+                y2 * orig_h * spatial_scale]
+        rois.append(torch.tensor(vals, dtype=torch.float32).tolist())
+        has.append(1)
+    return rois, has, spatial_scale
+
+
+class Engine:
+    def __init__(self, spec: GARSpec, state_dict: Dict[str, torch.Tensor], device: str = "cuda:0",
+                 max_tiles: int = 17, max_seq: int = 6144, max_batch: int = 8, max_new_tokens: int = 128):
+        if not torch.cuda.is_available():
+            raise _lib.GarError("grasp_any_region_b200 needs a CUDA device: there is no CPU fallback")
+        self.lib = _lib.load()
+        self.spec = spec
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        v, t = spec.vision, spec.text
+        self.vocab_padded = ((t.vocab_size + 255) // 256) * 256
+        self.max_tiles, self.max_seq, self.max_batch, self.max_new_tokens = max_tiles, max_seq, max_batch, max_new_tokens
+        d = GarModelDesc()
+        d.vit_dim, d.vit_depth, d.vit_heads, d.vit_mlp = v.embed_dim, v.depth, v.num_heads, v.mlp_dim
+        d.vit_use_cls, d.img_size, d.patch_size, d.ln_eps = int(v.use_cls_token), v.img_size, v.patch_size, v.ln_eps
+        d.pool_ratio = spec.projector_pooling_ratio
+        d.llm_dim, d.llm_layers, d.llm_heads, d.llm_kv_heads = t.hidden_size, t.num_layers, t.num_heads, t.num_kv_heads
+        d.llm_head_dim, d.llm_inter, d.vocab, d.vocab_padded = t.head_dim, t.intermediate_size, t.vocab_size, self.vocab_padded
+        d.rms_eps = t.rms_eps
+        d.prompt_numbers = spec.prompt_numbers
+        d.image_token_id = spec.image_token_id
+        for i in range(8):
+            d.crop_token_ids[i] = spec.crop_tokens_ids[i] if i < len(spec.crop_tokens_ids) else -1
+        d.max_tiles, d.max_seq, d.max_batch, d.max_new_tokens = max_tiles, max_seq, max_batch, max_new_tokens
+        self._desc = d
+        h = C.c_void_p()
+        check(self.lib.gar_engine_create(C.byref(d), C.byref(h)), "gar_engine_create")
+        self._h = h
+        self._keep: Dict[str, torch.Tensor] = {}
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._load_weights(state_dict)
+
+    # ------------------------------------------------------------------ weights
+    def _set(self, name: str, tensor: torch.Tensor):
+        tensor = tensor.detach().to(device=self.device, dtype=torch.bfloat16).contiguous()
+        self._keep[name] = tensor
+        check(self.lib.gar_engine_set_weight(self._h, name.encode(), C.c_void_p(tensor.data_ptr())),
+              f"set_weight {name}")
+
+    def _load_weights(self, sd: Dict[str, torch.Tensor]):
+        spec, v, t = self.spec, self.spec.vision, self.spec.text
+        kpad = ((3 * v.patch_size ** 2 + 63) // 64) * 64
+
+        def conv_matrix(w):
+            m = w.reshape(w.shape[0], -1)
+            out = torch.zeros((m.shape[0], kpad), dtype=m.dtype, device=m.device)
+            out[:, : m.shape[1]] = m
+            return out
+
+        self._set("vit.patch_w", conv_matrix(sd[VT + "patch_embed.proj.weight"]))
+        self._set("vit.mask_w", conv_matrix(sd["mask_patch_embedding.weight"]))
+        if v.use_cls_token:
+            self._set("vit.cls", sd[VT + "cls_token"].reshape(-1))
+        self._set("vit.pos", sd[VT + "pos_embed"].reshape(v.tokens, v.embed_dim))
+        self._set("vit.norm_pre.w", sd[VT + "norm_pre.weight"])
+        self._set("vit.norm_pre.b", sd[VT + "norm_pre.bias"])
+        self._set("vit.rope", vit_rope_table(v))
+        for i in range(v.depth):
+            b = f"{VT}blocks.{i}."
+            self._set(f"vit.{i}.ln1.w", sd[b + "norm1.weight"])
+            self._set(f"vit.{i}.ln1.b", sd[b + "norm1.bias"])
+            self._set(f"vit.{i}.qkv.w", sd[b + "attn.qkv.weight"])
+            self._set(f"vit.{i}.qkv.b", sd[b + "attn.qkv.bias"])
+            self._set(f"vit.{i}.proj.w", sd[b + "attn.proj.weight"])
+            self._set(f"vit.{i}.proj.b", sd[b + "attn.proj.bias"])
+            self._set(f"vit.{i}.g1", sd[b + "gamma_1"])
+            self._set(f"vit.{i}.ln2.w", sd[b + "norm2.weight"])
+            self._set(f"vit.{i}.ln2.b", sd[b + "norm2.bias"])
+            self._set(f"vit.{i}.fc1.w", sd[b + "mlp.fc1.weight"])
+            self._set(f"vit.{i}.fc1.b", sd[b + "mlp.fc1.bias"])
+            self._set(f"vit.{i}.fc2.w", sd[b + "mlp.fc2.weight"])
+            self._set(f"vit.{i}.fc2.b", sd[b + "mlp.fc2.bias"])
+            self._set(f"vit.{i}.g2", sd[b + "gamma_2"])
+        self._set("proj.l1.w", sd[PJ + "linear_1.weight"])
+        self._set("proj.l1.b", sd[PJ + "linear_1.bias"])
+        self._set("proj.l2.w", sd[PJ + "linear_2.weight"])
+        self._set("proj.l2.b", sd[PJ + "linear_2.bias"])
+        self._set("llm.embed", sd[LM + "embed_tokens.weight"])
+        for i in range(t.num_layers):
+            b = f"{LM}layers.{i}."
+            self._set(f"llm.{i}.ln1", sd[b + "input_layernorm.weight"])
+            self._set(f"llm.{i}.qkv.w", torch.cat([sd[b + "self_attn.q_proj.weight"], sd[b + "self_attn.k_proj.weight"],
+                                                   sd[b + "self_attn.v_proj.weight"]], 0))
+            self._set(f"llm.{i}.o.w", sd[b + "self_attn.o_proj.weight"])
+            self._set(f"llm.{i}.ln2", sd[b + "post_attention_layernorm.weight"])
+            self._set(f"llm.{i}.gu.w", torch.cat([sd[b + "mlp.gate_proj.weight"], sd[b + "mlp.up_proj.weight"]], 0))
+            self._set(f"llm.{i}.down.w", sd[b + "mlp.down_proj.weight"])
+        self._set("llm.norm", sd[LM + "norm.weight"])
+        head = sd["mllm.lm_head.weight"]
+        padded = torch.zeros((self.vocab_padded, head.shape[1]), dtype=head.dtype, device=head.device)
+        padded[: head.shape[0]] = head
+        self._set("llm.lm_head", padded)
+        cos, sin = llama_cos_sin(t, self.max_seq)
+        self._set("llm.cos", cos)
+        self._set("llm.sin", sin)
+
+    # ------------------------------------------------------------------ stages
+    def _s(self):
+        return C.c_void_p(self.stream.cuda_stream)
+
+    def buffer(self, name: str, shape, dtype=torch.bfloat16) -> torch.Tensor:
+        """Copy of an engine-internal buffer (parity taps)."""
+        ptr, nbytes = C.c_void_p(), C.c_longlong()
+        check(self.lib.gar_engine_get_buffer(self._h, name.encode(), C.byref(ptr), C.byref(nbytes)), "get_buffer")
+        out = torch.empty(shape, dtype=dtype, device=self.device)
+        assert out.numel() * out.element_size() <= nbytes.value, (name, shape, nbytes.value)
+        self.stream.synchronize()
+        rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), ptr.value, out.numel() * out.element_size(), 3)
+        assert int(rc) == 0, rc
+        return out
+
+    def vit_encode(self, pixel_values: torch.Tensor, mask_values: Optional[torch.Tensor]):
+        T = pixel_values.shape[0]
+        check(self.lib.gar_engine_vit_encode(self._h, C.c_void_p(pixel_values.data_ptr()),
+                                             None if mask_values is None else C.c_void_p(mask_values.data_ptr()),
+                                             T, self._s()), "gar_engine_vit_encode")
+
+    def assemble(self, slot: int, input_ids: torch.Tensor, T: int, bboxes, ncw: int, nch: int):
+        rois, has, scale = roi_boxes_f32(self.spec, bboxes, ncw, nch)
+        n = len(has)
+        c_rois = (C.c_float * (5 * n))(*[x for r in rois for x in r])
+        c_has = (C.c_int * n)(*has)
+        S = input_ids.numel()
+        check(self.lib.gar_engine_assemble(self._h, slot, C.c_void_p(input_ids.data_ptr()), S, T, c_rois, c_has,
+                                           float(scale), ncw, nch, self._s()), "gar_engine_assemble")
+
+    def prefill(self, slot: int, S: int):
+        check(self.lib.gar_engine_prefill(self._h, slot, S, self._s()), "gar_engine_prefill")
+
+    def prefill_all_logits(self, slot: int, S: int) -> torch.Tensor:
+        out = torch.empty((S, self.vocab_padded), dtype=torch.bfloat16, device=self.device)
+        check(self.lib.gar_engine_prefill_all_logits(self._h, slot, S, C.c_void_p(out.data_ptr()), self._s()),
+              "gar_engine_prefill_all_logits")
+        return out
+
+    def request(self, slot: int, pixel_values, global_mask_values, input_ids, bboxes, aspect_ratio):
+        """ViT -> assemble -> prefill for one (image, mask-set, prompt) request into KV slot `slot`.
+        Inputs must already be on the device in bf16 / int64; runs on the engine stream."""
+        ncw, nch = int(aspect_ratio[0]), int(aspect_ratio[1])
+        T = pixel_values.shape[0]
+        self.vit_encode(pixel_values, global_mask_values)
+        self.assemble(slot, input_ids, T, bboxes, ncw, nch)
+        self.prefill(slot, input_ids.numel())
+
+    def generate(self, batch: int, max_new_tokens: int, eos_token_id: Optional[int]) -> List[List[int]]:
+        buf = (C.c_int * (batch * max_new_tokens))()
+        check(self.lib.gar_engine_generate(self._h, batch, max_new_tokens,
+                                           -1 if eos_token_id is None else int(eos_token_id), buf, self._s()),
+              "gar_engine_generate")
+        out = []
+        for b in range(batch):
+            row = [buf[b * max_new_tokens + i] for i in range(max_new_tokens)]
+            out.append([t for t in row if t >= 0])
+        return out
+
+    def status(self, slot: int) -> int:
+        st = C.c_int()
+        check(self.lib.gar_engine_status(self._h, slot, C.byref(st)), "gar_engine_status")
+        return st.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.gar_engine_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.gar_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,149 @@
+/* gar_b200.h -- C ABI of libgar_b200.so: the B200 (sm_100a) implementation of Grasp-Any-Region's
+ * region-captioning inference hot path.
+ *
+ * The reference (Haochen-Wang409/Grasp-Any-Region) is pure Python and has no FFI; this is the
+ * boundary a maintainer binds from `projects/grasp_any_region/hf_models/modeling_gar.py`
+ * (see INTEGRATION.md for the ctypes stub).  Each entry point cites the reference code it replaces.
+ *
+ * Conventions: every pointer named *_dev / taking activations or weights is a CUDA device pointer to
+ * bf16 data unless stated otherwise; `stream` is a cudaStream_t passed as void*; all functions
+ * return 0 on success or a GAR_ERR_* code, with a message available from gar_last_error().
+ * Nothing here falls back to the CPU: without a CUDA device every compute call fails.
+ */
+#ifndef GAR_B200_H
+#define GAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAR_OK 0
+#define GAR_ERR_ARG 1
+#define GAR_ERR_CUDA 2
+#define GAR_ERR_SHAPE 3
+#define GAR_ERR_STATE 4
+
+/* assemble status bits (gar_engine_status): the reference's Python exceptions */
+#define GAR_STATUS_IMAGE_TOKEN_MISMATCH 1 /* ValueError modeling_perception_lm.py:309-315 */
+#define GAR_STATUS_BAD_CROP_RUN 2         /* run != 256 contiguous tokens, modeling_gar.py:357-411 */
+#define GAR_STATUS_MISSING_BBOX 4         /* KeyError bboxes[str(crop_token)], modeling_gar.py:367 */
+
+const char* gar_last_error(void);
+int gar_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-kernel entry points (unit parity; the engine below is built from exactly these)
+ * ---------------------------------------------------------------------------------------- */
+
+/* GEMM epilogues, reproducing the bf16 rounding points of the torch ops they fuse */
+#define GAR_EPI_NONE 0        /* C = bf16(A B^T)                                  nn.Linear(bias=False) */
+#define GAR_EPI_BIAS 1        /* C = bf16(A B^T + bias)                           nn.Linear */
+#define GAR_EPI_BIAS_GELU 2   /* C = bf16(gelu_erf(bf16(A B^T + bias)))           Linear -> GELU (timm Mlp, projector) */
+#define GAR_EPI_BIAS_LS_RES 3 /* C = bf16(res + bf16(gamma * bf16(A B^T + bias))) EvaBlock x + gamma * f(x) */
+#define GAR_EPI_RES 4         /* C = bf16(res + bf16(A B^T))                      Llama h + o_proj/down_proj */
+
+/* C[M,N] = epi(A[M,K] * B[N,K]^T): tcgen05 / TMEM / TMA GEMM.  Replaces the cuBLAS GEMMs behind every
+ * nn.Linear and both k=s=14 convs of the path (timm EvaBlock, modeling_perception_lm.py:85-92,
+ * modeling_gar.py:326-328, HF LlamaDecoderLayer).  K % 64 == 0, N % 32 == 0, ld* % 8 == 0.
+ * block_n_hint: 0 = auto, or 64/128/256. */
+int gar_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K, int epi,
+                  const void* bias, const void* gamma, const void* res, int ldres, int block_n_hint, void* stream);
+
+/* mask-id decode + im2col of both stride-14 convs (modeling_gar.py:315-328; timm PatchEmbed) */
+int gar_patchify(const void* pixel_values, const void* mask_values, void* a_img, void* a_mask, int T, int img,
+                 int patch, int ldk, int prompt_numbers, void* stream);
+/* cls concat + pos_embed add + norm_pre (timm Eva._pos_embed / norm_pre; modeling_perception_lm.py:197-198) */
+int gar_vit_embed_ln(const void* patch, const void* cls, const void* pos, const void* w, const void* b, void* x, int T,
+                     int ntok, int npt, int d, float eps, void* stream);
+int gar_layernorm(const void* x, int ldx, const void* w, const void* b, void* y, int ldy, int rows, int d, float eps,
+                  void* stream);
+/* LlamaRMSNorm (HF modeling_llama.py:53-70) */
+int gar_rmsnorm(const void* x, int ldx, const void* w, void* y, int ldy, int rows, int d, float eps, void* stream);
+/* timm apply_rot_embed_cat on q,k of the fused qkv buffer, in place (prefix tokens untouched) */
+int gar_vit_rope(void* qkv, const void* rope, int rows, int ntok, int npt, int heads, int hd, void* stream);
+/* HF apply_rotary_pos_emb on q (in place) and k (into the KV cache) + V append (DynamicCache.update) */
+int gar_llama_rope_kv(void* qkv, int rows, int hq, int hkv, int hd, const void* cos_t, const void* sin_t, int pos0,
+                      const int* pos_dev, const int* slot_dev, int slot0, void* kcache, void* vcache, int max_seq,
+                      void* stream);
+/* HF LlamaMLP act_fn(gate) * up on a fused [gate | up] buffer */
+int gar_swiglu(const void* gu, void* act, int rows, int inter, void* stream);
+/* PerceptionLMAdaptiveAvgPooling 2x2 (+ cls drop), modeling_perception_lm.py:42-60,263-264 */
+int gar_pool2x2(const void* x, void* y, int T, int ntok, int npt, int grid, int D, void* stream);
+int gar_embed_gather(const void* table, const long long* ids64, const int* ids32, void* out, int rows, int D,
+                     void* stream);
+/* greedy argmax + device-side decode bookkeeping (HF GenerationMixin greedy step) */
+int gar_argmax_step(const void* logits, int ld, int V, int batch, int* next_tok, int* out_tokens, int out_ld,
+                    const int* step_ptr, int* pos, int* finished, int eos, int advance_pos, void* stream);
+int gar_bump_step(int* step, void* stream);
+
+/* Fused embed + image-feature scatter + RoI-aligned feature replay (modeling_gar.py:332-414).
+ * rois: n_regions x [0,x1,y1,x2,y2] fp32 host array computed like modeling_gar.py:367-387;
+ * plan_ws: S ints (device); status_dev: 2 ints (device): [status bits, n image tokens]. */
+int gar_assemble_embeds(const long long* input_ids_dev, int S, const void* embed_table, int vocab,
+                        const void* image_features, int n_image_rows, int D, const long long* crop_ids,
+                        const float* rois, const int* has_roi, int n_regions, float spatial_scale, int ncw, int nch,
+                        int tpt, long long image_token_id, void* out, int* plan_ws, int* status_dev, void* stream);
+
+/* softmax(QK^T*scale)V, head_dim 64, tcgen05 + TMEM (timm SDPA non-causal; flash-attn 2 causal GQA prefill).
+ * All strides/offsets in bf16 elements.  K/V batch coordinate = b*kv_batch_mul + kv_head*kv_batch_head_mul. */
+int gar_attn_fwd(const void* q, long long q_row_stride, long long q_batch_stride, int q_col0, const void* k,
+                 const void* v, long long kv_row_stride, long long kv_batch_stride, int kv_batches, int k_col0,
+                 int v_col0, int kv_head_cols, int kv_batch_mul, int kv_batch_head_mul, void* o, long long o_row_stride,
+                 long long o_batch_stride, int o_col0, int batch, int heads, int kv_heads, int head_dim, int q_len,
+                 int kv_len, int kv_rows_alloc, int causal, float scale, void* stream);
+/* q_len = 1 attention over the KV cache, split-KV + combine (flash-attn 2 decode + DynamicCache) */
+int gar_decode_attn(const void* qkv, int ldq, const void* kcache, const void* vcache, const int* pos_dev,
+                    const int* slot_dev, int batch, int hq, int hkv, int head_dim, int max_seq, int splits, float scale,
+                    void* o_part_ws, void* ml_part_ws, void* out, int ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Engine: GARModel.generate() (modeling_gar.py:295-428) as a device-resident pipeline
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gar_engine gar_engine;
+
+typedef struct gar_model_desc {
+  /* PE ViT (timm Eva) */
+  int vit_dim, vit_depth, vit_heads, vit_mlp, vit_use_cls, img_size, patch_size;
+  float ln_eps;
+  /* projector */
+  int pool_ratio;
+  /* Llama */
+  int llm_dim, llm_layers, llm_heads, llm_kv_heads, llm_head_dim, llm_inter, vocab, vocab_padded;
+  float rms_eps;
+  /* GAR */
+  int prompt_numbers;
+  long long image_token_id;
+  long long crop_token_ids[8];
+  /* capacity */
+  int max_tiles, max_seq, max_batch, max_new_tokens;
+} gar_model_desc;
+
+int gar_engine_create(const gar_model_desc* desc, gar_engine** out);
+int gar_engine_destroy(gar_engine* e);
+/* weights stay owned by the caller (torch tensors); names listed in DESIGN.md §4 */
+int gar_engine_set_weight(gar_engine* e, const char* name, const void* dev_ptr);
+/* internal buffers for parity taps: "image_features", "inputs_embeds", "logits", "mask_embeds", "vit_x" ... */
+int gar_engine_get_buffer(gar_engine* e, const char* name, void** dev_ptr, long long* bytes);
+
+/* R2-R5: pixel_values/global_mask_values (T,3,img,img) -> image features (T, tokens_per_tile, llm_dim) */
+int gar_engine_vit_encode(gar_engine* e, const void* pixel_values, const void* mask_values, int T, void* stream);
+/* R6-R7 on the engine's image features -> inputs_embeds (S, llm_dim) */
+int gar_engine_assemble(gar_engine* e, int slot, const long long* input_ids_dev, int S, int T, const float* rois,
+                        const int* has_roi, float spatial_scale, int ncw, int nch, void* stream);
+/* R8: causal prefill of the engine's inputs_embeds into KV-cache slot; last-position logits -> logits[slot] */
+int gar_engine_prefill(gar_engine* e, int slot, int S, void* stream);
+/* same, teacher-forced: all-position logits (S, vocab_padded) into caller memory (forward(mode="loss")) */
+int gar_engine_prefill_all_logits(gar_engine* e, int slot, int S, void* logits_out, void* stream);
+/* R9: greedy decode of slots [0,batch): first token from the prefill logits, then max_new_tokens-1 steps
+ * (CUDA-graph replay, no host sync inside).  out_tokens_host: batch x max_new_tokens int32 (-1 after EOS).
+ * eos < 0 disables EOS. */
+int gar_engine_generate(gar_engine* e, int batch, int max_new_tokens, int eos, int* out_tokens_host, void* stream);
+int gar_engine_status(gar_engine* e, int slot, int* status_bits);
+long long gar_engine_launch_count(gar_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAR_B200_H */

@@ -1,0 +1,241 @@
+"""GPU parity of every per-kernel C-ABI entry point against plain torch restatements of the op the
+reference executes (same bf16 rounding points).  Calls go through libgar_b200.so (ctypes)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():  # collected on the CPU box, executed only with -m gpu on a B200
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from grasp_any_region_b200 import ops  # noqa: E402
+
+DEV = "cuda:0"
+bf = torch.bfloat16
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(bf).to(DEV)
+
+
+def r(x):  # one bf16 rounding point
+    return x.to(bf).float()
+
+
+def gemm_ref(a, b, epi, bias=None, gamma=None, res=None):
+    acc = a.float() @ b.float().t()
+    if epi in (ops.EPI_BIAS, ops.EPI_BIAS_GELU, ops.EPI_BIAS_LS_RES):
+        acc = acc + bias.float()
+    y = r(acc)
+    if epi == ops.EPI_BIAS_GELU:
+        y = r(F.gelu(y))
+    if epi == ops.EPI_BIAS_LS_RES:
+        y = r(res.float() + r(gamma.float() * y))
+    if epi == ops.EPI_RES:
+        y = r(res.float() + y)
+    return y
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 512, 256), (1, 256, 128), (8, 1024, 512), (2050, 768, 1024),
+                                   (129, 96, 640), (4100, 3072, 1024)])
+@pytest.mark.parametrize("block_n", [0, 64, 128, 256])
+def test_gemm_plain(M, N, K, block_n):
+    a, b = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2)
+    out = ops.gemm(a, b, block_n=block_n)
+    torch.cuda.synchronize()
+    ref = gemm_ref(a, b, ops.EPI_NONE)
+    err = (out.float() - ref).abs().max().item()
+    tol = 2e-2 * max(1.0, ref.abs().max().item())  # <= 1 bf16 ulp flips from accumulation order
+    assert err <= tol, (err, tol)
+    mism = (out.float() != ref).float().mean().item()
+    assert mism < 0.02, f"{mism:.4f} of outputs differ from the fp32-accumulated reference by a bf16 ulp"
+
+
+@pytest.mark.parametrize("epi", [ops.EPI_BIAS, ops.EPI_BIAS_GELU, ops.EPI_BIAS_LS_RES, ops.EPI_RES])
+@pytest.mark.parametrize("M,N,K", [(333, 512, 256), (1025, 1024, 1024)])
+def test_gemm_epilogues(epi, M, N, K):
+    a, b = rnd(M, K, seed=3), rnd(N, K, scale=0.05, seed=4)
+    bias, gamma, res = rnd(N, scale=0.1, seed=5), rnd(N, scale=0.2, seed=6), rnd(M, N, seed=7)
+    out = ops.gemm(a, b, epi=epi, bias=bias, gamma=gamma, res=res)
+    torch.cuda.synchronize()
+    ref = gemm_ref(a, b, epi, bias, gamma, res)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 4e-2 * max(1.0, ref.abs().max().item()), err
+    assert (out.float() != ref).float().mean().item() < 0.02
+
+
+def test_gemm_inplace_residual():
+    M, N, K = 700, 512, 512
+    a, b, x = rnd(M, K, seed=8), rnd(N, K, scale=0.05, seed=9), rnd(M, N, seed=10)
+    ref = gemm_ref(a, b, ops.EPI_RES, res=x)
+    out = ops.gemm(a, b, epi=ops.EPI_RES, res=x, out=x)
+    torch.cuda.synchronize()
+    assert out.data_ptr() == x.data_ptr()
+    assert (out.float() - ref).abs().max().item() <= 4e-2 * ref.abs().max().item()
+
+
+def test_layernorm_rmsnorm():
+    x = rnd(1000, 1024, seed=11)
+    w, b = (1 + rnd(1024, scale=0.1, seed=12).float()).to(bf), rnd(1024, scale=0.1, seed=13)
+    y = ops.layernorm(x, w, b, 1e-5)
+    ref = F.layer_norm(x.float(), (1024,), w.float(), b.float(), 1e-5).to(bf)
+    assert (y.float() - ref.float()).abs().max().item() <= 2e-2
+    assert (y != ref).float().mean().item() < 0.01
+    x2 = rnd(333, 2048, seed=14)
+    w2 = (1 + rnd(2048, scale=0.1, seed=15).float()).to(bf)
+    y2 = ops.rmsnorm(x2, w2, 1e-5)
+    x32 = x2.float()
+    ref2 = w2 * (x32 * torch.rsqrt(x32.pow(2).mean(-1, keepdim=True) + 1e-5)).to(bf)
+    assert (y2.float() - ref2.float()).abs().max().item() <= 2e-2
+    assert (y2 != ref2).float().mean().item() < 0.01
+
+
+def test_patchify_and_mask_decode():
+    T, P = 3, 5
+    px = rnd(T, 3, 448, 448, seed=16)
+    ids = torch.randint(0, P + 2, (T, 1, 448, 448), generator=torch.Generator().manual_seed(1)).float()
+    mv = (2.0 * ids / 255.0 - 1.0).expand(T, 3, 448, 448).contiguous().to(bf).to(DEV)
+    a_img, a_mask = ops.patchify(px, mv, 14, 640, P)
+    torch.cuda.synchronize()
+    # reference: unfold == conv im2col with (c, ky, kx) column order
+    cols = F.unfold(px.float(), 14, stride=14).transpose(1, 2).reshape(T * 1024, 588)
+    assert torch.equal(a_img[:, :588].float(), cols)
+    assert a_img[:, 588:].abs().max().item() == 0
+    dec = torch.clamp(torch.round((mv + 1.0) / 2.0 * 255.0).long(), 0, P)
+    binm = (dec != P).to(bf)
+    mcols = F.unfold(binm.float(), 14, stride=14).transpose(1, 2).reshape(T * 1024, 588)
+    assert torch.equal(a_mask[:, :588].float(), mcols)
+
+
+def test_vit_embed_ln():
+    T, ntok, d = 2, 1025, 256
+    patch = rnd(T * 1024, d, seed=17)
+    cls, pos = rnd(d, seed=18), rnd(ntok, d, scale=0.1, seed=19)
+    w, b = (1 + rnd(d, scale=0.1, seed=20).float()).to(bf), rnd(d, scale=0.1, seed=21)
+    x = ops.vit_embed_ln(patch, cls, pos, w, b, T, ntok, 1, 1e-5)
+    full = torch.cat([cls.view(1, 1, d).expand(T, 1, d), patch.view(T, 1024, d)], 1)
+    full = full + pos  # bf16 add
+    ref = F.layer_norm(full.float(), (d,), w.float(), b.float(), 1e-5).to(bf).view(T * ntok, d)
+    assert (x.float() - ref.float()).abs().max().item() <= 2e-2
+    assert (x != ref).float().mean().item() < 0.01
+
+
+def test_vit_rope():
+    from grasp_any_region_b200.config import VisionSpec
+    from grasp_any_region_b200.rope import vit_rope_table
+
+    v = VisionSpec(embed_dim=128, depth=1, num_heads=2, mlp_dim=256)
+    T, ntok, H, hd = 2, 1025, 2, 64
+    qkv = rnd(T * ntok, 3 * H * hd, seed=22)
+    table = vit_rope_table(v).to(bf).to(DEV)
+    ref = qkv.clone().view(T, ntok, 3, H, hd)
+    sin, cos = table[:, :hd], table[:, hd:]
+
+    def rot(x):
+        return torch.stack([-x[..., 1::2], x[..., ::2]], -1).reshape(x.shape)
+
+    for part in (0, 1):
+        x = ref[:, 1:, part]  # (T, 1024, H, hd)
+        ref[:, 1:, part] = x * cos[None, :, None, :] + rot(x) * sin[None, :, None, :]
+    out = ops.vit_rope_(qkv.clone(), table, ntok, 1, H, hd)
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(T, ntok, 3, H, hd), ref)
+
+
+def test_llama_rope_kv_and_swiglu_pool_argmax():
+    from grasp_any_region_b200.config import TextSpec
+    from grasp_any_region_b200.rope import llama_cos_sin
+
+    t = TextSpec()
+    hq, hkv, hd, S, max_seq = 8, 2, 64, 200, 256
+    cos, sin = llama_cos_sin(t, max_seq)
+    cos, sin = cos.to(bf).to(DEV), sin.to(bf).to(DEV)
+    qkv = rnd(S, (hq + 2 * hkv) * hd, seed=23)
+    kc = torch.zeros(3, hkv, max_seq, hd, dtype=bf, device=DEV)
+    vc = torch.zeros_like(kc)
+    out = ops.llama_rope_kv_(qkv.clone(), hq, hkv, hd, cos, sin, kc, vc, max_seq, pos0=5, slot0=1)
+    torch.cuda.synchronize()
+    c = torch.cat([cos, cos], -1)[5:5 + S, None, :]
+    s = torch.cat([sin, sin], -1)[5:5 + S, None, :]
+
+    def rh(x):
+        return torch.cat([-x[..., hd // 2:], x[..., :hd // 2]], -1)
+
+    q = qkv[:, :hq * hd].view(S, hq, hd)
+    k = qkv[:, hq * hd:(hq + hkv) * hd].view(S, hkv, hd)
+    vv = qkv[:, (hq + hkv) * hd:].view(S, hkv, hd)
+    assert torch.equal(out[:, :hq * hd].view(S, hq, hd), q * c + rh(q) * s)
+    assert torch.equal(kc[1, :, 5:5 + S], (k * c + rh(k) * s).transpose(0, 1))
+    assert torch.equal(vc[1, :, 5:5 + S], vv.transpose(0, 1))
+    assert kc[0].abs().max().item() == 0 and kc[2].abs().max().item() == 0
+
+    gu = rnd(77, 2 * 512, seed=24)
+    act = ops.swiglu(gu)
+    ref = F.silu(gu[:, :512]) * gu[:, 512:]
+    assert torch.equal(act, ref)
+
+    x = rnd(2 * 1025, 256, seed=25)
+    y = ops.pool2x2(x, 2, 1025, 1, 32)
+    xr = x.view(2, 1025, 256)[:, 1:].permute(0, 2, 1).reshape(2, 256, 32, 32)
+    refp = F.adaptive_avg_pool2d(xr, (16, 16)).flatten(2).transpose(1, 2)
+    assert (y.float() - refp.float()).abs().max().item() <= 1e-2
+    assert (y != refp).float().mean().item() < 0.002
+
+    lg = rnd(4, 1000, seed=26)
+    lg[1, 17] = lg[1].max() + 1
+    lg[2, 5] = lg[2, 900] = lg[2].max() + 2  # tie -> lowest index
+    nxt = ops.argmax_step(lg, 999)
+    torch.cuda.synchronize()
+    assert nxt.tolist() == lg[:, :999].float().argmax(-1).tolist()
+    assert nxt[2].item() == 5
+
+
+@pytest.mark.parametrize("T,ntok,heads", [(1, 128, 1), (2, 1025, 2), (1, 1024, 4), (3, 300, 2)])
+def test_attention_vit_layout(T, ntok, heads):
+    hd = 64
+    qkv = rnd(T * ntok, 3 * heads * hd, seed=27)
+    out = ops.attn_fwd_packed_qkv(qkv, T, ntok, heads, hd)
+    torch.cuda.synchronize()
+    q, k, v = qkv.view(T, ntok, 3, heads, hd).permute(2, 0, 3, 1, 4).float()
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(T * ntok, heads * hd)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2, err
+
+
+@pytest.mark.parametrize("S", [64, 128, 333, 1000])
+def test_attention_causal_gqa_cache_layout(S):
+    hq, hkv, hd, max_seq = 8, 2, 64, 1024
+    q = rnd(S, (hq + 2 * hkv) * hd, seed=28)
+    kc = torch.zeros(hkv, max_seq, hd, dtype=bf, device=DEV)
+    vc = torch.zeros_like(kc)
+    kc[:, :S] = rnd(hkv, S, hd, seed=29)
+    vc[:, :S] = rnd(hkv, S, hd, seed=30)
+    out = ops.attn_fwd_cache(q, q.stride(0), kc, vc, hq, hkv, hd, S, max_seq)
+    torch.cuda.synchronize()
+    qq = q[:, :hq * hd].view(S, hq, hd).transpose(0, 1).float()[None]
+    kk = kc[:, :S].float().repeat_interleave(hq // hkv, 0)[None]
+    vv = vc[:, :S].float().repeat_interleave(hq // hkv, 0)[None]
+    ref = F.scaled_dot_product_attention(qq, kk, vv, is_causal=True)[0].transpose(0, 1).reshape(S, hq * hd)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2, err
+
+
+def test_decode_attention():
+    B, hq, hkv, hd, max_seq = 3, 8, 2, 64, 700
+    qkv = rnd(B, (hq + 2 * hkv) * hd, seed=31)
+    kc, vc = rnd(B, hkv, max_seq, hd, seed=32), rnd(B, hkv, max_seq, hd, seed=33)
+    pos = torch.tensor([0, 333, 698], dtype=torch.int32, device=DEV)
+    out = ops.decode_attn(qkv, kc, vc, pos, hq, hkv, hd, max_seq)
+    torch.cuda.synchronize()
+    for b in range(B):
+        n = int(pos[b]) + 1
+        q = qkv[b, :hq * hd].view(hq, 1, hd).float()[None]
+        k = kc[b, :, :n].float().repeat_interleave(hq // hkv, 0)[None]
+        v = vc[b, :, :n].float().repeat_interleave(hq // hkv, 0)[None]
+        ref = F.scaled_dot_product_attention(q, k, v)[0, :, 0].reshape(hq * hd)
+        err = (out[b].float() - ref).abs().max().item()
+        assert err <= 2e-2, (b, err)
