@@ -55,6 +55,8 @@ SIGNATURES = {
     "gar_engine_generate": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _vp]),
     "gar_engine_status": (_i, [_vp, _i, C.POINTER(_i)]),
     "gar_engine_launch_count": (_ll, [_vp]),
+    "gar_engine_profile": (_i, [_vp, _i]),
+    "gar_engine_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
 }
 
 _lib = None

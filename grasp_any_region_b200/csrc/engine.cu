@@ -38,7 +38,13 @@ struct gar_engine {
   int graph_batch = -1;
   long long launches = 0;
   int launches_per_step = 0;
+  // optional per-kernel-class timing (CUDA events on the launching stream; bench.py roofline)
+  bool profiling = false;
+  struct ProfRec { cudaEvent_t a, b; int kind; double work; };
+  std::vector<ProfRec> prof;
 };
+
+enum ProfKind { PK_GEMM = 0, PK_ATTN = 1, PK_ASSEMBLE = 2, PK_DECODE_ATTN = 3, PK_OTHER = 4, PK_COUNT = 5 };
 
 namespace {
 
@@ -68,9 +74,30 @@ std::string L(const char* prefix, int i, const char* suffix) {
   return std::string(prefix) + "." + std::to_string(i) + "." + suffix;
 }
 
+struct ProfScope {
+  gar_engine* e;
+  cudaStream_t s;
+  int idx = -1;
+  ProfScope(gar_engine* e_, void* s_, int kind, double work) : e(e_), s(static_cast<cudaStream_t>(s_)) {
+    if (!e->profiling) return;
+    gar_engine::ProfRec r;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    r.kind = kind;
+    r.work = work;
+    cudaEventRecord(r.a, s);
+    e->prof.push_back(r);
+    idx = static_cast<int>(e->prof.size()) - 1;
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(e->prof[idx].b, s);
+  }
+};
+
 int gemm(gar_engine* e, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K, int epi,
          const void* bias, const void* gamma, const void* res, int ldres, void* s) {
   e->launches += 1;
+  ProfScope ps(e, s, PK_GEMM, 2.0 * M * static_cast<double>(N) * K);
   return gar_gemm_bf16(A, lda, B, ldb, C, ldc, M, N, K, epi, bias, gamma, res, ldres, 0, s);
 }
 
@@ -101,12 +128,15 @@ int llm_layers(gar_engine* e, bf16* h, bf16* ln, int rows, bool decode, int slot
     }
     e->launches += 2;
     if (decode) {
+      ProfScope ps(e, s, PK_DECODE_ATTN, 0.0);
       TRY(gar_decode_attn(e->qkv_l, qkv_w, kc, vc, e->pos, nullptr, rows, hq, hkv, hd, d.max_seq, e->dec_splits, scale,
                           e->o_part, e->ml_part, e->att_l, hq * hd, s));
       e->launches += 2;
     } else {
       const bf16* kslot = kc + static_cast<size_t>(slot) * hkv * d.max_seq * hd;
       const bf16* vslot = vc + static_cast<size_t>(slot) * hkv * d.max_seq * hd;
+      // causal: half of the 4*S*S*hd*heads MACs-as-flops
+      ProfScope ps(e, s, PK_ATTN, 2.0 * rows * static_cast<double>(rows) * hd * hq);
       TRY(gar_attn_fwd(e->qkv_l, qkv_w, static_cast<long long>(rows) * qkv_w, 0, kslot, vslot, hd,
                        static_cast<long long>(d.max_seq) * hd, hkv, 0, 0, 0, 0, 1, e->att_l, hq * hd,
                        static_cast<long long>(rows) * hq * hd, 0, 1, hq, hkv, hd, rows, rows, d.max_seq, 1, scale, s));
@@ -304,9 +334,12 @@ int gar_engine_vit_encode(gar_engine* e, const void* pixel_values, const void* m
     TRY(gar_layernorm(e->x, dv, l1w, l1b, e->ln, dv, rows, dv, d.ln_eps, s));
     TRY(gemm(e, e->ln, dv, wqkv, dv, e->qkv_v, 3 * dv, rows, 3 * dv, dv, GAR_EPI_BIAS, bqkv, nullptr, nullptr, 0, s));
     TRY(gar_vit_rope(e->qkv_v, rope, rows, NT, e->npt, d.vit_heads, e->hd_v, s));
+    {
+    ProfScope ps(e, s, PK_ATTN, 4.0 * T * static_cast<double>(NT) * NT * dv);
     TRY(gar_attn_fwd(e->qkv_v, 3 * dv, static_cast<long long>(NT) * 3 * dv, 0, e->qkv_v, e->qkv_v, 3 * dv,
                      static_cast<long long>(NT) * 3 * dv, T, dv, 2 * dv, e->hd_v, 1, 0, e->att_v, dv,
                      static_cast<long long>(NT) * dv, 0, T, d.vit_heads, d.vit_heads, e->hd_v, NT, NT, NT, 0, scale, s));
+    }
     TRY(gemm(e, e->att_v, dv, wpr, dv, e->x, dv, rows, dv, dv, GAR_EPI_BIAS_LS_RES, bpr, g1, e->x, dv, s));
     TRY(gar_layernorm(e->x, dv, l2w, l2b, e->ln, dv, rows, dv, d.ln_eps, s));
     TRY(gemm(e, e->ln, dv, w1, dv, e->mlp_v, d.vit_mlp, rows, d.vit_mlp, dv, GAR_EPI_BIAS_GELU, b1, nullptr, nullptr, 0,
@@ -346,6 +379,8 @@ int gar_engine_assemble(gar_engine* e, int slot, const long long* input_ids_dev,
   const gar_model_desc& d = e->d;
   NEEDW(table, "llm.embed");
   e->launches += 2;
+  // algorithmic bytes: write S*D*2 + read one D-row per non-replay row + <=16 cells per region
+  ProfScope ps(e, s, PK_ASSEMBLE, 2.0 * (2.0 * S - 0.0) * d.llm_dim);
   return gar_assemble_embeds(input_ids_dev, S, table, d.vocab, e->feats, T * e->tokens_per_tile, d.llm_dim,
                              d.crop_token_ids, rois, has_roi, d.prompt_numbers, spatial_scale, ncw, nch, e->tpt,
                              d.image_token_id, e->emb, e->plan, e->status + 2 * slot, s);
@@ -405,7 +440,9 @@ int gar_engine_generate(gar_engine* e, int batch, int max_new_tokens, int eos, i
     const long long before = e->launches;
     TRY(decode_step(e, batch, eos, s));
     e->launches_per_step = static_cast<int>(e->launches - before);
-    if (steps > 1) {
+    if (steps > 1 && e->profiling) {
+      for (int i = 1; i < steps; ++i) TRY(decode_step(e, batch, eos, s));
+    } else if (steps > 1) {
       if (e->graph_exec == nullptr || e->graph_batch != batch) {
         if (s == nullptr || s == cudaStreamLegacy) {
           gar_set_error("gar_engine_generate: needs a non-default stream (CUDA graph capture)");
@@ -447,5 +484,29 @@ int gar_engine_status(gar_engine* e, int slot, int* status_bits) {
 }
 
 long long gar_engine_launch_count(gar_engine* e) { return e ? e->launches : 0; }
+
+int gar_engine_profile(gar_engine* e, int enable) {
+  if (!e) return GAR_ERR_ARG;
+  for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  e->prof.clear();
+  e->profiling = enable != 0;
+  return GAR_OK;
+}
+
+// per kernel class k (GAR_PROF_*): ms[k] = summed CUDA-event durations, work[k] = summed algorithmic
+// work (flops for GEMM/attention, bytes for assemble), count[k] = launches.  Synchronises the device.
+int gar_engine_profile_read(gar_engine* e, double* ms, double* work, long long* count) {
+  if (!e || !ms || !work || !count) return GAR_ERR_ARG;
+  GAR_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int k = 0; k < PK_COUNT; ++k) { ms[k] = 0; work[k] = 0; count[k] = 0; }
+  for (auto& r : e->prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) continue;
+    ms[r.kind] += t;
+    work[r.kind] += r.work;
+    count[r.kind] += 1;
+  }
+  return GAR_OK;
+}
 
 }  // extern "C"

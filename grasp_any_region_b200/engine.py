@@ -210,6 +210,17 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.gar_engine_launch_count(self._h))
 
+    def profile(self, enable: bool):
+        check(self.lib.gar_engine_profile(self._h, int(enable)), "gar_engine_profile")
+
+    def profile_read(self):
+        """{class: (ms, work, launches)} summed over the launches recorded since profile(True)."""
+        n = 5
+        ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_longlong * n)()
+        check(self.lib.gar_engine_profile_read(self._h, ms, work, cnt), "gar_engine_profile_read")
+        names = ["gemm", "attn", "assemble", "decode_attn", "other"]
+        return {names[i]: (ms[i], work[i], cnt[i]) for i in range(n)}
+
     def close(self):
         if getattr(self, "_h", None):
             self.lib.gar_engine_destroy(self._h)

@@ -1,0 +1,276 @@
+"""Drop-in ``GARModel`` for the reference's region-captioning path, backed by libgar_b200.so.
+
+Mirrors the reference interface (projects/grasp_any_region/hf_models/modeling_gar.py:17-72 ctor and
+attributes, :74-95 ``forward(data, data_samples, mode)``, :295-308 ``generate(...)``) with the same
+argument meaning and error behaviour, so ``demo/gar_with_mask.py`` / ``gar_relationship.py`` and the
+evaluation drivers run unchanged.  Parameters live under the reference's HF state-dict names.
+
+Host code here is plumbing only: dtype/device moves, the box arithmetic the reference does in Python
+floats (:367-387), and argument checks.  All math runs in the CUDA library; nothing falls back to
+torch ops or the CPU.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from .config import GARSpec
+from .configuration_gar import GARConfig
+from .engine import LM, PJ, VT, Engine
+
+try:  # same base class as the reference when transformers is importable
+    from transformers.modeling_utils import PreTrainedModel as _Base
+
+    _HAS_HF = True
+except Exception:  # pragma: no cover
+    _Base = nn.Module
+    _HAS_HF = False
+
+
+def parameter_shapes(spec: GARSpec) -> Dict[str, tuple]:
+    """HF state-dict layout of a GAR checkpoint."""
+    v, t = spec.vision, spec.text
+    d, D = v.embed_dim, t.hidden_size
+    out = {"mask_patch_embedding.weight": (d, 3, v.patch_size, v.patch_size),
+           VT + "patch_embed.proj.weight": (d, 3, v.patch_size, v.patch_size),
+           VT + "pos_embed": (1, v.tokens, d), VT + "norm_pre.weight": (d,), VT + "norm_pre.bias": (d,)}
+    if v.use_cls_token:
+        out[VT + "cls_token"] = (1, 1, d)
+    for i in range(v.depth):
+        b = f"{VT}blocks.{i}."
+        out.update({b + "norm1.weight": (d,), b + "norm1.bias": (d,), b + "attn.qkv.weight": (3 * d, d),
+                    b + "attn.qkv.bias": (3 * d,), b + "attn.proj.weight": (d, d), b + "attn.proj.bias": (d,),
+                    b + "gamma_1": (d,), b + "norm2.weight": (d,), b + "norm2.bias": (d,),
+                    b + "mlp.fc1.weight": (v.mlp_dim, d), b + "mlp.fc1.bias": (v.mlp_dim,),
+                    b + "mlp.fc2.weight": (d, v.mlp_dim), b + "mlp.fc2.bias": (d,), b + "gamma_2": (d,)})
+    out.update({PJ + "linear_1.weight": (D, d), PJ + "linear_1.bias": (D,), PJ + "linear_2.weight": (D, D),
+                PJ + "linear_2.bias": (D,), LM + "embed_tokens.weight": (t.vocab_size, D), LM + "norm.weight": (D,),
+                "mllm.lm_head.weight": (t.vocab_size, D)})
+    q, kv = t.num_heads * t.head_dim, t.num_kv_heads * t.head_dim
+    for i in range(t.num_layers):
+        b = f"{LM}layers.{i}."
+        out.update({b + "input_layernorm.weight": (D,), b + "post_attention_layernorm.weight": (D,),
+                    b + "self_attn.q_proj.weight": (q, D), b + "self_attn.k_proj.weight": (kv, D),
+                    b + "self_attn.v_proj.weight": (kv, D), b + "self_attn.o_proj.weight": (D, q),
+                    b + "mlp.gate_proj.weight": (t.intermediate_size, D),
+                    b + "mlp.up_proj.weight": (t.intermediate_size, D),
+                    b + "mlp.down_proj.weight": (D, t.intermediate_size)})
+    return out
+
+
+class _Node(nn.Module):
+    """Parameter container reproducing the reference's module paths (no forward of its own)."""
+
+
+def _attach(root: nn.Module, dotted: str, shape, dtype):
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if not hasattr(mod, p):
+            mod.add_module(p, _Node())
+        mod = getattr(mod, p)
+    mod.register_parameter(parts[-1], nn.Parameter(torch.empty(shape, dtype=dtype), requires_grad=False))
+
+
+@dataclasses.dataclass
+class GenerateOutput:
+    """What callers read from HF's GenerateDecoderOnlyOutput: only the NEW tokens (quirk 9)."""
+    sequences: torch.LongTensor
+
+
+class GARModel(_Base):
+    config_class = GARConfig
+    main_input_name = "pixel_values"
+    base_model_prefix = "language_model"
+    _no_split_modules = ["LlamaDecoderLayer"]
+    _supports_flash_attn_2 = True
+    supports_gradient_checkpointing = True
+
+    def __init__(self, config: GARConfig, mllm=None, mask_patch_embedding=None, use_flash_attn=True):
+        if _HAS_HF:
+            super().__init__(config)
+        else:  # pragma: no cover
+            super().__init__()
+            self.config = config
+        self.prompt_numbers = config.prompt_numbers
+        self.crop_tokens_ids = config.crop_tokens_ids
+        self.spec = config.spec
+        for name, shape in parameter_shapes(self.spec).items():
+            _attach(self, name, shape, torch.bfloat16)
+        if mllm is not None or mask_patch_embedding is not None:
+            # reference ctor lets callers inject modules; accept anything exposing a state_dict
+            sd = {}
+            if mllm is not None:
+                sd.update({"mllm." + k: v for k, v in mllm.state_dict().items()})
+            if mask_patch_embedding is not None:
+                sd.update({"mask_patch_embedding." + k: v for k, v in mask_patch_embedding.state_dict().items()})
+            self.load_state_dict(sd, strict=False)
+        self._engine: Optional[Engine] = None
+        self._engine_caps = dict(max_tiles=37, max_seq=12288, max_batch=8, max_new_tokens=1024)
+
+    # ------------------------------------------------------------------ reference surface
+    @property
+    def lm_head(self):
+        return self.mllm.lm_head
+
+    def get_input_embeddings(self):
+        return self.mllm.model.language_model.embed_tokens
+
+    def get_output_embeddings(self):
+        return self.mllm.lm_head
+
+    def _init_weights(self, module):  # parameters always come from a checkpoint / random_init_
+        pass
+
+    @property
+    def dtype(self):
+        return torch.bfloat16
+
+    # ------------------------------------------------------------------ engine management
+    def random_init_(self, seed: int = 0) -> "GARModel":
+        """Deterministic random weights of the reference architecture (benchmarks have no checkpoint)."""
+        g = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for name, p in self.named_parameters():
+                if name.endswith("gamma_1") or name.endswith("gamma_2"):
+                    p.fill_(0.1)
+                elif "norm" in name and name.endswith("weight"):
+                    p.copy_((1.0 + 0.05 * torch.randn(p.shape, generator=g)).to(p.dtype))
+                else:
+                    p.copy_((0.02 * torch.randn(p.shape, generator=g)).to(p.dtype))
+        self._engine = None
+        return self
+
+    def configure_engine(self, **caps) -> "GARModel":
+        """Capacity of the device arenas: max_tiles, max_seq, max_batch, max_new_tokens."""
+        self._engine_caps.update(caps)
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+        return self
+
+    def engine(self) -> Engine:
+        if self._engine is None:
+            p = next(self.parameters())
+            if p.device.type != "cuda":
+                raise _lib.GarError("GARModel must live on a CUDA device (model.to('cuda:0')): no CPU path exists")
+            if p.dtype != torch.bfloat16:
+                raise _lib.GarError(f"the B200 engine computes in bf16; got parameters in {p.dtype}")
+            self._engine = Engine(self.spec, self.state_dict(), device=str(p.device), **self._engine_caps)
+        return self._engine
+
+    # ------------------------------------------------------------------ request plumbing
+    def _stage_request(self, eng: Engine, slot, pixel_values, global_mask_values, aspect_ratios, bboxes, input_ids,
+                       batch_idx=0):
+        dev = eng.device
+        if input_ids.shape[0] != 1:
+            raise AssertionError("Currently only support batch_size=1")
+        px = pixel_values.to(dev, non_blocking=True).to(torch.bfloat16)
+        if px.dim() == 5:
+            px = px.flatten(0, 1)
+        assert px.dim() == 4, (
+            f"pixel_values should be of shape (batch_size * num_tiles, channels, height, width). But got {px.shape}.")
+        mv = None
+        if global_mask_values is not None:
+            # the reference decodes ids in the tensor's own dtype (bf16 after the dataset's cast, quirk 7)
+            mv = global_mask_values.to(dev, non_blocking=True).to(torch.bfloat16).contiguous()
+        ids = input_ids[batch_idx].to(dev, non_blocking=True).to(torch.long).contiguous()
+        ar = aspect_ratios[batch_idx]
+        ncw, nch = int(ar[0]), int(ar[1])
+        eng.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(eng.stream):
+            eng.request(slot, px.contiguous(), mv, ids, bboxes[batch_idx], (ncw, nch))
+        for t in (px, mv, ids):
+            if t is not None:
+                t.record_stream(eng.stream)
+        return ids.numel()
+
+    def _raise_on_status(self, eng: Engine, slot: int, n_feats=None):
+        st = eng.status(slot)
+        if st & 1:
+            raise ValueError("Image features and image tokens do not match")
+        if st & 4:
+            raise KeyError("bboxes has no entry for a crop token present in input_ids")
+        if st & 2:
+            raise AssertionError("each crop-token run must be 256 contiguous tokens")
+
+    @torch.no_grad()
+    def generate(self, pixel_values: Optional[torch.FloatTensor] = None,
+                 global_mask_values: Optional[torch.Tensor] = None,
+                 aspect_ratios: Optional[torch.Tensor] = None, bboxes=None,
+                 input_ids: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
+                 generation_config=None, output_hidden_states: Optional[bool] = None,
+                 return_dict: Optional[bool] = None, **generate_kwargs) -> GenerateOutput:
+        if pixel_values is None:
+            raise NotImplementedError("text-only generate() is outside the region-captioning hot path")
+        max_new, eos, do_sample = 20, None, False
+        if generation_config is not None:
+            max_new = getattr(generation_config, "max_new_tokens", None) or max_new
+            eos = getattr(generation_config, "eos_token_id", None)
+            do_sample = bool(getattr(generation_config, "do_sample", False))
+        max_new = generate_kwargs.pop("max_new_tokens", max_new)
+        if do_sample:
+            raise NotImplementedError("only greedy decoding (do_sample=False) is implemented, as every reference caller uses")
+        if isinstance(eos, (list, tuple)):
+            eos = eos[0]
+        eng = self.engine()
+        if max_new > eng.max_new_tokens:
+            self.configure_engine(max_new_tokens=int(max_new))
+            eng = self.engine()
+        self._stage_request(eng, 0, pixel_values, global_mask_values, aspect_ratios, bboxes, input_ids)
+        toks = eng.generate(1, int(max_new), eos)
+        self._raise_on_status(eng, 0)
+        seq = torch.tensor([toks[0]], dtype=torch.long, device=eng.device)
+        return GenerateOutput(sequences=seq)
+
+    @torch.no_grad()
+    def generate_batch(self, requests: List[dict], max_new_tokens: int = 128, eos_token_id: Optional[int] = None):
+        """B200 scheduler extension: independent requests (each the dict the reference's dataset emits)
+        share one batched decode.  Per-request results equal the batch-1 ``generate`` results."""
+        eng = self.engine()
+        if len(requests) > eng.max_batch:
+            raise ValueError(f"{len(requests)} requests > engine max_batch {eng.max_batch}")
+        for slot, r in enumerate(requests):
+            self._stage_request(eng, slot, r["pixel_values"], r.get("global_mask_values"), r["aspect_ratios"],
+                                r["bboxes"], r["input_ids"])
+        toks = eng.generate(len(requests), int(max_new_tokens), eos_token_id)
+        for slot in range(len(requests)):
+            self._raise_on_status(eng, slot)
+        return toks
+
+    def forward(self, data, data_samples=None, mode="loss"):
+        """Teacher-forced LM loss, reference modeling_gar.py:74-246 (only mode="loss" exists there)."""
+        if mode != "loss":
+            if mode in ("predict", "tensor"):
+                raise UnboundLocalError("outputs")  # reference falls through to an unbound name (:239-246)
+            raise NotImplementedError
+        input_ids = data["input_ids"]
+        assert input_ids.shape[0] == 1, "Currently only support batch_size=1"
+        eng = self.engine()
+        # stage ViT + assemble only, then all-position logits
+        dev = eng.device
+        px = data["pixel_values"].to(dev).to(torch.bfloat16)
+        if px.dim() == 5:
+            px = px.flatten(0, 1)
+        mv = data["global_mask_values"].to(dev).to(torch.bfloat16).contiguous()
+        ids = input_ids[0].to(dev).to(torch.long).contiguous()
+        ar = data["aspect_ratios"][0]
+        eng.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(eng.stream):
+            eng.vit_encode(px.contiguous(), mv)
+            eng.assemble(0, ids, px.shape[0], data["bboxes"][0], int(ar[0]), int(ar[1]))
+            logits = eng.prefill_all_logits(0, ids.numel())
+        torch.cuda.current_stream(dev).wait_stream(eng.stream)
+        self._raise_on_status(eng, 0)
+        labels = data["labels"][0].to(dev).clone()
+        for c in self.crop_tokens_ids:  # replayed rows carry no label (reference :180-191)
+            labels[ids == c] = -100
+        V = self.spec.text.vocab_size
+        # HF ForCausalLMLoss: upcast, shift, mean over non-ignored targets
+        lg = logits[:-1, :V].float()
+        loss = torch.nn.functional.cross_entropy(lg, labels[1:], ignore_index=-100)
+        return {"loss": loss}

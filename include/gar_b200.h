@@ -142,6 +142,15 @@ int gar_engine_prefill_all_logits(gar_engine* e, int slot, int S, void* logits_o
 int gar_engine_generate(gar_engine* e, int batch, int max_new_tokens, int eos, int* out_tokens_host, void* stream);
 int gar_engine_status(gar_engine* e, int slot, int* status_bits);
 long long gar_engine_launch_count(gar_engine* e);
+/* optional per-kernel-class CUDA-event timing for bench.py's roofline (decode runs ungraphed while on) */
+#define GAR_PROF_GEMM 0
+#define GAR_PROF_ATTN 1
+#define GAR_PROF_ASSEMBLE 2
+#define GAR_PROF_DECODE_ATTN 3
+#define GAR_PROF_OTHER 4
+#define GAR_PROF_COUNT 5
+int gar_engine_profile(gar_engine* e, int enable);
+int gar_engine_profile_read(gar_engine* e, double* ms, double* work, long long* count);
 
 #ifdef __cplusplus
 }

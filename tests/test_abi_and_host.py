@@ -1,0 +1,102 @@
+"""CPU-side checks: the C-ABI library builds, loads without a GPU and exports every symbol that
+include/gar_b200.h declares; host-side request plumbing (config round trip, synthetic requests, box
+arithmetic) matches the reference's conventions; the product refuses to run without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from grasp_any_region_b200 import _lib
+from grasp_any_region_b200.config import gar_1b, gar_8b, gar_tiny
+from grasp_any_region_b200.configuration_gar import GARConfig
+from grasp_any_region_b200.engine import roi_boxes_f32
+from grasp_any_region_b200.synth import make_request
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from grasp_any_region_b200.build import build_library
+
+    build_library()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "gar_b200.h")).read()
+    declared = set(re.findall(r"\b(gar_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in gar_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.gar_abi_version() == 1
+
+
+def test_desc_struct_layout_matches_header():
+    # 9 ints/floats, 8 ints, float, int, (pad), int64, 8 x int64, 4 ints
+    assert ctypes.sizeof(_lib.GarModelDesc) == 4 * 20 + 8 + 64 + 16
+    assert _lib.GarModelDesc.image_token_id.offset == 80
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(lib):
+    from grasp_any_region_b200 import GARModel
+
+    m = GARModel(GARConfig.from_spec(gar_tiny()))
+    with pytest.raises(_lib.GarError):
+        m.engine()
+    d = _lib.GarModelDesc()
+    d.vit_dim, d.vit_heads, d.img_size, d.patch_size, d.llm_head_dim = 128, 2, 448, 14, 64
+    h = ctypes.c_void_p()
+    assert lib.gar_engine_create(ctypes.byref(d), ctypes.byref(h)) != 0
+    assert b"CUDA" in lib.gar_last_error()
+
+
+def test_config_round_trip():
+    for spec in (gar_1b(), gar_8b(), gar_tiny()):
+        cfg = GARConfig.from_spec(spec)
+        assert cfg.spec.to_dict() == spec.to_dict()
+        again = GARConfig(**{k: v for k, v in cfg.to_dict().items()
+                             if k in ("mllm_config", "prompt_numbers", "crop_tokens_ids")})
+        assert again.spec.to_dict() == spec.to_dict()
+    assert GARConfig.from_spec(gar_1b()).kernel_size == [14, 14]
+    with pytest.raises(AssertionError):
+        GARConfig(prompt_numbers=4)
+
+
+@pytest.mark.parametrize("n_masks,mnt", [(1, 16), (4, 16), (2, 4)])
+def test_synthetic_request_layout(n_masks, mnt):
+    spec = gar_1b()
+    r = make_request(spec, seed=3, n_masks=n_masks, max_num_tiles=mnt)
+    T = int(np.floor(np.sqrt(mnt))) ** 2 + 1
+    assert r["pixel_values"].shape == (T, 3, 448, 448) and r["global_mask_values"].shape == (T, 3, 448, 448)
+    ids = r["input_ids"][0]
+    assert int((ids == spec.image_token_id).sum()) == T * 256
+    for k in range(n_masks):
+        pos = (ids == spec.crop_tokens_ids[k]).nonzero().flatten()
+        assert pos.numel() == 256 and int(pos.max() - pos.min()) == 255
+        x1, y1, x2, y2 = r["bboxes"][0][str(spec.crop_tokens_ids[k])]
+        assert 0 <= x1 <= x2 < 1 and 0 <= y1 <= y2 < 1
+    # ids decode exactly in bf16 (reference quirk 7)
+    dec = torch.clamp(torch.round((r["global_mask_values"] + 1.0) / 2.0 * 255.0).long(), 0, spec.prompt_numbers)
+    assert set(dec.unique().tolist()) <= set(range(spec.prompt_numbers + 1))
+    assert spec.prompt_numbers in dec.unique().tolist() and 0 in dec.unique().tolist()
+    if mnt == 16 and n_masks == 1:
+        assert ids.numel() == 4672
+
+
+def test_roi_box_host_arithmetic_matches_oracle():
+    from oracle.gar_oracle import roi_box_f32
+
+    spec = gar_1b()
+    boxes = {str(spec.crop_tokens_ids[0]): (0.1234567, 0.2, 0.7654321, 0.9),
+             str(spec.crop_tokens_ids[3]): (0.0, 0.0, 0.999, 0.999)}
+    rois, has, scale = roi_boxes_f32(spec, boxes, 4, 4)
+    assert has == [1, 0, 0, 1, 0]
+    for k in (0, 3):
+        want, s = roi_box_f32(boxes[str(spec.crop_tokens_ids[k])], 64, 64)
+        assert rois[k] == want.tolist() and s == scale
