@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--max-num-tiles", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel-class event timing step")
     return ap.parse_args()
 
 
@@ -276,7 +277,7 @@ def main():
 
     # ---- per-kernel-class timing of ONE more step (CUDA events around every launch of the class)
     roof, stages = None, None
-    if rank == 0:
+    if rank == 0 and not args.no_profile:
         eng.profile(True)
         step_resident()
         prof = eng.profile_read()

@@ -1,0 +1,80 @@
+"""Single-region captioning CLI with the reference's flags (reference: demo/gar_with_mask.py:20-128),
+running on the B200 engine.  Needs a GAR checkpoint directory (config.json + safetensors with the
+reference's state-dict names) and its HF processor; `--synthetic` exercises the same code path with
+random-init weights and a synthetic request when neither is available (no network in this image).
+
+    torchrun --nproc-per-node 1 --master-addr 127.0.0.1 demo/gar_with_mask.py \
+        --model_name_or_path <dir> --image_path assets/demo_image_1.png --mask_path assets/demo_mask_1.png
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from grasp_any_region_b200 import GARConfig, GARModel, config as presets  # noqa: E402
+
+TORCH_DTYPE_MAP = dict(fp16=torch.float16, bf16=torch.bfloat16, fp32=torch.float32)
+
+
+def parse_args():
+    p = argparse.ArgumentParser(description="Inference demo of Grasp Any Region models (B200 engine).")
+    p.add_argument("--model_name_or_path", help="HF model name or path", default="HaochenWang/GAR-8B")
+    p.add_argument("--image_path", help="image path", required=False)
+    p.add_argument("--mask_path", help="mask path", required=False)
+    p.add_argument("--data_type", help="data dtype", type=str, choices=["fp16", "bf16", "fp32"], default="bf16")
+    p.add_argument("--seed", type=int, default=0, help="Random seed for reproducible text generation")
+    p.add_argument("--synthetic", default=None, choices=sorted(presets.PRESETS),
+                   help="no checkpoint: random-init weights of this architecture + a synthetic request")
+    p.add_argument("--max_new_tokens", type=int, default=1024)
+    return p.parse_args()
+
+
+def main():
+    args = parse_args()
+    if args.data_type != "bf16":
+        raise SystemExit("the B200 engine computes in bf16 (--data_type bf16); fp16/fp32 are not built")
+    torch.manual_seed(args.seed)
+    torch.cuda.set_device(0)
+    if "RANK" in os.environ and not torch.distributed.is_initialized():
+        torch.distributed.init_process_group(backend="nccl")  # the reference does this too (:80-81)
+
+    from transformers import GenerationConfig
+
+    if args.synthetic:
+        from grasp_any_region_b200.synth import make_request
+
+        spec = presets.PRESETS[args.synthetic]()
+        model = GARModel(GARConfig.from_spec(spec)).random_init_(args.seed).to("cuda:0").eval()
+        sample = make_request(spec, seed=args.seed, n_masks=1)
+        eos = pad = None
+        decode = lambda ids: " ".join(str(int(t)) for t in ids)  # noqa: E731  (no tokenizer offline)
+    else:
+        from PIL import Image
+        from transformers import AutoProcessor
+
+        from evaluation.eval_dataset import SingleRegionCaptionDataset  # the reference's request builder
+
+        model = GARModel.from_pretrained(args.model_name_or_path, torch_dtype=torch.bfloat16).to("cuda:0").eval()
+        processor = AutoProcessor.from_pretrained(args.model_name_or_path, trust_remote_code=True)
+        img = Image.open(args.image_path)
+        mask = np.array(Image.open(args.mask_path).convert("L")).astype(bool)
+        n = model.config.prompt_numbers
+        prompt_tokens = [f"<Prompt{i}>" for i in range(n)] + ["<NO_Prompt>"]
+        sample = SingleRegionCaptionDataset(image=img, mask=mask, processor=processor, prompt_number=n,
+                                            visual_prompt_tokens=prompt_tokens, data_dtype=torch.bfloat16)[0]
+        eos, pad = processor.tokenizer.eos_token_id, processor.tokenizer.pad_token_id
+        decode = lambda ids: processor.tokenizer.decode(ids, skip_special_tokens=True).strip()  # noqa: E731
+
+    with torch.no_grad():
+        out = model.generate(**sample, generation_config=GenerationConfig(
+            max_new_tokens=args.max_new_tokens, do_sample=False, eos_token_id=eos, pad_token_id=pad),
+            return_dict=True)
+    print(decode(out.sequences[0]))
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,8 @@ class GarModelDesc(C.Structure):
 SIGNATURES = {
     "gar_last_error": (C.c_char_p, []),
     "gar_abi_version": (_i, []),
+    "gar_copy_d2d": (_i, [_vp, _vp, _ll, _vp]),
+    "gar_gemm_skinny_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "gar_gemm_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "gar_patchify": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gar_vit_embed_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
@@ -55,6 +57,7 @@ SIGNATURES = {
     "gar_engine_generate": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _vp]),
     "gar_engine_status": (_i, [_vp, _i, C.POINTER(_i)]),
     "gar_engine_launch_count": (_ll, [_vp]),
+    "gar_engine_set_option": (_i, [_vp, C.c_char_p, _i]),
     "gar_engine_profile": (_i, [_vp, _i]),
     "gar_engine_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
 }

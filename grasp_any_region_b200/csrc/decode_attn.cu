@@ -60,12 +60,19 @@ decode_attn_split_kernel(const bf16* __restrict__ qkv, int ldq, const bf16* __re
   const bf16* kbase = kcache + (static_cast<size_t>(slot) * hkv + kvh) * max_seq * HD;
   const bf16* vbase = vcache + (static_cast<size_t>(slot) * hkv + kvh) * max_seq * HD;
   constexpr int ROWS_PER_ITER = (DEC_THREADS / 32) * 4;
-  for (int r0 = k_begin + warp * 4 + grp; r0 < k_end; r0 += ROWS_PER_ITER) {
+  // warp-uniform trip count: the shuffles below need all 32 lanes, so tail rows are predicated, not skipped
+  for (int rb = k_begin + warp * 4; rb < k_end; rb += ROWS_PER_ITER) {
+    const int r0 = rb + grp;
+    const bool valid = r0 < k_end;
     uint4 kr[VPL], vr[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-      kr[v] = *reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(r0) * HD + v * 64 + sub * 8);
-      vr[v] = *reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(r0) * HD + v * 64 + sub * 8);
+      kr[v] = make_uint4(0, 0, 0, 0);
+      vr[v] = make_uint4(0, 0, 0, 0);
+      if (valid) {
+        kr[v] = *reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(r0) * HD + v * 64 + sub * 8);
+        vr[v] = *reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(r0) * HD + v * 64 + sub * 8);
+      }
     }
     float kf[VPL][8], vf[VPL][8];
 #pragma unroll
@@ -89,17 +96,19 @@ decode_attn_split_kernel(const bf16* __restrict__ qkv, int ldq, const bf16* __re
       d += __shfl_xor_sync(0xffffffffu, d, 1);
       d += __shfl_xor_sync(0xffffffffu, d, 2);
       d += __shfl_xor_sync(0xffffffffu, d, 4);
-      const float sc = d * scale_log2;
-      const float m_new = fmaxf(m[g], sc);
-      const float alpha = exp2f(m[g] - m_new);
-      const float pexp = exp2f(sc - m_new);
-      l[g] = l[g] * alpha + pexp;
-      m[g] = m_new;
-      const float pb = bf16r(pexp);
+      if (valid) {
+        const float sc = d * scale_log2;
+        const float m_new = fmaxf(m[g], sc);
+        const float alpha = exp2f(m[g] - m_new);
+        const float pexp = exp2f(sc - m_new);
+        l[g] = l[g] * alpha + pexp;
+        m[g] = m_new;
+        const float pb = bf16r(pexp);
 #pragma unroll
-      for (int v = 0; v < VPL; ++v)
+        for (int v = 0; v < VPL; ++v)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[g][v][j] = acc[g][v][j] * alpha + pb * vf[v][j];
+          for (int j = 0; j < 8; ++j) acc[g][v][j] = acc[g][v][j] * alpha + pb * vf[v][j];
+      }
     }
   }
   // merge the 4 row-groups of a warp, then the warps, through shared memory

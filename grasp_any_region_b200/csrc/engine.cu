@@ -33,6 +33,7 @@ struct gar_engine {
   int *plan, *status, *next_tok, *out_tokens, *pos, *finished, *step;
   long long* ids_scratch;
   int dec_splits;
+  int use_skinny = 1;
   // decode graph
   cudaGraphExec_t graph_exec = nullptr;
   int graph_batch = -1;
@@ -98,6 +99,8 @@ int gemm(gar_engine* e, const void* A, int lda, const void* B, int ldb, void* C,
          const void* bias, const void* gamma, const void* res, int ldres, void* s) {
   e->launches += 1;
   ProfScope ps(e, s, PK_GEMM, 2.0 * M * static_cast<double>(N) * K);
+  if (e->use_skinny && M <= 16 && (epi == GAR_EPI_NONE || epi == GAR_EPI_RES))
+    return gar_gemm_skinny_bf16(A, lda, B, ldb, C, ldc, M, N, K, epi, res, ldres, s);
   return gar_gemm_bf16(A, lda, B, ldb, C, ldc, M, N, K, epi, bias, gamma, res, ldres, 0, s);
 }
 
@@ -484,6 +487,19 @@ int gar_engine_status(gar_engine* e, int slot, int* status_bits) {
 }
 
 long long gar_engine_launch_count(gar_engine* e) { return e ? e->launches : 0; }
+
+int gar_engine_set_option(gar_engine* e, const char* name, int value) {
+  if (!e || !name) return GAR_ERR_ARG;
+  const std::string n(name);
+  if (n == "skinny_gemm") e->use_skinny = value;
+  else if (n == "decode_splits" && value >= 1 && value <= 8) e->dec_splits = value;
+  else {
+    gar_set_error("gar_engine_set_option: unknown option '%s'=%d", name, value);
+    return GAR_ERR_ARG;
+  }
+  if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_batch = -1; }
+  return GAR_OK;
+}
 
 int gar_engine_profile(gar_engine* e, int enable) {
   if (!e) return GAR_ERR_ARG;

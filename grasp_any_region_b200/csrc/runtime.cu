@@ -16,6 +16,13 @@ void gar_set_error(const char* fmt, ...) {
 extern "C" const char* gar_last_error(void) { return g_err; }
 extern "C" int gar_abi_version(void) { return 1; }
 
+// plain device-to-device copy on a stream (parity taps read engine-internal buffers with it)
+extern "C" int gar_copy_d2d(void* dst, const void* src, long long bytes, void* stream) {
+  GAR_CUDA_CHECK(cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDeviceToDevice,
+                                 static_cast<cudaStream_t>(stream)));
+  return GAR_OK;
+}
+
 int gar_num_sms() {
   static int sms = 0;
   if (sms == 0) {

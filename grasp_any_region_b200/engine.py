@@ -153,9 +153,9 @@ class Engine:
         check(self.lib.gar_engine_get_buffer(self._h, name.encode(), C.byref(ptr), C.byref(nbytes)), "get_buffer")
         out = torch.empty(shape, dtype=dtype, device=self.device)
         assert out.numel() * out.element_size() <= nbytes.value, (name, shape, nbytes.value)
+        check(self.lib.gar_copy_d2d(C.c_void_p(out.data_ptr()), ptr, out.numel() * out.element_size(), self._s()),
+              "gar_copy_d2d")
         self.stream.synchronize()
-        rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), ptr.value, out.numel() * out.element_size(), 3)
-        assert int(rc) == 0, rc
         return out
 
     def vit_encode(self, pixel_values: torch.Tensor, mask_values: Optional[torch.Tensor]):
@@ -209,6 +209,9 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.gar_engine_launch_count(self._h))
+
+    def set_option(self, name: str, value: int):
+        check(self.lib.gar_engine_set_option(self._h, name.encode(), int(value)), "gar_engine_set_option")
 
     def profile(self, enable: bool):
         check(self.lib.gar_engine_profile(self._h, int(enable)), "gar_engine_profile")

@@ -41,6 +41,19 @@ def gemm(a, b, epi=EPI_NONE, bias=None, gamma=None, res=None, out=None, block_n=
     return out
 
 
+def gemm_skinny(x, w, epi=EPI_NONE, res=None, out=None):
+    """out[M<=16,N] = epi(x[M,K] @ w[N,K]^T) through the decode weight-streaming kernel."""
+    _req(x), _req(w)
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().gar_gemm_skinny_bf16(_p(x), x.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K,
+                                           epi, _p(res), 0 if res is None else res.stride(0), _stream()),
+          "gar_gemm_skinny_bf16")
+    return out
+
+
 def layernorm(x, w, b, eps):
     _req(x)
     y = torch.empty_like(x)

@@ -32,6 +32,7 @@ extern "C" {
 
 const char* gar_last_error(void);
 int gar_abi_version(void);
+int gar_copy_d2d(void* dst, const void* src, long long bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Per-kernel entry points (unit parity; the engine below is built from exactly these)
@@ -50,6 +51,11 @@ int gar_abi_version(void);
  * block_n_hint: 0 = auto, or 64/128/256. */
 int gar_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K, int epi,
                   const void* bias, const void* gamma, const void* res, int ldres, int block_n_hint, void* stream);
+
+/* out[M<=16,N] = epi(X[M,K] W[N,K]^T), epi in {GAR_EPI_NONE, GAR_EPI_RES}: swap-AB tcgen05 weight-streaming GEMM with
+ * cluster split-K reduced through distributed shared memory (the decode step's cuBLAS GEMV-like calls). */
+int gar_gemm_skinny_bf16(const void* X, int ldx, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
+                         int epi, const void* res, int ldres, void* stream);
 
 /* mask-id decode + im2col of both stride-14 convs (modeling_gar.py:315-328; timm PatchEmbed) */
 int gar_patchify(const void* pixel_values, const void* mask_values, void* a_img, void* a_mask, int T, int img,
@@ -142,6 +148,8 @@ int gar_engine_prefill_all_logits(gar_engine* e, int slot, int S, void* logits_o
 int gar_engine_generate(gar_engine* e, int batch, int max_new_tokens, int eos, int* out_tokens_host, void* stream);
 int gar_engine_status(gar_engine* e, int slot, int* status_bits);
 long long gar_engine_launch_count(gar_engine* e);
+/* options: "skinny_gemm" (1 = decode GEMMs use gar_gemm_skinny_bf16, default 1), "decode_splits" */
+int gar_engine_set_option(gar_engine* e, const char* name, int value);
 /* optional per-kernel-class CUDA-event timing for bench.py's roofline (decode runs ungraphed while on) */
 #define GAR_PROF_GEMM 0
 #define GAR_PROF_ATTN 1

@@ -78,6 +78,24 @@ def test_gemm_inplace_residual():
     assert (out.float() - ref).abs().max().item() <= 4e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("M,N,K", [(1, 256, 256), (8, 3072, 2048), (8, 2048, 8192), (16, 1024, 512), (3, 128512, 512),
+                                   (8, 16384, 2048), (5, 384, 128)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_gemm_skinny(M, N, K, with_res):
+    x, w = rnd(M, K, seed=40), rnd(N, K, scale=0.05, seed=41)
+    res = rnd(M, N, seed=42) if with_res else None
+    out = ops.gemm_skinny(x, w, epi=ops.EPI_RES if with_res else ops.EPI_NONE, res=res)
+    torch.cuda.synchronize()
+    ref = gemm_ref(x, w, ops.EPI_RES if with_res else ops.EPI_NONE, res=res)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 4e-2 * max(1.0, ref.abs().max().item()), err
+    assert (out.float() != ref).float().mean().item() < 0.02
+    # deterministic split-K: bitwise repeatable
+    out2 = ops.gemm_skinny(x, w, epi=ops.EPI_RES if with_res else ops.EPI_NONE, res=res)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
 def test_layernorm_rmsnorm():
     x = rnd(1000, 1024, seed=11)
     w, b = (1 + rnd(1024, scale=0.1, seed=12).float()).to(bf), rnd(1024, scale=0.1, seed=13)

@@ -10,7 +10,7 @@ FILES="${@:-tests/test_gpu_kernels.py tests/test_gpu_engine.py}"
 FUNCS=$(python -m pytest $FILES --collect-only -q -m gpu 2>/dev/null | grep '::' | sed 's/\[.*//' | sort -u)
 for f in $FUNCS; do
   echo "=== $f" >> $LOG
-  timeout 600 python -m pytest "$f" -q -m gpu --tb=short -s -p no:cacheprovider 2>&1 | tail -60 >> $LOG
+  timeout 150 python -m pytest "$f" -q -m gpu --tb=short -s -p no:cacheprovider 2>&1 | tail -60 >> $LOG
   echo "=== exit ${PIPESTATUS[0]}" >> $LOG
 done
 grep -E "^=== |passed|failed|error" $LOG | tail -80
