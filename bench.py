@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel-class event timing step")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (pdl, skinny_gemm, decode_splits)")
     return ap.parse_args()
 
 
@@ -201,6 +202,9 @@ def main():
     T = reqs_host[0]["pixel_values"].shape[0]
     model.configure_engine(max_tiles=T, max_seq=((S + NT + 127) // 128) * 128, max_batch=B, max_new_tokens=NT)
     eng = model.engine()
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
 
     def pin(r):
         o = dict(r)
@@ -275,6 +279,24 @@ def main():
         e2e = {"value": world * B * args.steps / (ms_e / 1e3), "unit": "captions/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps}
 
+    # ---- phase split of one more step (events on the engine stream between the phases)
+    phases = None
+    if rank == 0:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.cuda.synchronize()
+        ev[0].record(eng.stream)
+        with torch.cuda.stream(eng.stream):
+            for slot, r in enumerate(reqs_dev):
+                eng.request(slot, r["pixel_values"], r["global_mask_values"], r["input_ids"][0], r["bboxes"][0],
+                            r["aspect_ratios"][0].tolist())
+        ev[1].record(eng.stream)
+        eng.generate(B, NT, None)
+        ev[2].record(eng.stream)
+        torch.cuda.synchronize()
+        enc, dec = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+        phases = {"vit_assemble_prefill_ms_per_request": enc / B, "decode_ms_total": dec,
+                  "decode_ms_per_token_step": dec / max(1, NT - 1), "batch": B}
+
     # ---- per-kernel-class timing of ONE more step (CUDA events around every launch of the class)
     roof, stages = None, None
     if rank == 0 and not args.no_profile:
@@ -317,7 +339,7 @@ def main():
             "config": {"workload": workload_name(args), "requests_per_gpu_per_step": B, "tiles": T, "prompt_len": S,
                        "l2": "inputs+weights per step (3.2 GB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"dp{world} (independent requests per rank, one all-gather of token ids)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "stages": stages,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "stages": stages, "phases": phases,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

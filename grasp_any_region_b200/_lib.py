@@ -30,6 +30,7 @@ SIGNATURES = {
     "gar_copy_d2d": (_i, [_vp, _vp, _ll, _vp]),
     "gar_gemm_skinny_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "gar_gemm_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "gar_gemm_bf16_rope2d": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gar_patchify": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gar_vit_embed_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "gar_layernorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
@@ -39,7 +40,7 @@ SIGNATURES = {
     "gar_swiglu": (_i, [_vp, _vp, _i, _i, _vp]),
     "gar_pool2x2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gar_embed_gather": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
-    "gar_argmax_step": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "gar_argmax_step": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "gar_bump_step": (_i, [_vp, _vp]),
     "gar_assemble_embeds": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, C.POINTER(_ll), C.POINTER(_f), C.POINTER(_i), _i,
                                  _f, _i, _i, _i, _ll, _vp, _vp, _vp, _vp]),

@@ -158,7 +158,8 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tmem_ld_wait();
       const int kv0 = j * BKV;
       const bool need_mask = (kv0 + BKV > p.kv_len) || (p.causal && kv0 + BKV - 1 > q0 + shift);
-      float mx = -INFINITY;
+      // row max with 4 independent chains (a single 128-long fmax chain is pure latency)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
       if (need_mask) {
         const int lim = p.causal ? min(p.kv_len - 1, q_pos) : p.kv_len - 1;
 #pragma unroll
@@ -166,15 +167,20 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           float v = __uint_as_float(s[i]);
           v = (kv0 + i <= lim) ? v : -INFINITY;
           s[i] = __float_as_uint(v);
-          mx = fmaxf(mx, v);
+          mx4[i & 3] = fmaxf(mx4[i & 3], v);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+        for (int i = 0; i < 128; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s[i]));
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      // Lazy rescale: keep exponentiating against the old reference max until the true max has grown by
+      // more than 2^8; P then stays <= 256 (harmless in bf16/fp32) and most O rescales disappear.
+      const float m_cand = fmaxf(m_run, mx * p.scale_log2);
+      const bool bump = (m_cand - m_run) > 8.0f || m_run == -INFINITY;
+      const float m_new = bump ? m_cand : m_run;
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m_run - m_use);
+      const float alpha = bump ? exp2f(m_run - m_use) : 1.0f;
       // rescale O (s_full(j) implies PV(j-1) retired, so O and the P buffer are quiescent)
       if (j > 0) {
         const bool any = __any_sync(0xffffffffu, alpha != 1.0f);
@@ -193,18 +199,19 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       // P = exp2(S*scale - m) -> bf16 -> smem, canonical K-major 128B-swizzled layout:
       // row r, 16B chunk c at r*128 + ((c ^ (r&7))<<4); two [128 x 64] sub-tiles
-      float rs = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
       {
         const uint32_t rbase = sbase + SMEM_P + (row >> 3) * 1024 + (row & 7) * 128;
         const uint32_t sw = row & 7;
+        const float neg_m = -m_use;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           uint32_t w[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float p0 = exp2f(__uint_as_float(s[c * 8 + 2 * i]) * p.scale_log2 - m_use);
-            const float p1 = exp2f(__uint_as_float(s[c * 8 + 2 * i + 1]) * p.scale_log2 - m_use);
-            rs += p0 + p1;
+            const float p0 = exp2f(fmaf(__uint_as_float(s[c * 8 + 2 * i]), p.scale_log2, neg_m));
+            const float p1 = exp2f(fmaf(__uint_as_float(s[c * 8 + 2 * i + 1]), p.scale_log2, neg_m));
+            rs4[i] += p0 + p1;
             w[i] = pack_bf16x2(p0, p1);
           }
           const uint32_t addr = rbase + (c >> 3) * TILE_BYTES + (((c & 7) ^ sw) << 4);
@@ -212,6 +219,7 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                        : "memory");
         }
       }
+      const float rs = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
       l_run = l_run * alpha + rs;
       m_run = m_new;
       fence_proxy_async_smem();

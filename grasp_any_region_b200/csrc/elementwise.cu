@@ -147,6 +147,8 @@ __device__ __forceinline__ void norm_row(const uint4* __restrict__ xin, const bf
 template <bool RMS>
 __global__ void norm_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ w,
                             const bf16* __restrict__ b, bf16* __restrict__ y, int ldy, int rows, int d, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
@@ -221,6 +223,8 @@ __global__ void llama_rope_kv_kernel(bf16* __restrict__ qkv, int rows, int hq, i
                                      const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t, int pos0,
                                      const int* __restrict__ pos_dev, const int* __restrict__ slot_dev, int slot0,
                                      bf16* __restrict__ kcache, bf16* __restrict__ vcache, int max_seq) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = hd / 2;
   const int vec_per_head = half / 8;  // each work item: 8 low elements + their 8 high partners
   const int heads_total = hq + 2 * hkv;
@@ -268,6 +272,8 @@ __global__ void llama_rope_kv_kernel(bf16* __restrict__ qkv, int rows, int hq, i
 
 // SwiGLU: act = bf16( bf16(silu(g)) * u ) with gu rows = [gate(I) | up(I)]   (HF LlamaMLP :182-184)
 __global__ void swiglu_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int rows, int inter) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vec_per_row = inter / 8;
   const long long total = static_cast<long long>(rows) * vec_per_row;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -326,6 +332,8 @@ __global__ void pool2x2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
 // rows of the embedding table gathered by (device) token ids: h[b] = table[tok[b]]
 __global__ void embed_gather_kernel(const bf16* __restrict__ table, const long long* __restrict__ ids64,
                                     const int* __restrict__ ids32, bf16* __restrict__ out, int rows, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vec = D / 8;
   const long long total = static_cast<long long>(rows) * vec;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -339,25 +347,20 @@ __global__ void embed_gather_kernel(const bf16* __restrict__ table, const long l
 
 // greedy step: tok[b] = argmax_v logits[b, v] (lowest index on ties, like torch.argmax), then
 // bookkeeping for the device-side decode loop: append to out_tokens[b, step], bump position,
-// latch EOS.  One block per sequence.
-__global__ void argmax_step_kernel(const bf16* __restrict__ logits, int ld, int V, int* __restrict__ next_tok,
-                                   int* __restrict__ out_tokens, int out_ld, const int* __restrict__ step_ptr,
-                                   int* __restrict__ pos, int* __restrict__ finished, int eos, int advance_pos) {
-  const int b = blockIdx.x;
-  const bf16* row = logits + static_cast<size_t>(b) * ld;
-  float best = -INFINITY;
-  int bidx = 0x7fffffff;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
-    const float f = bf2f(row[v]);
-    if (f > best || (f == best && v < bidx)) { best = f; bidx = v; }
-  }
-  __shared__ float sb[32];
-  __shared__ int si[32];
+// latch EOS.  Stage 1 (optional): grid (chunks, batch) reduces 4096-wide chunks into (max, idx) pairs;
+// stage 2: one block per sequence reduces the pairs (or scans the row itself when no workspace is given).
+constexpr int ARGMAX_CHUNK = 4096;
+
+__device__ __forceinline__ void argmax_merge(float& best, int& bidx, float ob, int oi) {
+  if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+}
+
+__device__ __forceinline__ void argmax_block_reduce(float& best, int& bidx, float* sb, int* si) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-    if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    argmax_merge(best, bidx, ob, oi);
   }
   if ((threadIdx.x & 31) == 0) { sb[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bidx; }
   __syncthreads();
@@ -369,16 +372,82 @@ __global__ void argmax_step_kernel(const bf16* __restrict__ logits, int ld, int 
     for (int o = 16; o > 0; o >>= 1) {
       const float ob = __shfl_xor_sync(0xffffffffu, best, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-      if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+      argmax_merge(best, bidx, ob, oi);
     }
+  }
+}
+
+__global__ void argmax_partial_kernel(const bf16* __restrict__ logits, int ld, int V, float* __restrict__ pmax,
+                                      int* __restrict__ pidx, int chunks) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float sb[32];
+  __shared__ int si[32];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const bf16* row = logits + static_cast<size_t>(b) * ld;
+  const int lo = c * ARGMAX_CHUNK, hi = min(V, lo + ARGMAX_CHUNK);
+  float best = -INFINITY;
+  int bidx = 0x7fffffff;
+  for (int v0 = lo + threadIdx.x * 8; v0 < hi; v0 += blockDim.x * 8) {
+    if (v0 + 8 <= hi) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(row + v0);  // ld % 8 == 0 and lo % 8 == 0
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(rw[j]);
+        argmax_merge(best, bidx, f.x, v0 + 2 * j);
+        argmax_merge(best, bidx, f.y, v0 + 2 * j + 1);
+      }
+    } else {
+      for (int v = v0; v < hi; ++v) argmax_merge(best, bidx, bf2f(row[v]), v);
+    }
+  }
+  argmax_block_reduce(best, bidx, sb, si);
+  if (threadIdx.x == 0) {
+    pmax[static_cast<size_t>(b) * chunks + c] = best;
+    pidx[static_cast<size_t>(b) * chunks + c] = bidx;
+  }
+}
+
+__global__ void argmax_step_kernel(const bf16* __restrict__ logits, int ld, int V, const float* __restrict__ pmax,
+                                   const int* __restrict__ pidx, int chunks, int* __restrict__ next_tok,
+                                   int* __restrict__ out_tokens, int out_ld, int* __restrict__ step_ptr,
+                                   int* __restrict__ pos, int* __restrict__ finished, int eos, int advance_pos,
+                                   int bump_step) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float sb[32];
+  __shared__ int si[32];
+  const int b = blockIdx.x;
+  float best = -INFINITY;
+  int bidx = 0x7fffffff;
+  if (pmax != nullptr) {
+    for (int c = threadIdx.x; c < chunks; c += blockDim.x)
+      argmax_merge(best, bidx, pmax[static_cast<size_t>(b) * chunks + c], pidx[static_cast<size_t>(b) * chunks + c]);
+  } else {
+    const bf16* row = logits + static_cast<size_t>(b) * ld;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) argmax_merge(best, bidx, bf2f(row[v]), v);
+  }
+  argmax_block_reduce(best, bidx, sb, si);
+  if (threadIdx.x == 0) {
+    const int step = step_ptr ? *step_ptr : 0;
+    const int fin = finished ? finished[b] : 0;
+    const int tok = fin ? (eos >= 0 ? eos : bidx) : bidx;
+    next_tok[b] = tok;
+    if (out_tokens) out_tokens[static_cast<size_t>(b) * out_ld + step] = fin ? -1 : tok;
+    if (finished && eos >= 0 && tok == eos) finished[b] = 1;
+    if (pos && advance_pos) pos[b] += 1;
+  }
+  // the last block to finish bumps the step counter (replaces a separate 1-thread launch)
+  if (bump_step && step_ptr) {
+    __shared__ int last;
+    __threadfence();
+    __syncthreads();
     if (threadIdx.x == 0) {
-      const int step = step_ptr ? *step_ptr : 0;
-      const int fin = finished ? finished[b] : 0;
-      const int tok = fin ? (eos >= 0 ? eos : bidx) : bidx;
-      next_tok[b] = tok;
-      if (out_tokens) out_tokens[static_cast<size_t>(b) * out_ld + step] = fin ? -1 : tok;
-      if (finished && eos >= 0 && tok == eos) finished[b] = 1;
-      if (pos && advance_pos) pos[b] += 1;
+      // ticket lives in step_ptr[1]
+      const int t = atomicAdd(step_ptr + 1, 1);
+      last = (t == static_cast<int>(gridDim.x) - 1);
+      if (last) { step_ptr[1] = 0; step_ptr[0] += 1; }
     }
   }
 }
@@ -427,9 +496,10 @@ int gar_rmsnorm(const void* x, int ldx, const void* w, void* y, int ldy, int row
     gar_set_error("gar_rmsnorm: d=%d unsupported (need d%%8==0, d<=%d)", d, NORM_MAXV * 256);
     return GAR_ERR_SHAPE;
   }
-  norm_kernel<true><<<grid_for(static_cast<long long>(rows) * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), ldx, static_cast<const bf16*>(w), nullptr, static_cast<bf16*>(y), ldy, rows, d, eps);
-  GAR_CUDA_CHECK(cudaGetLastError());
+  GAR_CUDA_CHECK(gar_launch(norm_kernel<true>, dim3(grid_for(static_cast<long long>(rows) * 32, 128)), dim3(128), 0,
+                            static_cast<cudaStream_t>(stream), true, dim3(1, 1, 1), static_cast<const bf16*>(x), ldx,
+                            static_cast<const bf16*>(w), static_cast<const bf16*>(nullptr), static_cast<bf16*>(y), ldy,
+                            rows, d, eps));
   return GAR_OK;
 }
 
@@ -458,19 +528,18 @@ int gar_llama_rope_kv(void* qkv, int rows, int hq, int hkv, int hd, const void* 
                       void* stream) {
   if (hd % 16) return GAR_ERR_SHAPE;
   const long long total = static_cast<long long>(rows) * (hq + 2 * hkv) * (hd / 16);
-  llama_rope_kv_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<bf16*>(qkv), rows, hq, hkv, hd, static_cast<const bf16*>(cos_t), static_cast<const bf16*>(sin_t),
-      pos0, pos_dev, slot_dev, slot0, static_cast<bf16*>(kcache), static_cast<bf16*>(vcache), max_seq);
-  GAR_CUDA_CHECK(cudaGetLastError());
+  GAR_CUDA_CHECK(gar_launch(llama_rope_kv_kernel, dim3(grid_for(total, 256)), dim3(256), 0,
+                            static_cast<cudaStream_t>(stream), true, dim3(1, 1, 1), static_cast<bf16*>(qkv), rows, hq,
+                            hkv, hd, static_cast<const bf16*>(cos_t), static_cast<const bf16*>(sin_t), pos0, pos_dev,
+                            slot_dev, slot0, static_cast<bf16*>(kcache), static_cast<bf16*>(vcache), max_seq));
   return GAR_OK;
 }
 
 int gar_swiglu(const void* gu, void* act, int rows, int inter, void* stream) {
   if (inter % 8) return GAR_ERR_SHAPE;
-  swiglu_kernel<<<grid_for(static_cast<long long>(rows) * (inter / 8), 256), 256, 0,
-                  static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(gu), static_cast<bf16*>(act), rows,
-                                                       inter);
-  GAR_CUDA_CHECK(cudaGetLastError());
+  GAR_CUDA_CHECK(gar_launch(swiglu_kernel, dim3(grid_for(static_cast<long long>(rows) * (inter / 8), 256)), dim3(256),
+                            0, static_cast<cudaStream_t>(stream), true, dim3(1, 1, 1), static_cast<const bf16*>(gu),
+                            static_cast<bf16*>(act), rows, inter));
   return GAR_OK;
 }
 
@@ -486,18 +555,29 @@ int gar_pool2x2(const void* x, void* y, int T, int ntok, int npt, int grid, int 
 int gar_embed_gather(const void* table, const long long* ids64, const int* ids32, void* out, int rows, int D,
                      void* stream) {
   if (D % 8 || (!ids64 && !ids32)) return GAR_ERR_SHAPE;
-  embed_gather_kernel<<<grid_for(static_cast<long long>(rows) * (D / 8), 256), 256, 0,
-                        static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(table), ids64, ids32,
-                                                             static_cast<bf16*>(out), rows, D);
-  GAR_CUDA_CHECK(cudaGetLastError());
+  GAR_CUDA_CHECK(gar_launch(embed_gather_kernel, dim3(grid_for(static_cast<long long>(rows) * (D / 8), 256)),
+                            dim3(256), 0, static_cast<cudaStream_t>(stream), true, dim3(1, 1, 1),
+                            static_cast<const bf16*>(table), ids64, ids32, static_cast<bf16*>(out), rows, D));
   return GAR_OK;
 }
 
 int gar_argmax_step(const void* logits, int ld, int V, int batch, int* next_tok, int* out_tokens, int out_ld,
-                    const int* step_ptr, int* pos, int* finished, int eos, int advance_pos, void* stream) {
-  argmax_step_kernel<<<batch, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(logits), ld, V, next_tok, out_tokens, out_ld, step_ptr, pos, finished, eos, advance_pos);
-  GAR_CUDA_CHECK(cudaGetLastError());
+                    int* step_ptr, int* pos, int* finished, int eos, int advance_pos, int bump_step, void* partial_ws,
+                    void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int chunks = (V + ARGMAX_CHUNK - 1) / ARGMAX_CHUNK;
+  float* pmax = nullptr;
+  int* pidx = nullptr;
+  if (partial_ws != nullptr && (ld % 8) == 0) {
+    pmax = static_cast<float*>(partial_ws);
+    pidx = reinterpret_cast<int*>(pmax + static_cast<size_t>(batch) * chunks);
+    GAR_CUDA_CHECK(gar_launch(argmax_partial_kernel, dim3(chunks, batch), dim3(256), 0, s, true, dim3(1, 1, 1),
+                              static_cast<const bf16*>(logits), ld, V, pmax, pidx, chunks));
+  }
+  GAR_CUDA_CHECK(gar_launch(argmax_step_kernel, dim3(batch), dim3(pmax ? 64 : 1024), 0, s, true, dim3(1, 1, 1),
+                            static_cast<const bf16*>(logits), ld, V, static_cast<const float*>(pmax),
+                            static_cast<const int*>(pidx), chunks, next_tok, out_tokens, out_ld, step_ptr, pos,
+                            finished, eos, advance_pos, bump_step));
   return GAR_OK;
 }
 

@@ -29,11 +29,12 @@ struct gar_engine {
   bf16 *a_img, *a_mask, *pe, *x, *ln, *qkv_v, *att_v, *mlp_v, *p1, *p2, *feats;
   // LLM workspaces
   bf16 *emb, *h, *lnl, *qkv_l, *att_l, *gu, *act, *logits, *kcache, *vcache, *hdec, *lndec;
-  float *o_part, *ml_part;
+  float *o_part, *ml_part, *argmax_ws;
   int *plan, *status, *next_tok, *out_tokens, *pos, *finished, *step;
   long long* ids_scratch;
   int dec_splits;
   int use_skinny = 1;
+  int fuse_rope = 1;
   // decode graph
   cudaGraphExec_t graph_exec = nullptr;
   int graph_batch = -1;
@@ -132,7 +133,12 @@ int llm_layers(gar_engine* e, bf16* h, bf16* ln, int rows, bool decode, int slot
     e->launches += 2;
     if (decode) {
       ProfScope ps(e, s, PK_DECODE_ATTN, 0.0);
-      TRY(gar_decode_attn(e->qkv_l, qkv_w, kc, vc, e->pos, nullptr, rows, hq, hkv, hd, d.max_seq, e->dec_splits, scale,
+      int splits = e->dec_splits;
+      if (splits <= 0) {  // ~4 CTAs per SM across (split, kv head, sequence)
+        splits = (4 * gar_num_sms() + rows * hkv - 1) / (rows * hkv);
+        splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
+      }
+      TRY(gar_decode_attn(e->qkv_l, qkv_w, kc, vc, e->pos, nullptr, rows, hq, hkv, hd, d.max_seq, splits, scale,
                           e->o_part, e->ml_part, e->att_l, hq * hd, s));
       e->launches += 2;
     } else {
@@ -173,8 +179,7 @@ int decode_step(gar_engine* e, int batch, int eos, void* s) {
   TRY(llm_layers(e, e->hdec, e->lndec, batch, true, 0, s));
   TRY(lm_head(e, e->hdec, d.llm_dim, batch, e->logits, s));
   TRY(gar_argmax_step(e->logits, d.vocab_padded, d.vocab, batch, e->next_tok, e->out_tokens, d.max_new_tokens, e->step,
-                      e->pos, e->finished, eos, 1, s));
-  TRY(gar_bump_step(e->step, s));
+                      e->pos, e->finished, eos, 1, 1, e->argmax_ws, s));
   e->launches += 2;
   return GAR_OK;
 }
@@ -205,7 +210,7 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   e->kpad = ((3 * d.patch_size * d.patch_size + 63) / 64) * 64;
   e->tpt = e->grid / d.pool_ratio;
   e->tokens_per_tile = e->tpt * e->tpt;
-  e->dec_splits = 8;
+  e->dec_splits = 0;  // 0 = pick per batch so the split kernel fills the GPU
   const size_t T = d.max_tiles, NP = static_cast<size_t>(e->grid) * e->grid, NT = e->ntok;
   const size_t dv = d.vit_dim, D = d.llm_dim, S = d.max_seq, B = d.max_batch;
   const size_t qkv_w = static_cast<size_t>(d.llm_heads + 2 * d.llm_kv_heads) * d.llm_head_dim;
@@ -234,15 +239,16 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   const size_t kv_elems = static_cast<size_t>(d.llm_layers) * B * d.llm_kv_heads * S * d.llm_head_dim;
   rc |= dev_alloc(e, &e->kcache, kv_elems, true);  // zero-filled: TMA tiles past the live length must be finite
   rc |= dev_alloc(e, &e->vcache, kv_elems, true);
-  rc |= dev_alloc(e, &e->o_part, B * d.llm_heads * e->dec_splits * d.llm_head_dim);
-  rc |= dev_alloc(e, &e->ml_part, B * d.llm_heads * e->dec_splits * 2);
+  rc |= dev_alloc(e, &e->o_part, B * d.llm_heads * 32 * d.llm_head_dim);
+  rc |= dev_alloc(e, &e->ml_part, B * d.llm_heads * 32 * 2);
   rc |= dev_alloc(e, &e->plan, S);
   rc |= dev_alloc(e, &e->status, 2 * B, true);
   rc |= dev_alloc(e, &e->next_tok, B, true);
   rc |= dev_alloc(e, &e->out_tokens, B * d.max_new_tokens, true);
   rc |= dev_alloc(e, &e->pos, B, true);
   rc |= dev_alloc(e, &e->finished, B, true);
-  rc |= dev_alloc(e, &e->step, 1, true);
+  rc |= dev_alloc(e, &e->step, 2, true);
+  rc |= dev_alloc(e, &e->argmax_ws, B * ((static_cast<size_t>(d.vocab) + 4095) / 4096) * 2, true);
   rc |= dev_alloc(e, &e->ids_scratch, S);
   if (rc) {
     gar_engine_destroy(e);
@@ -335,8 +341,16 @@ int gar_engine_vit_encode(gar_engine* e, const void* pixel_values, const void* m
     NEEDW(b2, L("vit", i, "fc2.b"));
     NEEDW(g2, L("vit", i, "g2"));
     TRY(gar_layernorm(e->x, dv, l1w, l1b, e->ln, dv, rows, dv, d.ln_eps, s));
-    TRY(gemm(e, e->ln, dv, wqkv, dv, e->qkv_v, 3 * dv, rows, 3 * dv, dv, GAR_EPI_BIAS, bqkv, nullptr, nullptr, 0, s));
-    TRY(gar_vit_rope(e->qkv_v, rope, rows, NT, e->npt, d.vit_heads, e->hd_v, s));
+    if (e->fuse_rope) {
+      e->launches += 1;
+      ProfScope ps(e, s, PK_GEMM, 2.0 * rows * 3.0 * dv * dv);
+      TRY(gar_gemm_bf16_rope2d(e->ln, dv, wqkv, dv, e->qkv_v, 3 * dv, rows, 3 * dv, dv, bqkv, rope, NT, e->npt, e->hd_v,
+                               2 * dv, s));
+    } else {
+      TRY(gemm(e, e->ln, dv, wqkv, dv, e->qkv_v, 3 * dv, rows, 3 * dv, dv, GAR_EPI_BIAS, bqkv, nullptr, nullptr, 0, s));
+      TRY(gar_vit_rope(e->qkv_v, rope, rows, NT, e->npt, d.vit_heads, e->hd_v, s));
+      e->launches += 1;
+    }
     {
     ProfScope ps(e, s, PK_ATTN, 4.0 * T * static_cast<double>(NT) * NT * dv);
     TRY(gar_attn_fwd(e->qkv_v, 3 * dv, static_cast<long long>(NT) * 3 * dv, 0, e->qkv_v, e->qkv_v, 3 * dv,
@@ -349,7 +363,7 @@ int gar_engine_vit_encode(gar_engine* e, const void* pixel_values, const void* m
              s));
     TRY(gemm(e, e->mlp_v, d.vit_mlp, w2, d.vit_mlp, e->x, dv, rows, dv, d.vit_mlp, GAR_EPI_BIAS_LS_RES, b2, g2, e->x, dv,
              s));
-    e->launches += 4;
+    e->launches += 3;
   }
   // projector on every token row (cls rows are computed and then skipped by the pool: 0.1% extra work)
   NEEDW(pw1, "proj.l1.w");
@@ -429,13 +443,12 @@ int gar_engine_generate(gar_engine* e, int batch, int max_new_tokens, int eos, i
     return GAR_ERR_ARG;
   }
   const gar_model_desc& d = e->d;
-  GAR_CUDA_CHECK(cudaMemsetAsync(e->step, 0, sizeof(int), s));
+  GAR_CUDA_CHECK(cudaMemsetAsync(e->step, 0, 2 * sizeof(int), s));
   GAR_CUDA_CHECK(cudaMemsetAsync(e->finished, 0, sizeof(int) * batch, s));
   GAR_CUDA_CHECK(cudaMemsetAsync(e->out_tokens, 0xff, sizeof(int) * d.max_batch * d.max_new_tokens, s));
   // token 0 from the prefill logits (position bookkeeping already at S per slot)
   TRY(gar_argmax_step(e->logits, d.vocab_padded, d.vocab, batch, e->next_tok, e->out_tokens, d.max_new_tokens, e->step,
-                      e->pos, e->finished, eos, 0, s));
-  TRY(gar_bump_step(e->step, s));
+                      e->pos, e->finished, eos, 0, 1, e->argmax_ws, s));
   e->launches += 2;
   const int steps = max_new_tokens - 1;
   if (steps > 0) {
@@ -492,7 +505,9 @@ int gar_engine_set_option(gar_engine* e, const char* name, int value) {
   if (!e || !name) return GAR_ERR_ARG;
   const std::string n(name);
   if (n == "skinny_gemm") e->use_skinny = value;
-  else if (n == "decode_splits" && value >= 1 && value <= 8) e->dec_splits = value;
+  else if (n == "fuse_rope") e->fuse_rope = value;
+  else if (n == "decode_splits" && value >= 0 && value <= 32) e->dec_splits = value;
+  else if (n == "pdl") gar_set_pdl(value);
   else {
     gar_set_error("gar_engine_set_option: unknown option '%s'=%d", name, value);
     return GAR_ERR_ARG;

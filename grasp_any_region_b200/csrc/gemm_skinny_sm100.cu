@@ -49,6 +49,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const int kb0 = split * kb_per_split;
   const int num_kb = max(0, min(kb_per_split, num_kb_total - kb0));
 
+  pdl_launch_dependents();  // let the next kernel's prologue (and its weight prefetch) start early
   if (threadIdx.x == 0) {
     for (int s = 0; s < SK_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
@@ -70,9 +71,19 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
+      // Weights never depend on the previous kernel: stream the first ring of W tiles before the
+      // programmatic-dependency wait, so the weight fetch overlaps the predecessor's tail.
+      const int pre = min(num_kb, SK_STAGES);
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_expect_tx(full_bar(kb), SK_STAGE_BYTES);
+        tma_load_2d(sbase + kb * SK_STAGE_BYTES, &tmap_w, (kb0 + kb) * SK_BLOCK_K, n_blk * SK_BLOCK_W, full_bar(kb));
+      }
+      pdl_wait();
+      for (int kb = 0; kb < pre; ++kb)
+        tma_load_2d(sbase + kb * SK_STAGE_BYTES + SK_W_BYTES, &tmap_x, (kb0 + kb) * SK_BLOCK_K, 0, full_bar(kb));
       int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      uint32_t phase = 1;  // the ring has been filled once
+      for (int kb = pre; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         mbar_expect_tx(full_bar(stage), SK_STAGE_BYTES);
         const uint32_t sa = sbase + stage * SK_STAGE_BYTES;
@@ -105,6 +116,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     float v[SK_NB];
+    pdl_wait();  // `res` / `out` belong to the dependency chain
     if (num_kb > 0) {
       mbar_wait(done_bar, 0);
       tc_fence_after();
@@ -186,20 +198,8 @@ extern "C" int gar_gemm_skinny_bf16(const void* X, int ldx, const void* Wt, int 
     GAR_CUDA_CHECK(cudaFuncSetAttribute(gemm_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(n_tiles, split, 1);
-  cfg.blockDim = dim3(SK_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = SK_SMEM;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = split;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  GAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel, tw, tx, M, N, K, kb_per_split,
-                                    static_cast<bf16*>(out), ldo, epi == 4 ? static_cast<const bf16*>(res) : nullptr,
-                                    ldres));
+  GAR_CUDA_CHECK(gar_launch(gemm_skinny_kernel, dim3(n_tiles, split, 1), dim3(SK_THREADS), SK_SMEM, stream, true,
+                            dim3(1, split, 1), tw, tx, M, N, K, kb_per_split, static_cast<bf16*>(out), ldo,
+                            epi == 4 ? static_cast<const bf16*>(res) : static_cast<const bf16*>(nullptr), ldres));
   return GAR_OK;
 }

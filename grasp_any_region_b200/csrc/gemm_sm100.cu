@@ -23,7 +23,7 @@ constexpr int EPI_THREADS = 256;
 constexpr int C_CHUNK = 32;                               // columns per TMA store box
 constexpr int C_STAGE_BYTES = BLOCK_M * C_CHUNK * 2;      // 8 KB, 64B-swizzled rows
 
-enum Epi { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_BIAS_LS_RES = 3, EPI_RES = 4 };
+enum Epi { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_BIAS_LS_RES = 3, EPI_RES = 4, EPI_BIAS_ROPE2D = 5 };
 
 template <int BLOCK_N>
 struct Cfg {
@@ -40,6 +40,10 @@ struct EpiArgs {
   const bf16* gamma;
   const bf16* res;
   int ldres;
+  // EPI_BIAS_ROPE2D: PE-ViT interleaved-pair RoPE on columns < rope_cols of rows whose token index
+  // (row % ntok) is >= npt; table row = cat(sin[hd], cos[hd])
+  const bf16* rope;
+  int ntok, npt, hd, rope_cols;
 };
 
 template <int BLOCK_N, int EPI>
@@ -178,7 +182,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_LS_RES) {
+          if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_LS_RES || EPI == EPI_BIAS_ROPE2D) {
             const uint4* bp = reinterpret_cast<const uint4*>(ea.bias + gn);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -198,6 +202,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          }
+          if (EPI == EPI_BIAS_ROPE2D) {
+            const int tok = gm % ea.ntok;
+            if (gn < ea.rope_cols && gm < M && tok >= ea.npt) {
+              const bf16* tr = ea.rope + static_cast<size_t>(tok - ea.npt) * 2 * ea.hd + (gn % ea.hd);
+              const uint4* sp = reinterpret_cast<const uint4*>(tr);
+              const uint4* cp = reinterpret_cast<const uint4*>(tr + ea.hd);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 sv = __ldg(sp + q), cv = __ldg(cp + q);
+                const uint32_t sw4[4] = {sv.x, sv.y, sv.z, sv.w};
+                const uint32_t cw4[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 sn = unpack_bf16x2(sw4[j]), cs = unpack_bf16x2(cw4[j]);
+                  const float x0 = v[q * 8 + j * 2], x1 = v[q * 8 + j * 2 + 1];
+                  v[q * 8 + j * 2] = bf16r(x0 * cs.x) + bf16r(-x1 * sn.x);
+                  v[q * 8 + j * 2 + 1] = bf16r(x1 * cs.y) + bf16r(x0 * sn.y);
+                }
+              }
+            }
           }
           if (EPI == EPI_BIAS_LS_RES) {
             const uint4* gp = reinterpret_cast<const uint4*>(ea.gamma + gn);
@@ -293,6 +318,7 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CU
     case EPI_BIAS_GELU: return launch_gemm<BLOCK_N, EPI_BIAS_GELU>(ta, tb, tc, M, N, K, ea, stream);
     case EPI_BIAS_LS_RES: return launch_gemm<BLOCK_N, EPI_BIAS_LS_RES>(ta, tb, tc, M, N, K, ea, stream);
     case EPI_RES: return launch_gemm<BLOCK_N, EPI_RES>(ta, tb, tc, M, N, K, ea, stream);
+    case EPI_BIAS_ROPE2D: return launch_gemm<BLOCK_N, EPI_BIAS_ROPE2D>(ta, tb, tc, M, N, K, ea, stream);
   }
   gar_set_error("gar_gemm_bf16: unknown epilogue %d", epi);
   return GAR_ERR_ARG;
@@ -300,16 +326,18 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CU
 
 }  // namespace
 
-extern "C" int gar_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* Cout, int ldc, int M, int N, int K,
-                             int epi, const void* bias, const void* gamma, const void* res, int ldres,
-                             int block_n_hint, void* stream_) {
+static int gemm_impl(const void* A, int lda, const void* B, int ldb, void* Cout, int ldc, int M, int N, int K, int epi,
+                     const void* bias, const void* gamma, const void* res, int ldres, const void* rope, int ntok,
+                     int npt, int hd, int rope_cols, int block_n_hint, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0 || (K % BLOCK_K) != 0 || (N % 32) != 0 || (lda % 8) || (ldb % 8) || (ldc % 8)) {
     gar_set_error("gar_gemm_bf16: unsupported shape M=%d N=%d K=%d lda=%d ldb=%d ldc=%d (need K%%64==0, N%%32==0, ld%%8==0)",
                   M, N, K, lda, ldb, ldc);
     return GAR_ERR_SHAPE;
   }
-  if ((epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_LS_RES) && !bias) return GAR_ERR_ARG;
+  if ((epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_LS_RES || epi == EPI_BIAS_ROPE2D) && !bias)
+    return GAR_ERR_ARG;
+  if (epi == EPI_BIAS_ROPE2D && (!rope || hd % 32 || ntok <= 0 || rope_cols % 32)) return GAR_ERR_ARG;
   if (epi == EPI_BIAS_LS_RES && !gamma) return GAR_ERR_ARG;
   if ((epi == EPI_BIAS_LS_RES || epi == EPI_RES) && (!res || (ldres % 8))) return GAR_ERR_ARG;
   int bn = block_n_hint;
@@ -328,8 +356,29 @@ extern "C" int gar_gemm_bf16(const void* A, int lda, const void* B, int ldb, voi
   if ((rc = gar_make_tmap_2d(&ta, A, K, M, lda, BLOCK_K, BLOCK_M, GAR_SW_128))) return rc;
   if ((rc = gar_make_tmap_2d(&tb, B, K, N, ldb, BLOCK_K, bn, GAR_SW_128))) return rc;
   if ((rc = gar_make_tmap_2d(&tc, Cout, N, M, ldc, C_CHUNK, BLOCK_M, GAR_SW_64))) return rc;
-  EpiArgs ea{static_cast<const bf16*>(bias), static_cast<const bf16*>(gamma), static_cast<const bf16*>(res), ldres};
+  EpiArgs ea{static_cast<const bf16*>(bias), static_cast<const bf16*>(gamma), static_cast<const bf16*>(res), ldres,
+             static_cast<const bf16*>(rope), ntok, npt, hd, rope_cols};
   if (bn == 256) return dispatch_epi<256>(epi, ta, tb, tc, M, N, K, ea, stream);
   if (bn == 128) return dispatch_epi<128>(epi, ta, tb, tc, M, N, K, ea, stream);
   return dispatch_epi<64>(epi, ta, tb, tc, M, N, K, ea, stream);
+}
+
+extern "C" int gar_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* Cout, int ldc, int M, int N, int K,
+                             int epi, const void* bias, const void* gamma, const void* res, int ldres,
+                             int block_n_hint, void* stream) {
+  if (epi == EPI_BIAS_ROPE2D) {
+    gar_set_error("gar_gemm_bf16: GAR_EPI_BIAS_ROPE2D needs gar_gemm_bf16_rope2d");
+    return GAR_ERR_ARG;
+  }
+  return gemm_impl(A, lda, B, ldb, Cout, ldc, M, N, K, epi, bias, gamma, res, ldres, nullptr, 0, 0, 0, 0, block_n_hint,
+                   stream);
+}
+
+// qkv projection of the PE ViT with the 2-D RoPE of q,k fused into the epilogue:
+// C = rope2d(bf16(A B^T + bias)) on columns < rope_cols for tokens (row % ntok) >= npt.
+extern "C" int gar_gemm_bf16_rope2d(const void* A, int lda, const void* B, int ldb, void* Cout, int ldc, int M, int N,
+                                    int K, const void* bias, const void* rope, int ntok, int npt, int hd,
+                                    int rope_cols, void* stream) {
+  return gemm_impl(A, lda, B, ldb, Cout, ldc, M, N, K, EPI_BIAS_ROPE2D, bias, nullptr, nullptr, 0, rope, ntok, npt, hd,
+                   rope_cols, 0, stream);
 }

@@ -23,6 +23,10 @@ extern "C" int gar_copy_d2d(void* dst, const void* src, long long bytes, void* s
   return GAR_OK;
 }
 
+static int g_pdl = 1;
+int gar_pdl_enabled() { return g_pdl; }
+void gar_set_pdl(int on) { g_pdl = on; }
+
 int gar_num_sms() {
   static int sms = 0;
   if (sms == 0) {

@@ -41,6 +41,16 @@ def gemm(a, b, epi=EPI_NONE, bias=None, gamma=None, res=None, out=None, block_n=
     return out
 
 
+def gemm_rope2d(a, b, bias, rope, ntok, npt, hd, rope_cols):
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    check(_lib.load().gar_gemm_bf16_rope2d(_p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0), M, N, K,
+                                           _p(bias), _p(rope), ntok, npt, hd, rope_cols, _stream()),
+          "gar_gemm_bf16_rope2d")
+    return out
+
+
 def gemm_skinny(x, w, epi=EPI_NONE, res=None, out=None):
     """out[M<=16,N] = epi(x[M,K] @ w[N,K]^T) through the decode weight-streaming kernel."""
     _req(x), _req(w)
@@ -163,9 +173,10 @@ def assemble_embeds(input_ids, table, feats, crop_ids, rois, has_roi, spatial_sc
     return out, status
 
 
-def argmax_step(logits, V):
+def argmax_step(logits, V, two_stage=True):
     B = logits.shape[0]
     nxt = torch.empty((B,), dtype=torch.int32, device=logits.device)
-    check(_lib.load().gar_argmax_step(_p(logits), logits.stride(0), V, B, _p(nxt), None, 0, None, None, None, -1, 0,
-                                      _stream()), "gar_argmax_step")
+    ws = torch.empty((B * ((V + 4095) // 4096) * 2,), dtype=torch.float32, device=logits.device) if two_stage else None
+    check(_lib.load().gar_argmax_step(_p(logits), logits.stride(0), V, B, _p(nxt), None, 0, None, None, None, -1, 0, 0,
+                                      _p(ws), _stream()), "gar_argmax_step")
     return nxt

@@ -52,6 +52,11 @@ int gar_copy_d2d(void* dst, const void* src, long long bytes, void* stream);
 int gar_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K, int epi,
                   const void* bias, const void* gamma, const void* res, int ldres, int block_n_hint, void* stream);
 
+/* Same GEMM with timm's apply_rot_embed_cat fused after the bias (PE-ViT qkv projection): columns < rope_cols of
+ * rows with (row % ntok) >= npt are rotated with table row (row % ntok - npt) = cat(sin[hd], cos[hd]). */
+int gar_gemm_bf16_rope2d(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
+                         const void* bias, const void* rope, int ntok, int npt, int hd, int rope_cols, void* stream);
+
 /* out[M<=16,N] = epi(X[M,K] W[N,K]^T), epi in {GAR_EPI_NONE, GAR_EPI_RES}: swap-AB tcgen05 weight-streaming GEMM with
  * cluster split-K reduced through distributed shared memory (the decode step's cuBLAS GEMV-like calls). */
 int gar_gemm_skinny_bf16(const void* X, int ldx, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
@@ -80,8 +85,11 @@ int gar_pool2x2(const void* x, void* y, int T, int ntok, int npt, int grid, int 
 int gar_embed_gather(const void* table, const long long* ids64, const int* ids32, void* out, int rows, int D,
                      void* stream);
 /* greedy argmax + device-side decode bookkeeping (HF GenerationMixin greedy step) */
+/* step_ptr: 2 ints {step, ticket}; bump_step: the last block increments step (no extra launch);
+ * partial_ws: batch*ceil(V/4096)*8 bytes for the two-stage reduction (NULL = single-stage scan). */
 int gar_argmax_step(const void* logits, int ld, int V, int batch, int* next_tok, int* out_tokens, int out_ld,
-                    const int* step_ptr, int* pos, int* finished, int eos, int advance_pos, void* stream);
+                    int* step_ptr, int* pos, int* finished, int eos, int advance_pos, int bump_step, void* partial_ws,
+                    void* stream);
 int gar_bump_step(int* step, void* stream);
 
 /* Fused embed + image-feature scatter + RoI-aligned feature replay (modeling_gar.py:332-414).

@@ -164,6 +164,20 @@ def test_vit_rope():
     assert torch.equal(out.view(T, ntok, 3, H, hd), ref)
 
 
+def test_gemm_fused_rope2d_equals_gemm_then_rope():
+    from grasp_any_region_b200.config import VisionSpec
+    from grasp_any_region_b200.rope import vit_rope_table
+
+    v = VisionSpec(embed_dim=256, depth=1, num_heads=4, mlp_dim=256)
+    T, ntok, H, hd, d = 2, 1025, 4, 64, 256
+    a, w, bias = rnd(T * ntok, d, seed=50), rnd(3 * d, d, scale=0.05, seed=51), rnd(3 * d, scale=0.1, seed=52)
+    table = vit_rope_table(v).to(bf).to(DEV)
+    want = ops.vit_rope_(ops.gemm(a, w, epi=ops.EPI_BIAS, bias=bias), table, ntok, 1, H, hd)
+    got = ops.gemm_rope2d(a, w, bias, table, ntok, 1, hd, 2 * d)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+
+
 def test_llama_rope_kv_and_swiglu_pool_argmax():
     from grasp_any_region_b200.config import TextSpec
     from grasp_any_region_b200.rope import llama_cos_sin

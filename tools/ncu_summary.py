@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Condense ncu outputs into the small text files committed under profiles/.
+
+  python tools/ncu_summary.py list  gpurun_out/launches.csv   > profiles/rNN_launches.txt
+  python tools/ncu_summary.py full  gpurun_out/prof.ncu-rep   > profiles/rNN_<kernel>_full.txt
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+KEEP = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_tensor.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
+    "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor", "sm__cycles_elapsed.max",
+    "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+]
+
+
+def clean(name):
+    name = re.sub(r"\(.*", "", name)
+    return name.replace("<unnamed>::", "").replace("void ", "").strip()
+
+
+def launch_list(path):
+    lines = open(path).readlines()
+    start = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
+    agg = collections.OrderedDict()
+    total = 0.0
+    n = 0
+    for r in csv.DictReader(lines[start:]):
+        if r["Metric Name"] != "gpu__time_duration.sum":
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        v = v / 1e3 if r["Metric Unit"] == "ns" else (v * 1e3 if r["Metric Unit"] == "ms" else v)
+        k = clean(r["Kernel Name"])
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+        total += v
+        n += 1
+    print(f"# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised): {n} launches, {total/1e3:.2f} ms")
+    print(f"{'us total':>12} {'share':>6} {'n':>6} {'us avg':>9}  kernel")
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{t:12.1f} {100*t/total:5.1f}% {c:6d} {t/c:9.1f}  {k[:100]}")
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for row in rows[2:]:
+        d = dict(zip(hdr, row))
+        print("kernel:", clean(d.get("Kernel Name", "?")), "grid", d.get("Grid Size"), "block", d.get("Block Size"))
+        for k in KEEP:
+            if k in d:
+                print(f"  {k:75s} {d[k]:>16} {units[hdr.index(k)]}")
+        print()
+
+
+if __name__ == "__main__":
+    {"list": launch_list, "full": full}[sys.argv[1]](sys.argv[2])
