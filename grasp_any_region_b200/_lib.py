@@ -37,7 +37,7 @@ SIGNATURES = {
     "gar_rmsnorm": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _f, _vp]),
     "gar_vit_rope": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gar_llama_rope_kv": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
-    "gar_swiglu": (_i, [_vp, _vp, _i, _i, _vp]),
+    "gar_swiglu": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "gar_pool2x2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gar_embed_gather": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "gar_argmax_step": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -271,7 +271,8 @@ __global__ void llama_rope_kv_kernel(bf16* __restrict__ qkv, int rows, int hq, i
 }
 
 // SwiGLU: act = bf16( bf16(silu(g)) * u ) with gu rows = [gate(I) | up(I)]   (HF LlamaMLP :182-184)
-__global__ void swiglu_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int rows, int inter) {
+__global__ void swiglu_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, int rows, int inter,
+                              int interleaved) {
   pdl_launch_dependents();
   pdl_wait();
   const int vec_per_row = inter / 8;
@@ -280,8 +281,12 @@ __global__ void swiglu_kernel(const bf16* __restrict__ gu, bf16* __restrict__ ac
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int row = static_cast<int>(i / vec_per_row);
     const int v = static_cast<int>(i % vec_per_row);
-    const uint4 g = *reinterpret_cast<const uint4*>(gu + static_cast<size_t>(row) * 2 * inter + v * 8);
-    const uint4 u = *reinterpret_cast<const uint4*>(gu + static_cast<size_t>(row) * 2 * inter + inter + v * 8);
+    // feature f = v*8: plain layout gate at f, up at inter+f; interleaved: 64*(f/32) + f%32 and +32
+    const int f = v * 8;
+    const size_t goff = interleaved ? static_cast<size_t>(64 * (f / 32) + (f % 32)) : static_cast<size_t>(f);
+    const size_t uoff = interleaved ? goff + 32 : static_cast<size_t>(inter + f);
+    const uint4 g = *reinterpret_cast<const uint4*>(gu + static_cast<size_t>(row) * 2 * inter + goff);
+    const uint4 u = *reinterpret_cast<const uint4*>(gu + static_cast<size_t>(row) * 2 * inter + uoff);
     const uint32_t* gw = reinterpret_cast<const uint32_t*>(&g);
     const uint32_t* uw = reinterpret_cast<const uint32_t*>(&u);
     uint4 o;
@@ -535,11 +540,11 @@ int gar_llama_rope_kv(void* qkv, int rows, int hq, int hkv, int hd, const void* 
   return GAR_OK;
 }
 
-int gar_swiglu(const void* gu, void* act, int rows, int inter, void* stream) {
-  if (inter % 8) return GAR_ERR_SHAPE;
+int gar_swiglu(const void* gu, void* act, int rows, int inter, int interleaved, void* stream) {
+  if (inter % 8 || (interleaved && inter % 32)) return GAR_ERR_SHAPE;
   GAR_CUDA_CHECK(gar_launch(swiglu_kernel, dim3(grid_for(static_cast<long long>(rows) * (inter / 8), 256)), dim3(256),
                             0, static_cast<cudaStream_t>(stream), true, dim3(1, 1, 1), static_cast<const bf16*>(gu),
-                            static_cast<bf16*>(act), rows, inter));
+                            static_cast<bf16*>(act), rows, inter, interleaved));
   return GAR_OK;
 }
 

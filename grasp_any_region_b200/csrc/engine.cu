@@ -153,8 +153,13 @@ int llm_layers(gar_engine* e, bf16* h, bf16* ln, int rows, bool decode, int slot
     }
     TRY(gemm(e, e->att_l, hq * hd, wo, hq * hd, h, D, rows, D, hq * hd, GAR_EPI_RES, nullptr, nullptr, h, D, s));
     TRY(gar_rmsnorm(h, D, ln2, ln, D, rows, D, d.rms_eps, s));
-    TRY(gemm(e, ln, D, wgu, D, e->gu, 2 * I, rows, 2 * I, D, GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s));
-    TRY(gar_swiglu(e->gu, e->act, rows, I, s));
+    // "llm.{i}.gu.w" rows are interleaved [32 gate | 32 up]: prefill fuses SwiGLU into the GEMM epilogue
+    if (!decode && rows > 16) {
+      TRY(gemm(e, ln, D, wgu, D, e->act, I, rows, 2 * I, D, GAR_EPI_SWIGLU, nullptr, nullptr, nullptr, 0, s));
+    } else {
+      TRY(gemm(e, ln, D, wgu, D, e->gu, 2 * I, rows, 2 * I, D, GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s));
+      TRY(gar_swiglu(e->gu, e->act, rows, I, 1, s));
+    }
     TRY(gemm(e, e->act, I, wdown, I, h, D, rows, D, I, GAR_EPI_RES, nullptr, nullptr, h, D, s));
     e->launches += 1;
   }

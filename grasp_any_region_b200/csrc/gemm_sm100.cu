@@ -23,7 +23,7 @@ constexpr int EPI_THREADS = 256;
 constexpr int C_CHUNK = 32;                               // columns per TMA store box
 constexpr int C_STAGE_BYTES = BLOCK_M * C_CHUNK * 2;      // 8 KB, 64B-swizzled rows
 
-enum Epi { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_BIAS_LS_RES = 3, EPI_RES = 4, EPI_BIAS_ROPE2D = 5 };
+enum Epi { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_BIAS_LS_RES = 3, EPI_RES = 4, EPI_BIAS_ROPE2D = 5, EPI_SWIGLU = 6 };
 
 template <int BLOCK_N>
 struct Cfg {
@@ -158,6 +158,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     int cbuf = 0;
+    float gate[EPI == EPI_SWIGLU ? 32 : 1];  // EPI_SWIGLU: bf16-rounded gate chunk waiting for its up chunk
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % num_m, n_blk = tile / num_m;
       const int gm = m_blk * BLOCK_M + row;
@@ -199,6 +200,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           // first rounding point: the Linear's bf16 output
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = bf16r(v[i]);
+          if (EPI == EPI_SWIGLU) {
+            // weight rows are interleaved in 32-row blocks [gate | up]: even chunks carry gate features,
+            // the following odd chunk the matching up features: act = bf16(bf16(silu(g)) * u)
+            if ((c & 1) == 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) gate[i] = v[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = bf16r(silu_f(gate[i])) * v[i];
+            }
+          }
           if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
@@ -257,6 +269,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
         }
+        if (EPI == EPI_SWIGLU && (c & 1) == 0) continue;  // nothing to store for a gate chunk
         // staging buffer reuse: the TMA store issued two chunks ago must have finished reading smem
         if (issuer) tma_store_wait_read<1>();
         named_bar_sync(bar_id, 128);
@@ -274,7 +287,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
         if (issuer && col_ok) {
-          tma_store_2d(&tmap_c, stage_c0 + cbuf * C_STAGE_BYTES, gn, m_blk * BLOCK_M);
+          const int gn_out = EPI == EPI_SWIGLU ? (gn - C_CHUNK) / 2 : gn;
+          tma_store_2d(&tmap_c, stage_c0 + cbuf * C_STAGE_BYTES, gn_out, m_blk * BLOCK_M);
         }
         if (issuer) tma_store_commit();
         cbuf ^= 1;
@@ -319,6 +333,7 @@ int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CU
     case EPI_BIAS_LS_RES: return launch_gemm<BLOCK_N, EPI_BIAS_LS_RES>(ta, tb, tc, M, N, K, ea, stream);
     case EPI_RES: return launch_gemm<BLOCK_N, EPI_RES>(ta, tb, tc, M, N, K, ea, stream);
     case EPI_BIAS_ROPE2D: return launch_gemm<BLOCK_N, EPI_BIAS_ROPE2D>(ta, tb, tc, M, N, K, ea, stream);
+    case EPI_SWIGLU: return launch_gemm<BLOCK_N, EPI_SWIGLU>(ta, tb, tc, M, N, K, ea, stream);
   }
   gar_set_error("gar_gemm_bf16: unknown epilogue %d", epi);
   return GAR_ERR_ARG;
@@ -351,11 +366,15 @@ static int gemm_impl(const void* A, int lda, const void* B, int ldb, void* Cout,
       if (num_m * ((N + cand[i] - 1) / cand[i]) >= sms) { bn = cand[i]; break; }
     }
   }
+  if (epi == EPI_SWIGLU) {
+    if (N % 64) return GAR_ERR_SHAPE;
+    if (bn < 128) bn = 128;  // a column group must hold whole [gate | up] chunk pairs
+  }
   CUtensorMap ta, tb, tc;
   int rc;
   if ((rc = gar_make_tmap_2d(&ta, A, K, M, lda, BLOCK_K, BLOCK_M, GAR_SW_128))) return rc;
   if ((rc = gar_make_tmap_2d(&tb, B, K, N, ldb, BLOCK_K, bn, GAR_SW_128))) return rc;
-  if ((rc = gar_make_tmap_2d(&tc, Cout, N, M, ldc, C_CHUNK, BLOCK_M, GAR_SW_64))) return rc;
+  if ((rc = gar_make_tmap_2d(&tc, Cout, epi == EPI_SWIGLU ? N / 2 : N, M, ldc, C_CHUNK, BLOCK_M, GAR_SW_64))) return rc;
   EpiArgs ea{static_cast<const bf16*>(bias), static_cast<const bf16*>(gamma), static_cast<const bf16*>(res), ldres,
              static_cast<const bf16*>(rope), ntok, npt, hd, rope_cols};
   if (bn == 256) return dispatch_epi<256>(epi, ta, tb, tc, M, N, K, ea, stream);

@@ -132,7 +132,10 @@ class Engine:
                                                    sd[b + "self_attn.v_proj.weight"]], 0))
             self._set(f"llm.{i}.o.w", sd[b + "self_attn.o_proj.weight"])
             self._set(f"llm.{i}.ln2", sd[b + "post_attention_layernorm.weight"])
-            self._set(f"llm.{i}.gu.w", torch.cat([sd[b + "mlp.gate_proj.weight"], sd[b + "mlp.up_proj.weight"]], 0))
+            gw, uw = sd[b + "mlp.gate_proj.weight"], sd[b + "mlp.up_proj.weight"]
+            inter, k = gw.shape  # rows interleaved in 32-row groups [gate | up] (GAR_EPI_SWIGLU layout)
+            self._set(f"llm.{i}.gu.w", torch.stack([gw.reshape(inter // 32, 32, k), uw.reshape(inter // 32, 32, k)],
+                                                   1).reshape(2 * inter, k))
             self._set(f"llm.{i}.down.w", sd[b + "mlp.down_proj.weight"])
         self._set("llm.norm", sd[LM + "norm.weight"])
         head = sd["mllm.lm_head.weight"]

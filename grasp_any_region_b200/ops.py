@@ -12,6 +12,7 @@ from . import _lib
 from ._lib import check
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_LS_RES, EPI_RES = range(5)
+EPI_SWIGLU = 6
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -34,7 +35,7 @@ def gemm(a, b, epi=EPI_NONE, bias=None, gamma=None, res=None, out=None, block_n=
     M, K = a.shape
     N = b.shape[0]
     if out is None:
-        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+        out = torch.empty((M, N // 2 if epi == EPI_SWIGLU else N), dtype=torch.bfloat16, device=a.device)
     check(_lib.load().gar_gemm_bf16(_p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0), M, N, K, epi,
                                     _p(bias), _p(gamma), _p(res), 0 if res is None else res.stride(0), block_n,
                                     _stream()), "gar_gemm_bf16")
@@ -110,11 +111,19 @@ def llama_rope_kv_(qkv, hq, hkv, hd, cos_t, sin_t, kcache, vcache, max_seq, pos0
     return qkv
 
 
-def swiglu(gu):
+def swiglu(gu, interleaved=False):
     rows, two_i = gu.shape
     act = torch.empty((rows, two_i // 2), dtype=torch.bfloat16, device=gu.device)
-    check(_lib.load().gar_swiglu(_p(gu), _p(act), rows, two_i // 2, _stream()), "gar_swiglu")
+    check(_lib.load().gar_swiglu(_p(gu), _p(act), rows, two_i // 2, int(interleaved), _stream()), "gar_swiglu")
     return act
+
+
+def interleave_gate_up(gate_w, up_w, block=32):
+    """[gate(I,K); up(I,K)] -> rows interleaved in `block`-row groups [gate | up] (GAR_EPI_SWIGLU layout)."""
+    I, K = gate_w.shape
+    g = gate_w.reshape(I // block, block, K)
+    u = up_w.reshape(I // block, block, K)
+    return torch.stack([g, u], 1).reshape(2 * I, K).contiguous()
 
 
 def pool2x2(x, T, ntok, npt, grid):

@@ -44,6 +44,7 @@ int gar_copy_d2d(void* dst, const void* src, long long bytes, void* stream);
 #define GAR_EPI_BIAS_GELU 2   /* C = bf16(gelu_erf(bf16(A B^T + bias)))           Linear -> GELU (timm Mlp, projector) */
 #define GAR_EPI_BIAS_LS_RES 3 /* C = bf16(res + bf16(gamma * bf16(A B^T + bias))) EvaBlock x + gamma * f(x) */
 #define GAR_EPI_RES 4         /* C = bf16(res + bf16(A B^T))                      Llama h + o_proj/down_proj */
+#define GAR_EPI_SWIGLU 6      /* C[M,N/2] = bf16(bf16(silu(g)) * u), B rows interleaved [32 gate | 32 up] (LlamaMLP) */
 
 /* C[M,N] = epi(A[M,K] * B[N,K]^T): tcgen05 / TMEM / TMA GEMM.  Replaces the cuBLAS GEMMs behind every
  * nn.Linear and both k=s=14 convs of the path (timm EvaBlock, modeling_perception_lm.py:85-92,
@@ -78,8 +79,9 @@ int gar_vit_rope(void* qkv, const void* rope, int rows, int ntok, int npt, int h
 int gar_llama_rope_kv(void* qkv, int rows, int hq, int hkv, int hd, const void* cos_t, const void* sin_t, int pos0,
                       const int* pos_dev, const int* slot_dev, int slot0, void* kcache, void* vcache, int max_seq,
                       void* stream);
-/* HF LlamaMLP act_fn(gate) * up on a fused [gate | up] buffer */
-int gar_swiglu(const void* gu, void* act, int rows, int inter, void* stream);
+/* HF LlamaMLP act_fn(gate) * up on a fused buffer: rows = [gate(I) | up(I)], or with interleaved != 0
+ * 32-column groups [gate | up] (the GAR_EPI_SWIGLU weight layout) */
+int gar_swiglu(const void* gu, void* act, int rows, int inter, int interleaved, void* stream);
 /* PerceptionLMAdaptiveAvgPooling 2x2 (+ cls drop), modeling_perception_lm.py:42-60,263-264 */
 int gar_pool2x2(const void* x, void* y, int T, int ntok, int npt, int grid, int D, void* stream);
 int gar_embed_gather(const void* table, const long long* ids64, const int* ids32, void* out, int rows, int D,

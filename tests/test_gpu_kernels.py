@@ -68,6 +68,17 @@ def test_gemm_epilogues(epi, M, N, K):
     assert (out.float() != ref).float().mean().item() < 0.02
 
 
+@pytest.mark.parametrize("M,I,K", [(300, 512, 256), (1000, 8192, 512), (130, 192, 128)])
+def test_gemm_fused_swiglu(M, I, K):
+    a = rnd(M, K, seed=60)
+    gw, uw = rnd(I, K, scale=0.05, seed=61), rnd(I, K, scale=0.05, seed=62)
+    want = ops.swiglu(torch.cat([ops.gemm(a, gw), ops.gemm(a, uw)], 1).contiguous())
+    got = ops.gemm(a, ops.interleave_gate_up(gw, uw), epi=ops.EPI_SWIGLU)
+    torch.cuda.synchronize()
+    assert got.shape == (M, I)
+    assert torch.equal(got, want)
+
+
 def test_gemm_inplace_residual():
     M, N, K = 700, 512, 512
     a, b, x = rnd(M, K, seed=8), rnd(N, K, scale=0.05, seed=9), rnd(M, N, seed=10)
@@ -209,6 +220,8 @@ def test_llama_rope_kv_and_swiglu_pool_argmax():
     act = ops.swiglu(gu)
     ref = F.silu(gu[:, :512]) * gu[:, 512:]
     assert torch.equal(act, ref)
+    gi = torch.stack([gu[:, :512].reshape(77, 16, 32), gu[:, 512:].reshape(77, 16, 32)], 2).reshape(77, 1024)
+    assert torch.equal(ops.swiglu(gi.contiguous(), interleaved=True), ref)
 
     x = rnd(2 * 1025, 256, seed=25)
     y = ops.pool2x2(x, 2, 1025, 1, 32)
