@@ -31,6 +31,9 @@ SIGNATURES = {
     "gar_gemm_skinny_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "gar_gemm_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "gar_gemm_bf16_rope2d": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "gar_gemv_decode": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _f, _vp,
+                             C.POINTER(_i), _vp]),
+    "gar_embed_gather_sumsq": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "gar_patchify": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gar_vit_embed_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "gar_layernorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),

@@ -41,6 +41,51 @@ struct AttnParams {
   float scale_log2;
 };
 
+// Row-per-thread softmax pieces, specialised on whether the block needs masking so the common
+// (unmasked) path carries no compares and the score registers are never written back.
+template <bool MASKED>
+__device__ __forceinline__ float row_max_128(const uint32_t (&s)[128], int kv0, int lim) {
+  float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int i = 0; i < 128; i += 8) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float a = __uint_as_float(s[i + 2 * q]), b = __uint_as_float(s[i + 2 * q + 1]);
+      if (MASKED) {
+        a = (kv0 + i + 2 * q <= lim) ? a : -INFINITY;
+        b = (kv0 + i + 2 * q + 1 <= lim) ? b : -INFINITY;
+      }
+      mx4[q] = fmax3(mx4[q], a, b);
+    }
+  }
+  return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+}
+
+template <bool MASKED>
+__device__ __forceinline__ float exp_pack_store_128(const uint32_t (&s)[128], int kv0, int lim, float scale_log2,
+                                                    float neg_m, uint32_t rbase, uint32_t sw) {
+  float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 8 + 2 * i]), scale_log2, neg_m));
+      float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 8 + 2 * i + 1]), scale_log2, neg_m));
+      if (MASKED) {
+        p0 = (kv0 + c * 8 + 2 * i <= lim) ? p0 : 0.f;
+        p1 = (kv0 + c * 8 + 2 * i + 1 <= lim) ? p1 : 0.f;
+      }
+      rs4[i] += p0 + p1;
+      w[i] = pack_bf16x2(p0, p1);
+    }
+    const uint32_t addr = rbase + (c >> 3) * TILE_BYTES + (((c & 7) ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                 : "memory");
+  }
+  return (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
@@ -158,29 +203,15 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tmem_ld_wait();
       const int kv0 = j * BKV;
       const bool need_mask = (kv0 + BKV > p.kv_len) || (p.causal && kv0 + BKV - 1 > q0 + shift);
-      // row max with 4 independent chains (a single 128-long fmax chain is pure latency)
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      if (need_mask) {
-        const int lim = p.causal ? min(p.kv_len - 1, q_pos) : p.kv_len - 1;
-#pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          float v = __uint_as_float(s[i]);
-          v = (kv0 + i <= lim) ? v : -INFINITY;
-          s[i] = __float_as_uint(v);
-          mx4[i & 3] = fmaxf(mx4[i & 3], v);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 128; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s[i]));
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const int lim = p.causal ? min(p.kv_len - 1, q_pos) : p.kv_len - 1;
+      const float mx = need_mask ? row_max_128<true>(s, kv0, lim) : row_max_128<false>(s, kv0, lim);
       // Lazy rescale: keep exponentiating against the old reference max until the true max has grown by
       // more than 2^8; P then stays <= 256 (harmless in bf16/fp32) and most O rescales disappear.
       const float m_cand = fmaxf(m_run, mx * p.scale_log2);
       const bool bump = (m_cand - m_run) > 8.0f || m_run == -INFINITY;
       const float m_new = bump ? m_cand : m_run;
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = bump ? exp2f(m_run - m_use) : 1.0f;
+      const float alpha = bump ? ex2_approx(m_run - m_use) : 1.0f;
       // rescale O (s_full(j) implies PV(j-1) retired, so O and the P buffer are quiescent)
       if (j > 0) {
         const bool any = __any_sync(0xffffffffu, alpha != 1.0f);
@@ -199,27 +230,9 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       // P = exp2(S*scale - m) -> bf16 -> smem, canonical K-major 128B-swizzled layout:
       // row r, 16B chunk c at r*128 + ((c ^ (r&7))<<4); two [128 x 64] sub-tiles
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      {
-        const uint32_t rbase = sbase + SMEM_P + (row >> 3) * 1024 + (row & 7) * 128;
-        const uint32_t sw = row & 7;
-        const float neg_m = -m_use;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          uint32_t w[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float p0 = exp2f(fmaf(__uint_as_float(s[c * 8 + 2 * i]), p.scale_log2, neg_m));
-            const float p1 = exp2f(fmaf(__uint_as_float(s[c * 8 + 2 * i + 1]), p.scale_log2, neg_m));
-            rs4[i] += p0 + p1;
-            w[i] = pack_bf16x2(p0, p1);
-          }
-          const uint32_t addr = rbase + (c >> 3) * TILE_BYTES + (((c & 7) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                       : "memory");
-        }
-      }
-      const float rs = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      const uint32_t p_rbase = sbase + SMEM_P + (row >> 3) * 1024 + (row & 7) * 128;
+      const float rs = need_mask ? exp_pack_store_128<true>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7)
+                                 : exp_pack_store_128<false>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7);
       l_run = l_run * alpha + rs;
       m_run = m_new;
       fence_proxy_async_smem();

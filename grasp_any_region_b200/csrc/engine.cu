@@ -35,6 +35,8 @@ struct gar_engine {
   int dec_splits;
   int use_skinny = 1;
   int fuse_rope = 1;
+  int use_gemv = 1;
+  float *sumsq_a, *sumsq_b;
   // decode graph
   cudaGraphExec_t graph_exec = nullptr;
   int graph_batch = -1;
@@ -176,8 +178,80 @@ int lm_head(gar_engine* e, const bf16* hrows, int ldh, int rows, bf16* logits, v
               GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s);
 }
 
+// Decode step on the latency-first GEMV kernels: RMSNorm, SwiGLU and residual adds live inside them, the
+// RMSNorm statistics travel as per-CTA partial sums of squares (7 launches per layer instead of 11).
+int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
+  const gar_model_desc& d = e->d;
+  const int D = d.llm_dim, hq = d.llm_heads, hkv = d.llm_kv_heads, hd = d.llm_head_dim, I = d.llm_inter;
+  const int qkv_w = (hq + 2 * hkv) * hd;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  NEEDW(table, "llm.embed");
+  NEEDW(cos_t, "llm.cos");
+  NEEDW(sin_t, "llm.sin");
+  TRY(gar_embed_gather_sumsq(table, e->next_tok, e->hdec, e->sumsq_a, batch, D, s));
+  e->launches += 1;
+  int n_part = 1, rows = 0;
+  for (int i = 0; i < d.llm_layers; ++i) {
+    NEEDW(ln1, L("llm", i, "ln1"));
+    NEEDW(wqkv, L("llm", i, "qkv.w"));
+    NEEDW(wo, L("llm", i, "o.w"));
+    NEEDW(ln2, L("llm", i, "ln2"));
+    NEEDW(wgu, L("llm", i, "gu.w"));
+    NEEDW(wdown, L("llm", i, "down.w"));
+    bf16* kc = e->kcache + static_cast<size_t>(i) * d.max_batch * hkv * d.max_seq * hd;
+    bf16* vc = e->vcache + static_cast<size_t>(i) * d.max_batch * hkv * d.max_seq * hd;
+    {
+      ProfScope ps(e, s, PK_GEMM, 2.0 * batch * static_cast<double>(qkv_w) * D);
+      TRY(gar_gemv_decode(e->hdec, D, wqkv, D, e->qkv_l, qkv_w, batch, qkv_w, D, 0, nullptr, 0, ln1, e->sumsq_a, n_part,
+                          d.rms_eps, nullptr, nullptr, s));
+    }
+    TRY(gar_llama_rope_kv(e->qkv_l, batch, hq, hkv, hd, cos_t, sin_t, 0, e->pos, nullptr, -1, kc, vc, d.max_seq, s));
+    {
+      ProfScope ps(e, s, PK_DECODE_ATTN, 0.0);
+      int splits = e->dec_splits;
+      if (splits <= 0) {
+        splits = (4 * gar_num_sms() + batch * hkv - 1) / (batch * hkv);
+        splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
+      }
+      TRY(gar_decode_attn(e->qkv_l, qkv_w, kc, vc, e->pos, nullptr, batch, hq, hkv, hd, d.max_seq, splits, scale,
+                          e->o_part, e->ml_part, e->att_l, hq * hd, s));
+    }
+    {
+      ProfScope ps(e, s, PK_GEMM, 2.0 * batch * static_cast<double>(D) * hq * hd);
+      TRY(gar_gemv_decode(e->att_l, hq * hd, wo, hq * hd, e->hdec, D, batch, D, hq * hd, 1, e->hdec, D, nullptr, nullptr, 0,
+                          0.f, e->sumsq_b, &rows, s));
+    }
+    {
+      ProfScope ps(e, s, PK_GEMM, 2.0 * batch * 2.0 * I * D);
+      TRY(gar_gemv_decode(e->hdec, D, wgu, D, e->act, I, batch, 2 * I, D, 2, nullptr, 0, ln2, e->sumsq_b, D / rows,
+                          d.rms_eps, nullptr, nullptr, s));
+    }
+    {
+      ProfScope ps(e, s, PK_GEMM, 2.0 * batch * static_cast<double>(D) * I);
+      TRY(gar_gemv_decode(e->act, I, wdown, I, e->hdec, D, batch, D, I, 1, e->hdec, D, nullptr, nullptr, 0, 0.f,
+                          e->sumsq_a, &rows, s));
+    }
+    n_part = D / rows;
+    e->launches += 7;
+  }
+  NEEDW(wn, "llm.norm");
+  NEEDW(wl, "llm.lm_head");
+  {
+    ProfScope ps(e, s, PK_GEMM, 2.0 * batch * static_cast<double>(d.vocab_padded) * D);
+    TRY(gar_gemv_decode(e->hdec, D, wl, D, e->logits, d.vocab_padded, batch, d.vocab_padded, D, 0, nullptr, 0, wn,
+                        e->sumsq_a, n_part, d.rms_eps, nullptr, nullptr, s));
+  }
+  TRY(gar_argmax_step(e->logits, d.vocab_padded, d.vocab, batch, e->next_tok, e->out_tokens, d.max_new_tokens, e->step,
+                      e->pos, e->finished, eos, 1, 1, e->argmax_ws, s));
+  e->launches += 3;
+  return GAR_OK;
+}
+
 int decode_step(gar_engine* e, int batch, int eos, void* s) {
   const gar_model_desc& d = e->d;
+  if (e->use_gemv && batch <= 8 && d.llm_dim % 256 == 0 && d.llm_inter % 256 == 0 &&
+      (d.llm_heads * d.llm_head_dim) % 256 == 0 && d.llm_inter % 32 == 0 && d.vocab_padded % 64 == 0)
+    return decode_step_gemv(e, batch, eos, s);
   NEEDW(table, "llm.embed");
   TRY(gar_embed_gather(table, nullptr, e->next_tok, e->hdec, batch, d.llm_dim, s));
   e->launches += 1;
@@ -255,6 +329,8 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   rc |= dev_alloc(e, &e->step, 2, true);
   rc |= dev_alloc(e, &e->argmax_ws, B * ((static_cast<size_t>(d.vocab) + 4095) / 4096) * 2, true);
   rc |= dev_alloc(e, &e->ids_scratch, S);
+  rc |= dev_alloc(e, &e->sumsq_a, (D / 16 + 1) * 8, true);
+  rc |= dev_alloc(e, &e->sumsq_b, (D / 16 + 1) * 8, true);
   if (rc) {
     gar_engine_destroy(e);
     return GAR_ERR_CUDA;
@@ -511,6 +587,7 @@ int gar_engine_set_option(gar_engine* e, const char* name, int value) {
   const std::string n(name);
   if (n == "skinny_gemm") e->use_skinny = value;
   else if (n == "fuse_rope") e->fuse_rope = value;
+  else if (n == "gemv_decode") e->use_gemv = value;
   else if (n == "decode_splits" && value >= 0 && value <= 32) e->dec_splits = value;
   else if (n == "pdl") gar_set_pdl(value);
   else {

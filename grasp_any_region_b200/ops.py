@@ -65,6 +65,24 @@ def gemm_skinny(x, w, epi=EPI_NONE, res=None, out=None):
     return out
 
 
+def gemv_decode(x, w, epi=0, res=None, norm_w=None, sumsq_in=None, eps=1e-5, want_sumsq=False, out=None):
+    """Decode linear layer (gar_gemv_decode).  Returns (out, sumsq_out or None)."""
+    _req(x), _req(w)
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N // 2 if epi == 2 else N), dtype=torch.bfloat16, device=x.device)
+    sq = torch.zeros((N // 16, 8), dtype=torch.float32, device=x.device) if want_sumsq else None
+    rows = C.c_int(0)
+    n_part = 0 if sumsq_in is None else sumsq_in.shape[0]
+    check(_lib.load().gar_gemv_decode(_p(x), x.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, epi,
+                                      _p(res), 0 if res is None else res.stride(0), _p(norm_w), _p(sumsq_in), n_part,
+                                      eps, _p(sq), C.byref(rows), _stream()), "gar_gemv_decode")
+    if sq is not None:
+        sq = sq[: N // rows.value]
+    return out, sq
+
+
 def layernorm(x, w, b, eps):
     _req(x)
     y = torch.empty_like(x)

@@ -63,6 +63,16 @@ int gar_gemm_bf16_rope2d(const void* A, int lda, const void* B, int ldb, void* C
 int gar_gemm_skinny_bf16(const void* X, int ldx, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
                          int epi, const void* res, int ldres, void* stream);
 
+/* Decode-step linear layer, latency-first (mma.sync weight stream, no TMEM/cluster/TMA setup):
+ * out[M<=8,N] = epi(norm?(X) W^T).  epi 0 none | 1 out = bf16(res + bf16(acc)), optionally emitting per-CTA sums of
+ * squares of out into sumsq_out[N/rows_per_cta][8] | 2 SwiGLU on W rows interleaved [32 gate | 32 up], out [M,N/2].
+ * norm_w != NULL applies LlamaRMSNorm to X on the fly using sumsq_in[n_part][8] (partials emitted by the producer).
+ * Returns GAR_ERR_SHAPE if K % 256 or N granularity does not fit (use gar_gemm_skinny_bf16 then). */
+int gar_gemv_decode(const void* X, int ldx, const void* W, int ldw, void* out, int ldo, int M, int N, int K, int epi,
+                    const void* res, int ldres, const void* norm_w, const float* sumsq_in, int n_part, float eps,
+                    float* sumsq_out, int* rows_per_cta, void* stream);
+int gar_embed_gather_sumsq(const void* table, const int* ids32, void* out, float* sumsq, int rows, int D, void* stream);
+
 /* mask-id decode + im2col of both stride-14 convs (modeling_gar.py:315-328; timm PatchEmbed) */
 int gar_patchify(const void* pixel_values, const void* mask_values, void* a_img, void* a_mask, int T, int img,
                  int patch, int ldk, int prompt_numbers, void* stream);

@@ -107,6 +107,46 @@ def test_gemm_skinny(M, N, K, with_res):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("M", [1, 5, 8])
+def test_gemv_decode_chain(M):
+    """o-proj(+res, sumsq) -> gate-up(norm + swiglu) -> down(+res, sumsq) -> head(norm): the decode layer tail."""
+    D, I, V = 512, 1536, 1024
+    att, h = rnd(M, D, seed=70), rnd(M, D, seed=71)
+    wo, wg, wu = rnd(D, D, scale=0.05, seed=72), rnd(I, D, scale=0.05, seed=73), rnd(I, D, scale=0.05, seed=74)
+    wd, wl = rnd(D, I, scale=0.05, seed=75), rnd(V, D, scale=0.05, seed=76)
+    ln2 = (1 + rnd(D, scale=0.1, seed=77).float()).to(bf)
+    lnf = (1 + rnd(D, scale=0.1, seed=78).float()).to(bf)
+
+    def rms(x, w):
+        x32 = x.float()
+        return w * (x32 * torch.rsqrt(x32.pow(2).mean(-1, keepdim=True) + 1e-5)).to(bf)
+
+    # reference chain built from the already-verified kernels' semantics in torch
+    h1 = gemm_ref(att, wo, ops.EPI_RES, res=h).to(bf)
+    n2 = rms(h1, ln2)
+    act = (F.silu(r(n2.float() @ wg.float().t()).to(bf)) * r(n2.float() @ wu.float().t()).to(bf))
+    h2 = gemm_ref(act, wd, ops.EPI_RES, res=h1).to(bf)
+    logits = r(rms(h2, lnf).float() @ wl.float().t())
+
+    g1, sq1 = ops.gemv_decode(att, wo, epi=1, res=h, want_sumsq=True)
+    assert (g1.float() - h1.float()).abs().max().item() <= 4e-2
+    assert torch.allclose(sq1.sum(0)[:M], g1.float().pow(2).sum(-1), rtol=1e-4)
+    gact, _ = ops.gemv_decode(g1, ops.interleave_gate_up(wg, wu), epi=2, norm_w=ln2, sumsq_in=sq1)
+    n2g = rms(g1, ln2)
+    actg = (F.silu(r(n2g.float() @ wg.float().t()).to(bf)) * r(n2g.float() @ wu.float().t()).to(bf))
+    assert (gact.float() - actg.float()).abs().max().item() <= 3e-2 * max(1.0, actg.float().abs().max().item())
+    assert (gact != actg).float().mean().item() < 0.03
+    g2, sq2 = ops.gemv_decode(gact, wd, epi=1, res=g1, want_sumsq=True)
+    gl, _ = ops.gemv_decode(g2, wl, epi=0, norm_w=lnf, sumsq_in=sq2)
+    torch.cuda.synchronize()
+    ref_l = r(rms(g2, lnf).float() @ wl.float().t())
+    assert (gl.float() - ref_l).abs().max().item() <= 4e-2 * max(1.0, ref_l.abs().max().item())
+    assert (gl.float() - logits).abs().max().item() <= 0.15 * max(1.0, logits.abs().max().item())
+    # bitwise repeatable
+    gl2, _ = ops.gemv_decode(g2, wl, epi=0, norm_w=lnf, sumsq_in=sq2)
+    assert torch.equal(gl, gl2)
+
+
 def test_layernorm_rmsnorm():
     x = rnd(1000, 1024, seed=11)
     w, b = (1 + rnd(1024, scale=0.1, seed=12).float()).to(bf), rnd(1024, scale=0.1, seed=13)
