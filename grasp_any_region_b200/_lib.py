@@ -28,6 +28,7 @@ SIGNATURES = {
     "gar_last_error": (C.c_char_p, []),
     "gar_abi_version": (_i, []),
     "gar_copy_d2d": (_i, [_vp, _vp, _ll, _vp]),
+    "gar_set_global_option": (_i, [C.c_char_p, _i]),
     "gar_gemm_skinny_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "gar_gemm_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "gar_gemm_bf16_rope2d": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -96,7 +96,8 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t B_QFULL = bar0, B_KFULL0 = bar0 + 8, B_KEMPTY0 = bar0 + 24, B_VFULL = bar0 + 40,
-                 B_VEMPTY = bar0 + 48, B_SFULL = bar0 + 56, B_PFULL = bar0 + 64, B_OFULL = bar0 + 72;
+                 B_VEMPTY = bar0 + 48, B_SFULL = bar0 + 56, B_PFULL = bar0 + 64, B_PVDONE = bar0 + 72,
+                 B_SCONS = bar0 + 80;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_qb = (p.q_len + BQ - 1) / BQ;
@@ -119,7 +120,8 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     mbar_init(B_VEMPTY, 1);
     mbar_init(B_SFULL, 1);
     mbar_init(B_PFULL, 128);
-    mbar_init(B_OFULL, 1);
+    mbar_init(B_PVDONE, 1);
+    mbar_init(B_SCONS, 128);
     fence_barrier_init();
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
@@ -165,11 +167,17 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem + TM_S, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0);
         umma_commit(B_KEMPTY0 + 8 * st);
-        umma_commit(B_SFULL);
+        umma_commit(B_SFULL);  // also covers every earlier MMA of this thread
       };
+      // Pipeline per KV block j:   S(j) -> [softmax loads S(j) into registers] -> S(j+1) issued at once
+      // (overlaps the softmax math of block j) -> P(j) ready -> O += P(j) V(j).
       issue_s(0);
       for (int j = 0; j < num_kvb; ++j) {
-        mbar_wait(B_PFULL, j & 1);  // P(j) in smem, S consumed, O rescaled
+        if (j + 1 < num_kvb) {
+          mbar_wait(B_SCONS, j & 1);  // every softmax thread holds S(j) in registers: TMEM S is free
+          issue_s(j + 1);
+        }
+        mbar_wait(B_PFULL, j & 1);  // P(j) in smem, O rescaled
         mbar_wait(B_VFULL, j & 1);
         tc_fence_after();
         // V tile: [kv rows][64 hd] 128B rows => MN-major B operand; 16 kv rows per MMA = 2048 B
@@ -180,8 +188,7 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           umma_bf16_ss(tmem + TM_O, pdesc, vdesc + 128u * k, idesc_o, (j | k) != 0);
         }
         umma_commit(B_VEMPTY);
-        if (j + 1 < num_kvb) issue_s(j + 1);  // its s_full commit also covers PV(j)
-        else umma_commit(B_OFULL);
+        umma_commit(B_PVDONE);
       }
     }
   } else {
@@ -201,6 +208,8 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         tmem_ld_32x32b_x32(tmem + lane_addr + TM_S + c * 32, sc);
       }
       tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(B_SCONS);  // S(j) is in registers: the MMA warp may overwrite TMEM S with S(j+1)
       const int kv0 = j * BKV;
       const bool need_mask = (kv0 + BKV > p.kv_len) || (p.causal && kv0 + BKV - 1 > q0 + shift);
       const int lim = p.causal ? min(p.kv_len - 1, q_pos) : p.kv_len - 1;
@@ -212,8 +221,10 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const float m_new = bump ? m_cand : m_run;
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = bump ? ex2_approx(m_run - m_use) : 1.0f;
-      // rescale O (s_full(j) implies PV(j-1) retired, so O and the P buffer are quiescent)
+      // O and the P buffer are quiescent only once PV(j-1) has retired
       if (j > 0) {
+        mbar_wait(B_PVDONE, (j - 1) & 1);
+        tc_fence_after();
         const bool any = __any_sync(0xffffffffu, alpha != 1.0f);
         if (any) {
 #pragma unroll
@@ -240,7 +251,7 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       mbar_arrive(B_PFULL);
     }
     // ---------------- finalize: O / l -> bf16 -> smem (reuse Q tile) -> TMA store ----------------
-    mbar_wait(B_OFULL, 0);
+    mbar_wait(B_PVDONE, (num_kvb - 1) & 1);
     tc_fence_after();
     const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
     const uint32_t rbase = sbase + SMEM_Q + (row >> 3) * 1024 + (row & 7) * 128;

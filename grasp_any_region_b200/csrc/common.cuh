@@ -92,21 +92,22 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+  // the suspend-time hint lets the waiting thread sleep in hardware instead of re-issuing the probe
+  // (a spinning TMA/MMA lane otherwise steals issue slots from the math warps of its sub-partition)
   asm volatile(
       "{\n.reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (++spins > (1u << 22)) {
       printf("gar_b200: mbarrier timeout block=(%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
              threadIdx.x, bar, parity);
       __trap();
@@ -245,6 +246,7 @@ int gar_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d
                      uint64_t p2, uint32_t b0, uint32_t b1, uint32_t b2, GarSwizzle sw);
 int gar_num_sms();
 int gar_pdl_enabled();
+int gar_global_option(const char* name);
 void gar_set_pdl(int on);
 
 // Launch helper: optional cluster dims and the programmatic-stream-serialization (PDL) attribute.

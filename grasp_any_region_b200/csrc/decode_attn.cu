@@ -193,6 +193,178 @@ decode_attn_split_kernel(const bf16* __restrict__ qkv, int ldq, const bf16* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core variant (mma.sync m16n8k16, flash-decoding layout): the CUDA-core kernel above is
+// instruction-bound (~22 warp-instructions per key); here a warp handles 16 keys with 16 MMAs:
+//   S[head, key]   = q (A, rows = the GROUP query heads of this kv head, zero padded to 16) x K^T (B, loaded
+//                    straight from the cache with 16-byte loads and a permuted-d fragment mapping)
+//   O[head, d]    += P (A, re-used from the S accumulator fragments) x V (B, via ldmatrix.trans from a
+//                    swizzled per-warp shared-memory stage)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int GROUP>
+__global__ void __launch_bounds__(DEC_THREADS)
+decode_attn_mma_kernel(const bf16* __restrict__ qkv, int ldq, const bf16* __restrict__ kcache,
+                       const bf16* __restrict__ vcache, const int* __restrict__ pos_dev,
+                       const int* __restrict__ slot_dev, int hq, int hkv, int max_seq, int splits, float scale_log2,
+                       float* __restrict__ o_part, float* __restrict__ ml_part) {
+  constexpr int HD = 64;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int len = pos_dev[b] + 1;
+  const int slot = slot_dev ? slot_dev[b] : b;
+  int chunk = (len + splits - 1) / splits;
+  chunk = (chunk + 15) & ~15;
+  const int k_begin = split * chunk;
+  const int k_end = min(len, k_begin + chunk);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+  constexpr int NW = DEC_THREADS / 32;
+
+  __shared__ __align__(16) bf16 vstage[NW][16 * HD];  // per-warp V block, 16-byte chunks XOR-swizzled by key
+  __shared__ float s_m[NW][8], s_l[NW][8];
+  __shared__ float s_o[NW][8][HD];
+
+  // q fragments (A operand rows = heads; rows >= GROUP and rows 8..15 are zero)
+  uint32_t qa[4] = {0, 0, 0, 0}, qb[4] = {0, 0, 0, 0};
+  if (g < GROUP) {
+    const bf16* qp = qkv + static_cast<size_t>(b) * ldq + static_cast<size_t>(kvh * GROUP + g) * HD;
+    const uint4 x = *reinterpret_cast<const uint4*>(qp + 8 * tig);
+    const uint4 y = *reinterpret_cast<const uint4*>(qp + 32 + 8 * tig);
+    qa[0] = x.x; qa[1] = x.y; qa[2] = x.z; qa[3] = x.w;
+    qb[0] = y.x; qb[1] = y.y; qb[2] = y.z; qb[3] = y.w;
+  }
+  const bf16* kbase = kcache + (static_cast<size_t>(slot) * hkv + kvh) * max_seq * HD;
+  const bf16* vbase = vcache + (static_cast<size_t>(slot) * hkv + kvh) * max_seq * HD;
+
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;  // per (lane row g): partial over this lane's key columns
+
+  const uint32_t vs_base = smem_u32(&vstage[warp][0]);
+  for (int kb = k_begin + warp * 16; kb < k_end; kb += NW * 16) {
+    // ---- K fragments: key (kb + g) and (kb + 8 + g), d permuted as [8tig..8tig+7] and [32+8tig..]
+    uint4 k0a = make_uint4(0, 0, 0, 0), k0b = k0a, k1a = k0a, k1b = k0a;
+    if (kb + g < k_end) {
+      const bf16* kp = kbase + static_cast<size_t>(kb + g) * HD;
+      k0a = *reinterpret_cast<const uint4*>(kp + 8 * tig);
+      k0b = *reinterpret_cast<const uint4*>(kp + 32 + 8 * tig);
+    }
+    if (kb + 8 + g < k_end) {
+      const bf16* kp = kbase + static_cast<size_t>(kb + 8 + g) * HD;
+      k1a = *reinterpret_cast<const uint4*>(kp + 8 * tig);
+      k1b = *reinterpret_cast<const uint4*>(kp + 32 + 8 * tig);
+    }
+    // ---- V block -> swizzled smem stage (128 chunks of 16 B, 4 per lane)
+    uint4 vv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int id = lane + 32 * i, key = id >> 3, c = id & 7;
+      vv[i] = make_uint4(0, 0, 0, 0);
+      if (kb + key < k_end) vv[i] = *reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(kb + key) * HD + 8 * c);
+    }
+    __syncwarp();  // previous iteration's ldmatrix reads are done
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int id = lane + 32 * i, key = id >> 3, c = id & 7;
+      *reinterpret_cast<uint4*>(&vstage[warp][key * HD + ((c ^ (key & 7)) << 3)]) = vv[i];
+    }
+    // ---- S = q K^T for two 8-key groups
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+    mma16816(s0, qa[0], 0u, qa[1], 0u, k0a.x, k0a.y);
+    mma16816(s0, qa[2], 0u, qa[3], 0u, k0a.z, k0a.w);
+    mma16816(s0, qb[0], 0u, qb[1], 0u, k0b.x, k0b.y);
+    mma16816(s0, qb[2], 0u, qb[3], 0u, k0b.z, k0b.w);
+    mma16816(s1, qa[0], 0u, qa[1], 0u, k1a.x, k1a.y);
+    mma16816(s1, qa[2], 0u, qa[3], 0u, k1a.z, k1a.w);
+    mma16816(s1, qb[0], 0u, qb[1], 0u, k1b.x, k1b.y);
+    mma16816(s1, qb[2], 0u, qb[3], 0u, k1b.z, k1b.w);
+    // lane holds row g (head), keys kb + 2tig, +1 (s0[0], s0[1]) and kb + 8 + 2tig, +1 (s1[0], s1[1])
+    float v0 = s0[0] * scale_log2, v1 = s0[1] * scale_log2, v2 = s1[0] * scale_log2, v3 = s1[1] * scale_log2;
+    v0 = (kb + 2 * tig < k_end) ? v0 : -INFINITY;
+    v1 = (kb + 2 * tig + 1 < k_end) ? v1 : -INFINITY;
+    v2 = (kb + 8 + 2 * tig < k_end) ? v2 : -INFINITY;
+    v3 = (kb + 8 + 2 * tig + 1 < k_end) ? v3 : -INFINITY;
+    float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(m_run, mx);
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+    const float alpha = ex2_approx(m_run - m_use);
+    const float p0 = ex2_approx(v0 - m_use), p1 = ex2_approx(v1 - m_use), p2 = ex2_approx(v2 - m_use),
+                p3 = ex2_approx(v3 - m_use);
+    l_run = l_run * alpha + ((p0 + p1) + (p2 + p3));
+    m_run = m_new;
+    const uint32_t pa0 = pack_bf16x2(p0, p1), pa2 = pack_bf16x2(p2, p3);  // P as A fragment (rows 8..15 zero)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      o[n][0] *= alpha;
+      o[n][1] *= alpha;
+    }
+    __syncwarp();  // V stage fully written
+    // ---- O += P V : B fragments through ldmatrix.trans (matrix rows = keys, cols = 8 d)
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {  // two 8-wide d chunks per ldmatrix.x4
+      const int mat = lane >> 3, r = lane & 7;
+      const int key = (mat & 1) * 8 + r;
+      const int c = np * 2 + (mat >> 1);
+      const uint32_t addr = vs_base + (key * HD + ((c ^ (key & 7)) << 3)) * 2;
+      uint32_t b0, b1, b2, b3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                   : "r"(addr));
+      mma16816(o[np * 2], pa0, 0u, pa2, 0u, b0, b1);
+      mma16816(o[np * 2 + 1], pa0, 0u, pa2, 0u, b2, b3);
+    }
+  }
+  // ---- per-warp row statistics: combine the 4 key-column lanes of each head row
+  float m_w = fmaxf(m_run, __shfl_xor_sync(0xffffffffu, m_run, 1));
+  m_w = fmaxf(m_w, __shfl_xor_sync(0xffffffffu, m_w, 2));
+  const float fix = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_w);
+  float l_w = l_run * fix;
+  l_w += __shfl_xor_sync(0xffffffffu, l_w, 1);
+  l_w += __shfl_xor_sync(0xffffffffu, l_w, 2);
+  // (all four lanes of a row always share m_run: the max was reduced across them every block, so fix == 1
+  //  whenever the row saw a key; the rescale keeps the code robust to future per-lane maxima)
+  if (g < GROUP) {
+    if (tig == 0) { s_m[warp][g] = m_w; s_l[warp][g] = l_w; }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      s_o[warp][g][n * 8 + 2 * tig] = o[n][0] * fix;
+      s_o[warp][g][n * 8 + 2 * tig + 1] = o[n][1] * fix;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < GROUP * HD; idx += DEC_THREADS) {
+    const int gg = idx / HD, e = idx % HD;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) mm = fmaxf(mm, s_m[w][gg]);
+    float ll = 0.f, oo = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const float wgt = (s_m[w][gg] == -INFINITY) ? 0.f : ex2_approx(s_m[w][gg] - mm);
+      ll += s_l[w][gg] * wgt;
+      oo += s_o[w][gg][e] * wgt;
+    }
+    const int h = kvh * GROUP + gg;
+    const size_t pidx = (static_cast<size_t>(b) * hq + h) * splits + split;
+    o_part[pidx * HD + e] = oo;
+    if (e == 0) { ml_part[pidx * 2] = mm; ml_part[pidx * 2 + 1] = ll; }
+  }
+}
+
 template <int HD>
 __global__ void decode_attn_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ ml_part,
                                            bf16* __restrict__ out, int ldo, int hq, int splits) {
@@ -228,7 +400,17 @@ extern "C" int gar_decode_attn(const void* qkv, int ldq, const void* kcache, con
                             static_cast<const bf16*>(qkv), ldq, static_cast<const bf16*>(kcache),                  \
                             static_cast<const bf16*>(vcache), pos_dev, slot_dev, hq, hkv, max_seq, splits, sl2,    \
                             static_cast<float*>(o_part_ws), static_cast<float*>(ml_part_ws)))
-  if (head_dim == 64 && group == 4) LAUNCH_DEC(64, 4);
+#define LAUNCH_MMA(G_)                                                                                              \
+  GAR_CUDA_CHECK(gar_launch(decode_attn_mma_kernel<G_>, grid, dim3(DEC_THREADS), 0, stream, true, dim3(1, 1, 1),      \
+                            static_cast<const bf16*>(qkv), ldq, static_cast<const bf16*>(kcache),                  \
+                            static_cast<const bf16*>(vcache), pos_dev, slot_dev, hq, hkv, max_seq, splits, sl2,    \
+                            static_cast<float*>(o_part_ws), static_cast<float*>(ml_part_ws)))
+  if (head_dim == 64 && gar_global_option("decode_attn_mma") && (group == 4 || group == 2 || group == 1 || group == 8)) {
+    if (group == 4) LAUNCH_MMA(4);
+    else if (group == 2) LAUNCH_MMA(2);
+    else if (group == 1) LAUNCH_MMA(1);
+    else LAUNCH_MMA(8);
+  } else if (head_dim == 64 && group == 4) LAUNCH_DEC(64, 4);
   else if (head_dim == 64 && group == 2) LAUNCH_DEC(64, 2);
   else if (head_dim == 64 && group == 1) LAUNCH_DEC(64, 1);
   else if (head_dim == 128 && group == 4) LAUNCH_DEC(128, 4);
@@ -237,6 +419,7 @@ extern "C" int gar_decode_attn(const void* qkv, int ldq, const void* kcache, con
     return GAR_ERR_SHAPE;
   }
 #undef LAUNCH_DEC
+#undef LAUNCH_MMA
   GAR_CUDA_CHECK(cudaGetLastError());
   dim3 cgrid(hq, batch);
   if (head_dim == 64)

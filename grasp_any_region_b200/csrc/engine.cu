@@ -13,6 +13,8 @@
 #include "../../include/gar_b200.h"
 #include "common.cuh"
 
+extern "C" int gar_set_global_option(const char* name, int value);
+
 #define TRY(x)                \
   do {                        \
     int _rc = (x);            \
@@ -589,7 +591,9 @@ int gar_engine_set_option(gar_engine* e, const char* name, int value) {
   else if (n == "fuse_rope") e->fuse_rope = value;
   else if (n == "gemv_decode") e->use_gemv = value;
   else if (n == "decode_splits" && value >= 0 && value <= 32) e->dec_splits = value;
-  else if (n == "pdl") gar_set_pdl(value);
+  else if (n == "pdl" || n == "decode_attn_mma") {
+    if (gar_set_global_option(name, value)) return GAR_ERR_ARG;
+  }
   else {
     gar_set_error("gar_engine_set_option: unknown option '%s'=%d", name, value);
     return GAR_ERR_ARG;

@@ -24,8 +24,25 @@ extern "C" int gar_copy_d2d(void* dst, const void* src, long long bytes, void* s
 }
 
 static int g_pdl = 1;
+static int g_decode_attn_mma = 1;
 int gar_pdl_enabled() { return g_pdl; }
 void gar_set_pdl(int on) { g_pdl = on; }
+int gar_global_option(const char* name) {
+  if (!strcmp(name, "decode_attn_mma")) return g_decode_attn_mma;
+  if (!strcmp(name, "pdl")) return g_pdl;
+  return 0;
+}
+// process-wide kernel-selection switches (A/B comparisons in tests and bench): "pdl", "decode_attn_mma"
+extern "C" int gar_set_global_option(const char* name, int value) {
+  if (!name) return GAR_ERR_ARG;
+  if (!strcmp(name, "decode_attn_mma")) g_decode_attn_mma = value;
+  else if (!strcmp(name, "pdl")) g_pdl = value;
+  else {
+    gar_set_error("gar_set_global_option: unknown option '%s'", name);
+    return GAR_ERR_ARG;
+  }
+  return GAR_OK;
+}
 
 int gar_num_sms() {
   static int sms = 0;

@@ -33,6 +33,8 @@ extern "C" {
 const char* gar_last_error(void);
 int gar_abi_version(void);
 int gar_copy_d2d(void* dst, const void* src, long long bytes, void* stream);
+/* process-wide kernel-selection switches for A/B runs: "pdl" (default 1), "decode_attn_mma" (default 1) */
+int gar_set_global_option(const char* name, int value);
 
 /* ------------------------------------------------------------------------------------------
  * Per-kernel entry points (unit parity; the engine below is built from exactly these)

@@ -309,7 +309,11 @@ def test_attention_causal_gqa_cache_layout(S):
     assert err <= 2e-2, err
 
 
-def test_decode_attention():
+@pytest.mark.parametrize("mma", [1, 0])
+def test_decode_attention(mma):
+    from grasp_any_region_b200 import _lib
+
+    _lib.check(_lib.load().gar_set_global_option(b"decode_attn_mma", mma))
     B, hq, hkv, hd, max_seq = 3, 8, 2, 64, 700
     qkv = rnd(B, (hq + 2 * hkv) * hd, seed=31)
     kc, vc = rnd(B, hkv, max_seq, hd, seed=32), rnd(B, hkv, max_seq, hd, seed=33)
@@ -324,3 +328,4 @@ def test_decode_attention():
         ref = F.scaled_dot_product_attention(q, k, v)[0, :, 0].reshape(hq * hd)
         err = (out[b].float() - ref).abs().max().item()
         assert err <= 2e-2, (b, err)
+    _lib.check(_lib.load().gar_set_global_option(b"decode_attn_mma", 1))

@@ -37,9 +37,13 @@ if which in ("all", "decode_attn"):
     qkv = torch.randn(B, (hq + 2 * hkv) * hd, device=dev).to(bf)
     kc = torch.randn(B, hkv, ms_, hd, device=dev).to(bf); vc = torch.randn(B, hkv, ms_, hd, device=dev).to(bf)
     pos = torch.full((B,), 4700, dtype=torch.int32, device=dev)
-    for sp in (8, 10, 16, 32):
-        timeit(f"decode attn B=8 len=4701 splits={sp}", lambda: ops.decode_attn(qkv, kc, vc, pos, hq, hkv, hd, ms_, splits=sp),
-               B * hkv * 4701 * hd * 2 * 2, "GB/s")
+    from grasp_any_region_b200 import _lib
+    for impl in (1, 0):
+        _lib.load().gar_set_global_option(b"decode_attn_mma", impl)
+        for sp in (4, 8, 10, 16):
+            timeit(f"decode attn mma={impl} B=8 len=4701 splits={sp}",
+                   lambda: ops.decode_attn(qkv, kc, vc, pos, hq, hkv, hd, ms_, splits=sp), B * hkv * 4701 * hd * 2 * 2, "GB/s")
+    _lib.load().gar_set_global_option(b"decode_attn_mma", 1)
 if which in ("all", "skinny"):
     for (N, K) in ((3072, 2048), (2048, 2048), (16384, 2048), (2048, 8192), (128512, 2048)):
         x = torch.randn(8, K, device=dev).to(bf); w = (torch.randn(N, K, device=dev) * 0.05).to(bf)
