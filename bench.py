@@ -318,6 +318,9 @@ def main():
                                 "frac_hbm": (s_by / (s_ms * 1e-3) / 1e9) / peaks["hbm"] if s_ms > 0 else 0.0,
                                 "launches": s_n},
             "decode_attn": {"ms": prof["decode_attn"][0], "launches": prof["decode_attn"][2]},
+            "decode_gemv": {"ms": prof["gemv"][0], "launches": prof["gemv"][2],
+                            "GB/s": prof["gemv"][1] / (prof["gemv"][0] * 1e-3) / 1e9 if prof["gemv"][0] > 0 else 0.0,
+                            "frac_hbm": (prof["gemv"][1] / (prof["gemv"][0] * 1e-3) / 1e9) / peaks["hbm"] if prof["gemv"][0] > 0 else 0.0},
         }
 
     cpu = None

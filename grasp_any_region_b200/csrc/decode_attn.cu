@@ -13,6 +13,39 @@ namespace {
 
 constexpr int DEC_THREADS = 128;
 
+// Fused split combine: the last CTA of a (sequence, kv head) to finish -- decided by an atomic ticket --
+// merges all splits of its GROUP heads and writes the bf16 attention output, saving a launch per layer.
+template <int HD, int GROUP>
+__device__ __forceinline__ void fused_combine_tail(int* __restrict__ tickets, const float* o_part, const float* ml_part,
+                                                   bf16* __restrict__ out, int ldo, int b, int kvh, int hq, int hkv,
+                                                   int splits) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(&tickets[b * hkv + kvh], 1);
+    s_last = (t == splits - 1);
+    if (s_last) tickets[b * hkv + kvh] = 0;  // ready for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int idx = threadIdx.x; idx < GROUP * HD; idx += blockDim.x) {
+    const int h = kvh * GROUP + idx / HD, e = idx % HD;
+    const size_t base = (static_cast<size_t>(b) * hq + h) * splits;
+    float mm = -INFINITY;
+    for (int sidx = 0; sidx < splits; ++sidx) mm = fmaxf(mm, __ldcg(ml_part + (base + sidx) * 2));
+    float ll = 0.f, oo = 0.f;
+    for (int sidx = 0; sidx < splits; ++sidx) {
+      const float ms = __ldcg(ml_part + (base + sidx) * 2);
+      const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - mm);
+      ll += __ldcg(ml_part + (base + sidx) * 2 + 1) * w;
+      oo += __ldcg(o_part + (base + sidx) * HD + e) * w;
+    }
+    out[static_cast<size_t>(b) * ldo + h * HD + e] = __float2bfloat16_rn(ll > 0.f ? oo / ll : 0.f);
+  }
+}
+
 // Each 8-lane group owns one KV row at a time (lane l%8 holds elements [8*(l%8), +8) of each 64-wide
 // slice); a warp covers 4 consecutive rows per load instruction (512 contiguous bytes) and keeps
 // ROWS_U such instructions in flight for K and for V before touching the data.
@@ -23,7 +56,8 @@ __global__ void __launch_bounds__(DEC_THREADS)
 decode_attn_split_kernel(const bf16* __restrict__ qkv, int ldq, const bf16* __restrict__ kcache,
                          const bf16* __restrict__ vcache, const int* __restrict__ pos_dev,
                          const int* __restrict__ slot_dev, int hq, int hkv, int max_seq, int splits, float scale_log2,
-                         float* __restrict__ o_part, float* __restrict__ ml_part) {
+                         float* __restrict__ o_part, float* __restrict__ ml_part, int* __restrict__ tickets,
+                         bf16* __restrict__ out, int ldo) {
   constexpr int VPL = HD / 64;  // 16-byte vectors per lane per row
   pdl_launch_dependents();
   pdl_wait();
@@ -191,6 +225,7 @@ decode_attn_split_kernel(const bf16* __restrict__ qkv, int ldq, const bf16* __re
     o_part[pidx * HD + e] = oo;
     if (e == 0) { ml_part[pidx * 2] = mm; ml_part[pidx * 2 + 1] = ll; }
   }
+  if (tickets != nullptr) fused_combine_tail<HD, GROUP>(tickets, o_part, ml_part, out, ldo, b, kvh, hq, hkv, splits);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -214,7 +249,8 @@ __global__ void __launch_bounds__(DEC_THREADS)
 decode_attn_mma_kernel(const bf16* __restrict__ qkv, int ldq, const bf16* __restrict__ kcache,
                        const bf16* __restrict__ vcache, const int* __restrict__ pos_dev,
                        const int* __restrict__ slot_dev, int hq, int hkv, int max_seq, int splits, float scale_log2,
-                       float* __restrict__ o_part, float* __restrict__ ml_part) {
+                       float* __restrict__ o_part, float* __restrict__ ml_part, int* __restrict__ tickets,
+                       bf16* __restrict__ out, int ldo) {
   constexpr int HD = 64;
   pdl_launch_dependents();
   pdl_wait();
@@ -253,27 +289,40 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, int ldq, const bf16* __rest
   float m_run = -INFINITY, l_run = 0.f;  // per (lane row g): partial over this lane's key columns
 
   const uint32_t vs_base = smem_u32(&vstage[warp][0]);
-  for (int kb = k_begin + warp * 16; kb < k_end; kb += NW * 16) {
-    // ---- K fragments: key (kb + g) and (kb + 8 + g), d permuted as [8tig..8tig+7] and [32+8tig..]
-    uint4 k0a = make_uint4(0, 0, 0, 0), k0b = k0a, k1a = k0a, k1b = k0a;
+  // K fragments (key kb+g and kb+8+g; d permuted as [8tig..8tig+7] and [32+8tig..]) and the V block
+  // (128 chunks of 16 B, 4 per lane) of one 16-key step; loads are predicated on the key range.
+  struct Step { uint4 k0a, k0b, k1a, k1b, vv[4]; };
+  auto load_step = [&](Step& st, int kb) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    st.k0a = st.k0b = st.k1a = st.k1b = z;
     if (kb + g < k_end) {
       const bf16* kp = kbase + static_cast<size_t>(kb + g) * HD;
-      k0a = *reinterpret_cast<const uint4*>(kp + 8 * tig);
-      k0b = *reinterpret_cast<const uint4*>(kp + 32 + 8 * tig);
+      st.k0a = *reinterpret_cast<const uint4*>(kp + 8 * tig);
+      st.k0b = *reinterpret_cast<const uint4*>(kp + 32 + 8 * tig);
     }
     if (kb + 8 + g < k_end) {
       const bf16* kp = kbase + static_cast<size_t>(kb + 8 + g) * HD;
-      k1a = *reinterpret_cast<const uint4*>(kp + 8 * tig);
-      k1b = *reinterpret_cast<const uint4*>(kp + 32 + 8 * tig);
+      st.k1a = *reinterpret_cast<const uint4*>(kp + 8 * tig);
+      st.k1b = *reinterpret_cast<const uint4*>(kp + 32 + 8 * tig);
     }
-    // ---- V block -> swizzled smem stage (128 chunks of 16 B, 4 per lane)
-    uint4 vv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int id = lane + 32 * i, key = id >> 3, c = id & 7;
-      vv[i] = make_uint4(0, 0, 0, 0);
-      if (kb + key < k_end) vv[i] = *reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(kb + key) * HD + 8 * c);
+      st.vv[i] = z;
+      if (kb + key < k_end) st.vv[i] = *reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(kb + key) * HD + 8 * c);
     }
+  };
+  // register double buffering: the loads of step i+1 are in flight while step i is computed (the kernel is
+  // otherwise bound by one DRAM round trip per step)
+  Step cur, nxt;
+  const int kb_first = k_begin + warp * 16;
+  if (kb_first < k_end) load_step(cur, kb_first);
+  for (int kb = kb_first; kb < k_end; kb += NW * 16) {
+    if (kb + NW * 16 < k_end) load_step(nxt, kb + NW * 16);
+    const uint4 k0a = cur.k0a, k0b = cur.k0b, k1a = cur.k1a, k1b = cur.k1b;
+    uint4 vv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) vv[i] = cur.vv[i];
     __syncwarp();  // previous iteration's ldmatrix reads are done
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -327,6 +376,7 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, int ldq, const bf16* __rest
       mma16816(o[np * 2], pa0, 0u, pa2, 0u, b0, b1);
       mma16816(o[np * 2 + 1], pa0, 0u, pa2, 0u, b2, b3);
     }
+    cur = nxt;
   }
   // ---- per-warp row statistics: combine the 4 key-column lanes of each head row
   float m_w = fmaxf(m_run, __shfl_xor_sync(0xffffffffu, m_run, 1));
@@ -363,6 +413,7 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, int ldq, const bf16* __rest
     o_part[pidx * HD + e] = oo;
     if (e == 0) { ml_part[pidx * 2] = mm; ml_part[pidx * 2 + 1] = ll; }
   }
+  if (tickets != nullptr) fused_combine_tail<HD, GROUP>(tickets, o_part, ml_part, out, ldo, b, kvh, hq, hkv, splits);
 }
 
 template <int HD>
@@ -389,7 +440,8 @@ __global__ void decode_attn_combine_kernel(const float* __restrict__ o_part, con
 
 extern "C" int gar_decode_attn(const void* qkv, int ldq, const void* kcache, const void* vcache, const int* pos_dev,
                                const int* slot_dev, int batch, int hq, int hkv, int head_dim, int max_seq, int splits,
-                               float scale, void* o_part_ws, void* ml_part_ws, void* out, int ldo, void* stream_) {
+                               float scale, void* o_part_ws, void* ml_part_ws, int* tickets, void* out, int ldo,
+                               void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int group = hq / hkv;
   if (hq % hkv || splits < 1 || splits > 32) return GAR_ERR_ARG;
@@ -399,12 +451,14 @@ extern "C" int gar_decode_attn(const void* qkv, int ldq, const void* kcache, con
   GAR_CUDA_CHECK(gar_launch(decode_attn_split_kernel<HD_, G_>, grid, dim3(DEC_THREADS), 0, stream, true, dim3(1, 1, 1), \
                             static_cast<const bf16*>(qkv), ldq, static_cast<const bf16*>(kcache),                  \
                             static_cast<const bf16*>(vcache), pos_dev, slot_dev, hq, hkv, max_seq, splits, sl2,    \
-                            static_cast<float*>(o_part_ws), static_cast<float*>(ml_part_ws)))
+                            static_cast<float*>(o_part_ws), static_cast<float*>(ml_part_ws), tickets,              \
+                            static_cast<bf16*>(out), ldo))
 #define LAUNCH_MMA(G_)                                                                                              \
   GAR_CUDA_CHECK(gar_launch(decode_attn_mma_kernel<G_>, grid, dim3(DEC_THREADS), 0, stream, true, dim3(1, 1, 1),      \
                             static_cast<const bf16*>(qkv), ldq, static_cast<const bf16*>(kcache),                  \
                             static_cast<const bf16*>(vcache), pos_dev, slot_dev, hq, hkv, max_seq, splits, sl2,    \
-                            static_cast<float*>(o_part_ws), static_cast<float*>(ml_part_ws)))
+                            static_cast<float*>(o_part_ws), static_cast<float*>(ml_part_ws), tickets,              \
+                            static_cast<bf16*>(out), ldo))
   if (head_dim == 64 && gar_global_option("decode_attn_mma") && (group == 4 || group == 2 || group == 1 || group == 8)) {
     if (group == 4) LAUNCH_MMA(4);
     else if (group == 2) LAUNCH_MMA(2);
@@ -421,6 +475,7 @@ extern "C" int gar_decode_attn(const void* qkv, int ldq, const void* kcache, con
 #undef LAUNCH_DEC
 #undef LAUNCH_MMA
   GAR_CUDA_CHECK(cudaGetLastError());
+  if (tickets != nullptr) return GAR_OK;  // the split kernel's last CTA per (sequence, kv head) already combined
   dim3 cgrid(hq, batch);
   if (head_dim == 64)
     GAR_CUDA_CHECK(gar_launch(decode_attn_combine_kernel<64>, cgrid, dim3(64), 0, stream, true, dim3(1, 1, 1),

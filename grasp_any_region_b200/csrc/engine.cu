@@ -32,7 +32,7 @@ struct gar_engine {
   // LLM workspaces
   bf16 *emb, *h, *lnl, *qkv_l, *att_l, *gu, *act, *logits, *kcache, *vcache, *hdec, *lndec;
   float *o_part, *ml_part, *argmax_ws;
-  int *plan, *status, *next_tok, *out_tokens, *pos, *finished, *step;
+  int *plan, *status, *next_tok, *out_tokens, *pos, *finished, *step, *tickets;
   long long* ids_scratch;
   int dec_splits;
   int use_skinny = 1;
@@ -50,7 +50,7 @@ struct gar_engine {
   std::vector<ProfRec> prof;
 };
 
-enum ProfKind { PK_GEMM = 0, PK_ATTN = 1, PK_ASSEMBLE = 2, PK_DECODE_ATTN = 3, PK_OTHER = 4, PK_COUNT = 5 };
+enum ProfKind { PK_GEMM = 0, PK_ATTN = 1, PK_ASSEMBLE = 2, PK_DECODE_ATTN = 3, PK_GEMV = 4, PK_COUNT = 5 };
 
 namespace {
 
@@ -103,7 +103,7 @@ struct ProfScope {
 int gemm(gar_engine* e, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K, int epi,
          const void* bias, const void* gamma, const void* res, int ldres, void* s) {
   e->launches += 1;
-  ProfScope ps(e, s, PK_GEMM, 2.0 * M * static_cast<double>(N) * K);
+  ProfScope ps(e, s, M <= 16 ? PK_GEMV : PK_GEMM, M <= 16 ? 2.0 * N * static_cast<double>(K) : 2.0 * M * static_cast<double>(N) * K);
   if (e->use_skinny && M <= 16 && (epi == GAR_EPI_NONE || epi == GAR_EPI_RES))
     return gar_gemm_skinny_bf16(A, lda, B, ldb, C, ldc, M, N, K, epi, res, ldres, s);
   return gar_gemm_bf16(A, lda, B, ldb, C, ldc, M, N, K, epi, bias, gamma, res, ldres, 0, s);
@@ -139,11 +139,11 @@ int llm_layers(gar_engine* e, bf16* h, bf16* ln, int rows, bool decode, int slot
       ProfScope ps(e, s, PK_DECODE_ATTN, 0.0);
       int splits = e->dec_splits;
       if (splits <= 0) {  // ~4 CTAs per SM across (split, kv head, sequence)
-        splits = (4 * gar_num_sms() + rows * hkv - 1) / (rows * hkv);
+        splits = (3 * gar_num_sms()) / (rows * hkv);  // one resident wave of 3 CTAs per SM
         splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
       }
       TRY(gar_decode_attn(e->qkv_l, qkv_w, kc, vc, e->pos, nullptr, rows, hq, hkv, hd, d.max_seq, splits, scale,
-                          e->o_part, e->ml_part, e->att_l, hq * hd, s));
+                          e->o_part, e->ml_part, e->tickets, e->att_l, hq * hd, s));
       e->launches += 2;
     } else {
       const bf16* kslot = kc + static_cast<size_t>(slot) * hkv * d.max_seq * hd;
@@ -203,7 +203,7 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
     bf16* kc = e->kcache + static_cast<size_t>(i) * d.max_batch * hkv * d.max_seq * hd;
     bf16* vc = e->vcache + static_cast<size_t>(i) * d.max_batch * hkv * d.max_seq * hd;
     {
-      ProfScope ps(e, s, PK_GEMM, 2.0 * batch * static_cast<double>(qkv_w) * D);
+      ProfScope ps(e, s, PK_GEMV, 2.0 * qkv_w * static_cast<double>(D));
       TRY(gar_gemv_decode(e->hdec, D, wqkv, D, e->qkv_l, qkv_w, batch, qkv_w, D, 0, nullptr, 0, ln1, e->sumsq_a, n_part,
                           d.rms_eps, nullptr, nullptr, s));
     }
@@ -212,24 +212,24 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
       ProfScope ps(e, s, PK_DECODE_ATTN, 0.0);
       int splits = e->dec_splits;
       if (splits <= 0) {
-        splits = (4 * gar_num_sms() + batch * hkv - 1) / (batch * hkv);
+        splits = (3 * gar_num_sms()) / (batch * hkv);  // one resident wave of 3 CTAs per SM
         splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
       }
       TRY(gar_decode_attn(e->qkv_l, qkv_w, kc, vc, e->pos, nullptr, batch, hq, hkv, hd, d.max_seq, splits, scale,
-                          e->o_part, e->ml_part, e->att_l, hq * hd, s));
+                          e->o_part, e->ml_part, e->tickets, e->att_l, hq * hd, s));
     }
     {
-      ProfScope ps(e, s, PK_GEMM, 2.0 * batch * static_cast<double>(D) * hq * hd);
+      ProfScope ps(e, s, PK_GEMV, 2.0 * D * static_cast<double>(hq * hd));
       TRY(gar_gemv_decode(e->att_l, hq * hd, wo, hq * hd, e->hdec, D, batch, D, hq * hd, 1, e->hdec, D, nullptr, nullptr, 0,
                           0.f, e->sumsq_b, &rows, s));
     }
     {
-      ProfScope ps(e, s, PK_GEMM, 2.0 * batch * 2.0 * I * D);
+      ProfScope ps(e, s, PK_GEMV, 2.0 * 2.0 * I * D);
       TRY(gar_gemv_decode(e->hdec, D, wgu, D, e->act, I, batch, 2 * I, D, 2, nullptr, 0, ln2, e->sumsq_b, D / rows,
                           d.rms_eps, nullptr, nullptr, s));
     }
     {
-      ProfScope ps(e, s, PK_GEMM, 2.0 * batch * static_cast<double>(D) * I);
+      ProfScope ps(e, s, PK_GEMV, 2.0 * D * static_cast<double>(I));
       TRY(gar_gemv_decode(e->act, I, wdown, I, e->hdec, D, batch, D, I, 1, e->hdec, D, nullptr, nullptr, 0, 0.f,
                           e->sumsq_a, &rows, s));
     }
@@ -239,7 +239,7 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
   NEEDW(wn, "llm.norm");
   NEEDW(wl, "llm.lm_head");
   {
-    ProfScope ps(e, s, PK_GEMM, 2.0 * batch * static_cast<double>(d.vocab_padded) * D);
+    ProfScope ps(e, s, PK_GEMV, 2.0 * d.vocab_padded * static_cast<double>(D));
     TRY(gar_gemv_decode(e->hdec, D, wl, D, e->logits, d.vocab_padded, batch, d.vocab_padded, D, 0, nullptr, 0, wn,
                         e->sumsq_a, n_part, d.rms_eps, nullptr, nullptr, s));
   }
@@ -329,6 +329,7 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   rc |= dev_alloc(e, &e->pos, B, true);
   rc |= dev_alloc(e, &e->finished, B, true);
   rc |= dev_alloc(e, &e->step, 2, true);
+  rc |= dev_alloc(e, &e->tickets, B * d.llm_kv_heads, true);
   rc |= dev_alloc(e, &e->argmax_ws, B * ((static_cast<size_t>(d.vocab) + 4095) / 4096) * 2, true);
   rc |= dev_alloc(e, &e->ids_scratch, S);
   rc |= dev_alloc(e, &e->sumsq_a, (D / 16 + 1) * 8, true);

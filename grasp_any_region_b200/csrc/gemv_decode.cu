@@ -20,8 +20,6 @@
 
 namespace {
 
-constexpr int GV_WARPS = 8;
-constexpr int GV_THREADS = GV_WARPS * 32;
 enum { GV_EPI_NONE = 0, GV_EPI_RES = 1, GV_EPI_SWIGLU = 2 };
 
 struct GvArgs {
@@ -50,8 +48,11 @@ __device__ __forceinline__ uint4 ldg_stream(const bf16* p) {  // weights: read o
   return r;
 }
 
-template <int R, int EPI, bool NORM>
-__global__ void __launch_bounds__(GV_THREADS, 2) gemv_decode_kernel(GvArgs a) {
+// WARPS K-slices per CTA: 8 (two CTAs per SM) or, for long K (down_proj), 16 so that a 128-CTA grid
+// still keeps enough weight bytes in flight per SM.
+template <int R, int EPI, bool NORM, int GV_WARPS>
+__global__ void __launch_bounds__(GV_WARPS * 32, 16 / GV_WARPS) gemv_decode_kernel(GvArgs a) {
+  constexpr int GV_THREADS = GV_WARPS * 32;
   constexpr int U = 8 / R;  // k-steps (32 k each) whose weight loads are in flight together
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,24 +91,41 @@ __global__ void __launch_bounds__(GV_THREADS, 2) gemv_decode_kernel(GvArgs a) {
     }
   pdl_wait();
 
+  // activations of the first chunk go in flight before the RMSNorm statistics are reduced
+  uint4 xv[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    xv[u] = make_uint4(0, 0, 0, 0);
+    if (u < steps && xvalid) xv[u] = *reinterpret_cast<const uint4*>(xp + u * 32);
+  }
+
   float rstd = 0.f;
   if (NORM) {
-    // fixed-order sum of the producer's partial sums of squares for batch row g
-    float s = 0.f;
-    if (xvalid)
-      for (int p = tig; p < a.n_part; p += 4) s += a.sumsq_in[static_cast<size_t>(p) * 8 + g];
+    // fixed-order sum of the producer's partial sums of squares for batch row g; 16 independent loads in
+    // flight per lane so the whole reduction costs about one L2 round trip
+    float acc16[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc16[j] = 0.f;
+    if (xvalid) {
+      for (int p0 = tig; p0 < a.n_part; p0 += 64) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int p = p0 + 4 * j;
+          if (p < a.n_part) acc16[j] += a.sumsq_in[static_cast<size_t>(p) * 8 + g];
+        }
+      }
+    }
+#pragma unroll
+    for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+      for (int j = 0; j < w; ++j) acc16[j] += acc16[j + w];
+    float s = acc16[0];
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     rstd = rsqrtf(s / static_cast<float>(a.K) + a.eps);
   }
 
   for (int s0 = 0; s0 < steps; s0 += U) {
-    uint4 xv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      xv[u] = make_uint4(0, 0, 0, 0);
-      if (s0 + u < steps && xvalid) xv[u] = *reinterpret_cast<const uint4*>(xp + (s0 + u) * 32);
-    }
     if (NORM) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -133,9 +151,9 @@ __global__ void __launch_bounds__(GV_THREADS, 2) gemv_decode_kernel(GvArgs a) {
         }
       }
     }
-    // next chunk of weights
+    // next chunk of weights and activations
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         if (s0 + U + u < steps) {
@@ -143,6 +161,9 @@ __global__ void __launch_bounds__(GV_THREADS, 2) gemv_decode_kernel(GvArgs a) {
           wh[u][r] = ldg_stream(whi[r] + (s0 + U + u) * 32);
         }
       }
+      xv[u] = make_uint4(0, 0, 0, 0);
+      if (s0 + U + u < steps && xvalid) xv[u] = *reinterpret_cast<const uint4*>(xp + (s0 + U + u) * 32);
+    }
   }
 
   // ---- reduce the 8 K-slices (fixed order), then the fused epilogue ----
@@ -229,8 +250,15 @@ int launch_gv(const GvArgs& a, bool norm, cudaStream_t s) {
   const int out_feats = (EPI == GV_EPI_SWIGLU ? 8 : 16) * R;
   const int n_out = EPI == GV_EPI_SWIGLU ? a.N / 2 : a.N;
   dim3 grid(n_out / out_feats);
-  if (norm) GAR_CUDA_CHECK(gar_launch(gemv_decode_kernel<R, EPI, true>, grid, dim3(GV_THREADS), 0, s, true, dim3(1, 1, 1), a));
-  else GAR_CUDA_CHECK(gar_launch(gemv_decode_kernel<R, EPI, false>, grid, dim3(GV_THREADS), 0, s, true, dim3(1, 1, 1), a));
+  // 16 K-slices when K is long and the grid alone cannot fill the machine (R == 1 only: register budget)
+  const bool wide = R == 1 && a.K % 512 == 0 && a.K >= 4096 && static_cast<int>(grid.x) < 2 * gar_num_sms();
+  if (wide) {
+    if (norm) GAR_CUDA_CHECK(gar_launch(gemv_decode_kernel<R, EPI, true, 16>, grid, dim3(512), 0, s, true, dim3(1, 1, 1), a));
+    else GAR_CUDA_CHECK(gar_launch(gemv_decode_kernel<R, EPI, false, 16>, grid, dim3(512), 0, s, true, dim3(1, 1, 1), a));
+    return GAR_OK;
+  }
+  if (norm) GAR_CUDA_CHECK(gar_launch(gemv_decode_kernel<R, EPI, true, 8>, grid, dim3(256), 0, s, true, dim3(1, 1, 1), a));
+  else GAR_CUDA_CHECK(gar_launch(gemv_decode_kernel<R, EPI, false, 8>, grid, dim3(256), 0, s, true, dim3(1, 1, 1), a));
   return GAR_OK;
 }
 
@@ -243,7 +271,7 @@ extern "C" int gar_gemv_decode(const void* X, int ldx, const void* W, int ldw, v
                                int epi, const void* res, int ldres, const void* norm_w, const float* sumsq_in,
                                int n_part, float eps, float* sumsq_out, int* rows_per_cta, void* stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
-  if (M <= 0 || M > 8 || K % (GV_WARPS * 32) || (ldx % 8) || (ldw % 8) || epi < 0 || epi > 2) return GAR_ERR_SHAPE;
+  if (M <= 0 || M > 8 || K % 256 || (ldx % 8) || (ldw % 8) || epi < 0 || epi > 2) return GAR_ERR_SHAPE;
   if (norm_w != nullptr && (sumsq_in == nullptr || n_part <= 0)) return GAR_ERR_ARG;
   GvArgs a;
   a.W = static_cast<const bf16*>(W); a.ldw = ldw;

@@ -224,7 +224,7 @@ class Engine:
         n = 5
         ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_longlong * n)()
         check(self.lib.gar_engine_profile_read(self._h, ms, work, cnt), "gar_engine_profile_read")
-        names = ["gemm", "attn", "assemble", "decode_attn", "other"]
+        names = ["gemm", "attn", "assemble", "decode_attn", "gemv"]
         return {names[i]: (ms[i], work[i], cnt[i]) for i in range(n)}
 
     def close(self):

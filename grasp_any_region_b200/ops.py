@@ -170,14 +170,15 @@ def attn_fwd_cache(q, q_ld, kcache_slot, vcache_slot, hq, hkv, hd, S, max_seq):
     return out
 
 
-def decode_attn(qkv, kcache, vcache, pos_dev, hq, hkv, hd, max_seq, splits=8):
+def decode_attn(qkv, kcache, vcache, pos_dev, hq, hkv, hd, max_seq, splits=8, fused_combine=True):
     B = qkv.shape[0]
+    tickets = torch.zeros((B * hkv,), dtype=torch.int32, device=qkv.device) if fused_combine else None
     o_part = torch.empty((B, hq, splits, hd), dtype=torch.float32, device=qkv.device)
     ml = torch.empty((B, hq, splits, 2), dtype=torch.float32, device=qkv.device)
     out = torch.empty((B, hq * hd), dtype=torch.bfloat16, device=qkv.device)
     check(_lib.load().gar_decode_attn(_p(qkv), qkv.stride(0), _p(kcache), _p(vcache), _p(pos_dev), None, B, hq, hkv, hd,
-                                      max_seq, splits, 1.0 / math.sqrt(hd), _p(o_part), _p(ml), _p(out), hq * hd,
-                                      _stream()), "gar_decode_attn")
+                                      max_seq, splits, 1.0 / math.sqrt(hd), _p(o_part), _p(ml), _p(tickets), _p(out),
+                                      hq * hd, _stream()), "gar_decode_attn")
     return out
 
 

@@ -122,9 +122,10 @@ int gar_attn_fwd(const void* q, long long q_row_stride, long long q_batch_stride
                  long long o_batch_stride, int o_col0, int batch, int heads, int kv_heads, int head_dim, int q_len,
                  int kv_len, int kv_rows_alloc, int causal, float scale, void* stream);
 /* q_len = 1 attention over the KV cache, split-KV + combine (flash-attn 2 decode + DynamicCache) */
+/* tickets: batch*hkv zero-initialised ints -> the split kernel's last CTA combines (one launch); NULL -> separate combine */
 int gar_decode_attn(const void* qkv, int ldq, const void* kcache, const void* vcache, const int* pos_dev,
                     const int* slot_dev, int batch, int hq, int hkv, int head_dim, int max_seq, int splits, float scale,
-                    void* o_part_ws, void* ml_part_ws, void* out, int ldo, void* stream);
+                    void* o_part_ws, void* ml_part_ws, int* tickets, void* out, int ldo, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Engine: GARModel.generate() (modeling_gar.py:295-428) as a device-resident pipeline
@@ -177,7 +178,7 @@ int gar_engine_set_option(gar_engine* e, const char* name, int value);
 #define GAR_PROF_ATTN 1
 #define GAR_PROF_ASSEMBLE 2
 #define GAR_PROF_DECODE_ATTN 3
-#define GAR_PROF_OTHER 4
+#define GAR_PROF_GEMV 4 /* decode weight-stream kernels; work = weight bytes */
 #define GAR_PROF_COUNT 5
 int gar_engine_profile(gar_engine* e, int enable);
 int gar_engine_profile_read(gar_engine* e, double* ms, double* work, long long* count);
