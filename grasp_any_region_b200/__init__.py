@@ -3,7 +3,7 @@
 Public surface = the reference's: ``GARModel`` / ``GARConfig`` (hf_models/modeling_gar.py,
 configuration_gar.py).  Importing this package never touches CUDA; using it without the built
 library or without a GPU raises (no CPU / PyTorch fallback)."""
-from .config import GARSpec, gar_1b, gar_8b, gar_small, gar_tiny  # noqa: F401
+from .config import GARSpec, gar_1b, gar_8b, gar_8b_mini, gar_small, gar_tiny  # noqa: F401
 
 __all__ = ["GARModel", "GARConfig", "GARSpec", "gar_1b", "gar_8b", "gar_tiny", "gar_small"]
 

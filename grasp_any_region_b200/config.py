@@ -139,4 +139,15 @@ def gar_small() -> GARSpec:
     )
 
 
-PRESETS = {"gar-1b": gar_1b, "gar-8b": gar_8b, "gar-tiny": gar_tiny, "gar-small": gar_small}
+def gar_8b_mini() -> GARSpec:
+    """GAR-8B's kernel shapes at toy depth: ViT head_dim 96 without cls token, Llama head_dim 128 with GQA."""
+    return GARSpec(
+        name="gar-8b-mini",
+        vision=VisionSpec(embed_dim=192, depth=2, num_heads=2, mlp_dim=512, use_cls_token=False),
+        text=TextSpec(hidden_size=512, num_layers=2, num_heads=8, num_kv_heads=2, head_dim=128,
+                      intermediate_size=1024, rope_factor=8.0),
+    )
+
+
+PRESETS = {"gar-1b": gar_1b, "gar-8b": gar_8b, "gar-tiny": gar_tiny, "gar-small": gar_small,
+           "gar-8b-mini": gar_8b_mini}

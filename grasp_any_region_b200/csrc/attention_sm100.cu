@@ -1,4 +1,4 @@
-// Fused softmax(Q K^T * scale) V for head_dim 64 on tcgen05 tensor cores with TMEM accumulators.
+// Fused softmax(Q K^T * scale) V for head_dim 64 / 128 on tcgen05 tensor cores with TMEM accumulators.
 //
 // Replaces F.scaled_dot_product_attention in timm's AttentionRope (PE ViT, non-causal, N=1025) and
 // flash-attn 2 `flash_attn_func` behind HF Llama (causal, GQA) on the prefill -- SURVEY.md §2b K5/K9.
@@ -17,19 +17,27 @@
 
 namespace {
 
-constexpr int HD = 64;
 constexpr int BQ = 128;
 constexpr int BKV = 128;
 constexpr int ATT_THREADS = 192;
-constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows of 128 B
-constexpr int SMEM_Q = 0;
-constexpr int SMEM_K = TILE_BYTES;                   // 2 stages
-constexpr int SMEM_V = SMEM_K + 2 * TILE_BYTES;      // 1 stage
-constexpr int SMEM_P = SMEM_V + TILE_BYTES;          // 2 sub-tiles [128 x 64]
-constexpr int SMEM_TOTAL = SMEM_P + 2 * TILE_BYTES;  // 96 KB
-constexpr int ATT_SMEM_BYTES = SMEM_TOTAL + 1024;
-constexpr int TMEM_COLS_ATT = 256;  // S: 128 cols, O: 64 cols (power-of-two allocation)
+constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows of 128 B (one 64-wide, 128B-swizzled sub-tile)
+constexpr int TMEM_COLS_ATT = 256;        // S: 128 cols, O: HD cols (power-of-two allocation)
 constexpr uint32_t TM_S = 0, TM_O = 128;
+
+// head_dim 64: 96 KB smem, two CTAs per SM.  head_dim 128 (GAR-8B Llama; PE-G's 96 is zero-padded to 128):
+// rows are 2 sub-tiles wide, 160 KB smem, one CTA per SM.
+template <int HD>
+struct AttCfg {
+  static constexpr int NSUB = HD / 64;
+  static constexpr int ROW_BYTES = NSUB * TILE_BYTES;  // a [128 x HD] operand tile
+  static constexpr int SMEM_Q = 0;
+  static constexpr int SMEM_K = ROW_BYTES;                    // 2 stages
+  static constexpr int SMEM_V = SMEM_K + 2 * ROW_BYTES;       // 1 stage
+  static constexpr int SMEM_P = SMEM_V + ROW_BYTES;           // 2 sub-tiles [128 x 64]
+  static constexpr int SMEM_TOTAL = SMEM_P + 2 * TILE_BYTES;
+  static constexpr int SMEM_BYTES = SMEM_TOTAL + 1024;
+  static constexpr int CTAS_PER_SM = HD == 64 ? 2 : 1;
+};
 
 struct AttnParams {
   int q_len, kv_len;       // per sequence
@@ -86,10 +94,14 @@ __device__ __forceinline__ float exp_pack_store_128(const uint32_t (&s)[128], in
   return (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
-attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+template <int HD>
+__global__ void __launch_bounds__(ATT_THREADS, AttCfg<HD>::CTAS_PER_SM)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
                      AttnParams p) {
+  using Cfg = AttCfg<HD>;
+  constexpr int NSUB = Cfg::NSUB, SMEM_Q = Cfg::SMEM_Q, SMEM_K = Cfg::SMEM_K, SMEM_V = Cfg::SMEM_V, SMEM_P = Cfg::SMEM_P;
+  constexpr int ROW_BYTES = Cfg::ROW_BYTES;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[12];
   __shared__ uint32_t tmem_ptr_sh;
@@ -140,17 +152,24 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   if (warp == 0) {
     if (lane == 0) {
       const int kb_coord = b * p.kv_batch_mul + kvh * p.kv_batch_head_mul;
-      mbar_expect_tx(B_QFULL, TILE_BYTES);
-      tma_load_3d(sbase + SMEM_Q, &tmap_q, p.q_col0 + h * p.q_head_cols, q0, b, B_QFULL);
+      mbar_expect_tx(B_QFULL, ROW_BYTES);
+#pragma unroll
+      for (int u = 0; u < NSUB; ++u)
+        tma_load_3d(sbase + SMEM_Q + u * TILE_BYTES, &tmap_q, p.q_col0 + h * p.q_head_cols + 64 * u, q0, b, B_QFULL);
       for (int j = 0; j < num_kvb; ++j) {
         const int st = j & 1;
         mbar_wait(B_KEMPTY0 + 8 * st, ((j >> 1) & 1) ^ 1u);
-        mbar_expect_tx(B_KFULL0 + 8 * st, TILE_BYTES);
-        tma_load_3d(sbase + SMEM_K + st * TILE_BYTES, &tmap_k, p.k_col0 + kvh * p.kv_head_cols, j * BKV, kb_coord,
-                    B_KFULL0 + 8 * st);
+        mbar_expect_tx(B_KFULL0 + 8 * st, ROW_BYTES);
+#pragma unroll
+        for (int u = 0; u < NSUB; ++u)
+          tma_load_3d(sbase + SMEM_K + st * ROW_BYTES + u * TILE_BYTES, &tmap_k, p.k_col0 + kvh * p.kv_head_cols + 64 * u,
+                      j * BKV, kb_coord, B_KFULL0 + 8 * st);
         mbar_wait(B_VEMPTY, (j & 1) ^ 1u);
-        mbar_expect_tx(B_VFULL, TILE_BYTES);
-        tma_load_3d(sbase + SMEM_V, &tmap_v, p.v_col0 + kvh * p.kv_head_cols, j * BKV, kb_coord, B_VFULL);
+        mbar_expect_tx(B_VFULL, ROW_BYTES);
+#pragma unroll
+        for (int u = 0; u < NSUB; ++u)
+          tma_load_3d(sbase + SMEM_V + u * TILE_BYTES, &tmap_v, p.v_col0 + kvh * p.kv_head_cols + 64 * u, j * BKV, kb_coord,
+                      B_VFULL);
       }
     }
   } else if (warp == 1) {
@@ -158,14 +177,17 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0, 0);  // Q, K both K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD, 0, 1);   // P K-major, V MN-major
       mbar_wait(B_QFULL, 0);
-      const uint64_t qdesc = umma_desc_sw128(sbase + SMEM_Q, 0, 1024);
       auto issue_s = [&](int j) {
         const int st = j & 1;
         mbar_wait(B_KFULL0 + 8 * st, (j >> 1) & 1);
         tc_fence_after();
-        const uint64_t kdesc = umma_desc_sw128(sbase + SMEM_K + st * TILE_BYTES, 0, 1024);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem + TM_S, qdesc + 2u * k, kdesc + 2u * k, idesc_s, k != 0);
+        for (int k = 0; k < HD / 16; ++k) {
+          // 64-wide sub-tile (k >> 2), 16-element step (k & 3) inside its 128B swizzle row
+          const uint64_t qdesc = umma_desc_sw128(sbase + SMEM_Q + (k >> 2) * TILE_BYTES, 0, 1024) + 2u * (k & 3);
+          const uint64_t kdesc = umma_desc_sw128(sbase + SMEM_K + st * ROW_BYTES + (k >> 2) * TILE_BYTES, 0, 1024) + 2u * (k & 3);
+          umma_bf16_ss(tmem + TM_S, qdesc, kdesc, idesc_s, k != 0);
+        }
         umma_commit(B_KEMPTY0 + 8 * st);
         umma_commit(B_SFULL);  // also covers every earlier MMA of this thread
       };
@@ -180,8 +202,9 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         mbar_wait(B_PFULL, j & 1);  // P(j) in smem, O rescaled
         mbar_wait(B_VFULL, j & 1);
         tc_fence_after();
-        // V tile: [kv rows][64 hd] 128B rows => MN-major B operand; 16 kv rows per MMA = 2048 B
-        const uint64_t vdesc = umma_desc_sw128(sbase + SMEM_V, 0, 1024);
+        // V tile: NSUB sub-tiles [kv rows][64 hd] of 128B rows => MN-major B operand (N = HD): LBO = stride
+        // between 64-wide N blocks (one sub-tile), SBO = 8 kv rows; 16 kv rows per MMA = 2048 B
+        const uint64_t vdesc = umma_desc_sw128(sbase + SMEM_V, TILE_BYTES, 1024);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           const uint64_t pdesc = umma_desc_sw128(sbase + SMEM_P + (k >> 2) * TILE_BYTES, 0, 1024) + 2u * (k & 3);
@@ -228,7 +251,7 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const bool any = __any_sync(0xffffffffu, alpha != 1.0f);
         if (any) {
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < HD / 32; ++c) {
             uint32_t o[32];
             tmem_ld_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
             tmem_ld_wait();
@@ -257,7 +280,7 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t rbase = sbase + SMEM_Q + (row >> 3) * 1024 + (row & 7) * 128;
     const uint32_t sw = row & 7;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < HD / 32; ++c) {
       uint32_t o[32];
       tmem_ld_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
       tmem_ld_wait();
@@ -267,7 +290,7 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           w[i] = pack_bf16x2(__uint_as_float(o[q * 8 + 2 * i]) * inv_l, __uint_as_float(o[q * 8 + 2 * i + 1]) * inv_l);
-        const uint32_t addr = rbase + ((static_cast<uint32_t>(c * 4 + q) ^ sw) << 4);
+        const uint32_t addr = rbase + (c >> 1) * TILE_BYTES + ((static_cast<uint32_t>((c & 1) * 4 + q) ^ sw) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
                      : "memory");
       }
@@ -275,10 +298,12 @@ attn_fwd_hd64_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     fence_proxy_async_smem();
     named_bar_sync(1, 128);
     if (warp == 2 && lane == 0) {
-      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                       reinterpret_cast<uint64_t>(&tmap_o)),
-                   "r"(sbase + SMEM_Q), "r"(p.o_col0 + h * p.q_head_cols), "r"(q0), "r"(b)
-                   : "memory");
+#pragma unroll
+      for (int u = 0; u < NSUB; ++u)
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(&tmap_o)),
+                     "r"(sbase + SMEM_Q + u * TILE_BYTES), "r"(p.o_col0 + h * p.q_head_cols + 64 * u), "r"(q0), "r"(b)
+                     : "memory");
       tma_store_commit();
       tma_store_wait<0>();
     }
@@ -302,8 +327,8 @@ extern "C" int gar_attn_fwd(const void* q, long long q_row_stride, long long q_b
                             int o_col0, int batch, int heads, int kv_heads, int head_dim, int q_len, int kv_len,
                             int kv_rows_alloc, int causal, float scale, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (head_dim != HD) {
-    gar_set_error("gar_attn_fwd: head_dim %d not built (this round: 64)", head_dim);
+  if (head_dim != 64 && head_dim != 128) {
+    gar_set_error("gar_attn_fwd: head_dim %d not built (64 and 128; pad 96 to 128)", head_dim);
     return GAR_ERR_SHAPE;
   }
   if (heads % kv_heads || q_len <= 0 || kv_len <= 0 || q_len > kv_len) return GAR_ERR_ARG;
@@ -335,12 +360,15 @@ extern "C" int gar_attn_fwd(const void* q, long long q_row_stride, long long q_b
   p.scale_log2 = scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
-    GAR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_hd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        ATT_SMEM_BYTES));
+    GAR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        AttCfg<64>::SMEM_BYTES));
+    GAR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        AttCfg<128>::SMEM_BYTES));
     attr_set = true;
   }
   dim3 grid((q_len + BQ - 1) / BQ, heads, batch);
-  attn_fwd_hd64_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  if (head_dim == 64) attn_fwd_kernel<64><<<grid, ATT_THREADS, AttCfg<64>::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  else attn_fwd_kernel<128><<<grid, ATT_THREADS, AttCfg<128>::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
   GAR_CUDA_CHECK(cudaGetLastError());
   return GAR_OK;
 }

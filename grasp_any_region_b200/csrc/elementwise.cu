@@ -59,7 +59,7 @@ __global__ void patchify_kernel(const bf16* __restrict__ px, const bf16* __restr
 // -------------------------------------------------------------------------------------
 // warp-per-row normalisation helpers
 // -------------------------------------------------------------------------------------
-constexpr int NORM_MAXV = 8;  // up to 8 x 16B per lane kept in registers (d <= 2048); larger d re-reads
+constexpr int NORM_MAXV = 16;  // up to 16 x 16B per lane kept in registers (d <= 4096)
 
 template <bool RMS>
 __device__ __forceinline__ void norm_row(const uint4* __restrict__ xin, const bf16* __restrict__ w,

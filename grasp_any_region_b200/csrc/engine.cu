@@ -26,7 +26,7 @@ struct gar_engine {
   std::map<std::string, const void*> w;
   std::vector<void*> allocs;
   // geometry
-  int grid, ntok, npt, hd_v, kpad, tpt, tokens_per_tile;
+  int grid, ntok, npt, hd_v, hdp_v, dq_v, kpad, tpt, tokens_per_tile;  // hdp_v: ViT head dim padded to 64/128
   // ViT workspaces
   bf16 *a_img, *a_mask, *pe, *x, *ln, *qkv_v, *att_v, *mlp_v, *p1, *p2, *feats;
   // LLM workspaces
@@ -272,9 +272,10 @@ extern "C" {
 int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   if (!desc || !out) return GAR_ERR_ARG;
   const gar_model_desc& d = *desc;
-  if (d.vit_dim % d.vit_heads || d.img_size % d.patch_size || d.vit_dim / d.vit_heads != 64 || d.llm_head_dim != 64) {
-    gar_set_error("gar_engine_create: this build supports head_dim 64 only (vit %d, llm %d)", d.vit_dim / d.vit_heads,
-                  d.llm_head_dim);
+  if (d.vit_dim % d.vit_heads || d.img_size % d.patch_size || d.vit_dim / d.vit_heads > 128 ||
+      (d.llm_head_dim != 64 && d.llm_head_dim != 128)) {
+    gar_set_error("gar_engine_create: unsupported head dims (vit %d <= 128 padded to 64/128, llm %d in {64,128})",
+                  d.vit_dim / d.vit_heads, d.llm_head_dim);
     return GAR_ERR_SHAPE;
   }
   int ndev = 0;
@@ -288,6 +289,8 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   e->npt = d.vit_use_cls ? 1 : 0;
   e->ntok = e->grid * e->grid + e->npt;
   e->hd_v = d.vit_dim / d.vit_heads;
+  e->hdp_v = e->hd_v <= 64 ? 64 : 128;  // qkv/proj weights arrive zero-padded per head when hd_v != hdp_v
+  e->dq_v = d.vit_heads * e->hdp_v;
   e->kpad = ((3 * d.patch_size * d.patch_size + 63) / 64) * 64;
   e->tpt = e->grid / d.pool_ratio;
   e->tokens_per_tile = e->tpt * e->tpt;
@@ -301,8 +304,8 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   rc |= dev_alloc(e, &e->pe, T * NP * dv);
   rc |= dev_alloc(e, &e->x, T * NT * dv);
   rc |= dev_alloc(e, &e->ln, T * NT * dv);
-  rc |= dev_alloc(e, &e->qkv_v, T * NT * 3 * dv);
-  rc |= dev_alloc(e, &e->att_v, T * NT * dv);
+  rc |= dev_alloc(e, &e->qkv_v, T * NT * 3 * e->dq_v);
+  rc |= dev_alloc(e, &e->att_v, T * NT * e->dq_v);
   rc |= dev_alloc(e, &e->mlp_v, T * NT * d.vit_mlp);
   rc |= dev_alloc(e, &e->p1, T * NT * D);
   rc |= dev_alloc(e, &e->p2, T * NT * D);
@@ -425,23 +428,24 @@ int gar_engine_vit_encode(gar_engine* e, const void* pixel_values, const void* m
     NEEDW(b2, L("vit", i, "fc2.b"));
     NEEDW(g2, L("vit", i, "g2"));
     TRY(gar_layernorm(e->x, dv, l1w, l1b, e->ln, dv, rows, dv, d.ln_eps, s));
+    const int dq = e->dq_v, hdp = e->hdp_v;
     if (e->fuse_rope) {
       e->launches += 1;
-      ProfScope ps(e, s, PK_GEMM, 2.0 * rows * 3.0 * dv * dv);
-      TRY(gar_gemm_bf16_rope2d(e->ln, dv, wqkv, dv, e->qkv_v, 3 * dv, rows, 3 * dv, dv, bqkv, rope, NT, e->npt, e->hd_v,
-                               2 * dv, s));
+      ProfScope ps(e, s, PK_GEMM, 2.0 * rows * 3.0 * dq * dv);
+      TRY(gar_gemm_bf16_rope2d(e->ln, dv, wqkv, dv, e->qkv_v, 3 * dq, rows, 3 * dq, dv, bqkv, rope, NT, e->npt, hdp,
+                               2 * dq, s));
     } else {
-      TRY(gemm(e, e->ln, dv, wqkv, dv, e->qkv_v, 3 * dv, rows, 3 * dv, dv, GAR_EPI_BIAS, bqkv, nullptr, nullptr, 0, s));
-      TRY(gar_vit_rope(e->qkv_v, rope, rows, NT, e->npt, d.vit_heads, e->hd_v, s));
+      TRY(gemm(e, e->ln, dv, wqkv, dv, e->qkv_v, 3 * dq, rows, 3 * dq, dv, GAR_EPI_BIAS, bqkv, nullptr, nullptr, 0, s));
+      TRY(gar_vit_rope(e->qkv_v, rope, rows, NT, e->npt, d.vit_heads, hdp, s));
       e->launches += 1;
     }
     {
-    ProfScope ps(e, s, PK_ATTN, 4.0 * T * static_cast<double>(NT) * NT * dv);
-    TRY(gar_attn_fwd(e->qkv_v, 3 * dv, static_cast<long long>(NT) * 3 * dv, 0, e->qkv_v, e->qkv_v, 3 * dv,
-                     static_cast<long long>(NT) * 3 * dv, T, dv, 2 * dv, e->hd_v, 1, 0, e->att_v, dv,
-                     static_cast<long long>(NT) * dv, 0, T, d.vit_heads, d.vit_heads, e->hd_v, NT, NT, NT, 0, scale, s));
+    ProfScope ps(e, s, PK_ATTN, 4.0 * T * static_cast<double>(NT) * NT * dq);
+    TRY(gar_attn_fwd(e->qkv_v, 3 * dq, static_cast<long long>(NT) * 3 * dq, 0, e->qkv_v, e->qkv_v, 3 * dq,
+                     static_cast<long long>(NT) * 3 * dq, T, dq, 2 * dq, hdp, 1, 0, e->att_v, dq,
+                     static_cast<long long>(NT) * dq, 0, T, d.vit_heads, d.vit_heads, hdp, NT, NT, NT, 0, scale, s));
     }
-    TRY(gemm(e, e->att_v, dv, wpr, dv, e->x, dv, rows, dv, dv, GAR_EPI_BIAS_LS_RES, bpr, g1, e->x, dv, s));
+    TRY(gemm(e, e->att_v, dq, wpr, dq, e->x, dv, rows, dv, dq, GAR_EPI_BIAS_LS_RES, bpr, g1, e->x, dv, s));
     TRY(gar_layernorm(e->x, dv, l2w, l2b, e->ln, dv, rows, dv, d.ln_eps, s));
     TRY(gemm(e, e->ln, dv, w1, dv, e->mlp_v, d.vit_mlp, rows, d.vit_mlp, dv, GAR_EPI_BIAS_GELU, b1, nullptr, nullptr, 0,
              s));

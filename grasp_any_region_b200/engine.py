@@ -103,14 +103,40 @@ class Engine:
         self._set("vit.pos", sd[VT + "pos_embed"].reshape(v.tokens, v.embed_dim))
         self._set("vit.norm_pre.w", sd[VT + "norm_pre.weight"])
         self._set("vit.norm_pre.b", sd[VT + "norm_pre.bias"])
-        self._set("vit.rope", vit_rope_table(v))
+        # Heads narrower than the attention kernel's tile (PE-G: 96) are zero-padded to 64/128 per head: padded q/k
+        # dims add 0 to every score, padded v dims give zero outputs that hit zero columns of proj.
+        hd, H, dv = v.head_dim, v.num_heads, v.embed_dim
+        hdp = 64 if hd <= 64 else 128
+
+        def pad_heads_rows(w):  # (3*H*hd, ...) -> (3*H*hdp, ...)
+            if hdp == hd:
+                return w
+            w = w.reshape(3, H, hd, *w.shape[1:])
+            out = torch.zeros((3, H, hdp, *w.shape[3:]), dtype=w.dtype, device=w.device)
+            out[:, :, :hd] = w
+            return out.reshape(3 * H * hdp, *w.shape[3:])
+
+        def pad_heads_cols(w):  # (dv, H*hd) -> (dv, H*hdp)
+            if hdp == hd:
+                return w
+            out = torch.zeros((w.shape[0], H, hdp), dtype=w.dtype, device=w.device)
+            out[:, :, :hd] = w.reshape(w.shape[0], H, hd)
+            return out.reshape(w.shape[0], H * hdp)
+
+        rope = vit_rope_table(v)  # (g*g, 2*hd) = cat(sin, cos)
+        if hdp != hd:
+            sin, cos = rope[:, :hd], rope[:, hd:]
+            rp = torch.zeros((rope.shape[0], 2 * hdp), dtype=rope.dtype)
+            rp[:, :hd], rp[:, hdp:hdp + hd] = sin, cos
+            rope = rp
+        self._set("vit.rope", rope)
         for i in range(v.depth):
             b = f"{VT}blocks.{i}."
             self._set(f"vit.{i}.ln1.w", sd[b + "norm1.weight"])
             self._set(f"vit.{i}.ln1.b", sd[b + "norm1.bias"])
-            self._set(f"vit.{i}.qkv.w", sd[b + "attn.qkv.weight"])
-            self._set(f"vit.{i}.qkv.b", sd[b + "attn.qkv.bias"])
-            self._set(f"vit.{i}.proj.w", sd[b + "attn.proj.weight"])
+            self._set(f"vit.{i}.qkv.w", pad_heads_rows(sd[b + "attn.qkv.weight"]))
+            self._set(f"vit.{i}.qkv.b", pad_heads_rows(sd[b + "attn.qkv.bias"]))
+            self._set(f"vit.{i}.proj.w", pad_heads_cols(sd[b + "attn.proj.weight"]))
             self._set(f"vit.{i}.proj.b", sd[b + "attn.proj.bias"])
             self._set(f"vit.{i}.g1", sd[b + "gamma_1"])
             self._set(f"vit.{i}.ln2.w", sd[b + "norm2.weight"])

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 if not torch.cuda.is_available():
     pytest.skip("needs a CUDA device", allow_module_level=True)
 
-from grasp_any_region_b200.config import gar_small, gar_tiny  # noqa: E402
+from grasp_any_region_b200.config import gar_8b_mini, gar_small, gar_tiny  # noqa: E402
 from grasp_any_region_b200.engine import Engine  # noqa: E402
 from grasp_any_region_b200.synth import make_request  # noqa: E402
 from oracle.gar_oracle import build_oracle  # noqa: E402
@@ -40,7 +40,7 @@ def _setup(spec, n_masks, seed, max_num_tiles=4, new_tokens=16, extra_seq=0):
     return oracle32, oracle16, eng, req
 
 
-@pytest.mark.parametrize("spec_fn,n_masks", [(gar_tiny, 1), (gar_small, 3)])
+@pytest.mark.parametrize("spec_fn,n_masks", [(gar_tiny, 1), (gar_small, 3), (gar_8b_mini, 2)])
 def test_engine_stage_parity(spec_fn, n_masks):
     spec = spec_fn()
     new_tokens = 12

@@ -279,9 +279,9 @@ def test_llama_rope_kv_and_swiglu_pool_argmax():
     assert nxt[2].item() == 5
 
 
+@pytest.mark.parametrize("hd", [64, 128])
 @pytest.mark.parametrize("T,ntok,heads", [(1, 128, 1), (2, 1025, 2), (1, 1024, 4), (3, 300, 2)])
-def test_attention_vit_layout(T, ntok, heads):
-    hd = 64
+def test_attention_vit_layout(T, ntok, heads, hd):
     qkv = rnd(T * ntok, 3 * heads * hd, seed=27)
     out = ops.attn_fwd_packed_qkv(qkv, T, ntok, heads, hd)
     torch.cuda.synchronize()
@@ -291,9 +291,10 @@ def test_attention_vit_layout(T, ntok, heads):
     assert err <= 2e-2, err
 
 
+@pytest.mark.parametrize("hd", [64, 128])
 @pytest.mark.parametrize("S", [64, 128, 333, 1000])
-def test_attention_causal_gqa_cache_layout(S):
-    hq, hkv, hd, max_seq = 8, 2, 64, 1024
+def test_attention_causal_gqa_cache_layout(S, hd):
+    hq, hkv, max_seq = 8, 2, 1024
     q = rnd(S, (hq + 2 * hkv) * hd, seed=28)
     kc = torch.zeros(hkv, max_seq, hd, dtype=bf, device=DEV)
     vc = torch.zeros_like(kc)
