@@ -60,6 +60,7 @@ SIGNATURES = {
     "gar_engine_prefill": (_i, [_vp, _i, _i, _vp]),
     "gar_engine_prefill_all_logits": (_i, [_vp, _i, _i, _vp, _vp]),
     "gar_engine_generate": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _vp]),
+    "gar_engine_generate_group": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_i), _vp]),
     "gar_engine_status": (_i, [_vp, _i, C.POINTER(_i)]),
     "gar_engine_launch_count": (_ll, [_vp]),
     "gar_engine_set_option": (_i, [_vp, C.c_char_p, _i]),

@@ -31,6 +31,9 @@ struct gar_engine {
   bf16 *a_img, *a_mask, *pe, *x, *ln, *qkv_v, *att_v, *mlp_v, *p1, *p2, *feats;
   // LLM workspaces
   bf16 *emb, *h, *lnl, *qkv_l, *att_l, *gu, *act, *logits, *kcache, *vcache, *hdec, *lndec;
+  // decode-private scratch: a decode group may run on its own stream while another group's ViT/prefill is in flight
+  bf16 *d_qkv, *d_att, *d_gu, *d_act;
+  int slot_base = 0;  // first KV slot of the group being decoded
   float *o_part, *ml_part, *argmax_ws;
   int *plan, *status, *next_tok, *out_tokens, *pos, *finished, *step, *tickets;
   long long* ids_scratch;
@@ -40,8 +43,8 @@ struct gar_engine {
   int use_gemv = 1;
   float *sumsq_a, *sumsq_b;
   // decode graph
-  cudaGraphExec_t graph_exec = nullptr;
-  int graph_batch = -1;
+  std::map<long long, cudaGraphExec_t> graphs;  // decode-step graphs keyed by (slot0, batch)
+  std::map<long long, int> graph_eos;
   long long launches = 0;
   int launches_per_step = 0;
   // optional per-kernel-class timing (CUDA events on the launching stream; bench.py roofline)
@@ -124,15 +127,21 @@ int llm_layers(gar_engine* e, bf16* h, bf16* ln, int rows, bool decode, int slot
     NEEDW(ln2, L("llm", i, "ln2"));
     NEEDW(wgu, L("llm", i, "gu.w"));
     NEEDW(wdown, L("llm", i, "down.w"));
-    bf16* kc = e->kcache + static_cast<size_t>(i) * d.max_batch * hkv * d.max_seq * hd;
-    bf16* vc = e->vcache + static_cast<size_t>(i) * d.max_batch * hkv * d.max_seq * hd;
+    const size_t slot_elems = static_cast<size_t>(hkv) * d.max_seq * hd;
+    bf16* kc = e->kcache + static_cast<size_t>(i) * d.max_batch * slot_elems + (decode ? e->slot_base * slot_elems : 0);
+    bf16* vc = e->vcache + static_cast<size_t>(i) * d.max_batch * slot_elems + (decode ? e->slot_base * slot_elems : 0);
+    bf16* b_qkv = decode ? e->d_qkv : e->qkv_l;
+    bf16* b_att = decode ? e->d_att : e->att_l;
+    bf16* b_gu = decode ? e->d_gu : e->gu;
+    bf16* b_act = decode ? e->d_act : e->act;
+    const int* b_pos = e->pos + e->slot_base;
     TRY(gar_rmsnorm(h, D, ln1, ln, D, rows, D, d.rms_eps, s));
-    TRY(gemm(e, ln, D, wqkv, D, e->qkv_l, qkv_w, rows, qkv_w, D, GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s));
+    TRY(gemm(e, ln, D, wqkv, D, b_qkv, qkv_w, rows, qkv_w, D, GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s));
     if (decode) {
       // decode: row b is sequence slot b, positions come from the device-side counters
-      TRY(gar_llama_rope_kv(e->qkv_l, rows, hq, hkv, hd, cos_t, sin_t, 0, e->pos, nullptr, -1, kc, vc, d.max_seq, s));
+      TRY(gar_llama_rope_kv(b_qkv, rows, hq, hkv, hd, cos_t, sin_t, 0, b_pos, nullptr, -1, kc, vc, d.max_seq, s));
     } else {
-      TRY(gar_llama_rope_kv(e->qkv_l, rows, hq, hkv, hd, cos_t, sin_t, 0, nullptr, nullptr, slot, kc, vc, d.max_seq, s));
+      TRY(gar_llama_rope_kv(b_qkv, rows, hq, hkv, hd, cos_t, sin_t, 0, nullptr, nullptr, slot, kc, vc, d.max_seq, s));
     }
     e->launches += 2;
     if (decode) {
@@ -142,29 +151,29 @@ int llm_layers(gar_engine* e, bf16* h, bf16* ln, int rows, bool decode, int slot
         splits = (3 * gar_num_sms()) / (rows * hkv);  // one resident wave of 3 CTAs per SM
         splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
       }
-      TRY(gar_decode_attn(e->qkv_l, qkv_w, kc, vc, e->pos, nullptr, rows, hq, hkv, hd, d.max_seq, splits, scale,
-                          e->o_part, e->ml_part, e->tickets, e->att_l, hq * hd, s));
+      TRY(gar_decode_attn(b_qkv, qkv_w, kc, vc, b_pos, nullptr, rows, hq, hkv, hd, d.max_seq, splits, scale,
+                          e->o_part, e->ml_part, e->tickets, b_att, hq * hd, s));
       e->launches += 2;
     } else {
       const bf16* kslot = kc + static_cast<size_t>(slot) * hkv * d.max_seq * hd;
       const bf16* vslot = vc + static_cast<size_t>(slot) * hkv * d.max_seq * hd;
       // causal: half of the 4*S*S*hd*heads MACs-as-flops
       ProfScope ps(e, s, PK_ATTN, 2.0 * rows * static_cast<double>(rows) * hd * hq);
-      TRY(gar_attn_fwd(e->qkv_l, qkv_w, static_cast<long long>(rows) * qkv_w, 0, kslot, vslot, hd,
-                       static_cast<long long>(d.max_seq) * hd, hkv, 0, 0, 0, 0, 1, e->att_l, hq * hd,
+      TRY(gar_attn_fwd(b_qkv, qkv_w, static_cast<long long>(rows) * qkv_w, 0, kslot, vslot, hd,
+                       static_cast<long long>(d.max_seq) * hd, hkv, 0, 0, 0, 0, 1, b_att, hq * hd,
                        static_cast<long long>(rows) * hq * hd, 0, 1, hq, hkv, hd, rows, rows, d.max_seq, 1, scale, s));
       e->launches += 1;
     }
-    TRY(gemm(e, e->att_l, hq * hd, wo, hq * hd, h, D, rows, D, hq * hd, GAR_EPI_RES, nullptr, nullptr, h, D, s));
+    TRY(gemm(e, b_att, hq * hd, wo, hq * hd, h, D, rows, D, hq * hd, GAR_EPI_RES, nullptr, nullptr, h, D, s));
     TRY(gar_rmsnorm(h, D, ln2, ln, D, rows, D, d.rms_eps, s));
     // "llm.{i}.gu.w" rows are interleaved [32 gate | 32 up]: prefill fuses SwiGLU into the GEMM epilogue
     if (!decode && rows > 16) {
-      TRY(gemm(e, ln, D, wgu, D, e->act, I, rows, 2 * I, D, GAR_EPI_SWIGLU, nullptr, nullptr, nullptr, 0, s));
+      TRY(gemm(e, ln, D, wgu, D, b_act, I, rows, 2 * I, D, GAR_EPI_SWIGLU, nullptr, nullptr, nullptr, 0, s));
     } else {
-      TRY(gemm(e, ln, D, wgu, D, e->gu, 2 * I, rows, 2 * I, D, GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s));
-      TRY(gar_swiglu(e->gu, e->act, rows, I, 1, s));
+      TRY(gemm(e, ln, D, wgu, D, b_gu, 2 * I, rows, 2 * I, D, GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s));
+      TRY(gar_swiglu(b_gu, b_act, rows, I, 1, s));
     }
-    TRY(gemm(e, e->act, I, wdown, I, h, D, rows, D, I, GAR_EPI_RES, nullptr, nullptr, h, D, s));
+    TRY(gemm(e, b_act, I, wdown, I, h, D, rows, D, I, GAR_EPI_RES, nullptr, nullptr, h, D, s));
     e->launches += 1;
   }
   return GAR_OK;
@@ -190,7 +199,7 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
   NEEDW(table, "llm.embed");
   NEEDW(cos_t, "llm.cos");
   NEEDW(sin_t, "llm.sin");
-  TRY(gar_embed_gather_sumsq(table, e->next_tok, e->hdec, e->sumsq_a, batch, D, s));
+  TRY(gar_embed_gather_sumsq(table, e->next_tok + e->slot_base, e->hdec, e->sumsq_a, batch, D, s));
   e->launches += 1;
   int n_part = 1, rows = 0;
   for (int i = 0; i < d.llm_layers; ++i) {
@@ -200,14 +209,15 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
     NEEDW(ln2, L("llm", i, "ln2"));
     NEEDW(wgu, L("llm", i, "gu.w"));
     NEEDW(wdown, L("llm", i, "down.w"));
-    bf16* kc = e->kcache + static_cast<size_t>(i) * d.max_batch * hkv * d.max_seq * hd;
-    bf16* vc = e->vcache + static_cast<size_t>(i) * d.max_batch * hkv * d.max_seq * hd;
+    const size_t slot_elems = static_cast<size_t>(hkv) * d.max_seq * hd;
+    bf16* kc = e->kcache + (static_cast<size_t>(i) * d.max_batch + e->slot_base) * slot_elems;
+    bf16* vc = e->vcache + (static_cast<size_t>(i) * d.max_batch + e->slot_base) * slot_elems;
     {
       ProfScope ps(e, s, PK_GEMV, 2.0 * qkv_w * static_cast<double>(D));
-      TRY(gar_gemv_decode(e->hdec, D, wqkv, D, e->qkv_l, qkv_w, batch, qkv_w, D, 0, nullptr, 0, ln1, e->sumsq_a, n_part,
+      TRY(gar_gemv_decode(e->hdec, D, wqkv, D, e->d_qkv, qkv_w, batch, qkv_w, D, 0, nullptr, 0, ln1, e->sumsq_a, n_part,
                           d.rms_eps, nullptr, nullptr, s));
     }
-    TRY(gar_llama_rope_kv(e->qkv_l, batch, hq, hkv, hd, cos_t, sin_t, 0, e->pos, nullptr, -1, kc, vc, d.max_seq, s));
+    TRY(gar_llama_rope_kv(e->d_qkv, batch, hq, hkv, hd, cos_t, sin_t, 0, e->pos + e->slot_base, nullptr, -1, kc, vc, d.max_seq, s));
     {
       ProfScope ps(e, s, PK_DECODE_ATTN, 0.0);
       int splits = e->dec_splits;
@@ -215,22 +225,22 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
         splits = (3 * gar_num_sms()) / (batch * hkv);  // one resident wave of 3 CTAs per SM
         splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
       }
-      TRY(gar_decode_attn(e->qkv_l, qkv_w, kc, vc, e->pos, nullptr, batch, hq, hkv, hd, d.max_seq, splits, scale,
-                          e->o_part, e->ml_part, e->tickets, e->att_l, hq * hd, s));
+      TRY(gar_decode_attn(e->d_qkv, qkv_w, kc, vc, e->pos + e->slot_base, nullptr, batch, hq, hkv, hd, d.max_seq, splits, scale,
+                          e->o_part, e->ml_part, e->tickets, e->d_att, hq * hd, s));
     }
     {
       ProfScope ps(e, s, PK_GEMV, 2.0 * D * static_cast<double>(hq * hd));
-      TRY(gar_gemv_decode(e->att_l, hq * hd, wo, hq * hd, e->hdec, D, batch, D, hq * hd, 1, e->hdec, D, nullptr, nullptr, 0,
+      TRY(gar_gemv_decode(e->d_att, hq * hd, wo, hq * hd, e->hdec, D, batch, D, hq * hd, 1, e->hdec, D, nullptr, nullptr, 0,
                           0.f, e->sumsq_b, &rows, s));
     }
     {
       ProfScope ps(e, s, PK_GEMV, 2.0 * 2.0 * I * D);
-      TRY(gar_gemv_decode(e->hdec, D, wgu, D, e->act, I, batch, 2 * I, D, 2, nullptr, 0, ln2, e->sumsq_b, D / rows,
+      TRY(gar_gemv_decode(e->hdec, D, wgu, D, e->d_act, I, batch, 2 * I, D, 2, nullptr, 0, ln2, e->sumsq_b, D / rows,
                           d.rms_eps, nullptr, nullptr, s));
     }
     {
       ProfScope ps(e, s, PK_GEMV, 2.0 * D * static_cast<double>(I));
-      TRY(gar_gemv_decode(e->act, I, wdown, I, e->hdec, D, batch, D, I, 1, e->hdec, D, nullptr, nullptr, 0, 0.f,
+      TRY(gar_gemv_decode(e->d_act, I, wdown, I, e->hdec, D, batch, D, I, 1, e->hdec, D, nullptr, nullptr, 0, 0.f,
                           e->sumsq_a, &rows, s));
     }
     n_part = D / rows;
@@ -240,11 +250,12 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
   NEEDW(wl, "llm.lm_head");
   {
     ProfScope ps(e, s, PK_GEMV, 2.0 * d.vocab_padded * static_cast<double>(D));
-    TRY(gar_gemv_decode(e->hdec, D, wl, D, e->logits, d.vocab_padded, batch, d.vocab_padded, D, 0, nullptr, 0, wn,
+    TRY(gar_gemv_decode(e->hdec, D, wl, D, e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded, batch, d.vocab_padded, D, 0, nullptr, 0, wn,
                         e->sumsq_a, n_part, d.rms_eps, nullptr, nullptr, s));
   }
-  TRY(gar_argmax_step(e->logits, d.vocab_padded, d.vocab, batch, e->next_tok, e->out_tokens, d.max_new_tokens, e->step,
-                      e->pos, e->finished, eos, 1, 1, e->argmax_ws, s));
+  TRY(gar_argmax_step(e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded, d.vocab, batch,
+                      e->next_tok + e->slot_base, e->out_tokens + static_cast<size_t>(e->slot_base) * d.max_new_tokens,
+                      d.max_new_tokens, e->step, e->pos + e->slot_base, e->finished + e->slot_base, eos, 1, 1, e->argmax_ws, s));
   e->launches += 3;
   return GAR_OK;
 }
@@ -255,12 +266,13 @@ int decode_step(gar_engine* e, int batch, int eos, void* s) {
       (d.llm_heads * d.llm_head_dim) % 256 == 0 && d.llm_inter % 32 == 0 && d.vocab_padded % 64 == 0)
     return decode_step_gemv(e, batch, eos, s);
   NEEDW(table, "llm.embed");
-  TRY(gar_embed_gather(table, nullptr, e->next_tok, e->hdec, batch, d.llm_dim, s));
+  TRY(gar_embed_gather(table, nullptr, e->next_tok + e->slot_base, e->hdec, batch, d.llm_dim, s));
   e->launches += 1;
   TRY(llm_layers(e, e->hdec, e->lndec, batch, true, 0, s));
-  TRY(lm_head(e, e->hdec, d.llm_dim, batch, e->logits, s));
-  TRY(gar_argmax_step(e->logits, d.vocab_padded, d.vocab, batch, e->next_tok, e->out_tokens, d.max_new_tokens, e->step,
-                      e->pos, e->finished, eos, 1, 1, e->argmax_ws, s));
+  TRY(lm_head(e, e->hdec, d.llm_dim, batch, e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, s));
+  TRY(gar_argmax_step(e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded, d.vocab, batch,
+                      e->next_tok + e->slot_base, e->out_tokens + static_cast<size_t>(e->slot_base) * d.max_new_tokens,
+                      d.max_new_tokens, e->step, e->pos + e->slot_base, e->finished + e->slot_base, eos, 1, 1, e->argmax_ws, s));
   e->launches += 2;
   return GAR_OK;
 }
@@ -314,6 +326,10 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   rc |= dev_alloc(e, &e->h, S * D);
   rc |= dev_alloc(e, &e->lnl, S * D);
   rc |= dev_alloc(e, &e->qkv_l, S * qkv_w);
+  rc |= dev_alloc(e, &e->d_qkv, B * qkv_w);
+  rc |= dev_alloc(e, &e->d_att, B * d.llm_heads * d.llm_head_dim);
+  rc |= dev_alloc(e, &e->d_gu, B * 2 * d.llm_inter);
+  rc |= dev_alloc(e, &e->d_act, B * d.llm_inter);
   rc |= dev_alloc(e, &e->att_l, S * d.llm_heads * d.llm_head_dim);
   rc |= dev_alloc(e, &e->gu, S * 2 * d.llm_inter);
   rc |= dev_alloc(e, &e->act, S * d.llm_inter);
@@ -347,7 +363,7 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
 
 int gar_engine_destroy(gar_engine* e) {
   if (!e) return GAR_OK;
-  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
   return GAR_OK;
@@ -523,20 +539,28 @@ int gar_engine_prefill_all_logits(gar_engine* e, int slot, int S, void* logits_o
               GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s);
 }
 
-int gar_engine_generate(gar_engine* e, int batch, int max_new_tokens, int eos, int* out_tokens_host, void* s_) {
+// Greedy decode of KV slots [slot0, slot0 + batch).  Only one decode runs at a time, but it may run on its own
+// stream while gar_engine_vit_encode / assemble / prefill for OTHER slots are in flight on another stream
+// (decode touches only decode-private scratch, its slots' KV / logits / counters, and the read-only weights).
+int gar_engine_generate_group(gar_engine* e, int slot0, int batch, int max_new_tokens, int eos, int* out_tokens_host,
+                              void* s_) {
   cudaStream_t s = static_cast<cudaStream_t>(s_);
-  if (!e || batch <= 0 || batch > e->d.max_batch || max_new_tokens <= 0 || max_new_tokens > e->d.max_new_tokens ||
-      !out_tokens_host) {
-    gar_set_error("gar_engine_generate: batch=%d max_new_tokens=%d outside capacity", batch, max_new_tokens);
+  if (!e || batch <= 0 || slot0 < 0 || slot0 + batch > e->d.max_batch || max_new_tokens <= 0 ||
+      max_new_tokens > e->d.max_new_tokens || !out_tokens_host) {
+    gar_set_error("gar_engine_generate: slot0=%d batch=%d max_new_tokens=%d outside capacity", slot0, batch,
+                  max_new_tokens);
     return GAR_ERR_ARG;
   }
   const gar_model_desc& d = e->d;
+  e->slot_base = slot0;
+  int* out_dev = e->out_tokens + static_cast<size_t>(slot0) * d.max_new_tokens;
   GAR_CUDA_CHECK(cudaMemsetAsync(e->step, 0, 2 * sizeof(int), s));
-  GAR_CUDA_CHECK(cudaMemsetAsync(e->finished, 0, sizeof(int) * batch, s));
-  GAR_CUDA_CHECK(cudaMemsetAsync(e->out_tokens, 0xff, sizeof(int) * d.max_batch * d.max_new_tokens, s));
+  GAR_CUDA_CHECK(cudaMemsetAsync(e->finished + slot0, 0, sizeof(int) * batch, s));
+  GAR_CUDA_CHECK(cudaMemsetAsync(out_dev, 0xff, sizeof(int) * batch * d.max_new_tokens, s));
   // token 0 from the prefill logits (position bookkeeping already at S per slot)
-  TRY(gar_argmax_step(e->logits, d.vocab_padded, d.vocab, batch, e->next_tok, e->out_tokens, d.max_new_tokens, e->step,
-                      e->pos, e->finished, eos, 0, 1, e->argmax_ws, s));
+  TRY(gar_argmax_step(e->logits + static_cast<size_t>(slot0) * d.vocab_padded, d.vocab_padded, d.vocab, batch,
+                      e->next_tok + slot0, out_dev, d.max_new_tokens, e->step, e->pos + slot0, e->finished + slot0, eos, 0,
+                      1, e->argmax_ws, s));
   e->launches += 2;
   const int steps = max_new_tokens - 1;
   if (steps > 0) {
@@ -547,13 +571,16 @@ int gar_engine_generate(gar_engine* e, int batch, int max_new_tokens, int eos, i
     if (steps > 1 && e->profiling) {
       for (int i = 1; i < steps; ++i) TRY(decode_step(e, batch, eos, s));
     } else if (steps > 1) {
-      if (e->graph_exec == nullptr || e->graph_batch != batch) {
+      const long long key = (static_cast<long long>(slot0) << 32) | (static_cast<long long>(batch) << 8) | (eos >= 0 ? 1 : 0);
+      auto it = e->graphs.find(key);
+      if (it == e->graphs.end() || e->graph_eos[key] != eos) {
         if (s == nullptr || s == cudaStreamLegacy) {
           gar_set_error("gar_engine_generate: needs a non-default stream (CUDA graph capture)");
           return GAR_ERR_ARG;
         }
-        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+        if (it != e->graphs.end()) cudaGraphExecDestroy(it->second);
         cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
         GAR_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         const long long keep = e->launches;
         int rc = decode_step(e, batch, eos, s);
@@ -561,22 +588,28 @@ int gar_engine_generate(gar_engine* e, int batch, int max_new_tokens, int eos, i
         cudaError_t ce = cudaStreamEndCapture(s, &graph);
         if (rc) return rc;
         GAR_CUDA_CHECK(ce);
-        GAR_CUDA_CHECK(cudaGraphInstantiate(&e->graph_exec, graph, 0));
+        GAR_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
         cudaGraphDestroy(graph);
-        e->graph_batch = batch;
+        e->graphs[key] = exec;
+        e->graph_eos[key] = eos;
+        it = e->graphs.find(key);
       }
       // EOS is latched on the device; sequences that finished keep stepping (outputs masked to -1)
-      for (int i = 1; i < steps; ++i) GAR_CUDA_CHECK(cudaGraphLaunch(e->graph_exec, s));
+      for (int i = 1; i < steps; ++i) GAR_CUDA_CHECK(cudaGraphLaunch(it->second, s));
       e->launches += static_cast<long long>(e->launches_per_step) * (steps - 1);
     }
   }
-  std::vector<int> tmp(static_cast<size_t>(d.max_batch) * d.max_new_tokens);
-  GAR_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), e->out_tokens, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+  std::vector<int> tmp(static_cast<size_t>(batch) * d.max_new_tokens);
+  GAR_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), out_dev, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
   GAR_CUDA_CHECK(cudaStreamSynchronize(s));
   for (int b = 0; b < batch; ++b)
     for (int t = 0; t < max_new_tokens; ++t)
       out_tokens_host[b * max_new_tokens + t] = tmp[static_cast<size_t>(b) * d.max_new_tokens + t];
   return GAR_OK;
+}
+
+int gar_engine_generate(gar_engine* e, int batch, int max_new_tokens, int eos, int* out_tokens_host, void* s) {
+  return gar_engine_generate_group(e, 0, batch, max_new_tokens, eos, out_tokens_host, s);
 }
 
 int gar_engine_status(gar_engine* e, int slot, int* status_bits) {
@@ -603,7 +636,8 @@ int gar_engine_set_option(gar_engine* e, const char* name, int value) {
     gar_set_error("gar_engine_set_option: unknown option '%s'=%d", name, value);
     return GAR_ERR_ARG;
   }
-  if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_batch = -1; }
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  e->graphs.clear();
   return GAR_OK;
 }
 

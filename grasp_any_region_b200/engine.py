@@ -77,6 +77,8 @@ class Engine:
         self._h = h
         self._keep: Dict[str, torch.Tensor] = {}
         self.stream = torch.cuda.Stream(device=self.device)
+        # decode of one request group may overlap the next group's ViT+prefill (see GARModel.generate_batches)
+        self.decode_stream = torch.cuda.Stream(device=self.device, priority=-1)
         self._load_weights(state_dict)
 
     # ------------------------------------------------------------------ weights
@@ -220,10 +222,13 @@ class Engine:
         self.assemble(slot, input_ids, T, bboxes, ncw, nch)
         self.prefill(slot, input_ids.numel())
 
-    def generate(self, batch: int, max_new_tokens: int, eos_token_id: Optional[int]) -> List[List[int]]:
+    def generate(self, batch: int, max_new_tokens: int, eos_token_id: Optional[int], slot0: int = 0,
+                 stream: Optional[torch.cuda.Stream] = None) -> List[List[int]]:
+        """Greedy decode of KV slots [slot0, slot0+batch); blocks until the tokens are on the host."""
         buf = (C.c_int * (batch * max_new_tokens))()
-        check(self.lib.gar_engine_generate(self._h, batch, max_new_tokens,
-                                           -1 if eos_token_id is None else int(eos_token_id), buf, self._s()),
+        s = C.c_void_p((stream or self.stream).cuda_stream)
+        check(self.lib.gar_engine_generate_group(self._h, slot0, batch, max_new_tokens,
+                                                 -1 if eos_token_id is None else int(eos_token_id), buf, s),
               "gar_engine_generate")
         out = []
         for b in range(batch):

@@ -242,6 +242,59 @@ class GARModel(_Base):
             self._raise_on_status(eng, slot)
         return toks
 
+    @torch.no_grad()
+    def generate_batches(self, batches: List[List[dict]], max_new_tokens: int = 128,
+                         eos_token_id: Optional[int] = None) -> List[List[List[int]]]:
+        """Throughput serving of a stream of request batches (B200 scheduler extension).
+
+        Two KV-slot groups ping-pong: while group g decodes on the engine's decode stream, the next batch's
+        ViT + assemble + prefill is enqueued (from a helper thread) on the main stream into group 1-g.  The
+        decode is a latency-bound weight stream and the encoder is tensor-bound, so they overlap well.  Every
+        request's result equals its batch-1 ``generate`` result."""
+        import threading
+
+        eng = self.engine()
+        if not batches:
+            return []
+        G = max(len(b) for b in batches)
+        if 2 * G > eng.max_batch:
+            raise ValueError(f"pipelining needs engine max_batch >= 2 x batch ({2 * G}), got {eng.max_batch}")
+        dev = eng.device
+
+        def stage(bi: int, group: int):
+            torch.cuda.set_device(dev)
+            for j, r in enumerate(batches[bi]):
+                self._stage_request(eng, group * G + j, r["pixel_values"], r.get("global_mask_values"),
+                                    r["aspect_ratios"], r["bboxes"], r["input_ids"])
+            ev = torch.cuda.Event()
+            ev.record(eng.stream)
+            return ev
+
+        out: List[List[List[int]]] = []
+        ev = stage(0, 0)
+        for i, batch in enumerate(batches):
+            g = i & 1
+            eng.decode_stream.wait_event(ev)
+            box, th = {}, None
+            if i + 1 < len(batches):
+                def work(bi=i + 1, grp=1 - g):
+                    try:
+                        box["ev"] = stage(bi, grp)
+                    except BaseException as ex:  # surfaced on the caller's thread
+                        box["err"] = ex
+                th = threading.Thread(target=work)
+                th.start()
+            toks = eng.generate(len(batch), int(max_new_tokens), eos_token_id, slot0=g * G, stream=eng.decode_stream)
+            if th is not None:
+                th.join()
+                if "err" in box:
+                    raise box["err"]
+                ev = box["ev"]
+            for j in range(len(batch)):
+                self._raise_on_status(eng, g * G + j)
+            out.append(toks)
+        return out
+
     def forward(self, data, data_samples=None, mode="loss"):
         """Teacher-forced LM loss, reference modeling_gar.py:74-246 (only mode="loss" exists there)."""
         if mode != "loss":

@@ -169,6 +169,10 @@ int gar_engine_prefill_all_logits(gar_engine* e, int slot, int S, void* logits_o
  * (CUDA-graph replay, no host sync inside).  out_tokens_host: batch x max_new_tokens int32 (-1 after EOS).
  * eos < 0 disables EOS. */
 int gar_engine_generate(gar_engine* e, int batch, int max_new_tokens, int eos, int* out_tokens_host, void* stream);
+/* same for KV slots [slot0, slot0+batch): lets one group decode on its own stream while another group's
+ * ViT/assemble/prefill runs on a second stream (pipelined serving; bench.py) */
+int gar_engine_generate_group(gar_engine* e, int slot0, int batch, int max_new_tokens, int eos, int* out_tokens_host,
+                              void* stream);
 int gar_engine_status(gar_engine* e, int slot, int* status_bits);
 long long gar_engine_launch_count(gar_engine* e);
 /* options: "skinny_gemm" (1 = decode GEMMs use gar_gemm_skinny_bf16, default 1), "decode_splits" */

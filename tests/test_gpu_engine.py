@@ -118,3 +118,25 @@ def test_engine_batched_decode_matches_single():
     print(singles, both)
     assert both[0] == singles[0] and both[1] == singles[1]
     eng.close()
+
+
+def test_pipelined_batches_match_sequential():
+    """generate_batches overlaps decode(i) with ViT+prefill(i+1) on two streams / KV-slot groups; every
+    request must still produce exactly its batch-1 tokens."""
+    from grasp_any_region_b200 import GARConfig, GARModel
+
+    spec = gar_small()
+    oracle = build_oracle(spec, seed=0, dtype=torch.float32)
+    sd = {k: v.to(bf) for k, v in oracle.state_dict().items()}
+    model = GARModel(GARConfig.from_spec(spec))
+    model.load_state_dict(sd)
+    model = model.to(DEV)
+    reqs = [make_request(spec, seed=40 + i, n_masks=1 + i % 3, max_num_tiles=4, dtype=bf) for i in range(5)]
+    S = max(r["input_ids"].shape[1] for r in reqs)
+    new_tokens = 9
+    model.configure_engine(max_tiles=5, max_seq=S + 32, max_batch=4, max_new_tokens=new_tokens)
+    singles = [model.generate_batch([r], max_new_tokens=new_tokens)[0] for r in reqs]
+    batches = [[reqs[0], reqs[1]], [reqs[2], reqs[3]], [reqs[4]], [reqs[1], reqs[0]]]
+    got = model.generate_batches(batches, max_new_tokens=new_tokens)
+    want = [[singles[0], singles[1]], [singles[2], singles[3]], [singles[4]], [singles[1], singles[0]]]
+    assert got == want
