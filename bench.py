@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel-class event timing step")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="overlap decode of batch i with ViT+prefill of batch i+1 (pays off only for many steps)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (pdl, skinny_gemm, decode_splits)")
     return ap.parse_args()
 
@@ -224,8 +226,11 @@ def main():
     d2h = B * NT * 4
 
     def run_steps(batch_list, steps):
-        """`steps` batches through the pipelined public API (decode of batch i overlaps ViT+prefill of i+1)."""
-        toks = model.generate_batches([batch_list] * steps, max_new_tokens=NT, eos_token_id=None)
+        """`steps` batches through the public API (GARModel.generate_batch; --pipeline: generate_batches)."""
+        if args.pipeline:
+            toks = model.generate_batches([batch_list] * steps, max_new_tokens=NT, eos_token_id=None)
+        else:
+            toks = [model.generate_batch(batch_list, max_new_tokens=NT, eos_token_id=None) for _ in range(steps)]
         if world > 1:  # the path's one collective: all-gather of the decoded ids (north_star)
             flat = [t + [-1] * (NT - len(t)) for step_toks in toks for t in step_toks]
             t = torch.tensor(flat, dtype=torch.int32, device=dev)
@@ -338,7 +343,7 @@ def main():
             "config": {"workload": workload_name(args), "requests_per_gpu_per_step": B, "tiles": T, "prompt_len": S,
                        "l2": "inputs+weights per step (3.2 GB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"dp{world} (independent requests per rank, one all-gather of token ids)",
-                       "pipeline": "decode of batch i on a second stream overlaps ViT+prefill of batch i+1 (two KV-slot groups); the timed region covers fill and drain"},
+                       "pipeline": bool(args.pipeline)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "stages": stages, "phases": phases,
             "cpu_baseline": cpu,
         }

@@ -47,6 +47,7 @@ struct AttnParams {
   int group;               // q heads per kv head
   int kv_batch_mul, kv_batch_head_mul;  // kv batch coordinate = b*kv_batch_mul + kvh*kv_batch_head_mul
   float scale_log2;
+  long long* timeline;  // optional debug: per-phase clock64 stamps of CTA (0,0,0), softmax warp 2 lane 0 and MMA lane
 };
 
 // Row-per-thread softmax pieces, specialised on whether the block needs masking so the common
@@ -221,9 +222,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const int q_pos = q0 + row + shift;  // last key this row may see (causal)
     float m_run = -INFINITY, l_run = 0.f;
+    const bool tl = p.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64;
     for (int j = 0; j < num_kvb; ++j) {
+      if (tl) p.timeline[j * 8 + 0] = clock64();
       mbar_wait(B_SFULL, j & 1);
       tc_fence_after();
+      if (tl) p.timeline[j * 8 + 1] = clock64();
       uint32_t s[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -231,6 +235,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tmem_ld_32x32b_x32(tmem + lane_addr + TM_S + c * 32, sc);
       }
       tmem_ld_wait();
+      if (tl) p.timeline[j * 8 + 2] = clock64();
       tc_fence_before();
       mbar_arrive(B_SCONS);  // S(j) is in registers: the MMA warp may overwrite TMEM S with S(j+1)
       const int kv0 = j * BKV;
@@ -244,10 +249,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const float m_new = bump ? m_cand : m_run;
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = bump ? ex2_approx(m_run - m_use) : 1.0f;
+      if (tl) p.timeline[j * 8 + 3] = clock64();
       // O and the P buffer are quiescent only once PV(j-1) has retired
       if (j > 0) {
         mbar_wait(B_PVDONE, (j - 1) & 1);
         tc_fence_after();
+        if (tl) p.timeline[j * 8 + 4] = clock64();
         const bool any = __any_sync(0xffffffffu, alpha != 1.0f);
         if (any) {
 #pragma unroll
@@ -269,9 +276,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                                  : exp_pack_store_128<false>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7);
       l_run = l_run * alpha + rs;
       m_run = m_new;
+      if (tl) p.timeline[j * 8 + 5] = clock64();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(B_PFULL);
+      if (tl) p.timeline[j * 8 + 6] = clock64();
     }
     // ---------------- finalize: O / l -> bf16 -> smem (reuse Q tile) -> TMA store ----------------
     mbar_wait(B_PVDONE, (num_kvb - 1) & 1);
@@ -318,6 +327,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
 }  // namespace
 
+static long long* g_attn_timeline = nullptr;
+// debug hook: device buffer of >= 8*num_kv_blocks int64 receiving clock64 stamps (NULL disables)
+extern "C" int gar_attn_debug_timeline(void* dev_buf) {
+  g_attn_timeline = static_cast<long long*>(dev_buf);
+  return GAR_OK;
+}
+
 // Generic strided description (all in bf16 elements):
 //   Q/O: [batch][q_len rows][row width], K/V: [kv_batches][kv rows][row width]
 extern "C" int gar_attn_fwd(const void* q, long long q_row_stride, long long q_batch_stride, int q_col0,
@@ -358,6 +374,7 @@ extern "C" int gar_attn_fwd(const void* q, long long q_row_stride, long long q_b
   p.kv_batch_mul = kv_batch_mul;
   p.kv_batch_head_mul = kv_batch_head_mul;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.timeline = g_attn_timeline;
   static bool attr_set = false;
   if (!attr_set) {
     GAR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,

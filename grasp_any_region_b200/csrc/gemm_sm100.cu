@@ -162,6 +162,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % num_m, n_blk = tile / num_m;
       const int gm = m_blk * BLOCK_M + row;
+      // residual rows are row-per-thread (strided) global loads: issue chunk c+1's while chunk c is processed,
+      // and chunk 0's before waiting for the accumulator, so their latency never sits on the epilogue path
+      uint4 rnext[4];
+      auto prefetch_res = [&](int c) {
+        if (EPI == EPI_BIAS_LS_RES || EPI == EPI_RES) {
+          const int gnp = n_blk * BLOCK_N + half * COLS_PER_HALF + c * C_CHUNK;
+          if (gm < M && gnp < N) {
+            const uint4* rp = reinterpret_cast<const uint4*>(ea.res + static_cast<size_t>(gm) * ea.ldres + gnp);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rnext[q] = rp[q];
+          }
+        }
+      };
+      prefetch_res(0);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -170,6 +184,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int gn = n_blk * BLOCK_N + col0;
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + col0, r);
+        uint4 rcur[4];
+        if (EPI == EPI_BIAS_LS_RES || EPI == EPI_RES) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
+          if (c + 1 < CHUNKS) prefetch_res(c + 1);
+        }
         tmem_ld_wait();
         if (c == CHUNKS - 1) {
           // all of this warp's TMEM reads for the tile are done -> release the accumulator stage
@@ -252,10 +272,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           if (EPI == EPI_BIAS_LS_RES || EPI == EPI_RES) {
             if (gm < M) {
-              const uint4* rp = reinterpret_cast<const uint4*>(ea.res + static_cast<size_t>(gm) * ea.ldres + gn);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const uint4 x = rp[q];
+                const uint4 x = rcur[q];
                 const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {

@@ -121,6 +121,8 @@ int gar_attn_fwd(const void* q, long long q_row_stride, long long q_batch_stride
                  int v_col0, int kv_head_cols, int kv_batch_mul, int kv_batch_head_mul, void* o, long long o_row_stride,
                  long long o_batch_stride, int o_col0, int batch, int heads, int kv_heads, int head_dim, int q_len,
                  int kv_len, int kv_rows_alloc, int causal, float scale, void* stream);
+/* debug: clock64 stamps of one CTA's softmax phases into dev_buf (int64[8*kv_blocks]); NULL disables */
+int gar_attn_debug_timeline(void* dev_buf);
 /* q_len = 1 attention over the KV cache, split-KV + combine (flash-attn 2 decode + DynamicCache) */
 /* tickets: batch*hkv zero-initialised ints -> the split kernel's last CTA combines (one launch); NULL -> separate combine */
 int gar_decode_attn(const void* qkv, int ldq, const void* kcache, const void* vcache, const int* pos_dev,
