@@ -18,25 +18,31 @@
 namespace {
 
 constexpr int BQ = 128;
-constexpr int BKV = 128;
 constexpr int ATT_THREADS = 192;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows of 128 B (one 64-wide, 128B-swizzled sub-tile)
-constexpr int TMEM_COLS_ATT = 256;        // S: 128 cols, O: HD cols (power-of-two allocation)
-constexpr uint32_t TM_S = 0, TM_O = 128;
+constexpr uint32_t TM_S = 0;
 
-// head_dim 64: 96 KB smem, two CTAs per SM.  head_dim 128 (GAR-8B Llama; PE-G's 96 is zero-padded to 128):
-// rows are 2 sub-tiles wide, 160 KB smem, one CTA per SM.
-template <int HD>
+// Tile configurations (BKV = keys per block):
+//   HD 64,  BKV 64 : 56 KB smem, 128 TMEM columns, three CTAs per SM -- the softmax is MUFU.EX2-bound, and a third
+//                    co-resident CTA keeps that pipe busy while the others wait on MMAs / barriers
+//   HD 64,  BKV 128: 96 KB smem, 256 TMEM columns, two CTAs per SM
+//   HD 128, BKV 128: 160 KB smem, one CTA per SM (GAR-8B Llama; PE-G's 96-wide heads are zero-padded to 128)
+template <int HD, int BKV>
 struct AttCfg {
   static constexpr int NSUB = HD / 64;
-  static constexpr int ROW_BYTES = NSUB * TILE_BYTES;  // a [128 x HD] operand tile
+  static constexpr int KV_TILE = BKV * 64 * 2;         // one 64-wide sub-tile of a K/V block
+  static constexpr int Q_BYTES = NSUB * TILE_BYTES;
+  static constexpr int KV_BYTES = NSUB * KV_TILE;
   static constexpr int SMEM_Q = 0;
-  static constexpr int SMEM_K = ROW_BYTES;                    // 2 stages
-  static constexpr int SMEM_V = SMEM_K + 2 * ROW_BYTES;       // 1 stage
-  static constexpr int SMEM_P = SMEM_V + ROW_BYTES;           // 2 sub-tiles [128 x 64]
-  static constexpr int SMEM_TOTAL = SMEM_P + 2 * TILE_BYTES;
+  static constexpr int SMEM_K = Q_BYTES;                      // 2 stages
+  static constexpr int SMEM_V = SMEM_K + 2 * KV_BYTES;        // 1 stage
+  static constexpr int SMEM_P = SMEM_V + KV_BYTES;            // BKV/64 sub-tiles [128 x 64]
+  static constexpr int SMEM_TOTAL = SMEM_P + (BKV / 64) * TILE_BYTES;
   static constexpr int SMEM_BYTES = SMEM_TOTAL + 1024;
-  static constexpr int CTAS_PER_SM = HD == 64 ? 2 : 1;
+  static constexpr int CTAS_PER_SM = HD == 64 ? (BKV == 64 ? 3 : 2) : 1;
+  static constexpr int MAXREG = CTAS_PER_SM == 3 ? 112 : (CTAS_PER_SM == 2 ? 168 : 255);  // 64K regs / (192 thr * CTAs)
+  static constexpr int TMEM_COLS = (BKV + HD) <= 128 ? 128 : 256;  // S: BKV columns, O: HD columns
+  static constexpr uint32_t TM_O = BKV;
 };
 
 struct AttnParams {
@@ -52,11 +58,11 @@ struct AttnParams {
 
 // Row-per-thread softmax pieces, specialised on whether the block needs masking so the common
 // (unmasked) path carries no compares and the score registers are never written back.
-template <bool MASKED>
-__device__ __forceinline__ float row_max_128(const uint32_t (&s)[128], int kv0, int lim) {
+template <bool MASKED, int NCOLS>
+__device__ __forceinline__ float row_max_n(const uint32_t (&s)[NCOLS], int kv0, int lim) {
   float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-  for (int i = 0; i < 128; i += 8) {
+  for (int i = 0; i < NCOLS; i += 8) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float a = __uint_as_float(s[i + 2 * q]), b = __uint_as_float(s[i + 2 * q + 1]);
@@ -70,12 +76,12 @@ __device__ __forceinline__ float row_max_128(const uint32_t (&s)[128], int kv0, 
   return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
 }
 
-template <bool MASKED>
-__device__ __forceinline__ float exp_pack_store_128(const uint32_t (&s)[128], int kv0, int lim, float scale_log2,
-                                                    float neg_m, uint32_t rbase, uint32_t sw) {
+template <bool MASKED, int NCOLS>
+__device__ __forceinline__ float exp_pack_store_n(const uint32_t (&s)[NCOLS], int kv0, int lim, float scale_log2,
+                                                  float neg_m, uint32_t rbase, uint32_t sw) {
   float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
+  for (int c = 0; c < NCOLS / 8; ++c) {
     uint32_t w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -95,14 +101,15 @@ __device__ __forceinline__ float exp_pack_store_128(const uint32_t (&s)[128], in
   return (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
 }
 
-template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS, AttCfg<HD>::CTAS_PER_SM)
+template <int HD, int BKV>
+__global__ void __launch_bounds__(ATT_THREADS) __maxnreg__((AttCfg<HD, BKV>::MAXREG))
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
                      AttnParams p) {
-  using Cfg = AttCfg<HD>;
+  using Cfg = AttCfg<HD, BKV>;
   constexpr int NSUB = Cfg::NSUB, SMEM_Q = Cfg::SMEM_Q, SMEM_K = Cfg::SMEM_K, SMEM_V = Cfg::SMEM_V, SMEM_P = Cfg::SMEM_P;
-  constexpr int ROW_BYTES = Cfg::ROW_BYTES;
+  constexpr int Q_BYTES = Cfg::Q_BYTES, KV_BYTES = Cfg::KV_BYTES, KV_TILE = Cfg::KV_TILE;
+  constexpr uint32_t TM_O = Cfg::TM_O;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[12];
   __shared__ uint32_t tmem_ptr_sh;
@@ -142,7 +149,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tma_prefetch_desc(&tmap_o);
   }
   if (warp == 0) {
-    tmem_alloc(smem_u32(&tmem_ptr_sh), TMEM_COLS_ATT);
+    tmem_alloc(smem_u32(&tmem_ptr_sh), Cfg::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -153,23 +160,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       const int kb_coord = b * p.kv_batch_mul + kvh * p.kv_batch_head_mul;
-      mbar_expect_tx(B_QFULL, ROW_BYTES);
+      mbar_expect_tx(B_QFULL, Q_BYTES);
 #pragma unroll
       for (int u = 0; u < NSUB; ++u)
         tma_load_3d(sbase + SMEM_Q + u * TILE_BYTES, &tmap_q, p.q_col0 + h * p.q_head_cols + 64 * u, q0, b, B_QFULL);
       for (int j = 0; j < num_kvb; ++j) {
         const int st = j & 1;
         mbar_wait(B_KEMPTY0 + 8 * st, ((j >> 1) & 1) ^ 1u);
-        mbar_expect_tx(B_KFULL0 + 8 * st, ROW_BYTES);
+        mbar_expect_tx(B_KFULL0 + 8 * st, KV_BYTES);
 #pragma unroll
         for (int u = 0; u < NSUB; ++u)
-          tma_load_3d(sbase + SMEM_K + st * ROW_BYTES + u * TILE_BYTES, &tmap_k, p.k_col0 + kvh * p.kv_head_cols + 64 * u,
+          tma_load_3d(sbase + SMEM_K + st * KV_BYTES + u * KV_TILE, &tmap_k, p.k_col0 + kvh * p.kv_head_cols + 64 * u,
                       j * BKV, kb_coord, B_KFULL0 + 8 * st);
         mbar_wait(B_VEMPTY, (j & 1) ^ 1u);
-        mbar_expect_tx(B_VFULL, ROW_BYTES);
+        mbar_expect_tx(B_VFULL, KV_BYTES);
 #pragma unroll
         for (int u = 0; u < NSUB; ++u)
-          tma_load_3d(sbase + SMEM_V + u * TILE_BYTES, &tmap_v, p.v_col0 + kvh * p.kv_head_cols + 64 * u, j * BKV, kb_coord,
+          tma_load_3d(sbase + SMEM_V + u * KV_TILE, &tmap_v, p.v_col0 + kvh * p.kv_head_cols + 64 * u, j * BKV, kb_coord,
                       B_VFULL);
       }
     }
@@ -186,7 +193,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int k = 0; k < HD / 16; ++k) {
           // 64-wide sub-tile (k >> 2), 16-element step (k & 3) inside its 128B swizzle row
           const uint64_t qdesc = umma_desc_sw128(sbase + SMEM_Q + (k >> 2) * TILE_BYTES, 0, 1024) + 2u * (k & 3);
-          const uint64_t kdesc = umma_desc_sw128(sbase + SMEM_K + st * ROW_BYTES + (k >> 2) * TILE_BYTES, 0, 1024) + 2u * (k & 3);
+          const uint64_t kdesc = umma_desc_sw128(sbase + SMEM_K + st * KV_BYTES + (k >> 2) * KV_TILE, 0, 1024) + 2u * (k & 3);
           umma_bf16_ss(tmem + TM_S, qdesc, kdesc, idesc_s, k != 0);
         }
         umma_commit(B_KEMPTY0 + 8 * st);
@@ -205,7 +212,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tc_fence_after();
         // V tile: NSUB sub-tiles [kv rows][64 hd] of 128B rows => MN-major B operand (N = HD): LBO = stride
         // between 64-wide N blocks (one sub-tile), SBO = 8 kv rows; 16 kv rows per MMA = 2048 B
-        const uint64_t vdesc = umma_desc_sw128(sbase + SMEM_V, TILE_BYTES, 1024);
+        const uint64_t vdesc = umma_desc_sw128(sbase + SMEM_V, KV_TILE, 1024);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           const uint64_t pdesc = umma_desc_sw128(sbase + SMEM_P + (k >> 2) * TILE_BYTES, 0, 1024) + 2u * (k & 3);
@@ -222,26 +229,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const int q_pos = q0 + row + shift;  // last key this row may see (causal)
     float m_run = -INFINITY, l_run = 0.f;
+#ifdef GAR_ATTN_TIMELINE  // debug build only: per-phase clock64 stamps of CTA (0,0,0), first softmax thread
     const bool tl = p.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64;
+#define TL_STAMP(i) if (tl) p.timeline[j * 8 + (i)] = clock64()
+#else
+#define TL_STAMP(i)
+#endif
     for (int j = 0; j < num_kvb; ++j) {
-      if (tl) p.timeline[j * 8 + 0] = clock64();
+      TL_STAMP(0);
       mbar_wait(B_SFULL, j & 1);
       tc_fence_after();
-      if (tl) p.timeline[j * 8 + 1] = clock64();
-      uint32_t s[128];
+      TL_STAMP(1);
+      uint32_t s[BKV];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < BKV / 32; ++c) {
         uint32_t(&sc)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
         tmem_ld_32x32b_x32(tmem + lane_addr + TM_S + c * 32, sc);
       }
       tmem_ld_wait();
-      if (tl) p.timeline[j * 8 + 2] = clock64();
+      TL_STAMP(2);
       tc_fence_before();
       mbar_arrive(B_SCONS);  // S(j) is in registers: the MMA warp may overwrite TMEM S with S(j+1)
       const int kv0 = j * BKV;
       const bool need_mask = (kv0 + BKV > p.kv_len) || (p.causal && kv0 + BKV - 1 > q0 + shift);
       const int lim = p.causal ? min(p.kv_len - 1, q_pos) : p.kv_len - 1;
-      const float mx = need_mask ? row_max_128<true>(s, kv0, lim) : row_max_128<false>(s, kv0, lim);
+      const float mx = need_mask ? row_max_n<true, BKV>(s, kv0, lim) : row_max_n<false, BKV>(s, kv0, lim);
       // Lazy rescale: keep exponentiating against the old reference max until the true max has grown by
       // more than 2^8; P then stays <= 256 (harmless in bf16/fp32) and most O rescales disappear.
       const float m_cand = fmaxf(m_run, mx * p.scale_log2);
@@ -249,12 +261,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const float m_new = bump ? m_cand : m_run;
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = bump ? ex2_approx(m_run - m_use) : 1.0f;
-      if (tl) p.timeline[j * 8 + 3] = clock64();
+      TL_STAMP(3);
       // O and the P buffer are quiescent only once PV(j-1) has retired
       if (j > 0) {
         mbar_wait(B_PVDONE, (j - 1) & 1);
         tc_fence_after();
-        if (tl) p.timeline[j * 8 + 4] = clock64();
+        TL_STAMP(4);
         const bool any = __any_sync(0xffffffffu, alpha != 1.0f);
         if (any) {
 #pragma unroll
@@ -272,15 +284,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // P = exp2(S*scale - m) -> bf16 -> smem, canonical K-major 128B-swizzled layout:
       // row r, 16B chunk c at r*128 + ((c ^ (r&7))<<4); two [128 x 64] sub-tiles
       const uint32_t p_rbase = sbase + SMEM_P + (row >> 3) * 1024 + (row & 7) * 128;
-      const float rs = need_mask ? exp_pack_store_128<true>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7)
-                                 : exp_pack_store_128<false>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7);
+      const float rs = need_mask ? exp_pack_store_n<true, BKV>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7)
+                                 : exp_pack_store_n<false, BKV>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7);
       l_run = l_run * alpha + rs;
       m_run = m_new;
-      if (tl) p.timeline[j * 8 + 5] = clock64();
+      TL_STAMP(5);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(B_PFULL);
-      if (tl) p.timeline[j * 8 + 6] = clock64();
+      TL_STAMP(6);
     }
     // ---------------- finalize: O / l -> bf16 -> smem (reuse Q tile) -> TMA store ----------------
     mbar_wait(B_PVDONE, (num_kvb - 1) & 1);
@@ -321,7 +333,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, TMEM_COLS_ATT);
+    tmem_dealloc(tmem, Cfg::TMEM_COLS);
   }
 }
 
@@ -336,6 +348,34 @@ extern "C" int gar_attn_debug_timeline(void* dev_buf) {
 
 // Generic strided description (all in bf16 elements):
 //   Q/O: [batch][q_len rows][row width], K/V: [kv_batches][kv rows][row width]
+template <int HD, int BKV>
+static int launch_attn(const void* q, long long q_row_stride, long long q_batch_stride, const void* k, const void* v,
+                       long long kv_row_stride, long long kv_batch_stride, int kv_batches, void* o,
+                       long long o_row_stride, long long o_batch_stride, int batch, int heads, int q_len,
+                       int kv_rows_alloc, const AttnParams& p, cudaStream_t stream) {
+  CUtensorMap tq, tk, tv, to;
+  int rc;
+  if ((rc = gar_make_tmap_3d(&tq, q, q_row_stride, q_len, batch, q_row_stride, q_batch_stride, 64, BQ, 1, GAR_SW_128))) return rc;
+  if ((rc = gar_make_tmap_3d(&tk, k, kv_row_stride, kv_rows_alloc, kv_batches, kv_row_stride, kv_batch_stride, 64, BKV, 1,
+                             GAR_SW_128)))
+    return rc;
+  if ((rc = gar_make_tmap_3d(&tv, v, kv_row_stride, kv_rows_alloc, kv_batches, kv_row_stride, kv_batch_stride, 64, BKV, 1,
+                             GAR_SW_128)))
+    return rc;
+  if ((rc = gar_make_tmap_3d(&to, o, o_row_stride, q_len, batch, o_row_stride, o_batch_stride, 64, BQ, 1, GAR_SW_128))) return rc;
+  using Cfg = AttCfg<HD, BKV>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GAR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<HD, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((q_len + BQ - 1) / BQ, heads, batch);
+  attn_fwd_kernel<HD, BKV><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  GAR_CUDA_CHECK(cudaGetLastError());
+  return GAR_OK;
+}
+
 extern "C" int gar_attn_fwd(const void* q, long long q_row_stride, long long q_batch_stride, int q_col0,
                             const void* k, const void* v, long long kv_row_stride, long long kv_batch_stride,
                             int kv_batches, int k_col0, int v_col0, int kv_head_cols, int kv_batch_mul,
@@ -348,18 +388,6 @@ extern "C" int gar_attn_fwd(const void* q, long long q_row_stride, long long q_b
     return GAR_ERR_SHAPE;
   }
   if (heads % kv_heads || q_len <= 0 || kv_len <= 0 || q_len > kv_len) return GAR_ERR_ARG;
-  CUtensorMap tq, tk, tv, to;
-  int rc;
-  const uint64_t qw = static_cast<uint64_t>(q_row_stride), kw = static_cast<uint64_t>(kv_row_stride),
-                 ow = static_cast<uint64_t>(o_row_stride);
-  if ((rc = gar_make_tmap_3d(&tq, q, qw, q_len, batch, q_row_stride, q_batch_stride, 64, BQ, 1, GAR_SW_128))) return rc;
-  if ((rc = gar_make_tmap_3d(&tk, k, kw, kv_rows_alloc, kv_batches, kv_row_stride, kv_batch_stride, 64, BKV, 1,
-                             GAR_SW_128)))
-    return rc;
-  if ((rc = gar_make_tmap_3d(&tv, v, kw, kv_rows_alloc, kv_batches, kv_row_stride, kv_batch_stride, 64, BKV, 1,
-                             GAR_SW_128)))
-    return rc;
-  if ((rc = gar_make_tmap_3d(&to, o, ow, q_len, batch, o_row_stride, o_batch_stride, 64, BQ, 1, GAR_SW_128))) return rc;
   AttnParams p;
   p.q_len = q_len;
   p.kv_len = kv_len;
@@ -375,17 +403,13 @@ extern "C" int gar_attn_fwd(const void* q, long long q_row_stride, long long q_b
   p.kv_batch_head_mul = kv_batch_head_mul;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.timeline = g_attn_timeline;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GAR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        AttCfg<64>::SMEM_BYTES));
-    GAR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        AttCfg<128>::SMEM_BYTES));
-    attr_set = true;
-  }
-  dim3 grid((q_len + BQ - 1) / BQ, heads, batch);
-  if (head_dim == 64) attn_fwd_kernel<64><<<grid, ATT_THREADS, AttCfg<64>::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
-  else attn_fwd_kernel<128><<<grid, ATT_THREADS, AttCfg<128>::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
-  GAR_CUDA_CHECK(cudaGetLastError());
+  if (head_dim == 128)
+    return launch_attn<128, 128>(q, q_row_stride, q_batch_stride, k, v, kv_row_stride, kv_batch_stride, kv_batches, o,
+                                 o_row_stride, o_batch_stride, batch, heads, q_len, kv_rows_alloc, p, stream);
+  if (gar_global_option("attn_bkv") == 128)
+    return launch_attn<64, 128>(q, q_row_stride, q_batch_stride, k, v, kv_row_stride, kv_batch_stride, kv_batches, o,
+                                o_row_stride, o_batch_stride, batch, heads, q_len, kv_rows_alloc, p, stream);
+  return launch_attn<64, 64>(q, q_row_stride, q_batch_stride, k, v, kv_row_stride, kv_batch_stride, kv_batches, o,
+                             o_row_stride, o_batch_stride, batch, heads, q_len, kv_rows_alloc, p, stream);
   return GAR_OK;
 }

@@ -279,9 +279,18 @@ def test_llama_rope_kv_and_swiglu_pool_argmax():
     assert nxt[2].item() == 5
 
 
+@pytest.fixture(params=[64, 128])
+def attn_bkv(request):
+    from grasp_any_region_b200 import _lib
+
+    _lib.check(_lib.load().gar_set_global_option(b"attn_bkv", request.param))
+    yield request.param
+    _lib.check(_lib.load().gar_set_global_option(b"attn_bkv", 64))
+
+
 @pytest.mark.parametrize("hd", [64, 128])
-@pytest.mark.parametrize("T,ntok,heads", [(1, 128, 1), (2, 1025, 2), (1, 1024, 4), (3, 300, 2)])
-def test_attention_vit_layout(T, ntok, heads, hd):
+@pytest.mark.parametrize("T,ntok,heads", [(1, 128, 1), (2, 1025, 2), (1, 1024, 4), (3, 300, 2), (1, 65, 1)])
+def test_attention_vit_layout(T, ntok, heads, hd, attn_bkv):
     qkv = rnd(T * ntok, 3 * heads * hd, seed=27)
     out = ops.attn_fwd_packed_qkv(qkv, T, ntok, heads, hd)
     torch.cuda.synchronize()
@@ -293,7 +302,7 @@ def test_attention_vit_layout(T, ntok, heads, hd):
 
 @pytest.mark.parametrize("hd", [64, 128])
 @pytest.mark.parametrize("S", [64, 128, 333, 1000])
-def test_attention_causal_gqa_cache_layout(S, hd):
+def test_attention_causal_gqa_cache_layout(S, hd, attn_bkv):
     hq, hkv, max_seq = 8, 2, 1024
     q = rnd(S, (hq + 2 * hkv) * hd, seed=28)
     kc = torch.zeros(hkv, max_seq, hd, dtype=bf, device=DEV)

@@ -23,15 +23,20 @@ def timeit(name, fn, work=None, unit="TFLOP/s"):
     print(f"{name:40s} {ms * 1e3:9.1f} us{extra}", flush=True)
 
 
-if which in ("all", "attn_vit"):
-    T, ntok, H, hd = 17, 1025, 16, 64
-    qkv = torch.randn(T * ntok, 3 * H * hd, device=dev).to(bf)
-    timeit("attn vit T=17 N=1025 H=16", lambda: ops.attn_fwd_packed_qkv(qkv, T, ntok, H, hd), 4.0 * T * ntok * ntok * H * hd)
-if which in ("all", "attn_causal"):
-    S, hq, hkv, hd, ms_ = 4672, 32, 8, 64, 4864
-    q = torch.randn(S, (hq + 2 * hkv) * hd, device=dev).to(bf)
-    kc = torch.randn(hkv, ms_, hd, device=dev).to(bf); vc = torch.randn(hkv, ms_, hd, device=dev).to(bf)
-    timeit("attn causal S=4672 32/8 heads", lambda: ops.attn_fwd_cache(q, q.stride(0), kc, vc, hq, hkv, hd, S, ms_), 2.0 * S * S * hq * hd)
+if which in ("all", "attn_vit", "attn_causal"):
+    from grasp_any_region_b200 import _lib as _l
+    for bkv in (64, 128):
+        _l.load().gar_set_global_option(b"attn_bkv", bkv)
+        if which in ("all", "attn_vit"):
+            T, ntok, H, hd = 17, 1025, 16, 64
+            qkv = torch.randn(T * ntok, 3 * H * hd, device=dev).to(bf)
+            timeit(f"attn vit T=17 N=1025 H=16 bkv={bkv}", lambda: ops.attn_fwd_packed_qkv(qkv, T, ntok, H, hd), 4.0 * T * ntok * ntok * H * hd)
+        if which in ("all", "attn_causal"):
+            S, hq, hkv, hd, ms_ = 4672, 32, 8, 64, 4864
+            q = torch.randn(S, (hq + 2 * hkv) * hd, device=dev).to(bf)
+            kc = torch.randn(hkv, ms_, hd, device=dev).to(bf); vc = torch.randn(hkv, ms_, hd, device=dev).to(bf)
+            timeit(f"attn causal S=4672 32/8 heads bkv={bkv}", lambda: ops.attn_fwd_cache(q, q.stride(0), kc, vc, hq, hkv, hd, S, ms_), 2.0 * S * S * hq * hd)
+    _l.load().gar_set_global_option(b"attn_bkv", 64)
 if which in ("all", "decode_attn"):
     B, hq, hkv, hd, ms_ = 8, 32, 8, 64, 4864
     qkv = torch.randn(B, (hq + 2 * hkv) * hd, device=dev).to(bf)
