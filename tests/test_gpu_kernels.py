@@ -285,7 +285,7 @@ def attn_bkv(request):
 
     _lib.check(_lib.load().gar_set_global_option(b"attn_bkv", request.param))
     yield request.param
-    _lib.check(_lib.load().gar_set_global_option(b"attn_bkv", 64))
+    _lib.check(_lib.load().gar_set_global_option(b"attn_bkv", 128))
 
 
 @pytest.mark.parametrize("hd", [64, 128])

@@ -36,7 +36,7 @@ if which in ("all", "attn_vit", "attn_causal"):
             q = torch.randn(S, (hq + 2 * hkv) * hd, device=dev).to(bf)
             kc = torch.randn(hkv, ms_, hd, device=dev).to(bf); vc = torch.randn(hkv, ms_, hd, device=dev).to(bf)
             timeit(f"attn causal S=4672 32/8 heads bkv={bkv}", lambda: ops.attn_fwd_cache(q, q.stride(0), kc, vc, hq, hkv, hd, S, ms_), 2.0 * S * S * hq * hd)
-    _l.load().gar_set_global_option(b"attn_bkv", 64)
+    _l.load().gar_set_global_option(b"attn_bkv", 128)
 if which in ("all", "decode_attn"):
     B, hq, hkv, hd, ms_ = 8, 32, 8, 64, 4864
     qkv = torch.randn(B, (hq + 2 * hkv) * hd, device=dev).to(bf)
