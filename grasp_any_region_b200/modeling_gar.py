@@ -111,6 +111,8 @@ class GARModel(_Base):
             self.load_state_dict(sd, strict=False)
         self._engine: Optional[Engine] = None
         self._engine_caps = dict(max_tiles=37, max_seq=12288, max_batch=8, max_new_tokens=1024)
+        if _HAS_HF and hasattr(self, "post_init"):
+            self.post_init()
 
     # ------------------------------------------------------------------ reference surface
     @property

@@ -100,3 +100,20 @@ def test_roi_box_host_arithmetic_matches_oracle():
     for k in (0, 3):
         want, s = roi_box_f32(boxes[str(spec.crop_tokens_ids[k])], 64, 64)
         assert rois[k] == want.tolist() and s == scale
+
+
+def test_checkpoint_round_trip_keeps_reference_key_layout(tmp_path):
+    """N2: save_pretrained / from_pretrained with the reference's HF state-dict names
+    (mllm.model.vision_tower.timm_model.*, ...language_model.*, mllm.lm_head, mask_patch_embedding)."""
+    from grasp_any_region_b200 import GARModel
+    from oracle.gar_oracle import build_oracle
+
+    spec = gar_tiny()
+    m = GARModel(GARConfig.from_spec(spec)).random_init_(3)
+    assert set(m.state_dict()) == set(build_oracle(spec).state_dict())
+    m.save_pretrained(tmp_path)
+    m2 = GARModel.from_pretrained(tmp_path, torch_dtype=torch.bfloat16)
+    a, b = m.state_dict(), m2.state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert m2.config.prompt_numbers == 5 and m2.crop_tokens_ids == spec.crop_tokens_ids
+    assert m2.lm_head.weight.shape == (spec.text.vocab_size, spec.text.hidden_size)

@@ -140,3 +140,42 @@ def test_pipelined_batches_match_sequential():
     got = model.generate_batches(batches, max_new_tokens=new_tokens)
     want = [[singles[0], singles[1]], [singles[2], singles[3]], [singles[4]], [singles[1], singles[0]]]
     assert got == want
+
+
+def test_forward_loss_matches_oracle():
+    """R10: GARModel.forward(data, mode="loss") -- teacher-forced LM loss over the assembled sequence
+    (reference modeling_gar.py:74-246; replayed rows carry label -100)."""
+    from grasp_any_region_b200 import GARConfig, GARModel
+
+    spec = gar_small()
+    oracle = build_oracle(spec, seed=0, dtype=torch.float32)
+    sd = {k: v.to(bf) for k, v in oracle.state_dict().items()}
+    oracle.load_state_dict({k: v.float() for k, v in sd.items()})
+    oracle = oracle.to(DEV)
+    model = GARModel(GARConfig.from_spec(spec))
+    model.load_state_dict(sd)
+    model = model.to(DEV)
+    req = make_request(spec, seed=77, n_masks=2, max_num_tiles=4, dtype=bf, device=DEV)
+    ids = req["input_ids"]
+    S = ids.shape[1]
+    labels = ids.clone()
+    labels[ids == spec.image_token_id] = -100
+    labels[:, :8] = -100
+    model.configure_engine(max_tiles=5, max_seq=S + 16, max_batch=1, max_new_tokens=4)
+    data = dict(req, labels=labels)
+    loss = model.forward(data, mode="loss")["loss"].item()
+    taps = oracle.prefill_embeds(req["pixel_values"].float(), req["global_mask_values"], req["aspect_ratios"],
+                                 req["bboxes"], ids)
+    lm = oracle.mllm.model.language_model
+    h = lm(taps["inputs_embeds"], torch.arange(S, device=DEV), None)
+    logits = oracle.mllm.lm_head(h)[0]
+    lab = labels[0].clone()
+    for c in spec.crop_tokens_ids:
+        lab[ids[0] == c] = -100
+    ref = torch.nn.functional.cross_entropy(logits[:-1].float(), lab[1:], ignore_index=-100).item()
+    print(f"loss ours={loss:.5f} oracle_fp32={ref:.5f}")
+    assert abs(loss - ref) <= 2e-2 * max(1.0, abs(ref))
+    with pytest.raises(AssertionError):
+        model.forward(dict(data, input_ids=torch.cat([ids, ids], 0)), mode="loss")
+    with pytest.raises(UnboundLocalError):
+        model.forward(data, mode="predict")
