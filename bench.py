@@ -188,12 +188,19 @@ def main():
     dev = f"cuda:{local_rank}"
     dist = None
     if world > 1:
+        import datetime
+
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        # short collective timeout: a rank that dies or wedges must fail the run in minutes, not hang it
+        dist.init_process_group("nccl", device_id=torch.device(dev), timeout=datetime.timedelta(seconds=240))
 
     from grasp_any_region_b200 import GARConfig, GARModel
     from grasp_any_region_b200.synth import make_request
+
+    def note(msg):
+        if os.environ.get("GAR_BENCH_VERBOSE") or world > 1:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
 
     peaks = load_peaks()
     B, NT = args.batch, args.new_tokens
@@ -202,8 +209,11 @@ def main():
                               dtype=torch.bfloat16) for i in range(B)]
     S = max(r["input_ids"].shape[1] for r in reqs_host)
     T = reqs_host[0]["pixel_values"].shape[0]
-    model.configure_engine(max_tiles=T, max_seq=((S + NT + 127) // 128) * 128, max_batch=2 * B, max_new_tokens=NT)
+    model.configure_engine(max_tiles=B * T, max_seq=((S + NT + 127) // 128) * 128, max_batch=2 * B if args.pipeline else B,
+                           max_new_tokens=NT, max_prefill_rows=B * S)
+    note("model initialised")
     eng = model.engine()
+    note("engine ready")
     for kv in args.opt:
         k, v = kv.split("=")
         eng.set_option(k, int(v))
@@ -265,12 +275,14 @@ def main():
         return ms.item()
 
     step_resident(max(args.warmup, 2))  # >= 2 so both KV-slot groups capture their decode graph
+    note("warm-up done")
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = eng.launch_count()
     ms = timed(step_resident, args.steps)
     launches = eng.launch_count() - l0
     clocks = sampler.stop()
+    note(f"timed region done: {ms:.1f} ms")
     value = world * B * args.steps / (ms / 1e3)
 
     e2e = None
@@ -286,10 +298,11 @@ def main():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         torch.cuda.synchronize()
         ev[0].record(eng.stream)
-        with torch.cuda.stream(eng.stream):
-            for slot, r in enumerate(reqs_dev):
-                eng.request(slot, r["pixel_values"], r["global_mask_values"], r["input_ids"][0], r["bboxes"][0],
-                            r["aspect_ratios"][0].tolist())
+        if not model._stage_requests_batched(eng, 0, reqs_dev):
+            with torch.cuda.stream(eng.stream):
+                for slot, r in enumerate(reqs_dev):
+                    eng.request(slot, r["pixel_values"], r["global_mask_values"], r["input_ids"][0], r["bboxes"][0],
+                                r["aspect_ratios"][0].tolist())
         ev[1].record(eng.stream)
         eng.generate(B, NT, None)
         ev[2].record(eng.stream)
@@ -343,7 +356,8 @@ def main():
             "config": {"workload": workload_name(args), "requests_per_gpu_per_step": B, "tiles": T, "prompt_len": S,
                        "l2": "inputs+weights per step (3.2 GB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"dp{world} (independent requests per rank, one all-gather of token ids)",
-                       "pipeline": bool(args.pipeline)},
+                       "pipeline": bool(args.pipeline),
+                       "encode": "the B requests of a step share one ViT pass and one prefill pass (equal shapes); decode batched"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "stages": stages, "phases": phases,
             "cpu_baseline": cpu,
         }

@@ -19,7 +19,7 @@ class GarModelDesc(C.Structure):
         ("llm_dim", _i), ("llm_layers", _i), ("llm_heads", _i), ("llm_kv_heads", _i), ("llm_head_dim", _i),
         ("llm_inter", _i), ("vocab", _i), ("vocab_padded", _i), ("rms_eps", _f),
         ("prompt_numbers", _i), ("image_token_id", _ll), ("crop_token_ids", _ll * 8),
-        ("max_tiles", _i), ("max_seq", _i), ("max_batch", _i), ("max_new_tokens", _i),
+        ("max_tiles", _i), ("max_seq", _i), ("max_batch", _i), ("max_new_tokens", _i), ("max_prefill_rows", _i),
     ]
 
 
@@ -40,7 +40,7 @@ SIGNATURES = {
     "gar_layernorm": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "gar_rmsnorm": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _f, _vp]),
     "gar_vit_rope": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "gar_llama_rope_kv": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "gar_llama_rope_kv": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "gar_swiglu": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "gar_pool2x2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gar_embed_gather": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
@@ -59,6 +59,8 @@ SIGNATURES = {
     "gar_engine_vit_encode": (_i, [_vp, _vp, _vp, _i, _vp]),
     "gar_engine_assemble": (_i, [_vp, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_i), _f, _i, _i, _vp]),
     "gar_engine_prefill": (_i, [_vp, _i, _i, _vp]),
+    "gar_engine_assemble_at": (_i, [_vp, _i, _vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_i), _f, _i, _i, _vp]),
+    "gar_engine_prefill_batch": (_i, [_vp, _i, _i, _i, _vp]),
     "gar_engine_prefill_all_logits": (_i, [_vp, _i, _i, _vp, _vp]),
     "gar_engine_generate": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _vp]),
     "gar_engine_generate_group": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_i), _vp]),

@@ -222,7 +222,7 @@ __global__ void vit_rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__
 __global__ void llama_rope_kv_kernel(bf16* __restrict__ qkv, int rows, int hq, int hkv, int hd,
                                      const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t, int pos0,
                                      const int* __restrict__ pos_dev, const int* __restrict__ slot_dev, int slot0,
-                                     bf16* __restrict__ kcache, bf16* __restrict__ vcache, int max_seq) {
+                                     bf16* __restrict__ kcache, bf16* __restrict__ vcache, int max_seq, int seq_len) {
   pdl_launch_dependents();
   pdl_wait();
   const int half = hd / 2;
@@ -236,8 +236,10 @@ __global__ void llama_rope_kv_kernel(bf16* __restrict__ qkv, int rows, int hq, i
     long long r = i / vec_per_head;
     const int head = static_cast<int>(r % heads_total);
     const int row = static_cast<int>(r / heads_total);
-    const int pos = pos_dev ? pos_dev[row] : pos0 + row;
-    const int slot = slot_dev ? slot_dev[row] : (slot0 >= 0 ? slot0 : row);  // slot0 < 0: row b -> slot b
+    // seq_len > 0: rows are nreq back-to-back sequences of seq_len positions in consecutive slots (batched prefill)
+    const int pos = pos_dev ? pos_dev[row] : pos0 + (seq_len > 0 ? row % seq_len : row);
+    const int slot = slot_dev ? slot_dev[row]
+                              : (slot0 >= 0 ? slot0 + (seq_len > 0 ? row / seq_len : 0) : row);  // slot0 < 0: row b -> slot b
     bf16* base = qkv + static_cast<size_t>(row) * ld + static_cast<size_t>(head) * hd + v * 8;
     uint4 lo = *reinterpret_cast<const uint4*>(base);
     uint4 hi = *reinterpret_cast<const uint4*>(base + half);
@@ -530,13 +532,13 @@ int gar_vit_rope(void* qkv, const void* rope, int rows, int ntok, int npt, int h
 
 int gar_llama_rope_kv(void* qkv, int rows, int hq, int hkv, int hd, const void* cos_t, const void* sin_t, int pos0,
                       const int* pos_dev, const int* slot_dev, int slot0, void* kcache, void* vcache, int max_seq,
-                      void* stream) {
+                      int seq_len, void* stream) {
   if (hd % 16) return GAR_ERR_SHAPE;
   const long long total = static_cast<long long>(rows) * (hq + 2 * hkv) * (hd / 16);
   GAR_CUDA_CHECK(gar_launch(llama_rope_kv_kernel, dim3(grid_for(total, 256)), dim3(256), 0,
                             static_cast<cudaStream_t>(stream), true, dim3(1, 1, 1), static_cast<bf16*>(qkv), rows, hq,
                             hkv, hd, static_cast<const bf16*>(cos_t), static_cast<const bf16*>(sin_t), pos0, pos_dev,
-                            slot_dev, slot0, static_cast<bf16*>(kcache), static_cast<bf16*>(vcache), max_seq));
+                            slot_dev, slot0, static_cast<bf16*>(kcache), static_cast<bf16*>(vcache), max_seq, seq_len));
   return GAR_OK;
 }
 

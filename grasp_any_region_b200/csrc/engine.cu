@@ -113,7 +113,7 @@ int gemm(gar_engine* e, const void* A, int lda, const void* B, int ldb, void* C,
 }
 
 // one Llama layer stack over `rows` rows of e->h (prefill: rows = S, one slot; decode: rows = batch)
-int llm_layers(gar_engine* e, bf16* h, bf16* ln, int rows, bool decode, int slot, void* s) {
+int llm_layers(gar_engine* e, bf16* h, bf16* ln, int rows, bool decode, int slot, void* s, int nreq = 1) {
   const gar_model_desc& d = e->d;
   const int D = d.llm_dim, hq = d.llm_heads, hkv = d.llm_kv_heads, hd = d.llm_head_dim, I = d.llm_inter;
   const int qkv_w = (hq + 2 * hkv) * hd;
@@ -139,9 +139,10 @@ int llm_layers(gar_engine* e, bf16* h, bf16* ln, int rows, bool decode, int slot
     TRY(gemm(e, ln, D, wqkv, D, b_qkv, qkv_w, rows, qkv_w, D, GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s));
     if (decode) {
       // decode: row b is sequence slot b, positions come from the device-side counters
-      TRY(gar_llama_rope_kv(b_qkv, rows, hq, hkv, hd, cos_t, sin_t, 0, b_pos, nullptr, -1, kc, vc, d.max_seq, s));
+      TRY(gar_llama_rope_kv(b_qkv, rows, hq, hkv, hd, cos_t, sin_t, 0, b_pos, nullptr, -1, kc, vc, d.max_seq, 0, s));
     } else {
-      TRY(gar_llama_rope_kv(b_qkv, rows, hq, hkv, hd, cos_t, sin_t, 0, nullptr, nullptr, slot, kc, vc, d.max_seq, s));
+      TRY(gar_llama_rope_kv(b_qkv, rows, hq, hkv, hd, cos_t, sin_t, 0, nullptr, nullptr, slot, kc, vc, d.max_seq,
+                            nreq > 1 ? rows / nreq : 0, s));
     }
     e->launches += 2;
     if (decode) {
@@ -157,11 +158,12 @@ int llm_layers(gar_engine* e, bf16* h, bf16* ln, int rows, bool decode, int slot
     } else {
       const bf16* kslot = kc + static_cast<size_t>(slot) * hkv * d.max_seq * hd;
       const bf16* vslot = vc + static_cast<size_t>(slot) * hkv * d.max_seq * hd;
+      const int sl = rows / nreq;  // per-request sequence length; requests occupy consecutive slots
       // causal: half of the 4*S*S*hd*heads MACs-as-flops
-      ProfScope ps(e, s, PK_ATTN, 2.0 * rows * static_cast<double>(rows) * hd * hq);
-      TRY(gar_attn_fwd(b_qkv, qkv_w, static_cast<long long>(rows) * qkv_w, 0, kslot, vslot, hd,
-                       static_cast<long long>(d.max_seq) * hd, hkv, 0, 0, 0, 0, 1, b_att, hq * hd,
-                       static_cast<long long>(rows) * hq * hd, 0, 1, hq, hkv, hd, rows, rows, d.max_seq, 1, scale, s));
+      ProfScope ps(e, s, PK_ATTN, 2.0 * nreq * sl * static_cast<double>(sl) * hd * hq);
+      TRY(gar_attn_fwd(b_qkv, qkv_w, static_cast<long long>(sl) * qkv_w, 0, kslot, vslot, hd,
+                       static_cast<long long>(d.max_seq) * hd, nreq * hkv, 0, 0, 0, hkv, 1, b_att, hq * hd,
+                       static_cast<long long>(sl) * hq * hd, 0, nreq, hq, hkv, hd, sl, sl, d.max_seq, 1, scale, s));
       e->launches += 1;
     }
     TRY(gemm(e, b_att, hq * hd, wo, hq * hd, h, D, rows, D, hq * hd, GAR_EPI_RES, nullptr, nullptr, h, D, s));
@@ -217,7 +219,7 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
       TRY(gar_gemv_decode(e->hdec, D, wqkv, D, e->d_qkv, qkv_w, batch, qkv_w, D, 0, nullptr, 0, ln1, e->sumsq_a, n_part,
                           d.rms_eps, nullptr, nullptr, s));
     }
-    TRY(gar_llama_rope_kv(e->d_qkv, batch, hq, hkv, hd, cos_t, sin_t, 0, e->pos + e->slot_base, nullptr, -1, kc, vc, d.max_seq, s));
+    TRY(gar_llama_rope_kv(e->d_qkv, batch, hq, hkv, hd, cos_t, sin_t, 0, e->pos + e->slot_base, nullptr, -1, kc, vc, d.max_seq, 0, s));
     {
       ProfScope ps(e, s, PK_DECODE_ATTN, 0.0);
       int splits = e->dec_splits;
@@ -309,6 +311,7 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   e->dec_splits = 0;  // 0 = pick per batch so the split kernel fills the GPU
   const size_t T = d.max_tiles, NP = static_cast<size_t>(e->grid) * e->grid, NT = e->ntok;
   const size_t dv = d.vit_dim, D = d.llm_dim, S = d.max_seq, B = d.max_batch;
+  const size_t PR = d.max_prefill_rows > d.max_seq ? d.max_prefill_rows : d.max_seq;  // rows of one prefill pass
   const size_t qkv_w = static_cast<size_t>(d.llm_heads + 2 * d.llm_kv_heads) * d.llm_head_dim;
   int rc = 0;
   rc |= dev_alloc(e, &e->a_img, T * NP * e->kpad, true);
@@ -322,17 +325,17 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   rc |= dev_alloc(e, &e->p1, T * NT * D);
   rc |= dev_alloc(e, &e->p2, T * NT * D);
   rc |= dev_alloc(e, &e->feats, T * e->tokens_per_tile * D);
-  rc |= dev_alloc(e, &e->emb, S * D);
-  rc |= dev_alloc(e, &e->h, S * D);
-  rc |= dev_alloc(e, &e->lnl, S * D);
-  rc |= dev_alloc(e, &e->qkv_l, S * qkv_w);
+  rc |= dev_alloc(e, &e->emb, PR * D);
+  rc |= dev_alloc(e, &e->h, PR * D);
+  rc |= dev_alloc(e, &e->lnl, PR * D);
+  rc |= dev_alloc(e, &e->qkv_l, PR * qkv_w);
   rc |= dev_alloc(e, &e->d_qkv, B * qkv_w);
   rc |= dev_alloc(e, &e->d_att, B * d.llm_heads * d.llm_head_dim);
   rc |= dev_alloc(e, &e->d_gu, B * 2 * d.llm_inter);
   rc |= dev_alloc(e, &e->d_act, B * d.llm_inter);
-  rc |= dev_alloc(e, &e->att_l, S * d.llm_heads * d.llm_head_dim);
-  rc |= dev_alloc(e, &e->gu, S * 2 * d.llm_inter);
-  rc |= dev_alloc(e, &e->act, S * d.llm_inter);
+  rc |= dev_alloc(e, &e->att_l, PR * d.llm_heads * d.llm_head_dim);
+  rc |= dev_alloc(e, &e->gu, PR * 2 * d.llm_inter);
+  rc |= dev_alloc(e, &e->act, PR * d.llm_inter);
   rc |= dev_alloc(e, &e->logits, B * d.vocab_padded, true);
   rc |= dev_alloc(e, &e->hdec, B * D);
   rc |= dev_alloc(e, &e->lndec, (B > 1 ? B : 1) * D);
@@ -341,7 +344,7 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   rc |= dev_alloc(e, &e->vcache, kv_elems, true);
   rc |= dev_alloc(e, &e->o_part, B * d.llm_heads * 32 * d.llm_head_dim);
   rc |= dev_alloc(e, &e->ml_part, B * d.llm_heads * 32 * 2);
-  rc |= dev_alloc(e, &e->plan, S);
+  rc |= dev_alloc(e, &e->plan, PR);
   rc |= dev_alloc(e, &e->status, 2 * B, true);
   rc |= dev_alloc(e, &e->next_tok, B, true);
   rc |= dev_alloc(e, &e->out_tokens, B * d.max_new_tokens, true);
@@ -505,6 +508,53 @@ int gar_engine_assemble(gar_engine* e, int slot, const long long* input_ids_dev,
   return gar_assemble_embeds(input_ids_dev, S, table, d.vocab, e->feats, T * e->tokens_per_tile, d.llm_dim,
                              d.crop_token_ids, rois, has_roi, d.prompt_numbers, spatial_scale, ncw, nch, e->tpt,
                              d.image_token_id, e->emb, e->plan, e->status + 2 * slot, s);
+}
+
+int gar_engine_assemble_at(gar_engine* e, int slot, const long long* input_ids_dev, int S, int T, int feat_tile0,
+                           int emb_row0, const float* rois, const int* has_roi, float spatial_scale, int ncw, int nch,
+                           void* s) {
+  const gar_model_desc& d = e->d;
+  const long long pr = d.max_prefill_rows > d.max_seq ? d.max_prefill_rows : d.max_seq;
+  if (!e || slot < 0 || slot >= d.max_batch || S <= 0 || S > d.max_seq || emb_row0 < 0 || emb_row0 + S > pr ||
+      feat_tile0 < 0 || feat_tile0 + T > d.max_tiles) {
+    gar_set_error("gar_engine_assemble_at: slot=%d S=%d T=%d tile0=%d row0=%d outside capacity", slot, S, T, feat_tile0,
+                  emb_row0);
+    return GAR_ERR_ARG;
+  }
+  if (ncw * nch != T - 1) {  // reference assert in _merge, modeling_gar.py:250
+    gar_set_error("%d != %d", ncw * nch, T - 1);
+    return GAR_ERR_SHAPE;
+  }
+  NEEDW(table, "llm.embed");
+  e->launches += 2;
+  ProfScope ps(e, s, PK_ASSEMBLE, 2.0 * (2.0 * S) * d.llm_dim);
+  return gar_assemble_embeds(input_ids_dev, S, table, d.vocab,
+                             e->feats + static_cast<size_t>(feat_tile0) * e->tokens_per_tile * d.llm_dim,
+                             T * e->tokens_per_tile, d.llm_dim, d.crop_token_ids, rois, has_roi, d.prompt_numbers,
+                             spatial_scale, ncw, nch, e->tpt, d.image_token_id,
+                             e->emb + static_cast<size_t>(emb_row0) * d.llm_dim, e->plan + emb_row0, e->status + 2 * slot, s);
+}
+
+int gar_engine_prefill_batch(gar_engine* e, int slot0, int nreq, int S, void* s) {
+  const gar_model_desc& d = e->d;
+  const long long pr = d.max_prefill_rows > d.max_seq ? d.max_prefill_rows : d.max_seq;
+  if (!e || nreq <= 0 || slot0 < 0 || slot0 + nreq > d.max_batch || S <= 0 || S + d.max_new_tokens > d.max_seq ||
+      static_cast<long long>(nreq) * S > pr) {
+    gar_set_error("gar_engine_prefill_batch: slot0=%d nreq=%d S=%d outside capacity (max_prefill_rows=%lld)", slot0, nreq,
+                  S, pr);
+    return GAR_ERR_ARG;
+  }
+  const int rows = nreq * S;
+  GAR_CUDA_CHECK(cudaMemcpyAsync(e->h, e->emb, static_cast<size_t>(rows) * d.llm_dim * 2, cudaMemcpyDeviceToDevice,
+                                 static_cast<cudaStream_t>(s)));
+  TRY(llm_layers(e, e->h, e->lnl, rows, false, slot0, s, nreq));
+  // last position of every request: rows (r+1)*S-1, i.e. a strided row view of h
+  TRY(lm_head(e, e->h + static_cast<size_t>(S - 1) * d.llm_dim, S * d.llm_dim, nreq,
+              e->logits + static_cast<size_t>(slot0) * d.vocab_padded, s));
+  std::vector<int> pos(nreq, S);
+  GAR_CUDA_CHECK(cudaMemcpyAsync(e->pos + slot0, pos.data(), sizeof(int) * nreq, cudaMemcpyHostToDevice,
+                                 static_cast<cudaStream_t>(s)));
+  return GAR_OK;
 }
 
 int gar_engine_prefill(gar_engine* e, int slot, int S, void* s) {

@@ -49,7 +49,8 @@ def roi_boxes_f32(spec: GARSpec, bboxes: Dict[str, Sequence[float]], ncw: int, n
 
 class Engine:
     def __init__(self, spec: GARSpec, state_dict: Dict[str, torch.Tensor], device: str = "cuda:0",
-                 max_tiles: int = 17, max_seq: int = 6144, max_batch: int = 8, max_new_tokens: int = 128):
+                 max_tiles: int = 17, max_seq: int = 6144, max_batch: int = 8, max_new_tokens: int = 128,
+                 max_prefill_rows: int = 0):
         if not torch.cuda.is_available():
             raise _lib.GarError("grasp_any_region_b200 needs a CUDA device: there is no CPU fallback")
         self.lib = _lib.load()
@@ -71,6 +72,8 @@ class Engine:
         for i in range(8):
             d.crop_token_ids[i] = spec.crop_tokens_ids[i] if i < len(spec.crop_tokens_ids) else -1
         d.max_tiles, d.max_seq, d.max_batch, d.max_new_tokens = max_tiles, max_seq, max_batch, max_new_tokens
+        d.max_prefill_rows = max(int(max_prefill_rows), max_seq)
+        self.max_prefill_rows = d.max_prefill_rows
         self._desc = d
         h = C.c_void_p()
         check(self.lib.gar_engine_create(C.byref(d), C.byref(h)), "gar_engine_create")
@@ -221,6 +224,32 @@ class Engine:
         self.vit_encode(pixel_values, global_mask_values)
         self.assemble(slot, input_ids, T, bboxes, ncw, nch)
         self.prefill(slot, input_ids.numel())
+
+    def request_batch(self, slot0: int, requests):
+        """ViT -> assemble -> prefill for several requests in ONE pass (one GEMM / attention launch covers all of
+        them): requires equal tile counts and prompt lengths.  `requests` = list of
+        (pixel_values, global_mask_values, input_ids(S,), bboxes, (ncw, nch)) already on the device.
+        Per-request results are identical to request(); only the launch count and tile quantisation change."""
+        n = len(requests)
+        T = requests[0][0].shape[0]
+        S = requests[0][2].numel()
+        assert all(r[0].shape[0] == T and r[2].numel() == S for r in requests)
+        assert n * T <= self.max_tiles and n * S <= self.max_prefill_rows and slot0 + n <= self.max_batch
+        with_mask = requests[0][1] is not None
+        px = torch.cat([r[0] for r in requests], 0)
+        mv = torch.cat([r[1] for r in requests], 0) if with_mask else None
+        self.vit_encode(px, mv)
+        keep = [px, mv]
+        for i, (_, _, ids, bboxes, (ncw, nch)) in enumerate(requests):
+            rois, has, scale = roi_boxes_f32(self.spec, bboxes, ncw, nch)
+            k = len(has)
+            c_rois = (C.c_float * (5 * k))(*[x for r in rois for x in r])
+            c_has = (C.c_int * k)(*has)
+            check(self.lib.gar_engine_assemble_at(self._h, slot0 + i, C.c_void_p(ids.data_ptr()), S, T, i * T, i * S,
+                                                  c_rois, c_has, float(scale), ncw, nch, self._s()),
+                  "gar_engine_assemble_at")
+        check(self.lib.gar_engine_prefill_batch(self._h, slot0, n, S, self._s()), "gar_engine_prefill_batch")
+        return keep
 
     def generate(self, batch: int, max_new_tokens: int, eos_token_id: Optional[int], slot0: int = 0,
                  stream: Optional[torch.cuda.Stream] = None) -> List[List[int]]:

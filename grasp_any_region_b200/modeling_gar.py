@@ -110,7 +110,7 @@ class GARModel(_Base):
                 sd.update({"mask_patch_embedding." + k: v for k, v in mask_patch_embedding.state_dict().items()})
             self.load_state_dict(sd, strict=False)
         self._engine: Optional[Engine] = None
-        self._engine_caps = dict(max_tiles=37, max_seq=12288, max_batch=8, max_new_tokens=1024)
+        self._engine_caps = dict(max_tiles=37, max_seq=12288, max_batch=8, max_new_tokens=1024, max_prefill_rows=0)
         if _HAS_HF and hasattr(self, "post_init"):
             self.post_init()
 
@@ -148,7 +148,8 @@ class GARModel(_Base):
         return self
 
     def configure_engine(self, **caps) -> "GARModel":
-        """Capacity of the device arenas: max_tiles, max_seq, max_batch, max_new_tokens."""
+        """Capacity of the device arenas: max_tiles, max_seq, max_batch, max_new_tokens, max_prefill_rows
+        (max_tiles >= n*T and max_prefill_rows >= n*S let generate_batch encode n requests in one pass)."""
         self._engine_caps.update(caps)
         if self._engine is not None:
             self._engine.close()
@@ -166,6 +167,46 @@ class GARModel(_Base):
         return self._engine
 
     # ------------------------------------------------------------------ request plumbing
+    def _prepare_request(self, eng: Engine, pixel_values, global_mask_values, aspect_ratios, bboxes, input_ids,
+                         batch_idx=0):
+        """Device-side copies of one request in the dtypes the engine reads (bf16 / int64)."""
+        dev = eng.device
+        if input_ids.shape[0] != 1:
+            raise AssertionError("Currently only support batch_size=1")
+        px = pixel_values.to(dev, non_blocking=True).to(torch.bfloat16)
+        if px.dim() == 5:
+            px = px.flatten(0, 1)
+        assert px.dim() == 4, (
+            f"pixel_values should be of shape (batch_size * num_tiles, channels, height, width). But got {px.shape}.")
+        mv = None
+        if global_mask_values is not None:
+            mv = global_mask_values.to(dev, non_blocking=True).to(torch.bfloat16).contiguous()
+        ids = input_ids[batch_idx].to(dev, non_blocking=True).to(torch.long).contiguous()
+        ar = aspect_ratios[batch_idx]
+        return px.contiguous(), mv, ids, bboxes[batch_idx], (int(ar[0]), int(ar[1]))
+
+    def _stage_requests_batched(self, eng: Engine, slot0: int, requests: List[dict]) -> bool:
+        """One ViT/prefill pass for all requests when they share tile count and prompt length (and the engine
+        was sized for it); returns False when the caller must stage them one by one."""
+        prepared = [self._prepare_request(eng, r["pixel_values"], r.get("global_mask_values"), r["aspect_ratios"],
+                                          r["bboxes"], r["input_ids"]) for r in requests]
+        n, T, S = len(prepared), prepared[0][0].shape[0], prepared[0][2].numel()
+        uniform = all(p[0].shape[0] == T and p[2].numel() == S and (p[1] is None) == (prepared[0][1] is None)
+                      for p in prepared)
+        if not (uniform and n > 1 and n * T <= eng.max_tiles and n * S <= eng.max_prefill_rows):
+            return False
+        eng.stream.wait_stream(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(eng.stream):
+            keep = eng.request_batch(slot0, prepared)
+        for p in prepared:
+            for t in (p[0], p[1], p[2]):
+                if t is not None:
+                    t.record_stream(eng.stream)
+        for t in keep:
+            if t is not None:
+                t.record_stream(eng.stream)
+        return True
+
     def _stage_request(self, eng: Engine, slot, pixel_values, global_mask_values, aspect_ratios, bboxes, input_ids,
                        batch_idx=0):
         dev = eng.device
@@ -236,9 +277,10 @@ class GARModel(_Base):
         eng = self.engine()
         if len(requests) > eng.max_batch:
             raise ValueError(f"{len(requests)} requests > engine max_batch {eng.max_batch}")
-        for slot, r in enumerate(requests):
-            self._stage_request(eng, slot, r["pixel_values"], r.get("global_mask_values"), r["aspect_ratios"],
-                                r["bboxes"], r["input_ids"])
+        if not self._stage_requests_batched(eng, 0, requests):
+            for slot, r in enumerate(requests):
+                self._stage_request(eng, slot, r["pixel_values"], r.get("global_mask_values"), r["aspect_ratios"],
+                                    r["bboxes"], r["input_ids"])
         toks = eng.generate(len(requests), int(max_new_tokens), eos_token_id)
         for slot in range(len(requests)):
             self._raise_on_status(eng, slot)

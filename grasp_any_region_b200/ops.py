@@ -125,7 +125,7 @@ def vit_rope_(qkv, rope, ntok, npt, heads, hd):
 
 def llama_rope_kv_(qkv, hq, hkv, hd, cos_t, sin_t, kcache, vcache, max_seq, pos0=0, pos_dev=None, slot0=0):
     check(_lib.load().gar_llama_rope_kv(_p(qkv), qkv.shape[0], hq, hkv, hd, _p(cos_t), _p(sin_t), pos0, _p(pos_dev),
-                                        None, slot0, _p(kcache), _p(vcache), max_seq, _stream()), "gar_llama_rope_kv")
+                                        None, slot0, _p(kcache), _p(vcache), max_seq, 0, _stream()), "gar_llama_rope_kv")
     return qkv
 
 

@@ -88,9 +88,10 @@ int gar_rmsnorm(const void* x, int ldx, const void* w, void* y, int ldy, int row
 /* timm apply_rot_embed_cat on q,k of the fused qkv buffer, in place (prefix tokens untouched) */
 int gar_vit_rope(void* qkv, const void* rope, int rows, int ntok, int npt, int heads, int hd, void* stream);
 /* HF apply_rotary_pos_emb on q (in place) and k (into the KV cache) + V append (DynamicCache.update) */
+/* seq_len > 0: rows hold nreq sequences of seq_len positions each, written to slots slot0, slot0+1, ... */
 int gar_llama_rope_kv(void* qkv, int rows, int hq, int hkv, int hd, const void* cos_t, const void* sin_t, int pos0,
                       const int* pos_dev, const int* slot_dev, int slot0, void* kcache, void* vcache, int max_seq,
-                      void* stream);
+                      int seq_len, void* stream);
 /* HF LlamaMLP act_fn(gate) * up on a fused buffer: rows = [gate(I) | up(I)], or with interleaved != 0
  * 32-column groups [gate | up] (the GAR_EPI_SWIGLU weight layout) */
 int gar_swiglu(const void* gu, void* act, int rows, int inter, int interleaved, void* stream);
@@ -149,6 +150,7 @@ typedef struct gar_model_desc {
   long long crop_token_ids[8];
   /* capacity */
   int max_tiles, max_seq, max_batch, max_new_tokens;
+  int max_prefill_rows; /* rows of one (batched) prefill pass; 0 = max_seq */
 } gar_model_desc;
 
 int gar_engine_create(const gar_model_desc* desc, gar_engine** out);
@@ -163,6 +165,13 @@ int gar_engine_vit_encode(gar_engine* e, const void* pixel_values, const void* m
 /* R6-R7 on the engine's image features -> inputs_embeds (S, llm_dim) */
 int gar_engine_assemble(gar_engine* e, int slot, const long long* input_ids_dev, int S, int T, const float* rois,
                         const int* has_roi, float spatial_scale, int ncw, int nch, void* stream);
+/* R6-R7 for request r of a batched pass: features start at tile feat_tile0, rows are written at emb_row0 */
+int gar_engine_assemble_at(gar_engine* e, int slot, const long long* input_ids_dev, int S, int T, int feat_tile0,
+                           int emb_row0, const float* rois, const int* has_roi, float spatial_scale, int ncw, int nch,
+                           void* stream);
+/* R8 for nreq equal-length requests at once (rows = nreq*S of inputs_embeds, slots slot0..slot0+nreq-1): same math per
+ * request as gar_engine_prefill, 1/nreq of the launches */
+int gar_engine_prefill_batch(gar_engine* e, int slot0, int nreq, int S, void* stream);
 /* R8: causal prefill of the engine's inputs_embeds into KV-cache slot; last-position logits -> logits[slot] */
 int gar_engine_prefill(gar_engine* e, int slot, int S, void* stream);
 /* same, teacher-forced: all-position logits (S, vocab_padded) into caller memory (forward(mode="loss")) */

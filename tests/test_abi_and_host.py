@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_desc_struct_layout_matches_header():
     # 9 ints/floats, 8 ints, float, int, (pad), int64, 8 x int64, 4 ints
-    assert ctypes.sizeof(_lib.GarModelDesc) == 4 * 20 + 8 + 64 + 16
+    assert ctypes.sizeof(_lib.GarModelDesc) == 4 * 20 + 8 + 64 + 24  # 5 capacity ints + tail padding
     assert _lib.GarModelDesc.image_token_id.offset == 80
 
 

@@ -179,3 +179,37 @@ def test_forward_loss_matches_oracle():
         model.forward(dict(data, input_ids=torch.cat([ids, ids], 0)), mode="loss")
     with pytest.raises(UnboundLocalError):
         model.forward(data, mode="predict")
+
+
+def test_batched_encode_matches_per_request():
+    """generate_batch encodes equal-shaped requests in one ViT pass + one prefill pass; tokens and the prefill
+    logits of every request must be bit-identical to the one-request-at-a-time path."""
+    from grasp_any_region_b200 import GARConfig, GARModel
+
+    spec = gar_small()
+    oracle = build_oracle(spec, seed=0, dtype=torch.float32)
+    sd = {k: v.to(bf) for k, v in oracle.state_dict().items()}
+    model = GARModel(GARConfig.from_spec(spec))
+    model.load_state_dict(sd)
+    model = model.to(DEV)
+    reqs = [make_request(spec, seed=60 + i, n_masks=2, max_num_tiles=4, dtype=bf) for i in range(3)]
+    S = reqs[0]["input_ids"].shape[1]
+    assert all(r["input_ids"].shape[1] == S for r in reqs)
+    new_tokens = 7
+    model.configure_engine(max_tiles=5, max_seq=S + 32, max_batch=3, max_new_tokens=new_tokens)
+    seq = model.generate_batch(reqs, max_new_tokens=new_tokens)          # per-request encode (capacity for 1)
+    eng = model.engine()
+    lg_seq = None
+    model.configure_engine(max_tiles=15, max_seq=S + 32, max_batch=3, max_new_tokens=new_tokens, max_prefill_rows=3 * S)
+    eng = model.engine()
+    assert model._stage_requests_batched(eng, 0, reqs)
+    eng.stream.synchronize()
+    lg_bat = eng.buffer("logits", (3, eng.vocab_padded)).clone()
+    for slot, r in enumerate(reqs):
+        model._stage_request(eng, slot, r["pixel_values"], r["global_mask_values"], r["aspect_ratios"], r["bboxes"],
+                             r["input_ids"])
+    eng.stream.synchronize()
+    lg_seq = eng.buffer("logits", (3, eng.vocab_padded)).clone()
+    assert torch.equal(lg_bat, lg_seq)
+    bat = model.generate_batch(reqs, max_new_tokens=new_tokens)
+    assert bat == seq

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_engine.py -q -m gpu -k "forward_loss" -s 2>&1 | tail -8 | tee gpurun_out/forward_loss.log
-echo "== smoke"; timeout 600 python __graft_entry__.py smoke 2>&1 | tail -3 | tee gpurun_out/smoke.log
+timeout 900 python -m pytest tests/test_gpu_engine.py -q -m gpu -k "batched_encode or batched_decode or pipelined" 2>&1 | tail -6
+echo "== bench"; timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -3 | tee gpurun_out/bench_a.log
