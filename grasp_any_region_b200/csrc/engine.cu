@@ -679,7 +679,7 @@ int gar_engine_set_option(gar_engine* e, const char* name, int value) {
   else if (n == "fuse_rope") e->fuse_rope = value;
   else if (n == "gemv_decode") e->use_gemv = value;
   else if (n == "decode_splits" && value >= 0 && value <= 32) e->dec_splits = value;
-  else if (n == "pdl" || n == "decode_attn_mma" || n == "attn_bkv") {
+  else if (n == "pdl" || n == "decode_attn_mma" || n == "attn_bkv" || n == "gemm_2cta") {
     if (gar_set_global_option(name, value)) return GAR_ERR_ARG;
   }
   else {

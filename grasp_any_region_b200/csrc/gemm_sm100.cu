@@ -11,6 +11,8 @@
 //   warps 4..11 epilogue       : tcgen05.ld accumulator -> registers -> fused epilogue with the
 //                                reference's bf16 rounding points -> swizzled smem -> TMA store
 // Two TMEM accumulator stages let the epilogue of tile i overlap the mainloop of tile i+1.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -25,11 +27,14 @@ constexpr int C_STAGE_BYTES = BLOCK_M * C_CHUNK * 2;      // 8 KB, 64B-swizzled 
 
 enum Epi { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_BIAS_LS_RES = 3, EPI_RES = 4, EPI_BIAS_ROPE2D = 5, EPI_SWIGLU = 6 };
 
-template <int BLOCK_N>
+// CTA2: cta_group::2 -- a cluster of two CTAs computes a 256 x 256 tile; each CTA stages its 128 rows of A and
+// 128 of the 256 rows of B, so every SM's shared-memory traffic per MMA halves for B (the 1-CTA 128x256 tile
+// needs ~188 B/clk of smem traffic against a 128 B/clk port) and the ring gets two more stages.
+template <int BLOCK_N, bool CTA2 = false>
 struct Cfg {
-  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int STAGES = CTA2 ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_BYTES = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (power of two >= 32)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * C_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -46,11 +51,16 @@ struct EpiArgs {
   int ntok, npt, hd, rope_cols;
 };
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, EpiArgs ea) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, CTA2>;
+  static_assert(!CTA2 || BLOCK_N == 256, "the CTA-pair kernel uses 256 x 256 tiles");
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+  constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
+  const int tile0 = CTA2 ? blockIdx.x / 2 : blockIdx.x;
+  const int tile_step = CTA2 ? gridDim.x / 2 : gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_ab = smem_base;
@@ -67,7 +77,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int num_m = (M + TILE_M - 1) / TILE_M;
   const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m * num_n;
   const int num_kb = K / BLOCK_K;
@@ -84,16 +94,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), EPI_THREADS / 32);
+      mbar_init(tempty_bar(s), (CTA2 ? 2 : 1) * (EPI_THREADS / 32));  // pair: both CTAs' epilogue warps release it
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
-    tmem_relinquish();
+    if (CTA2) {
+      tmem_alloc_2cta(tmem_ptr_smem, C::TMEM_COLS);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / TMA signal
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -102,27 +118,35 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile % num_m, n_blk = tile / num_m;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
           const uint32_t sa = smem_ab + stage * C::STAGE_BYTES;
-          tma_load_2d(sa, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M, full_bar(stage));
-          tma_load_2d(sa + C::A_BYTES, &tmap_b, kb * BLOCK_K, n_blk * BLOCK_N, full_bar(stage));
+          if (CTA2) {
+            // both CTAs' bytes are accounted on the leader's barrier; the leader arms it for the pair
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+            tma_load_2d_2cta(sa, &tmap_a, kb * BLOCK_K, m_blk * TILE_M + cta_rank * BLOCK_M, full_bar(stage));
+            tma_load_2d_2cta(sa + C::A_BYTES, &tmap_b, kb * BLOCK_K, n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2),
+                             full_bar(stage));
+          } else {
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M, full_bar(stage));
+            tma_load_2d(sa + C::A_BYTES, &tmap_b, kb * BLOCK_K, n_blk * BLOCK_N, full_bar(stage));
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -135,12 +159,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the >>4 address field
-            umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CTA2) umma_bf16_ss_2cta(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if (CTA2) umma_commit_2cta(empty_bar(stage), 3);
+          else umma_commit(empty_bar(stage));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CTA2) umma_commit_2cta(tfull_bar(acc), 3);
+        else umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -159,9 +188,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t acc_phase = 0;
     int cbuf = 0;
     float gate[EPI == EPI_SWIGLU ? 32 : 1];  // EPI_SWIGLU: bf16-rounded gate chunk waiting for its up chunk
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile % num_m, n_blk = tile / num_m;
-      const int gm = m_blk * BLOCK_M + row;
+      const int m_base = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;  // this CTA's 128 rows of the tile
+      const int gm = m_base + row;
       // residual rows are row-per-thread (strided) global loads: issue chunk c+1's while chunk c is processed,
       // and chunk 0's before waiting for the accumulator, so their latency never sits on the epilogue path
       uint4 rnext[4];
@@ -195,7 +225,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           // all of this warp's TMEM reads for the tile are done -> release the accumulator stage
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if (CTA2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));  // the leader's MMA warp waits on it
+            else mbar_arrive(tempty_bar(acc));
+          }
         }
         const bool col_ok = gn < N;  // N % 32 == 0 is enforced on the host
         uint32_t packed[16];
@@ -307,7 +340,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         named_bar_sync(bar_id, 128);
         if (issuer && col_ok) {
           const int gn_out = EPI == EPI_SWIGLU ? (gn - C_CHUNK) / 2 : gn;
-          tma_store_2d(&tmap_c, stage_c0 + cbuf * C_STAGE_BYTES, gn_out, m_blk * BLOCK_M);
+          tma_store_2d(&tmap_c, stage_c0 + cbuf * C_STAGE_BYTES, gn_out, m_base);
         }
         if (issuer) tma_store_commit();
         cbuf ^= 1;
@@ -318,41 +351,50 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all();  // the peer may still signal this CTA's barriers / read its smem until here
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (CTA2) tmem_dealloc_2cta(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool CTA2>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
                 const EpiArgs& ea, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N>;
-  auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI>;
+  using C = Cfg<BLOCK_N, CTA2>;
+  auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI, CTA2>;
   static bool attr_set = false;
   if (!attr_set) {
     GAR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int num_tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int tile_m = CTA2 ? 2 * BLOCK_M : BLOCK_M;
+  const int num_tiles = ((M + tile_m - 1) / tile_m) * ((N + BLOCK_N - 1) / BLOCK_N);
+  if (CTA2) {
+    const int clusters = std::min(num_tiles, gar_num_sms() / 2);
+    GAR_CUDA_CHECK(gar_launch(kern, dim3(2 * clusters), dim3(NUM_THREADS), C::SMEM_BYTES, stream, false, dim3(2, 1, 1), ta,
+                              tb, tc, M, N, K, ea));
+    return GAR_OK;
+  }
   const int grid = num_tiles < gar_num_sms() ? num_tiles : gar_num_sms();
   kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tc, M, N, K, ea);
   GAR_CUDA_CHECK(cudaGetLastError());
   return GAR_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool CTA2 = false>
 int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
                  const EpiArgs& ea, cudaStream_t stream) {
   switch (epi) {
-    case EPI_NONE: return launch_gemm<BLOCK_N, EPI_NONE>(ta, tb, tc, M, N, K, ea, stream);
-    case EPI_BIAS: return launch_gemm<BLOCK_N, EPI_BIAS>(ta, tb, tc, M, N, K, ea, stream);
-    case EPI_BIAS_GELU: return launch_gemm<BLOCK_N, EPI_BIAS_GELU>(ta, tb, tc, M, N, K, ea, stream);
-    case EPI_BIAS_LS_RES: return launch_gemm<BLOCK_N, EPI_BIAS_LS_RES>(ta, tb, tc, M, N, K, ea, stream);
-    case EPI_RES: return launch_gemm<BLOCK_N, EPI_RES>(ta, tb, tc, M, N, K, ea, stream);
-    case EPI_BIAS_ROPE2D: return launch_gemm<BLOCK_N, EPI_BIAS_ROPE2D>(ta, tb, tc, M, N, K, ea, stream);
-    case EPI_SWIGLU: return launch_gemm<BLOCK_N, EPI_SWIGLU>(ta, tb, tc, M, N, K, ea, stream);
+    case EPI_NONE: return launch_gemm<BLOCK_N, EPI_NONE, CTA2>(ta, tb, tc, M, N, K, ea, stream);
+    case EPI_BIAS: return launch_gemm<BLOCK_N, EPI_BIAS, CTA2>(ta, tb, tc, M, N, K, ea, stream);
+    case EPI_BIAS_GELU: return launch_gemm<BLOCK_N, EPI_BIAS_GELU, CTA2>(ta, tb, tc, M, N, K, ea, stream);
+    case EPI_BIAS_LS_RES: return launch_gemm<BLOCK_N, EPI_BIAS_LS_RES, CTA2>(ta, tb, tc, M, N, K, ea, stream);
+    case EPI_RES: return launch_gemm<BLOCK_N, EPI_RES, CTA2>(ta, tb, tc, M, N, K, ea, stream);
+    case EPI_BIAS_ROPE2D: return launch_gemm<BLOCK_N, EPI_BIAS_ROPE2D, CTA2>(ta, tb, tc, M, N, K, ea, stream);
+    case EPI_SWIGLU: return launch_gemm<BLOCK_N, EPI_SWIGLU, CTA2>(ta, tb, tc, M, N, K, ea, stream);
   }
   gar_set_error("gar_gemm_bf16: unknown epilogue %d", epi);
   return GAR_ERR_ARG;
@@ -389,13 +431,18 @@ static int gemm_impl(const void* A, int lda, const void* B, int ldb, void* Cout,
     if (N % 64) return GAR_ERR_SHAPE;
     if (bn < 128) bn = 128;  // a column group must hold whole [gate | up] chunk pairs
   }
+  // CTA-pair kernel (256 x 256 tiles) whenever N allows it and there are enough tiles for every pair
+  const bool cta2 = gar_global_option("gemm_2cta") != 0 && block_n_hint == 0 && N % 256 == 0 &&
+                    ((M + 255) / 256) * (N / 256) >= gar_num_sms() / 2;
+  if (cta2) bn = 256;
   CUtensorMap ta, tb, tc;
   int rc;
   if ((rc = gar_make_tmap_2d(&ta, A, K, M, lda, BLOCK_K, BLOCK_M, GAR_SW_128))) return rc;
-  if ((rc = gar_make_tmap_2d(&tb, B, K, N, ldb, BLOCK_K, bn, GAR_SW_128))) return rc;
+  if ((rc = gar_make_tmap_2d(&tb, B, K, N, ldb, BLOCK_K, cta2 ? 128 : bn, GAR_SW_128))) return rc;
   if ((rc = gar_make_tmap_2d(&tc, Cout, epi == EPI_SWIGLU ? N / 2 : N, M, ldc, C_CHUNK, BLOCK_M, GAR_SW_64))) return rc;
   EpiArgs ea{static_cast<const bf16*>(bias), static_cast<const bf16*>(gamma), static_cast<const bf16*>(res), ldres,
              static_cast<const bf16*>(rope), ntok, npt, hd, rope_cols};
+  if (cta2) return dispatch_epi<256, true>(epi, ta, tb, tc, M, N, K, ea, stream);
   if (bn == 256) return dispatch_epi<256>(epi, ta, tb, tc, M, N, K, ea, stream);
   if (bn == 128) return dispatch_epi<128>(epi, ta, tb, tc, M, N, K, ea, stream);
   return dispatch_epi<64>(epi, ta, tb, tc, M, N, K, ea, stream);

@@ -56,7 +56,7 @@ def test_gemm_plain(M, N, K, block_n):
 
 
 @pytest.mark.parametrize("epi", [ops.EPI_BIAS, ops.EPI_BIAS_GELU, ops.EPI_BIAS_LS_RES, ops.EPI_RES])
-@pytest.mark.parametrize("M,N,K", [(333, 512, 256), (1025, 1024, 1024)])
+@pytest.mark.parametrize("M,N,K", [(333, 512, 256), (1025, 1024, 1024), (4000, 2048, 512)])
 def test_gemm_epilogues(epi, M, N, K):
     a, b = rnd(M, K, seed=3), rnd(N, K, scale=0.05, seed=4)
     bias, gamma, res = rnd(N, scale=0.1, seed=5), rnd(N, scale=0.2, seed=6), rnd(M, N, seed=7)
@@ -77,6 +77,24 @@ def test_gemm_fused_swiglu(M, I, K):
     torch.cuda.synchronize()
     assert got.shape == (M, I)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("epi", [ops.EPI_NONE, ops.EPI_BIAS_GELU, ops.EPI_BIAS_LS_RES, ops.EPI_SWIGLU])
+@pytest.mark.parametrize("M,N,K", [(4097, 2048, 1024), (17425, 1024, 512), (2300, 4096, 256)])
+def test_gemm_cta_pair_matches_single_cta(epi, M, N, K):
+    """The cta_group::2 kernel (256x256 tiles over two SMs) accumulates every output in the same order as the
+    single-CTA kernel, so the two must agree bit for bit."""
+    from grasp_any_region_b200 import _lib
+
+    a, b = rnd(M, K, seed=80), rnd(N, K, scale=0.05, seed=81)
+    bias, gamma, res = rnd(N, scale=0.1, seed=82), rnd(N, scale=0.2, seed=83), rnd(M, N, seed=84)
+    lib = _lib.load()
+    _lib.check(lib.gar_set_global_option(b"gemm_2cta", 0))
+    one = ops.gemm(a, b, epi=epi, bias=bias, gamma=gamma, res=res)
+    _lib.check(lib.gar_set_global_option(b"gemm_2cta", 1))
+    two = ops.gemm(a, b, epi=epi, bias=bias, gamma=gamma, res=res)
+    torch.cuda.synchronize()
+    assert torch.equal(one, two)
 
 
 def test_gemm_inplace_residual():
