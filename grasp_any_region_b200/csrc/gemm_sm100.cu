@@ -119,7 +119,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        const int m_blk = tile / num_n, n_blk = tile % num_n;  // n fastest: co-running CTAs share A rows, B stays in L2
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_ab + stage * C::STAGE_BYTES;
@@ -189,7 +189,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int cbuf = 0;
     float gate[EPI == EPI_SWIGLU ? 32 : 1];  // EPI_SWIGLU: bf16-rounded gate chunk waiting for its up chunk
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int m_blk = tile / num_n, n_blk = tile % num_n;  // n fastest: co-running CTAs share A rows, B stays in L2
       const int m_base = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;  // this CTA's 128 rows of the tile
       const int gm = m_base + row;
       // residual rows are row-per-thread (strided) global loads: issue chunk c+1's while chunk c is processed,

@@ -79,3 +79,16 @@ if which == "attn_timeline":
         wpv = (r[4] - r[3]) if j > 0 else 0
         exp0 = r[4] if j > 0 else r[3]
         print(f"j={j}: {r[1]-r[0]:6d} | {r[2]-r[1]:6d} | {r[3]-r[2]:6d} | {wpv:6d} | {r[5]-exp0:6d} | {r[6]-r[5]:6d} | {r[6]-r[0]:6d}")
+
+if which == "gemm_big":
+    from grasp_any_region_b200 import _lib as _l2
+    for (M, N, K, epi) in ((139400, 3072, 1024, 1), (139400, 4096, 1024, 2), (139400, 1024, 4096, 3), (37376, 16384, 2048, 6),
+                           (37376, 2048, 8192, 4)):
+        a = torch.randn(M, K, device=dev).to(bf); w = (torch.randn(N, K, device=dev) * 0.05).to(bf)
+        bias = torch.randn(N, device=dev).to(bf); gamma = torch.randn(N, device=dev).to(bf)
+        res = torch.randn(M, N, device=dev).to(bf)
+        for two in (1, 0):
+            _l2.load().gar_set_global_option(b"gemm_2cta", two)
+            timeit(f"gemm 2cta={two} M={M} N={N} K={K} epi={epi}", lambda: ops.gemm(a, w, epi=epi, bias=bias, gamma=gamma, res=res), 2.0 * M * N * K)
+        del a, w, res
+    _l2.load().gar_set_global_option(b"gemm_2cta", 1)
