@@ -50,6 +50,8 @@ SIGNATURES = {
                                  _f, _i, _i, _i, _ll, _vp, _vp, _vp, _vp]),
     "gar_attn_fwd": (_i, [_vp, _ll, _ll, _i, _vp, _vp, _ll, _ll, _i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _i, _i, _i,
                           _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "gar_decode_attn_rope": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _i, _vp]),
     "gar_attn_debug_timeline": (_i, [_vp]),
     "gar_decode_attn": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     "gar_engine_create": (_i, [C.POINTER(GarModelDesc), C.POINTER(_vp)]),

@@ -13,6 +13,8 @@
 //                           O += P V   (128x64x128, P K-major from smem, V MN-major from smem)
 //   warps 2-5  softmax    : tcgen05.ld S row-per-thread -> online softmax -> P (bf16) into swizzled
 //                           smem, rescale O in TMEM, final O/l -> smem -> TMA store
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -213,10 +215,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // V tile: NSUB sub-tiles [kv rows][64 hd] of 128B rows => MN-major B operand (N = HD): LBO = stride
         // between 64-wide N blocks (one sub-tile), SBO = 8 kv rows; 16 kv rows per MMA = 2048 B
         const uint64_t vdesc = umma_desc_sw128(sbase + SMEM_V, KV_TILE, 1024);
+        const int nk = (BKV > 32 && kv_end - j * BKV <= 32) ? 2 : BKV / 16;  // short tail: 32 keys of P/V only
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t pdesc = umma_desc_sw128(sbase + SMEM_P + (k >> 2) * TILE_BYTES, 0, 1024) + 2u * (k & 3);
-          umma_bf16_ss(tmem + TM_O, pdesc, vdesc + 128u * k, idesc_o, (j | k) != 0);
+          if (k < nk) {
+            const uint64_t pdesc = umma_desc_sw128(sbase + SMEM_P + (k >> 2) * TILE_BYTES, 0, 1024) + 2u * (k & 3);
+            umma_bf16_ss(tmem + TM_O, pdesc, vdesc + 128u * k, idesc_o, (j | k) != 0);
+          }
         }
         umma_commit(B_VEMPTY);
         umma_commit(B_PVDONE);
@@ -235,59 +240,78 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #else
 #define TL_STAMP(i)
 #endif
+    // Tails cost what they hold, not a full tile: a softmax warp whose 32 query rows all lie past q_len only keeps the
+    // barrier protocol in step (the ViT's 1025-token tiles leave a 1-row last query block), and a last KV block with
+    // <= 32 live keys is handled on 32 score columns (and 2 of the BKV/16 PV MMAs) instead of BKV.
+    const bool warp_live = q0 + quarter * 32 < p.q_len;
+    const uint32_t p_rbase = sbase + SMEM_P + (row >> 3) * 1024 + (row & 7) * 128;
     for (int j = 0; j < num_kvb; ++j) {
       TL_STAMP(0);
       mbar_wait(B_SFULL, j & 1);
       tc_fence_after();
       TL_STAMP(1);
-      uint32_t s[BKV];
-#pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t(&sc)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
-        tmem_ld_32x32b_x32(tmem + lane_addr + TM_S + c * 32, sc);
+      if (!warp_live) {
+        tc_fence_before();
+        mbar_arrive(B_SCONS);
+        if (j > 0) mbar_wait(B_PVDONE, (j - 1) & 1);  // keeps this arrival in P's phase j (see the MMA loop)
+        mbar_arrive(B_PFULL);
+        continue;
       }
-      tmem_ld_wait();
-      TL_STAMP(2);
-      tc_fence_before();
-      mbar_arrive(B_SCONS);  // S(j) is in registers: the MMA warp may overwrite TMEM S with S(j+1)
       const int kv0 = j * BKV;
-      const bool need_mask = (kv0 + BKV > p.kv_len) || (p.causal && kv0 + BKV - 1 > q0 + shift);
       const int lim = p.causal ? min(p.kv_len - 1, q_pos) : p.kv_len - 1;
-      const float mx = need_mask ? row_max_n<true, BKV>(s, kv0, lim) : row_max_n<false, BKV>(s, kv0, lim);
-      // Lazy rescale: keep exponentiating against the old reference max until the true max has grown by
-      // more than 2^8; P then stays <= 256 (harmless in bf16/fp32) and most O rescales disappear.
-      const float m_cand = fmaxf(m_run, mx * p.scale_log2);
-      const bool bump = (m_cand - m_run) > 8.0f || m_run == -INFINITY;
-      const float m_new = bump ? m_cand : m_run;
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = bump ? ex2_approx(m_run - m_use) : 1.0f;
-      TL_STAMP(3);
-      // O and the P buffer are quiescent only once PV(j-1) has retired
-      if (j > 0) {
-        mbar_wait(B_PVDONE, (j - 1) & 1);
-        tc_fence_after();
-        TL_STAMP(4);
-        const bool any = __any_sync(0xffffffffu, alpha != 1.0f);
-        if (any) {
+      auto block = [&](auto nc_tag, bool need_mask) {
+        constexpr int NC = decltype(nc_tag)::value;
+        uint32_t s[NC];
 #pragma unroll
-          for (int c = 0; c < HD / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
-          }
-          tmem_st_wait();
+        for (int c = 0; c < NC / 32; ++c) {
+          uint32_t(&sc)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
+          tmem_ld_32x32b_x32(tmem + lane_addr + TM_S + c * 32, sc);
         }
+        tmem_ld_wait();
+        TL_STAMP(2);
+        tc_fence_before();
+        mbar_arrive(B_SCONS);  // S(j) is in registers: the MMA warp may overwrite TMEM S with S(j+1)
+        const float mx = need_mask ? row_max_n<true, NC>(s, kv0, lim) : row_max_n<false, NC>(s, kv0, lim);
+        // Lazy rescale: keep exponentiating against the old reference max until the true max has grown by
+        // more than 2^8; P then stays <= 256 (harmless in bf16/fp32) and most O rescales disappear.
+        const float m_cand = fmaxf(m_run, mx * p.scale_log2);
+        const bool bump = (m_cand - m_run) > 8.0f || m_run == -INFINITY;
+        const float m_new = bump ? m_cand : m_run;
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = bump ? ex2_approx(m_run - m_use) : 1.0f;
+        TL_STAMP(3);
+        // O and the P buffer are quiescent only once PV(j-1) has retired
+        if (j > 0) {
+          mbar_wait(B_PVDONE, (j - 1) & 1);
+          tc_fence_after();
+          TL_STAMP(4);
+          const bool any = __any_sync(0xffffffffu, alpha != 1.0f);
+          if (any) {
+#pragma unroll
+            for (int c = 0; c < HD / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
+            }
+            tmem_st_wait();
+          }
+        }
+        // P = exp2(S*scale - m) -> bf16 -> smem, canonical K-major 128B-swizzled layout:
+        // row r, 16B chunk c at r*128 + ((c ^ (r&7))<<4); two [128 x 64] sub-tiles
+        const float rs = need_mask ? exp_pack_store_n<true, NC>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7)
+                                   : exp_pack_store_n<false, NC>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7);
+        l_run = l_run * alpha + rs;
+        m_run = m_new;
+      };
+      if (BKV > 32 && kv_end - kv0 <= 32) {
+        block(std::integral_constant<int, 32>{}, true);
+      } else {
+        const bool need_mask = (kv0 + BKV > p.kv_len) || (p.causal && kv0 + BKV - 1 > q0 + shift);
+        block(std::integral_constant<int, BKV>{}, need_mask);
       }
-      // P = exp2(S*scale - m) -> bf16 -> smem, canonical K-major 128B-swizzled layout:
-      // row r, 16B chunk c at r*128 + ((c ^ (r&7))<<4); two [128 x 64] sub-tiles
-      const uint32_t p_rbase = sbase + SMEM_P + (row >> 3) * 1024 + (row & 7) * 128;
-      const float rs = need_mask ? exp_pack_store_n<true, BKV>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7)
-                                 : exp_pack_store_n<false, BKV>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7);
-      l_run = l_run * alpha + rs;
-      m_run = m_new;
       TL_STAMP(5);
       fence_proxy_async_smem();
       tc_fence_before();
@@ -302,6 +326,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t sw = row & 7;
 #pragma unroll
     for (int c = 0; c < HD / 32; ++c) {
+      if (!warp_live) break;  // rows past q_len are clipped by the TMA store
       uint32_t o[32];
       tmem_ld_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
       tmem_ld_wait();

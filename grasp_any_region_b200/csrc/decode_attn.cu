@@ -244,13 +244,34 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int GROUP>
+// rotate-half RoPE of one lane's slice: lo = dims [8tig, +8), hi = dims [32+8tig, +8) of a 64-wide head;
+// identical arithmetic (and rounding points) to llama_rope_kv_kernel
+__device__ __forceinline__ void rope_lo_hi(uint4& lo, uint4& hi, const bf16* cos_row, const bf16* sin_row, int tig) {
+  const uint4 cv = __ldg(reinterpret_cast<const uint4*>(cos_row + 8 * tig));
+  const uint4 sv = __ldg(reinterpret_cast<const uint4*>(sin_row + 8 * tig));
+  uint32_t* lw = reinterpret_cast<uint32_t*>(&lo);
+  uint32_t* hw = reinterpret_cast<uint32_t*>(&hi);
+  const uint32_t* cw = reinterpret_cast<const uint32_t*>(&cv);
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(&sv);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 a = unpack_bf16x2(lw[k]), b2 = unpack_bf16x2(hw[k]);
+    const float2 c = unpack_bf16x2(cw[k]), sn = unpack_bf16x2(sw[k]);
+    lw[k] = pack_bf16x2(bf16r(a.x * c.x) + bf16r(-b2.x * sn.x), bf16r(a.y * c.y) + bf16r(-b2.y * sn.y));
+    hw[k] = pack_bf16x2(bf16r(b2.x * c.x) + bf16r(a.x * sn.x), bf16r(b2.y * c.y) + bf16r(a.y * sn.y));
+  }
+}
+
+// ROPE: the step's q/k arrive un-rotated in `qkv`; q is rotated in registers, and the one CTA whose key range holds
+// the new position rotates that K row on the fly, appends it and the V row to the cache (DynamicCache.update) and
+// attends over it -- the separate RoPE/KV-append launch of the decode step disappears.
+template <int GROUP, bool ROPE>
 __global__ void __launch_bounds__(DEC_THREADS)
-decode_attn_mma_kernel(const bf16* __restrict__ qkv, int ldq, const bf16* __restrict__ kcache,
-                       const bf16* __restrict__ vcache, const int* __restrict__ pos_dev,
-                       const int* __restrict__ slot_dev, int hq, int hkv, int max_seq, int splits, float scale_log2,
-                       float* __restrict__ o_part, float* __restrict__ ml_part, int* __restrict__ tickets,
-                       bf16* __restrict__ out, int ldo) {
+decode_attn_mma_kernel(const bf16* __restrict__ qkv, int ldq, bf16* __restrict__ kcache, bf16* __restrict__ vcache,
+                       const int* __restrict__ pos_dev, const int* __restrict__ slot_dev, int hq, int hkv, int max_seq,
+                       int splits, float scale_log2, float* __restrict__ o_part, float* __restrict__ ml_part,
+                       int* __restrict__ tickets, bf16* __restrict__ out, int ldo, const bf16* __restrict__ cos_t,
+                       const bf16* __restrict__ sin_t) {
   constexpr int HD = 64;
   pdl_launch_dependents();
   pdl_wait();
@@ -273,13 +294,17 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, int ldq, const bf16* __rest
   uint32_t qa[4] = {0, 0, 0, 0}, qb[4] = {0, 0, 0, 0};
   if (g < GROUP) {
     const bf16* qp = qkv + static_cast<size_t>(b) * ldq + static_cast<size_t>(kvh * GROUP + g) * HD;
-    const uint4 x = *reinterpret_cast<const uint4*>(qp + 8 * tig);
-    const uint4 y = *reinterpret_cast<const uint4*>(qp + 32 + 8 * tig);
+    uint4 x = *reinterpret_cast<const uint4*>(qp + 8 * tig);
+    uint4 y = *reinterpret_cast<const uint4*>(qp + 32 + 8 * tig);
+    if (ROPE) rope_lo_hi(x, y, cos_t + static_cast<size_t>(len - 1) * (HD / 2), sin_t + static_cast<size_t>(len - 1) * (HD / 2), tig);
     qa[0] = x.x; qa[1] = x.y; qa[2] = x.z; qa[3] = x.w;
     qb[0] = y.x; qb[1] = y.y; qb[2] = y.z; qb[3] = y.w;
   }
-  const bf16* kbase = kcache + (static_cast<size_t>(slot) * hkv + kvh) * max_seq * HD;
-  const bf16* vbase = vcache + (static_cast<size_t>(slot) * hkv + kvh) * max_seq * HD;
+  bf16* kbase = kcache + (static_cast<size_t>(slot) * hkv + kvh) * max_seq * HD;
+  bf16* vbase = vcache + (static_cast<size_t>(slot) * hkv + kvh) * max_seq * HD;
+  const int new_pos = len - 1;  // ROPE: this row is not in the cache yet
+  const bf16* knew = qkv + static_cast<size_t>(b) * ldq + static_cast<size_t>(hq + kvh) * HD;
+  const bf16* vnew = qkv + static_cast<size_t>(b) * ldq + static_cast<size_t>(hq + hkv + kvh) * HD;
 
   float o[8][4];
 #pragma unroll
@@ -295,21 +320,34 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, int ldq, const bf16* __rest
   auto load_step = [&](Step& st, int kb) {
     const uint4 z = make_uint4(0, 0, 0, 0);
     st.k0a = st.k0b = st.k1a = st.k1b = z;
-    if (kb + g < k_end) {
-      const bf16* kp = kbase + static_cast<size_t>(kb + g) * HD;
-      st.k0a = *reinterpret_cast<const uint4*>(kp + 8 * tig);
-      st.k0b = *reinterpret_cast<const uint4*>(kp + 32 + 8 * tig);
-    }
-    if (kb + 8 + g < k_end) {
-      const bf16* kp = kbase + static_cast<size_t>(kb + 8 + g) * HD;
-      st.k1a = *reinterpret_cast<const uint4*>(kp + 8 * tig);
-      st.k1b = *reinterpret_cast<const uint4*>(kp + 32 + 8 * tig);
-    }
+    auto load_k = [&](int key, uint4& lo, uint4& hi) {
+      if (key >= k_end) return;
+      if (ROPE && key == new_pos) {
+        lo = *reinterpret_cast<const uint4*>(knew + 8 * tig);
+        hi = *reinterpret_cast<const uint4*>(knew + 32 + 8 * tig);
+        rope_lo_hi(lo, hi, cos_t + static_cast<size_t>(new_pos) * (HD / 2), sin_t + static_cast<size_t>(new_pos) * (HD / 2), tig);
+        *reinterpret_cast<uint4*>(kbase + static_cast<size_t>(key) * HD + 8 * tig) = lo;
+        *reinterpret_cast<uint4*>(kbase + static_cast<size_t>(key) * HD + 32 + 8 * tig) = hi;
+      } else {
+        const bf16* kp = kbase + static_cast<size_t>(key) * HD;
+        lo = *reinterpret_cast<const uint4*>(kp + 8 * tig);
+        hi = *reinterpret_cast<const uint4*>(kp + 32 + 8 * tig);
+      }
+    };
+    load_k(kb + g, st.k0a, st.k0b);
+    load_k(kb + 8 + g, st.k1a, st.k1b);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int id = lane + 32 * i, key = id >> 3, c = id & 7;
       st.vv[i] = z;
-      if (kb + key < k_end) st.vv[i] = *reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(kb + key) * HD + 8 * c);
+      if (kb + key < k_end) {
+        if (ROPE && kb + key == new_pos) {
+          st.vv[i] = *reinterpret_cast<const uint4*>(vnew + 8 * c);
+          *reinterpret_cast<uint4*>(vbase + static_cast<size_t>(kb + key) * HD + 8 * c) = st.vv[i];
+        } else {
+          st.vv[i] = *reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(kb + key) * HD + 8 * c);
+        }
+      }
     }
   };
   // register double buffering: the loads of step i+1 are in flight while step i is computed (the kernel is
@@ -438,12 +476,19 @@ __global__ void decode_attn_combine_kernel(const float* __restrict__ o_part, con
 
 }  // namespace
 
-extern "C" int gar_decode_attn(const void* qkv, int ldq, const void* kcache, const void* vcache, const int* pos_dev,
-                               const int* slot_dev, int batch, int hq, int hkv, int head_dim, int max_seq, int splits,
-                               float scale, void* o_part_ws, void* ml_part_ws, int* tickets, void* out, int ldo,
-                               void* stream_) {
+static int decode_attn_impl(const void* qkv, int ldq, void* kcache, void* vcache, const int* pos_dev,
+                            const int* slot_dev, int batch, int hq, int hkv, int head_dim, int max_seq, int splits,
+                            float scale, void* o_part_ws, void* ml_part_ws, int* tickets, void* out, int ldo,
+                            const void* cos_t, const void* sin_t, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool rope = cos_t != nullptr;
+  bf16* kc_w = static_cast<bf16*>(kcache);
+  bf16* vc_w = static_cast<bf16*>(vcache);
   const int group = hq / hkv;
+  if (rope && !(head_dim == 64 && (group == 4 || group == 2 || group == 1 || group == 8))) {
+    gar_set_error("gar_decode_attn_rope: fused RoPE needs head_dim 64 (got %d, group %d)", head_dim, group);
+    return GAR_ERR_SHAPE;
+  }
   if (hq % hkv || splits < 1 || splits > 32) return GAR_ERR_ARG;
   const float sl2 = scale * 1.4426950408889634f;
   dim3 grid(splits, hkv, batch);
@@ -454,12 +499,21 @@ extern "C" int gar_decode_attn(const void* qkv, int ldq, const void* kcache, con
                             static_cast<float*>(o_part_ws), static_cast<float*>(ml_part_ws), tickets,              \
                             static_cast<bf16*>(out), ldo))
 #define LAUNCH_MMA(G_)                                                                                              \
-  GAR_CUDA_CHECK(gar_launch(decode_attn_mma_kernel<G_>, grid, dim3(DEC_THREADS), 0, stream, true, dim3(1, 1, 1),      \
-                            static_cast<const bf16*>(qkv), ldq, static_cast<const bf16*>(kcache),                  \
-                            static_cast<const bf16*>(vcache), pos_dev, slot_dev, hq, hkv, max_seq, splits, sl2,    \
-                            static_cast<float*>(o_part_ws), static_cast<float*>(ml_part_ws), tickets,              \
-                            static_cast<bf16*>(out), ldo))
-  if (head_dim == 64 && gar_global_option("decode_attn_mma") && (group == 4 || group == 2 || group == 1 || group == 8)) {
+  do {                                                                                                              \
+    if (rope)                                                                                                       \
+      GAR_CUDA_CHECK(gar_launch(decode_attn_mma_kernel<G_, true>, grid, dim3(DEC_THREADS), 0, stream, true,         \
+                                dim3(1, 1, 1), static_cast<const bf16*>(qkv), ldq, kc_w, vc_w, pos_dev, slot_dev, hq,  \
+                                hkv, max_seq, splits, sl2, static_cast<float*>(o_part_ws),                          \
+                                static_cast<float*>(ml_part_ws), tickets, static_cast<bf16*>(out), ldo,             \
+                                static_cast<const bf16*>(cos_t), static_cast<const bf16*>(sin_t)));                 \
+    else                                                                                                            \
+      GAR_CUDA_CHECK(gar_launch(decode_attn_mma_kernel<G_, false>, grid, dim3(DEC_THREADS), 0, stream, true,        \
+                                dim3(1, 1, 1), static_cast<const bf16*>(qkv), ldq, kc_w, vc_w, pos_dev, slot_dev, hq,  \
+                                hkv, max_seq, splits, sl2, static_cast<float*>(o_part_ws),                          \
+                                static_cast<float*>(ml_part_ws), tickets, static_cast<bf16*>(out), ldo,             \
+                                static_cast<const bf16*>(nullptr), static_cast<const bf16*>(nullptr)));             \
+  } while (0)
+  if (head_dim == 64 && (rope || gar_global_option("decode_attn_mma")) && (group == 4 || group == 2 || group == 1 || group == 8)) {
     if (group == 4) LAUNCH_MMA(4);
     else if (group == 2) LAUNCH_MMA(2);
     else if (group == 1) LAUNCH_MMA(1);
@@ -486,4 +540,24 @@ extern "C" int gar_decode_attn(const void* qkv, int ldq, const void* kcache, con
                               static_cast<const float*>(o_part_ws), static_cast<const float*>(ml_part_ws),
                               static_cast<bf16*>(out), ldo, hq, splits));
   return GAR_OK;
+}
+
+extern "C" int gar_decode_attn(const void* qkv, int ldq, const void* kcache, const void* vcache, const int* pos_dev,
+                               const int* slot_dev, int batch, int hq, int hkv, int head_dim, int max_seq, int splits,
+                               float scale, void* o_part_ws, void* ml_part_ws, int* tickets, void* out, int ldo,
+                               void* stream) {
+  return decode_attn_impl(qkv, ldq, const_cast<void*>(kcache), const_cast<void*>(vcache), pos_dev, slot_dev, batch, hq,
+                          hkv, head_dim, max_seq, splits, scale, o_part_ws, ml_part_ws, tickets, out, ldo, nullptr,
+                          nullptr, stream);
+}
+
+// Same, with HF apply_rotary_pos_emb + DynamicCache.update fused in: qkv holds the step's UN-rotated q/k/v rows,
+// cos/sin tables are [max_pos, head_dim/2]; the new K/V rows are appended to the cache at pos_dev[b].  head_dim 64.
+extern "C" int gar_decode_attn_rope(const void* qkv, int ldq, void* kcache, void* vcache, const int* pos_dev,
+                                    const int* slot_dev, int batch, int hq, int hkv, int head_dim, int max_seq,
+                                    int splits, float scale, const void* cos_t, const void* sin_t, void* o_part_ws,
+                                    void* ml_part_ws, int* tickets, void* out, int ldo, void* stream) {
+  if (!cos_t || !sin_t) return GAR_ERR_ARG;
+  return decode_attn_impl(qkv, ldq, kcache, vcache, pos_dev, slot_dev, batch, hq, hkv, head_dim, max_seq, splits, scale,
+                          o_part_ws, ml_part_ws, tickets, out, ldo, cos_t, sin_t, stream);
 }

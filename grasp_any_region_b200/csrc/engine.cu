@@ -41,6 +41,7 @@ struct gar_engine {
   int use_skinny = 1;
   int fuse_rope = 1;
   int use_gemv = 1;
+  int fuse_decode_rope = 1;
   float *sumsq_a, *sumsq_b;
   // decode graph
   std::map<long long, cudaGraphExec_t> graphs;  // decode-step graphs keyed by (slot0, batch)
@@ -219,7 +220,6 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
       TRY(gar_gemv_decode(e->hdec, D, wqkv, D, e->d_qkv, qkv_w, batch, qkv_w, D, 0, nullptr, 0, ln1, e->sumsq_a, n_part,
                           d.rms_eps, nullptr, nullptr, s));
     }
-    TRY(gar_llama_rope_kv(e->d_qkv, batch, hq, hkv, hd, cos_t, sin_t, 0, e->pos + e->slot_base, nullptr, -1, kc, vc, d.max_seq, 0, s));
     {
       ProfScope ps(e, s, PK_DECODE_ATTN, 0.0);
       int splits = e->dec_splits;
@@ -227,8 +227,17 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
         splits = (3 * gar_num_sms()) / (batch * hkv);  // one resident wave of 3 CTAs per SM
         splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
       }
-      TRY(gar_decode_attn(e->d_qkv, qkv_w, kc, vc, e->pos + e->slot_base, nullptr, batch, hq, hkv, hd, d.max_seq, splits, scale,
-                          e->o_part, e->ml_part, e->tickets, e->d_att, hq * hd, s));
+      if (e->fuse_decode_rope && hd == 64) {
+        // RoPE of q and of the new K row, the KV append and the attention in one launch
+        TRY(gar_decode_attn_rope(e->d_qkv, qkv_w, kc, vc, e->pos + e->slot_base, nullptr, batch, hq, hkv, hd, d.max_seq,
+                                 splits, scale, cos_t, sin_t, e->o_part, e->ml_part, e->tickets, e->d_att, hq * hd, s));
+        e->launches -= 1;
+      } else {
+        TRY(gar_llama_rope_kv(e->d_qkv, batch, hq, hkv, hd, cos_t, sin_t, 0, e->pos + e->slot_base, nullptr, -1, kc, vc,
+                              d.max_seq, 0, s));
+        TRY(gar_decode_attn(e->d_qkv, qkv_w, kc, vc, e->pos + e->slot_base, nullptr, batch, hq, hkv, hd, d.max_seq, splits,
+                            scale, e->o_part, e->ml_part, e->tickets, e->d_att, hq * hd, s));
+      }
     }
     {
       ProfScope ps(e, s, PK_GEMV, 2.0 * D * static_cast<double>(hq * hd));
@@ -678,6 +687,7 @@ int gar_engine_set_option(gar_engine* e, const char* name, int value) {
   if (n == "skinny_gemm") e->use_skinny = value;
   else if (n == "fuse_rope") e->fuse_rope = value;
   else if (n == "gemv_decode") e->use_gemv = value;
+  else if (n == "fuse_decode_rope") e->fuse_decode_rope = value;
   else if (n == "decode_splits" && value >= 0 && value <= 32) e->dec_splits = value;
   else if (n == "pdl" || n == "decode_attn_mma" || n == "attn_bkv" || n == "gemm_2cta") {
     if (gar_set_global_option(name, value)) return GAR_ERR_ARG;

@@ -182,6 +182,19 @@ def decode_attn(qkv, kcache, vcache, pos_dev, hq, hkv, hd, max_seq, splits=8, fu
     return out
 
 
+def decode_attn_rope(qkv, kcache, vcache, pos_dev, hq, hkv, hd, max_seq, cos_t, sin_t, splits=8):
+    """Fused RoPE + KV append + decode attention (qkv rows un-rotated; caches updated in place)."""
+    B = qkv.shape[0]
+    tickets = torch.zeros((B * hkv,), dtype=torch.int32, device=qkv.device)
+    o_part = torch.empty((B, hq, splits, hd), dtype=torch.float32, device=qkv.device)
+    ml = torch.empty((B, hq, splits, 2), dtype=torch.float32, device=qkv.device)
+    out = torch.empty((B, hq * hd), dtype=torch.bfloat16, device=qkv.device)
+    check(_lib.load().gar_decode_attn_rope(_p(qkv), qkv.stride(0), _p(kcache), _p(vcache), _p(pos_dev), None, B, hq, hkv,
+                                           hd, max_seq, splits, 1.0 / math.sqrt(hd), _p(cos_t), _p(sin_t), _p(o_part),
+                                           _p(ml), _p(tickets), _p(out), hq * hd, _stream()), "gar_decode_attn_rope")
+    return out
+
+
 def assemble_embeds(input_ids, table, feats, crop_ids, rois, has_roi, spatial_scale, ncw, nch, tpt, image_token_id):
     """input_ids (S,) int64 cuda; feats (T, tpt*tpt, D); rois list of 5-float lists (one per crop id)."""
     S = input_ids.numel()

@@ -130,6 +130,12 @@ int gar_decode_attn(const void* qkv, int ldq, const void* kcache, const void* vc
                     const int* slot_dev, int batch, int hq, int hkv, int head_dim, int max_seq, int splits, float scale,
                     void* o_part_ws, void* ml_part_ws, int* tickets, void* out, int ldo, void* stream);
 
+/* decode attention with HF apply_rotary_pos_emb + DynamicCache.update fused in (un-rotated q/k/v rows in `qkv`) */
+int gar_decode_attn_rope(const void* qkv, int ldq, void* kcache, void* vcache, const int* pos_dev, const int* slot_dev,
+                         int batch, int hq, int hkv, int head_dim, int max_seq, int splits, float scale,
+                         const void* cos_t, const void* sin_t, void* o_part_ws, void* ml_part_ws, int* tickets,
+                         void* out, int ldo, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Engine: GARModel.generate() (modeling_gar.py:295-428) as a device-resident pipeline
  * ---------------------------------------------------------------------------------------- */

@@ -357,3 +357,26 @@ def test_decode_attention(mma):
         err = (out[b].float() - ref).abs().max().item()
         assert err <= 2e-2, (b, err)
     _lib.check(_lib.load().gar_set_global_option(b"decode_attn_mma", 1))
+
+
+def test_decode_attention_fused_rope_matches_unfused():
+    """RoPE + KV append fused into the decode attention kernel == llama_rope_kv followed by decode attention,
+    bit for bit, including the cache rows it appends."""
+    from grasp_any_region_b200.config import TextSpec
+    from grasp_any_region_b200.rope import llama_cos_sin
+
+    B, hq, hkv, hd, max_seq = 4, 8, 2, 64, 600
+    cos, sin = llama_cos_sin(TextSpec(), max_seq)
+    cos, sin = cos.to(bf).to(DEV), sin.to(bf).to(DEV)
+    qkv = rnd(B, (hq + 2 * hkv) * hd, seed=90)
+    kc0, vc0 = rnd(B, hkv, max_seq, hd, seed=91), rnd(B, hkv, max_seq, hd, seed=92)
+    pos = torch.tensor([0, 17, 333, 598], dtype=torch.int32, device=DEV)
+    for splits in (1, 5, 8):
+        kc1, vc1, q1 = kc0.clone(), vc0.clone(), qkv.clone()
+        ops.llama_rope_kv_(q1, hq, hkv, hd, cos, sin, kc1, vc1, max_seq, pos_dev=pos, slot0=-1)
+        want = ops.decode_attn(q1, kc1, vc1, pos, hq, hkv, hd, max_seq, splits=splits)
+        kc2, vc2 = kc0.clone(), vc0.clone()
+        got = ops.decode_attn_rope(qkv.clone(), kc2, vc2, pos, hq, hkv, hd, max_seq, cos, sin, splits=splits)
+        torch.cuda.synchronize()
+        assert torch.equal(kc1, kc2) and torch.equal(vc1, vc2)
+        assert torch.equal(got, want)
