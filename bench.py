@@ -53,6 +53,16 @@ def parse_args():
     return ap.parse_args()
 
 
+def gemm_traffic_bytes():
+    """Mean DRAM bytes (read+write) per tcgen05 GEMM launch of this same command, from the committed ncu pass
+    (profiles/r01_gemm_traffic.json; ncu cannot run inside the timed bench).  None if the file is absent."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_gemm_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -235,13 +245,14 @@ def main():
               for k in ("pixel_values", "global_mask_values", "input_ids"))
     d2h = B * NT * 4
 
-    def run_steps(batch_list, steps):
-        """`steps` batches through the public API (GARModel.generate_batch; --pipeline: generate_batches)."""
+    def run_steps(batch_list, steps, gather=True):
+        """`steps` batches through the public API (GARModel.generate_batch; --pipeline: generate_batches).
+        gather=False for the rank-0-only diagnostic passes: a collective there would wait for ranks that never come."""
         if args.pipeline:
             toks = model.generate_batches([batch_list] * steps, max_new_tokens=NT, eos_token_id=None)
         else:
             toks = [model.generate_batch(batch_list, max_new_tokens=NT, eos_token_id=None) for _ in range(steps)]
-        if world > 1:  # the path's one collective: all-gather of the decoded ids (north_star)
+        if world > 1 and gather:  # the path's one collective: all-gather of the decoded ids (north_star)
             flat = [t + [-1] * (NT - len(t)) for step_toks in toks for t in step_toks]
             t = torch.tensor(flat, dtype=torch.int32, device=dev)
             buf = torch.empty((world * t.shape[0], NT), dtype=torch.int32, device=dev)
@@ -315,7 +326,7 @@ def main():
     roof, stages = None, None
     if rank == 0 and not args.no_profile:
         eng.profile(True)
-        step_resident(1)
+        run_steps(reqs_dev, 1, gather=False)
         prof = eng.profile_read()
         eng.profile(False)
         g_ms, g_fl, g_n = prof["gemm"]
@@ -324,7 +335,7 @@ def main():
         tf = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05)", "achieved": tf,
                 "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["tf_sustained"],
-                "peak_source": f"{peaks['source']} sustained bf16", "traffic": None,
+                "peak_source": f"{peaks['source']} sustained bf16", "traffic": gemm_traffic_bytes(),
                 "launches_per_step": g_n, "ms_per_step": g_ms, "share_of_step": g_ms / (ms / args.steps)}
         stages = {
             "attn_tcgen05": {"ms": a_ms, "TFLOP/s": a_fl / (a_ms * 1e-3) / 1e12 if a_ms > 0 else 0.0, "launches": a_n},

@@ -307,7 +307,7 @@ def attn_bkv(request):
 
 
 @pytest.mark.parametrize("hd", [64, 128])
-@pytest.mark.parametrize("T,ntok,heads", [(1, 128, 1), (2, 1025, 2), (1, 1024, 4), (3, 300, 2), (1, 65, 1)])
+@pytest.mark.parametrize("T,ntok,heads", [(1, 128, 1), (2, 1025, 2), (1, 1024, 4), (3, 300, 2), (1, 65, 1), (2, 160, 2), (1, 289, 1)])
 def test_attention_vit_layout(T, ntok, heads, hd, attn_bkv):
     qkv = rnd(T * ntok, 3 * heads * hd, seed=27)
     out = ops.attn_fwd_packed_qkv(qkv, T, ntok, heads, hd)
