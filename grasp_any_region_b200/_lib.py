@@ -48,6 +48,8 @@ SIGNATURES = {
     "gar_bump_step": (_i, [_vp, _vp]),
     "gar_assemble_embeds": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, C.POINTER(_ll), C.POINTER(_f), C.POINTER(_i), _i,
                                  _f, _i, _i, _i, _ll, _vp, _vp, _vp, _vp]),
+    "gar_assemble_embeds_batch": (_i, [_i, C.POINTER(_vp), _i, _vp, _i, _vp, _i, _i, C.POINTER(_ll), C.POINTER(_f),
+                                       C.POINTER(_i), _i, _f, C.POINTER(_i), C.POINTER(_i), _i, _ll, _vp, _vp, _vp, _vp]),
     "gar_attn_fwd": (_i, [_vp, _ll, _ll, _i, _vp, _vp, _ll, _ll, _i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _i, _i, _i,
                           _i, _i, _i, _i, _i, _i, _f, _vp]),
     "gar_decode_attn_rope": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -62,6 +64,8 @@ SIGNATURES = {
     "gar_engine_assemble": (_i, [_vp, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_i), _f, _i, _i, _vp]),
     "gar_engine_prefill": (_i, [_vp, _i, _i, _vp]),
     "gar_engine_assemble_at": (_i, [_vp, _i, _vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_i), _f, _i, _i, _vp]),
+    "gar_engine_assemble_batch": (_i, [_vp, _i, _i, C.POINTER(_vp), _i, _i, C.POINTER(_f), C.POINTER(_i), _f,
+                                       C.POINTER(_i), C.POINTER(_i), _vp]),
     "gar_engine_prefill_batch": (_i, [_vp, _i, _i, _i, _vp]),
     "gar_engine_prefill_all_logits": (_i, [_vp, _i, _i, _vp, _vp]),
     "gar_engine_generate": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _vp]),

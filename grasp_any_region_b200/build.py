@@ -29,7 +29,7 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for name in sorted(os.listdir(CSRC)) + ["../../include/gar_b200.h"]:
+    for name in sorted(n for n in os.listdir(CSRC) if n.endswith((".cu", ".cuh"))) + ["../../include/gar_b200.h"]:
         with open(os.path.join(CSRC, name), "rb") as f:
             h.update(name.encode())
             h.update(f.read())

@@ -5,13 +5,15 @@
 //   :341-346  get_placeholder_mask + masked_scatter of image_features  (bool mask S*D + scatter)
 //   :348-414  per crop token: `in` scan + 2 .item() syncs, _merge permute+contiguous, .float() of the
 //             whole map, torchvision.ops.roi_align, permute/cast, 3-way torch.cat
-// with two launches and no host synchronisation:
-//   plan_rows  : one block scans input_ids -> per-row source plan (text / image ordinal / crop offset),
-//                validates counts and run shapes into a status word
-//   assemble   : one warp per output row; text & image rows are 16-byte vector copies, crop rows
-//                evaluate roi_align for their (ph,pw) bin directly on the channel-contiguous
-//                (T,256,D) feature tensor (no merged map, no fp32 copy) in the operator's exact fp32
-//                operation order (oracle/roi_align_ref.py) and round once to bf16.
+// with three launches for a whole batch of requests and no host synchronisation:
+//   plan_rows    : one block per request scans input_ids -> per-row source plan (text / image ordinal /
+//                  crop offset), validates counts and run shapes into a status word
+//   gather_rows  : one warp per output row of every request; text & image rows are 16-byte vector
+//                  copies with all of a lane's loads in flight before its first store (the kernel is a
+//                  pure HBM stream: few registers, full occupancy)
+//   replay_rows  : one warp per crop row: roi_align for its (ph,pw) bin evaluated directly on the
+//                  channel-contiguous (T,256,D) feature tensor (no merged map, no fp32 copy) in the
+//                  operator's exact fp32 operation order (oracle/roi_align_ref.py), one bf16 rounding.
 // HBM-bound: ~2*S*D*2 bytes per request; no tensor cores on this path.
 #include "common.cuh"
 
@@ -20,19 +22,32 @@ namespace {
 constexpr int MAX_REGIONS = 8;
 constexpr int KIND_TEXT = 0, KIND_IMAGE = 1, KIND_CROP = 2;
 
-struct AssembleParams {
-  int n_regions;                 // number of crop token ids configured (prompt_numbers)
-  long long crop_ids[MAX_REGIONS];
+constexpr int MAX_REQS = 8;  // requests per launch (kernel-parameter space); larger batches are chunked
+
+struct RequestParams {
+  const long long* ids;          // (S,) int64 device
   float rois[MAX_REGIONS][5];    // [0, x1, y1, x2, y2] already in "feature coords" (reference quirk 1)
   int has_roi[MAX_REGIONS];      // bbox supplied for this crop id
+  int ncw, nch;                  // tile grid (w,h)
+};
+
+struct AssembleParams {
+  int n_regions;                 // number of crop token ids configured (prompt_numbers)
+  int nreq;
+  long long crop_ids[MAX_REGIONS];
   float spatial_scale;           // applied AGAIN inside roi_align, as the reference does
-  int ncw, nch, tpt;             // tile grid (w,h) and tokens per tile side (16)
+  int tpt;                       // tokens per tile side (16)
   long long image_token_id;
+  RequestParams r[MAX_REQS];
 };
 
 // plan word: kind in bits [30,32), payload in [0,30)
-__global__ void plan_rows_kernel(const long long* __restrict__ ids, int S, int n_image_feats, AssembleParams p,
-                                 int* __restrict__ plan, int* __restrict__ status) {
+__global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant__ AssembleParams p,
+                                 int* __restrict__ plan_all, int* __restrict__ status_all) {
+  const RequestParams& rq = p.r[blockIdx.x];
+  const long long* __restrict__ ids = rq.ids;
+  int* __restrict__ plan = plan_all + static_cast<size_t>(blockIdx.x) * S;
+  int* __restrict__ status = status_all + 2 * blockIdx.x;
   __shared__ int s_warp[32];
   __shared__ int s_min[MAX_REGIONS], s_max[MAX_REGIONS], s_cnt[MAX_REGIONS];
   __shared__ int s_total;
@@ -83,7 +98,7 @@ __global__ void plan_rows_kernel(const long long* __restrict__ ids, int S, int n
       ++ord;
     } else {
       for (int k = 0; k < p.n_regions; ++k) {
-        if (id == p.crop_ids[k] && p.has_roi[k]) {
+        if (id == p.crop_ids[k] && rq.has_roi[k]) {
           word = (KIND_CROP << 30) | (k << 16) | ((s - s_min[k]) & 0xffff);
         }
       }
@@ -96,7 +111,7 @@ __global__ void plan_rows_kernel(const long long* __restrict__ ids, int S, int n
     const int run = p.tpt * p.tpt;
     for (int k = 0; k < p.n_regions; ++k) {
       if (s_cnt[k] > 0) {
-        if (!p.has_roi[k]) st |= 4;                                          // reference: KeyError on bboxes[str(id)]
+        if (!rq.has_roi[k]) st |= 4;                                         // reference: KeyError on bboxes[str(id)]
         if (s_cnt[k] != run || s_max[k] - s_min[k] + 1 != run) st |= 2;      // replay would change the length
       }
     }
@@ -135,39 +150,75 @@ __device__ __forceinline__ Sample make_sample(float y, float x, int H, int W) {
   return sm;
 }
 
-__global__ void assemble_kernel(const long long* __restrict__ ids, const int* __restrict__ plan,
-                                const bf16* __restrict__ table, const bf16* __restrict__ feats,
-                                bf16* __restrict__ out, int S, int D, int vocab, AssembleParams p) {
+// Text and image rows of every request: out row <- one table / feature row.  CH 16-byte vectors per lane are loaded
+// before the first store, so a warp keeps CH*512 B in flight (12 resident blocks: ~100 KB per SM).
+template <int CH>
+__global__ void __launch_bounds__(128, 12)
+gather_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ table, const bf16* __restrict__ feats,
+                   bf16* __restrict__ out, int S, int D, int vocab, int rows_per_req_feats,
+                   const __grid_constant__ AssembleParams p) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nvec = D / 8;
-  for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < S; s += gridDim.x * wpb) {
-    const int word = plan[s];
+  const long long total = static_cast<long long>(p.nreq) * S;
+  for (long long g = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); g < total;
+       g += static_cast<long long>(gridDim.x) * wpb) {
+    const int word = plan[g];
     const int kind = (word >> 30) & 3;
-    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(s) * D);
-    if (kind != KIND_CROP) {
-      const uint4* src;
-      if (kind == KIND_IMAGE) {
-        src = reinterpret_cast<const uint4*>(feats + static_cast<size_t>(word & 0x3fffffff) * D);
-      } else {
-        long long id = ids[s];
-        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-        src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * D);
-      }
-      for (int v = lane; v < nvec; v += 32) dst[v] = __ldg(src + v);
-      continue;
+    if (kind == KIND_CROP) continue;
+    const int req = static_cast<int>(g / S), s = static_cast<int>(g - static_cast<long long>(req) * S);
+    const uint4* src;
+    if (kind == KIND_IMAGE) {
+      src = reinterpret_cast<const uint4*>(
+          feats + (static_cast<size_t>(req) * rows_per_req_feats + (word & 0x3fffffff)) * D);
+    } else {
+      long long id = p.r[req].ids[s];
+      id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+      src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * D);
     }
-    // ---- RoI replay row: bin (ph, pw) of region k ----
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(g) * D);
+    for (int v0 = 0; v0 < nvec; v0 += 32 * CH) {
+      uint4 buf[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int v = v0 + c * 32 + lane;
+        if (v < nvec) buf[c] = ld_nc_v4(src + v);
+      }
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int v = v0 + c * 32 + lane;
+        if (v < nvec) dst[v] = buf[c];
+      }
+    }
+  }
+}
+
+// RoI replay rows: bin (ph, pw) of region k of request req.  One warp per crop row (the plan says which rows).
+__global__ void __launch_bounds__(256)
+replay_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ feats_all, bf16* __restrict__ out, int S, int D,
+                   int rows_per_req_feats, const __grid_constant__ AssembleParams p) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = D / 8;
+  const long long total = static_cast<long long>(p.nreq) * S;
+  for (long long g = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); g < total;
+       g += static_cast<long long>(gridDim.x) * wpb) {
+    const int word = plan[g];
+    if (((word >> 30) & 3) != KIND_CROP) continue;
+    const int req = static_cast<int>(g / S);
+    const RequestParams& rq = p.r[req];
+    const bf16* feats = feats_all + static_cast<size_t>(req) * rows_per_req_feats * D;
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(g) * D);
     const int k = (word >> 16) & 0x3fff;
     const int off = word & 0xffff;
     const int tpt = p.tpt;
     const int ph = off / tpt, pw = off % tpt;
-    const int H = p.nch * tpt, W = p.ncw * tpt;
+    const int H = rq.nch * tpt, W = rq.ncw * tpt;
     const float scale = p.spatial_scale;
-    const float start_w = __fsub_rn(__fmul_rn(p.rois[k][1], scale), 0.5f);
-    const float start_h = __fsub_rn(__fmul_rn(p.rois[k][2], scale), 0.5f);
-    const float end_w = __fsub_rn(__fmul_rn(p.rois[k][3], scale), 0.5f);
-    const float end_h = __fsub_rn(__fmul_rn(p.rois[k][4], scale), 0.5f);
+    const float start_w = __fsub_rn(__fmul_rn(rq.rois[k][1], scale), 0.5f);
+    const float start_h = __fsub_rn(__fmul_rn(rq.rois[k][2], scale), 0.5f);
+    const float end_w = __fsub_rn(__fmul_rn(rq.rois[k][3], scale), 0.5f);
+    const float end_h = __fsub_rn(__fmul_rn(rq.rois[k][4], scale), 0.5f);
     const float bin_h = __fdiv_rn(__fsub_rn(end_h, start_h), static_cast<float>(tpt));
     const float bin_w = __fdiv_rn(__fsub_rn(end_w, start_w), static_cast<float>(tpt));
     Sample sm[4];
@@ -190,7 +241,7 @@ __global__ void assemble_kernel(const long long* __restrict__ ids, const int* __
       for (int c = 0; c < 4; ++c) {
         const int lin = sm[q].pos[c];
         const int y = lin / W, x = lin % W;
-        const size_t row = (static_cast<size_t>(1 + (y / tpt) * p.ncw + x / tpt) * tpt + (y % tpt)) * tpt + (x % tpt);
+        const size_t row = (static_cast<size_t>(1 + (y / tpt) * rq.ncw + x / tpt) * tpt + (y % tpt)) * tpt + (x % tpt);
         cell[q * 4 + c] = reinterpret_cast<const uint4*>(feats + row * D);
       }
     }
@@ -229,36 +280,68 @@ __global__ void assemble_kernel(const long long* __restrict__ ids, const int* __
 
 }  // namespace
 
+// Batched form: request r reads input_ids[r] (device pointers in a HOST array), features
+// image_features + r*n_image_rows*D, boxes rois[r][n_regions][5] / has_roi[r][n_regions] (host), tile grid
+// ncw[r] x nch[r]; writes rows [r*S, (r+1)*S) of out / plan_ws and status_dev[2r..2r+1].
+extern "C" int gar_assemble_embeds_batch(int nreq, const long long* const* input_ids, int S, const void* embed_table,
+                                         int vocab, const void* image_features, int n_image_rows, int D,
+                                         const long long* crop_ids, const float* rois, const int* has_roi,
+                                         int n_regions, float spatial_scale, const int* ncw, const int* nch, int tpt,
+                                         long long image_token_id, void* out, int* plan_ws, int* status_dev,
+                                         void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_regions > MAX_REGIONS || D % 8 || S <= 0 || nreq <= 0 || tpt * tpt > 0xffff) {
+    gar_set_error("gar_assemble_embeds_batch: bad args nreq=%d S=%d D=%d n_regions=%d", nreq, S, D, n_regions);
+    return GAR_ERR_ARG;
+  }
+  for (int r0 = 0; r0 < nreq; r0 += MAX_REQS) {
+    const int nr = nreq - r0 < MAX_REQS ? nreq - r0 : MAX_REQS;
+    AssembleParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_regions = n_regions;
+    p.nreq = nr;
+    for (int k = 0; k < MAX_REGIONS; ++k) p.crop_ids[k] = k < n_regions ? crop_ids[k] : -1;
+    p.spatial_scale = spatial_scale;
+    p.tpt = tpt;
+    p.image_token_id = image_token_id;
+    for (int r = 0; r < nr; ++r) {
+      RequestParams& rq = p.r[r];
+      rq.ids = input_ids[r0 + r];
+      rq.ncw = ncw[r0 + r];
+      rq.nch = nch[r0 + r];
+      for (int k = 0; k < n_regions; ++k) {
+        rq.has_roi[k] = has_roi[(r0 + r) * n_regions + k];
+        for (int j = 0; j < 5; ++j) rq.rois[k][j] = rois[((r0 + r) * n_regions + k) * 5 + j];
+      }
+    }
+    int* plan = plan_ws + static_cast<size_t>(r0) * S;
+    const bf16* feats = static_cast<const bf16*>(image_features) + static_cast<size_t>(r0) * n_image_rows * D;
+    bf16* o = static_cast<bf16*>(out) + static_cast<size_t>(r0) * S * D;
+    plan_rows_kernel<<<nr, 1024, 0, stream>>>(S, n_image_rows, p, plan, status_dev + 2 * r0);
+    GAR_CUDA_CHECK(cudaGetLastError());
+    const long long rows = static_cast<long long>(nr) * S;
+    const int wpb = 4;
+    // one row per warp; 4 vectors per lane in flight (2 passes over a 2048-wide row), 12 blocks/SM resident
+    const long long gblocks = (rows + wpb - 1) / wpb;
+    gather_rows_kernel<4><<<static_cast<unsigned>(gblocks), wpb * 32, 0, stream>>>(
+        plan, static_cast<const bf16*>(embed_table), feats, o, S, D, vocab, n_image_rows, p);
+    GAR_CUDA_CHECK(cudaGetLastError());
+    if (n_regions > 0) {
+      const long long rblocks = (rows + 7) / 8;
+      replay_rows_kernel<<<static_cast<unsigned>(rblocks), 256, 0, stream>>>(plan, feats, o, S, D, n_image_rows, p);
+      GAR_CUDA_CHECK(cudaGetLastError());
+    }
+  }
+  return GAR_OK;
+}
+
 // rois: n_regions x 5 fp32 host array; has_roi: n_regions ints; crop_ids: n_regions int64 (host)
 extern "C" int gar_assemble_embeds(const long long* input_ids, int S, const void* embed_table, int vocab,
                                    const void* image_features, int n_image_rows, int D, const long long* crop_ids,
                                    const float* rois, const int* has_roi, int n_regions, float spatial_scale, int ncw,
                                    int nch, int tpt, long long image_token_id, void* out, int* plan_ws,
                                    int* status_dev, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (n_regions > MAX_REGIONS || D % 8 || S <= 0 || tpt * tpt > 0xffff) {
-    gar_set_error("gar_assemble_embeds: bad args S=%d D=%d n_regions=%d", S, D, n_regions);
-    return GAR_ERR_ARG;
-  }
-  AssembleParams p;
-  p.n_regions = n_regions;
-  for (int k = 0; k < MAX_REGIONS; ++k) {
-    p.crop_ids[k] = k < n_regions ? crop_ids[k] : -1;
-    p.has_roi[k] = k < n_regions ? has_roi[k] : 0;
-    for (int j = 0; j < 5; ++j) p.rois[k][j] = k < n_regions ? rois[k * 5 + j] : 0.f;
-  }
-  p.spatial_scale = spatial_scale;
-  p.ncw = ncw;
-  p.nch = nch;
-  p.tpt = tpt;
-  p.image_token_id = image_token_id;
-  plan_rows_kernel<<<1, 1024, 0, stream>>>(input_ids, S, n_image_rows, p, plan_ws, status_dev);
-  GAR_CUDA_CHECK(cudaGetLastError());
-  const int wpb = 4;
-  int grid = (S + wpb - 1) / wpb;
-  assemble_kernel<<<grid, wpb * 32, 0, stream>>>(input_ids, plan_ws, static_cast<const bf16*>(embed_table),
-                                                  static_cast<const bf16*>(image_features), static_cast<bf16*>(out), S,
-                                                  D, vocab, p);
-  GAR_CUDA_CHECK(cudaGetLastError());
-  return GAR_OK;
+  return gar_assemble_embeds_batch(1, &input_ids, S, embed_table, vocab, image_features, n_image_rows, D, crop_ids, rois,
+                                   has_roi, n_regions, spatial_scale, &ncw, &nch, tpt, image_token_id, out, plan_ws,
+                                   status_dev, stream_);
 }

@@ -6,13 +6,17 @@
 // the PV product, fp32 O accumulation, one bf16 rounding of O / l at the end.
 //
 // One CTA = one (sequence, head, 128-query block); two CTAs co-reside per SM so one CTA's softmax
-// overlaps the other's MMAs.  Roles (192 threads):
+// overlaps the other's MMAs.  Roles (256 threads = two warpgroups):
 //   warp 0     TMA producer: Q once, K double-buffered, V single-buffered (3-D tensor maps so rows
 //              past a sequence end are zero-filled on load and clipped on store)
 //   warp 1     MMA issuer : S = Q K^T  (128x128x64, both operands K-major, 128B swizzle)
 //                           O += P V   (128x64x128, P K-major from smem, V MN-major from smem)
-//   warps 2-5  softmax    : tcgen05.ld S row-per-thread -> online softmax -> P (bf16) into swizzled
+//   warps 2-3  idle (they complete the control warpgroup so setmaxnreg can hand its registers over)
+//   warps 4-7  softmax    : tcgen05.ld S row-per-thread -> online softmax -> P (bf16) into swizzled
 //                           smem, rescale O in TMEM, final O/l -> smem -> TMA store
+// Registers: the kernel launches at MAXREG per thread; the control warpgroup drops to 40 and the
+// softmax warpgroup (a whole 128-wide score row per thread lives in registers) takes the difference,
+// so the row-per-thread softmax compiles without local-memory spills.
 #include <type_traits>
 
 #include "common.cuh"
@@ -20,7 +24,7 @@
 namespace {
 
 constexpr int BQ = 128;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 256;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows of 128 B (one 64-wide, 128B-swizzled sub-tile)
 constexpr uint32_t TM_S = 0;
 
@@ -42,7 +46,11 @@ struct AttCfg {
   static constexpr int SMEM_TOTAL = SMEM_P + (BKV / 64) * TILE_BYTES;
   static constexpr int SMEM_BYTES = SMEM_TOTAL + 1024;
   static constexpr int CTAS_PER_SM = HD == 64 ? (BKV == 64 ? 3 : 2) : 1;
-  static constexpr int MAXREG = CTAS_PER_SM == 3 ? 112 : (CTAS_PER_SM == 2 ? 168 : 255);  // 64K regs / (192 thr * CTAs)
+  // 64K regs / (256 thr * CTAs), multiple of 8; control warpgroup keeps REG_CTRL, the softmax warpgroup gets the rest
+  static constexpr int MAXREG = CTAS_PER_SM == 3 ? 80 : (CTAS_PER_SM == 2 ? 128 : 255);
+  static constexpr bool REALLOC = CTAS_PER_SM > 1;
+  static constexpr int REG_CTRL = 48;
+  static constexpr int REG_SOFTMAX = 2 * MAXREG - REG_CTRL;  // 112 / 208
   static constexpr int TMEM_COLS = (BKV + HD) <= 128 ? 128 : 256;  // S: BKV columns, O: HD columns
   static constexpr uint32_t TM_O = BKV;
 };
@@ -62,20 +70,23 @@ struct AttnParams {
 // (unmasked) path carries no compares and the score registers are never written back.
 template <bool MASKED, int NCOLS>
 __device__ __forceinline__ float row_max_n(const uint32_t (&s)[NCOLS], int kv0, int lim) {
-  float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  // 8 independent FMNMX3 chains (depth NCOLS/16) so the dependent-issue latency is covered by one warp alone
+  float mx[8];
 #pragma unroll
-  for (int i = 0; i < NCOLS; i += 8) {
+  for (int q = 0; q < 8; ++q) mx[q] = -INFINITY;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+  for (int i = 0; i < NCOLS; i += 16) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
       float a = __uint_as_float(s[i + 2 * q]), b = __uint_as_float(s[i + 2 * q + 1]);
       if (MASKED) {
         a = (kv0 + i + 2 * q <= lim) ? a : -INFINITY;
         b = (kv0 + i + 2 * q + 1 <= lim) ? b : -INFINITY;
       }
-      mx4[q] = fmax3(mx4[q], a, b);
+      mx[q] = fmax3(mx[q], a, b);
     }
   }
-  return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+  return fmaxf(fmax3(mx[0], mx[1], mx[2]), fmax3(fmax3(mx[3], mx[4], mx[5]), mx[6], mx[7]));
 }
 
 template <bool MASKED, int NCOLS>
@@ -159,6 +170,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&tmem_ptr_sh);
 
+  if (warp < 4) {
+  if constexpr (Cfg::REALLOC) setmaxnreg_dec<Cfg::REG_CTRL>();
   if (warp == 0) {
     if (lane == 0) {
       const int kb_coord = b * p.kv_batch_mul + kvh * p.kv_batch_head_mul;
@@ -227,7 +240,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         umma_commit(B_PVDONE);
       }
     }
+  }
   } else {
+    if constexpr (Cfg::REALLOC) setmaxnreg_inc<Cfg::REG_SOFTMAX>();
     // ---------------- softmax warps: thread <-> query row ----------------
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
@@ -235,7 +250,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int q_pos = q0 + row + shift;  // last key this row may see (causal)
     float m_run = -INFINITY, l_run = 0.f;
 #ifdef GAR_ATTN_TIMELINE  // debug build only: per-phase clock64 stamps of CTA (0,0,0), first softmax thread
-    const bool tl = p.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 64;
+    const bool tl = p.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
 #define TL_STAMP(i) if (tl) p.timeline[j * 8 + (i)] = clock64()
 #else
 #define TL_STAMP(i)
@@ -343,7 +358,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     fence_proxy_async_smem();
     named_bar_sync(1, 128);
-    if (warp == 2 && lane == 0) {
+    if (warp == 4 && lane == 0) {
 #pragma unroll
       for (int u = 0; u < NSUB; ++u)
         asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(

@@ -511,7 +511,7 @@ int gar_engine_assemble(gar_engine* e, int slot, const long long* input_ids_dev,
   }
   const gar_model_desc& d = e->d;
   NEEDW(table, "llm.embed");
-  e->launches += 2;
+  e->launches += 3;
   // algorithmic bytes: write S*D*2 + read one D-row per non-replay row + <=16 cells per region
   ProfScope ps(e, s, PK_ASSEMBLE, 2.0 * (2.0 * S - 0.0) * d.llm_dim);
   return gar_assemble_embeds(input_ids_dev, S, table, d.vocab, e->feats, T * e->tokens_per_tile, d.llm_dim,
@@ -535,13 +535,40 @@ int gar_engine_assemble_at(gar_engine* e, int slot, const long long* input_ids_d
     return GAR_ERR_SHAPE;
   }
   NEEDW(table, "llm.embed");
-  e->launches += 2;
+  e->launches += 3;
   ProfScope ps(e, s, PK_ASSEMBLE, 2.0 * (2.0 * S) * d.llm_dim);
   return gar_assemble_embeds(input_ids_dev, S, table, d.vocab,
                              e->feats + static_cast<size_t>(feat_tile0) * e->tokens_per_tile * d.llm_dim,
                              T * e->tokens_per_tile, d.llm_dim, d.crop_token_ids, rois, has_roi, d.prompt_numbers,
                              spatial_scale, ncw, nch, e->tpt, d.image_token_id,
                              e->emb + static_cast<size_t>(emb_row0) * d.llm_dim, e->plan + emb_row0, e->status + 2 * slot, s);
+}
+
+// R6-R7 for nreq equal-shape requests of a batched pass in ONE plan/gather/replay launch triple: request r reads
+// features from tile r*T, writes inputs_embeds rows [r*S, (r+1)*S) and status slot slot0+r.
+int gar_engine_assemble_batch(gar_engine* e, int slot0, int nreq, const long long* const* input_ids_dev, int S, int T,
+                              const float* rois, const int* has_roi, float spatial_scale, const int* ncw,
+                              const int* nch, void* s) {
+  if (!e) return GAR_ERR_ARG;
+  const gar_model_desc& d = e->d;
+  const long long pr = d.max_prefill_rows > d.max_seq ? d.max_prefill_rows : d.max_seq;
+  if (nreq <= 0 || slot0 < 0 || slot0 + nreq > d.max_batch || S <= 0 || S > d.max_seq ||
+      static_cast<long long>(nreq) * S > pr || nreq * T > d.max_tiles) {
+    gar_set_error("gar_engine_assemble_batch: slot0=%d nreq=%d S=%d T=%d outside capacity", slot0, nreq, S, T);
+    return GAR_ERR_ARG;
+  }
+  for (int r = 0; r < nreq; ++r) {
+    if (ncw[r] * nch[r] != T - 1) {  // reference assert in _merge, modeling_gar.py:250
+      gar_set_error("%d != %d", ncw[r] * nch[r], T - 1);
+      return GAR_ERR_SHAPE;
+    }
+  }
+  NEEDW(table, "llm.embed");
+  e->launches += 3 * ((nreq + 7) / 8);
+  ProfScope ps(e, s, PK_ASSEMBLE, 2.0 * (2.0 * S) * d.llm_dim * nreq);
+  return gar_assemble_embeds_batch(nreq, input_ids_dev, S, table, d.vocab, e->feats, T * e->tokens_per_tile, d.llm_dim,
+                                   d.crop_token_ids, rois, has_roi, d.prompt_numbers, spatial_scale, ncw, nch, e->tpt,
+                                   d.image_token_id, e->emb, e->plan, e->status + 2 * slot0, s);
 }
 
 int gar_engine_prefill_batch(gar_engine* e, int slot0, int nreq, int S, void* s) {

@@ -240,14 +240,18 @@ class Engine:
         mv = torch.cat([r[1] for r in requests], 0) if with_mask else None
         self.vit_encode(px, mv)
         keep = [px, mv]
-        for i, (_, _, ids, bboxes, (ncw, nch)) in enumerate(requests):
+        flat_rois, flat_has, ncws, nchs, scale = [], [], [], [], 1.0
+        for (_, _, ids, bboxes, (ncw, nch)) in requests:
             rois, has, scale = roi_boxes_f32(self.spec, bboxes, ncw, nch)
-            k = len(has)
-            c_rois = (C.c_float * (5 * k))(*[x for r in rois for x in r])
-            c_has = (C.c_int * k)(*has)
-            check(self.lib.gar_engine_assemble_at(self._h, slot0 + i, C.c_void_p(ids.data_ptr()), S, T, i * T, i * S,
-                                                  c_rois, c_has, float(scale), ncw, nch, self._s()),
-                  "gar_engine_assemble_at")
+            flat_rois += [x for r in rois for x in r]
+            flat_has += list(has)
+            ncws.append(int(ncw))
+            nchs.append(int(nch))
+        c_ids = (C.c_void_p * n)(*[r[2].data_ptr() for r in requests])
+        check(self.lib.gar_engine_assemble_batch(self._h, slot0, n, c_ids, S, T, (C.c_float * len(flat_rois))(*flat_rois),
+                                                 (C.c_int * len(flat_has))(*flat_has), float(scale),
+                                                 (C.c_int * n)(*ncws), (C.c_int * n)(*nchs), self._s()),
+              "gar_engine_assemble_batch")
         check(self.lib.gar_engine_prefill_batch(self._h, slot0, n, S, self._s()), "gar_engine_prefill_batch")
         return keep
 

@@ -214,6 +214,30 @@ def assemble_embeds(input_ids, table, feats, crop_ids, rois, has_roi, spatial_sc
     return out, status
 
 
+def assemble_embeds_batch(input_ids_list, table, feats, crop_ids, rois, has_roi, spatial_scale, grids, tpt,
+                          image_token_id):
+    """Batched form: input_ids_list = nreq (S,) int64 cuda tensors; feats (nreq, T, tpt*tpt, D); rois[r][k] 5 floats;
+    has_roi[r][k]; grids[r] = (ncw, nch).  Returns out (nreq, S, D), status (nreq, 2)."""
+    n = len(input_ids_list)
+    S = input_ids_list[0].numel()
+    D = table.shape[1]
+    k = len(crop_ids)
+    out = torch.empty((n, S, D), dtype=torch.bfloat16, device=table.device)
+    plan = torch.empty((n * S,), dtype=torch.int32, device=table.device)
+    status = torch.zeros((n, 2), dtype=torch.int32, device=table.device)
+    c_ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in input_ids_list])
+    c_ids = (C.c_longlong * k)(*crop_ids)
+    c_rois = (C.c_float * (5 * k * n))(*[float(v) for rr in rois for r in rr for v in r])
+    c_has = (C.c_int * (k * n))(*[int(h) for hh in has_roi for h in hh])
+    c_w = (C.c_int * n)(*[int(g[0]) for g in grids])
+    c_h = (C.c_int * n)(*[int(g[1]) for g in grids])
+    check(_lib.load().gar_assemble_embeds_batch(n, c_ptrs, S, _p(table), table.shape[0], _p(feats),
+                                                feats.shape[1] * feats.shape[2], D, c_ids, c_rois, c_has, k,
+                                                float(spatial_scale), c_w, c_h, tpt, image_token_id, _p(out), _p(plan),
+                                                _p(status), _stream()), "gar_assemble_embeds_batch")
+    return out, status
+
+
 def argmax_step(logits, V, two_stage=True):
     B = logits.shape[0]
     nxt = torch.empty((B,), dtype=torch.int32, device=logits.device)

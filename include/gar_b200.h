@@ -115,6 +115,16 @@ int gar_assemble_embeds(const long long* input_ids_dev, int S, const void* embed
                         const float* rois, const int* has_roi, int n_regions, float spatial_scale, int ncw, int nch,
                         int tpt, long long image_token_id, void* out, int* plan_ws, int* status_dev, void* stream);
 
+/* The same for nreq equal-length requests in one plan / gather / replay launch triple (HBM stream over all requests).
+ * input_ids_dev: HOST array of nreq device pointers; rois (nreq, n_regions, 5), has_roi (nreq, n_regions), ncw/nch
+ * (nreq) host arrays; request r uses features image_features + r*n_image_rows*D and writes rows [r*S,(r+1)*S) of out
+ * and plan_ws (nreq*S ints) and status_dev[2r..2r+1]. */
+int gar_assemble_embeds_batch(int nreq, const long long* const* input_ids_dev, int S, const void* embed_table,
+                              int vocab, const void* image_features, int n_image_rows, int D,
+                              const long long* crop_ids, const float* rois, const int* has_roi, int n_regions,
+                              float spatial_scale, const int* ncw, const int* nch, int tpt, long long image_token_id,
+                              void* out, int* plan_ws, int* status_dev, void* stream);
+
 /* softmax(QK^T*scale)V, head_dim 64, tcgen05 + TMEM (timm SDPA non-causal; flash-attn 2 causal GQA prefill).
  * All strides/offsets in bf16 elements.  K/V batch coordinate = b*kv_batch_mul + kv_head*kv_batch_head_mul. */
 int gar_attn_fwd(const void* q, long long q_row_stride, long long q_batch_stride, int q_col0, const void* k,
@@ -175,6 +185,11 @@ int gar_engine_assemble(gar_engine* e, int slot, const long long* input_ids_dev,
 int gar_engine_assemble_at(gar_engine* e, int slot, const long long* input_ids_dev, int S, int T, int feat_tile0,
                            int emb_row0, const float* rois, const int* has_roi, float spatial_scale, int ncw, int nch,
                            void* stream);
+/* R6-R7 for all nreq requests of a batched pass at once (request r: features from tile r*T, rows [r*S,(r+1)*S),
+ * status slot slot0+r); input_ids_dev is a HOST array of device pointers */
+int gar_engine_assemble_batch(gar_engine* e, int slot0, int nreq, const long long* const* input_ids_dev, int S, int T,
+                              const float* rois, const int* has_roi, float spatial_scale, const int* ncw,
+                              const int* nch, void* stream);
 /* R8 for nreq equal-length requests at once (rows = nreq*S of inputs_embeds, slots slot0..slot0+nreq-1): same math per
  * request as gar_engine_prefill, 1/nreq of the launches */
 int gar_engine_prefill_batch(gar_engine* e, int slot0, int nreq, int S, void* stream);

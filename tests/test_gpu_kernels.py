@@ -380,3 +380,56 @@ def test_decode_attention_fused_rope_matches_unfused():
         torch.cuda.synchronize()
         assert torch.equal(kc1, kc2) and torch.equal(vc1, vc2)
         assert torch.equal(got, want)
+
+
+# ---- R6+R7: assemble (embed + image scatter) and RoI replay, single and batched launch, bit-exact vs the oracle ----
+def _assemble_case(spec, g, ncw, nch, n_masks, text=9):
+    import numpy as np
+
+    T = ncw * nch + 1
+    ids = [128000] + [spec.image_token_id] * (T * spec.tokens_per_tile)
+    boxes = {}
+    for k in range(n_masks):
+        ids += [int(v) for v in g.integers(0, 128000, size=text)] + [spec.crop_tokens_ids[k]] * spec.tokens_per_tile
+        x0, y0 = g.uniform(0.0, 0.6, size=2)
+        w, h = g.uniform(0.05, 0.39, size=2)
+        boxes[str(spec.crop_tokens_ids[k])] = (float(x0), float(y0), float(x0 + w), float(y0 + h))
+    ids += [int(v) for v in g.integers(0, 128000, size=text)] + [128009]
+    return torch.tensor(ids, dtype=torch.long), boxes
+
+
+@pytest.mark.parametrize("nreq,ncw,nch,n_masks", [(1, 2, 2, 1), (3, 2, 2, 2), (2, 3, 2, 3), (10, 1, 2, 1), (1, 4, 4, 5)])
+def test_assemble_replay_batched_bit_exact(nreq, ncw, nch, n_masks):
+    import numpy as np
+
+    from grasp_any_region_b200.config import gar_tiny
+    from grasp_any_region_b200.engine import roi_boxes_f32
+    from oracle.gar_oracle import build_oracle
+
+    spec = gar_tiny()
+    oracle = build_oracle(spec, seed=0, dtype=torch.float32).to(bf)
+    table = oracle.mllm.model.language_model.embed_tokens.weight.detach().to(DEV).contiguous()
+    D = table.shape[1]
+    tpt = int(math.isqrt(spec.tokens_per_tile))
+    T = ncw * nch + 1
+    g = np.random.default_rng(nreq * 100 + ncw * 10 + n_masks)
+    cases = [_assemble_case(spec, g, ncw, nch, n_masks) for _ in range(nreq)]
+    feats = rnd(nreq, T, spec.tokens_per_tile, D, seed=3)
+    rois, has, grids = [], [], []
+    for _, boxes in cases:
+        rr, hh, scale = roi_boxes_f32(spec, boxes, ncw, nch)
+        rois.append(rr)
+        has.append(hh)
+        grids.append((ncw, nch))
+    ids_dev = [c[0].to(DEV) for c in cases]
+    out, status = ops.assemble_embeds_batch(ids_dev, table, feats, list(spec.crop_tokens_ids), rois, has, scale, grids,
+                                            tpt, spec.image_token_id)
+    torch.cuda.synchronize()
+    assert status[:, 0].tolist() == [0] * nreq and status[:, 1].tolist() == [T * spec.tokens_per_tile] * nreq
+    for i, (ids, boxes) in enumerate(cases):
+        want = oracle.assemble(ids[None], feats[i].cpu(), torch.tensor([[ncw, nch]]), [boxes])[0]
+        assert torch.equal(out[i].cpu(), want), f"request {i}: assemble / RoI replay rows differ"
+        # the single-request entry point is the same kernels with nreq = 1
+        one, st1 = ops.assemble_embeds(ids_dev[i], table, feats[i], list(spec.crop_tokens_ids), rois[i], has[i], scale,
+                                       ncw, nch, tpt, spec.image_token_id)
+        assert torch.equal(one, out[i]) and int(st1[0]) == 0
