@@ -42,6 +42,11 @@ struct gar_engine {
   int fuse_rope = 1;
   int use_gemv = 1;
   int fuse_decode_rope = 1;
+  int mega_unit_warps = 2;  // warps per attention unit of the persistent kernel (4 = key partition of gar_decode_attn)
+  int decode_mega = 0;      // opt-in: whole decode step as one persistent kernel (decode_mega.cu); measured 1.15 vs 1.09 ms/step
+  std::map<int, std::vector<gar_mega_layer>> mega_layers;  // per slot_base: layer pointer table
+  unsigned* gbar = nullptr;
+  int decode_prefetch = 0;  // decode kernels pull the following kernels' weight / KV streams into L2 (gar_prefetch)
   float *sumsq_a, *sumsq_b;
   // decode graph
   std::map<long long, cudaGraphExec_t> graphs;  // decode-step graphs keyed by (slot0, batch)
@@ -205,6 +210,32 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
   TRY(gar_embed_gather_sumsq(table, e->next_tok + e->slot_base, e->hdec, e->sumsq_a, batch, D, s));
   e->launches += 1;
   int n_part = 1, rows = 0;
+  // L2 prefetch schedule: every kernel of the step pulls the stream that is needed ~1.5 kernels later, so HBM keeps
+  // streaming while the short dependent kernels are latency-bound (stream order per layer: wqkv, K, V, wo, wgu, wdown)
+  const size_t slot_elems0 = static_cast<size_t>(hkv) * d.max_seq * hd;
+  // decode_prefetch is a bit mask of duties (see the option table in DESIGN.md):
+  //   1 qkv->K(i)  2 qkv->V(i)  4 attn->wo(i)  8 attn->wgu(i)  16 o->first half of wgu(i)  32 o->wdown(i)
+  //   64 gu->wqkv(i+1)  128 down->wqkv(i+1)  256 down->K(i+1)  512 last layer: gu/down -> head of lm_head
+  const int pfm = e->decode_prefetch;
+  auto pf_ptr = [](gar_prefetch& pf) -> const gar_prefetch* {
+    return (pf.ptr[0] || pf.ptr[1] || pf.kv_ptr[0]) ? &pf : nullptr;
+  };
+  auto pf_plain = [&](const void* p0, size_t b0, const void* p1 = nullptr, size_t b1 = 0) {
+    gar_prefetch pf;
+    memset(&pf, 0, sizeof(pf));
+    pf.ptr[0] = p0; pf.bytes[0] = b0; pf.ptr[1] = p1; pf.bytes[1] = b1;
+    return pf;
+  };
+  auto pf_add_kv = [&](gar_prefetch& pf, int layer, bool k, int lo, int hi) {
+    const bf16* base = (k ? e->kcache : e->vcache) + (static_cast<size_t>(layer) * d.max_batch + e->slot_base) * slot_elems0;
+    const int r = pf.kv_ptr[0] ? 1 : 0;
+    pf.kv_ptr[r] = base; pf.kv_lo[r] = lo; pf.kv_hi[r] = hi;
+    pf.pos_dev = e->pos + e->slot_base;
+    pf.kv_pairs = batch * hkv; pf.kv_hkv = hkv; pf.kv_row_bytes = hd * 2; pf.kv_max_rows = d.max_seq;
+    pf.kv_pair_stride_bytes = static_cast<long long>(d.max_seq) * hd * 2;
+  };
+  const size_t b_qkv = static_cast<size_t>(qkv_w) * D * 2, b_o = static_cast<size_t>(D) * hq * hd * 2,
+               b_gu = static_cast<size_t>(2) * I * D * 2, b_down = static_cast<size_t>(D) * I * 2;
   for (int i = 0; i < d.llm_layers; ++i) {
     NEEDW(ln1, L("llm", i, "ln1"));
     NEEDW(wqkv, L("llm", i, "qkv.w"));
@@ -217,8 +248,11 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
     bf16* vc = e->vcache + (static_cast<size_t>(i) * d.max_batch + e->slot_base) * slot_elems;
     {
       ProfScope ps(e, s, PK_GEMV, 2.0 * qkv_w * static_cast<double>(D));
-      TRY(gar_gemv_decode(e->hdec, D, wqkv, D, e->d_qkv, qkv_w, batch, qkv_w, D, 0, nullptr, 0, ln1, e->sumsq_a, n_part,
-                          d.rms_eps, nullptr, nullptr, s));
+      gar_prefetch pf = pf_plain(nullptr, 0);
+      if ((pfm & 1) && (i == 0 || !(pfm & 256))) pf_add_kv(pf, i, true, 0, 256);
+      if (pfm & 2) pf_add_kv(pf, i, false, 0, 256);
+      TRY(gar_gemv_decode_pf(e->hdec, D, wqkv, D, e->d_qkv, qkv_w, batch, qkv_w, D, 0, nullptr, 0, ln1, e->sumsq_a,
+                             n_part, d.rms_eps, nullptr, nullptr, pf_ptr(pf), s));
     }
     {
       ProfScope ps(e, s, PK_DECODE_ATTN, 0.0);
@@ -229,8 +263,10 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
       }
       if (e->fuse_decode_rope && hd == 64) {
         // RoPE of q and of the new K row, the KV append and the attention in one launch
-        TRY(gar_decode_attn_rope(e->d_qkv, qkv_w, kc, vc, e->pos + e->slot_base, nullptr, batch, hq, hkv, hd, d.max_seq,
-                                 splits, scale, cos_t, sin_t, e->o_part, e->ml_part, e->tickets, e->d_att, hq * hd, s));
+        gar_prefetch pf = pf_plain((pfm & 4) ? wo : nullptr, b_o, (pfm & 8) ? wgu : nullptr, b_gu);
+        TRY(gar_decode_attn_rope_pf(e->d_qkv, qkv_w, kc, vc, e->pos + e->slot_base, nullptr, batch, hq, hkv, hd,
+                                    d.max_seq, splits, scale, cos_t, sin_t, e->o_part, e->ml_part, e->tickets, e->d_att,
+                                    hq * hd, pf_ptr(pf), s));
         e->launches -= 1;
       } else {
         TRY(gar_llama_rope_kv(e->d_qkv, batch, hq, hkv, hd, cos_t, sin_t, 0, e->pos + e->slot_base, nullptr, -1, kc, vc,
@@ -241,18 +277,33 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
     }
     {
       ProfScope ps(e, s, PK_GEMV, 2.0 * D * static_cast<double>(hq * hd));
-      TRY(gar_gemv_decode(e->d_att, hq * hd, wo, hq * hd, e->hdec, D, batch, D, hq * hd, 1, e->hdec, D, nullptr, nullptr, 0,
-                          0.f, e->sumsq_b, &rows, s));
+      gar_prefetch pf = pf_plain((pfm & 16) && !(pfm & 8) ? wgu : nullptr, b_gu / 2, (pfm & 32) ? wdown : nullptr, b_down);
+      TRY(gar_gemv_decode_pf(e->d_att, hq * hd, wo, hq * hd, e->hdec, D, batch, D, hq * hd, 1, e->hdec, D, nullptr, nullptr,
+                             0, 0.f, e->sumsq_b, &rows, pf_ptr(pf), s));
     }
     {
       ProfScope ps(e, s, PK_GEMV, 2.0 * 2.0 * I * D);
-      TRY(gar_gemv_decode(e->hdec, D, wgu, D, e->d_act, I, batch, 2 * I, D, 2, nullptr, 0, ln2, e->sumsq_b, D / rows,
-                          d.rms_eps, nullptr, nullptr, s));
+      gar_prefetch pf = pf_plain(nullptr, 0);
+      if (i + 1 < d.llm_layers) {
+        if (pfm & 64) pf = pf_plain(W(e, L("llm", i + 1, "qkv.w")), b_qkv);
+      } else if (pfm & 512) {
+        pf = pf_plain(W(e, "llm.lm_head"), static_cast<size_t>(48) << 20);
+      }
+      TRY(gar_gemv_decode_pf(e->hdec, D, wgu, D, e->d_act, I, batch, 2 * I, D, 2, nullptr, 0, ln2, e->sumsq_b, D / rows,
+                             d.rms_eps, nullptr, nullptr, pf_ptr(pf), s));
     }
     {
       ProfScope ps(e, s, PK_GEMV, 2.0 * D * static_cast<double>(I));
-      TRY(gar_gemv_decode(e->d_act, I, wdown, I, e->hdec, D, batch, D, I, 1, e->hdec, D, nullptr, nullptr, 0, 0.f,
-                          e->sumsq_a, &rows, s));
+      gar_prefetch pf = pf_plain(nullptr, 0);
+      if (i + 1 < d.llm_layers) {
+        if ((pfm & 128) && !(pfm & 64)) pf = pf_plain(W(e, L("llm", i + 1, "qkv.w")), b_qkv);
+        if (pfm & 256) pf_add_kv(pf, i + 1, true, 0, 256);
+      } else if (pfm & 512) {
+        pf = pf_plain(static_cast<const char*>(W(e, "llm.lm_head")) + (static_cast<size_t>(48) << 20),
+                      static_cast<size_t>(48) << 20);
+      }
+      TRY(gar_gemv_decode_pf(e->d_act, I, wdown, I, e->hdec, D, batch, D, I, 1, e->hdec, D, nullptr, nullptr, 0, 0.f,
+                             e->sumsq_a, &rows, pf_ptr(pf), s));
     }
     n_part = D / rows;
     e->launches += 7;
@@ -271,8 +322,58 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
   return GAR_OK;
 }
 
+// Decode step as ONE persistent kernel + the argmax bookkeeping launch pair.
+int decode_step_mega(gar_engine* e, int batch, int eos, void* s) {
+  const gar_model_desc& d = e->d;
+  const int D = d.llm_dim, hq = d.llm_heads, hkv = d.llm_kv_heads, hd = d.llm_head_dim, I = d.llm_inter;
+  NEEDW(table, "llm.embed");
+  NEEDW(cos_t, "llm.cos");
+  NEEDW(sin_t, "llm.sin");
+  NEEDW(wn, "llm.norm");
+  NEEDW(wl, "llm.lm_head");
+  auto it = e->mega_layers.find(e->slot_base);
+  if (it == e->mega_layers.end()) {
+    std::vector<gar_mega_layer> host(d.llm_layers);
+    const size_t slot_elems = static_cast<size_t>(hkv) * d.max_seq * hd;
+    for (int i = 0; i < d.llm_layers; ++i) {
+      NEEDW(ln1, L("llm", i, "ln1"));
+      NEEDW(wqkv, L("llm", i, "qkv.w"));
+      NEEDW(wo, L("llm", i, "o.w"));
+      NEEDW(ln2, L("llm", i, "ln2"));
+      NEEDW(wgu, L("llm", i, "gu.w"));
+      NEEDW(wdown, L("llm", i, "down.w"));
+      host[i] = {wqkv, wo, wgu, wdown, ln1, ln2,
+                 e->kcache + (static_cast<size_t>(i) * d.max_batch + e->slot_base) * slot_elems,
+                 e->vcache + (static_cast<size_t>(i) * d.max_batch + e->slot_base) * slot_elems};
+    }
+    it = e->mega_layers.emplace(e->slot_base, host).first;
+  }
+  const int uw = e->mega_unit_warps == 4 ? 4 : 2;
+  int splits = e->dec_splits;
+  if (splits <= 0) {  // one round of items over the attention units (8 / uw per CTA)
+    splits = ((8 / uw) * gar_num_sms()) / (batch * hkv);
+    splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
+  }
+  bf16* logits = e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded;
+  {
+    ProfScope ps(e, s, PK_GEMV, 0.0);
+    TRY(gar_decode_mega_step(it->second.data(), d.llm_layers, table, wl, wn, cos_t, sin_t, e->next_tok + e->slot_base,
+                             e->pos + e->slot_base, e->hdec, e->d_qkv, e->d_att, e->d_act, logits, e->sumsq_a, e->sumsq_b,
+                             e->o_part, e->ml_part, e->tickets, e->gbar, batch, D, I, hq, hkv, hd, d.vocab_padded,
+                             d.max_seq, splits, uw, d.rms_eps, 1.0f / sqrtf(static_cast<float>(hd)), s));
+  }
+  TRY(gar_argmax_step(logits, d.vocab_padded, d.vocab, batch, e->next_tok + e->slot_base,
+                      e->out_tokens + static_cast<size_t>(e->slot_base) * d.max_new_tokens, d.max_new_tokens, e->step,
+                      e->pos + e->slot_base, e->finished + e->slot_base, eos, 1, 1, e->argmax_ws, s));
+  e->launches += 3;
+  return GAR_OK;
+}
+
 int decode_step(gar_engine* e, int batch, int eos, void* s) {
   const gar_model_desc& d = e->d;
+  if (e->decode_mega && d.llm_layers <= 32 && gar_decode_mega_supported(batch, d.llm_dim, d.llm_inter, d.llm_heads, d.llm_kv_heads,
+                                                   d.llm_head_dim, d.vocab_padded))
+    return decode_step_mega(e, batch, eos, s);
   if (e->use_gemv && batch <= 8 && d.llm_dim % 256 == 0 && d.llm_inter % 256 == 0 &&
       (d.llm_heads * d.llm_head_dim) % 256 == 0 && d.llm_inter % 32 == 0 && d.vocab_padded % 64 == 0)
     return decode_step_gemv(e, batch, eos, s);
@@ -365,6 +466,7 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   rc |= dev_alloc(e, &e->ids_scratch, S);
   rc |= dev_alloc(e, &e->sumsq_a, (D / 16 + 1) * 8, true);
   rc |= dev_alloc(e, &e->sumsq_b, (D / 16 + 1) * 8, true);
+  rc |= dev_alloc(e, &e->gbar, 2, true);
   if (rc) {
     gar_engine_destroy(e);
     return GAR_ERR_CUDA;
@@ -715,6 +817,9 @@ int gar_engine_set_option(gar_engine* e, const char* name, int value) {
   else if (n == "fuse_rope") e->fuse_rope = value;
   else if (n == "gemv_decode") e->use_gemv = value;
   else if (n == "fuse_decode_rope") e->fuse_decode_rope = value;
+  else if (n == "decode_prefetch") e->decode_prefetch = value;
+  else if (n == "decode_mega") e->decode_mega = value;
+  else if (n == "mega_unit_warps" && (value == 2 || value == 4)) e->mega_unit_warps = value;
   else if (n == "decode_splits" && value >= 0 && value <= 32) e->dec_splits = value;
   else if (n == "pdl" || n == "decode_attn_mma" || n == "attn_bkv" || n == "gemm_2cta") {
     if (gar_set_global_option(name, value)) return GAR_ERR_ARG;

@@ -16,6 +16,7 @@
 //   EPI_RES    : out = bf16(res + bf16(acc)); also emits this tile's sum of squares of `out`.
 //   EPI_SWIGLU : rows interleaved [32 gate | 32 up]: out = bf16(bf16(silu(bf16 g)) * bf16 u).
 // Weight loads are issued BEFORE the programmatic-dependency wait, so they overlap the previous kernel.
+#include "../../include/gar_b200.h"
 #include "common.cuh"
 
 namespace {
@@ -30,6 +31,7 @@ struct GvArgs {
   int M, N, K;
   const float* sumsq_in; int n_part; const bf16* norm_w; float eps;  // NORM prologue
   float* sumsq_out;                                                   // EPI_RES: [gridDim.x][8]
+  int has_pf; PfArgs pf;                                              // L2 prefetch duty for the following kernels
 };
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -89,7 +91,11 @@ __global__ void __launch_bounds__(GV_WARPS * 32, 16 / GV_WARPS) gemv_decode_kern
         wh[u][r] = ldg_stream(whi[r] + u * 32);
       }
     }
+  // this kernel's own first weight bytes are in flight: now pull the NEXT kernels' streams into L2
+  const unsigned pf_tid = blockIdx.x * GV_THREADS + threadIdx.x, pf_n = gridDim.x * GV_THREADS;
+  if (a.has_pf) pf_issue_plain(a.pf, pf_tid, pf_n);
   pdl_wait();
+  if (a.has_pf) pf_issue_kv(a.pf, pf_tid, pf_n);
 
   // activations of the first chunk go in flight before the RMSNorm statistics are reduced
   uint4 xv[U];
@@ -267,9 +273,34 @@ int launch_gv(const GvArgs& a, bool norm, cudaStream_t s) {
 // epi: 0 none, 1 residual (+ optional sumsq_out[(N/rows_per_cta)][8]), 2 swiglu (W rows interleaved, out is [M, N/2]).
 // norm_w != NULL enables the RMSNorm prologue with sumsq_in[n_part][8].  Returns GAR_ERR_SHAPE when the shape does
 // not fit this kernel (callers then use gar_gemm_skinny_bf16 / gar_rmsnorm / gar_swiglu).
+void gar_pf_to_args(const gar_prefetch* pf, PfArgs* o) {
+  for (int r = 0; r < 2; ++r) {
+    o->p[r] = static_cast<const char*>(pf->ptr[r]);
+    o->n[r] = pf->bytes[r];
+    o->kv[r] = static_cast<const char*>(pf->kv_ptr[r]);
+    o->lo[r] = pf->kv_lo[r];
+    o->hi[r] = pf->kv_hi[r];
+  }
+  o->pos = pf->pos_dev;
+  o->pairs = pf->kv_pairs;
+  o->hkv = pf->kv_hkv > 0 ? pf->kv_hkv : 1;
+  o->row_bytes = pf->kv_row_bytes;
+  o->max_rows = pf->kv_max_rows;
+  o->pair_stride = pf->kv_pair_stride_bytes;
+  if (o->pos == nullptr || o->pairs <= 0) o->kv[0] = o->kv[1] = nullptr;
+}
+
 extern "C" int gar_gemv_decode(const void* X, int ldx, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
                                int epi, const void* res, int ldres, const void* norm_w, const float* sumsq_in,
                                int n_part, float eps, float* sumsq_out, int* rows_per_cta, void* stream_) {
+  return gar_gemv_decode_pf(X, ldx, W, ldw, out, ldo, M, N, K, epi, res, ldres, norm_w, sumsq_in, n_part, eps, sumsq_out,
+                            rows_per_cta, nullptr, stream_);
+}
+
+extern "C" int gar_gemv_decode_pf(const void* X, int ldx, const void* W, int ldw, void* out, int ldo, int M, int N,
+                                  int K, int epi, const void* res, int ldres, const void* norm_w,
+                                  const float* sumsq_in, int n_part, float eps, float* sumsq_out, int* rows_per_cta,
+                                  const gar_prefetch* pf, void* stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   if (M <= 0 || M > 8 || K % 256 || (ldx % 8) || (ldw % 8) || epi < 0 || epi > 2) return GAR_ERR_SHAPE;
   if (norm_w != nullptr && (sumsq_in == nullptr || n_part <= 0)) return GAR_ERR_ARG;
@@ -281,6 +312,9 @@ extern "C" int gar_gemv_decode(const void* X, int ldx, const void* W, int ldw, v
   a.M = M; a.N = N; a.K = K;
   a.sumsq_in = sumsq_in; a.n_part = n_part; a.norm_w = static_cast<const bf16*>(norm_w); a.eps = eps;
   a.sumsq_out = sumsq_out;
+  a.has_pf = pf != nullptr;
+  memset(&a.pf, 0, sizeof(a.pf));
+  if (pf) gar_pf_to_args(pf, &a.pf);
   const bool norm = norm_w != nullptr;
   if (epi == GV_EPI_SWIGLU) {
     if (N % 64) return GAR_ERR_SHAPE;

@@ -213,3 +213,48 @@ def test_batched_encode_matches_per_request():
     assert torch.equal(lg_bat, lg_seq)
     bat = model.generate_batch(reqs, max_new_tokens=new_tokens)
     assert bat == seq
+
+
+def test_decode_megakernel_matches_per_kernel_step():
+    """The persistent decode-step kernel (decode_mega.cu) keeps the arithmetic and the summation order of the
+    per-kernel decode step (same k-slices, same split-KV partition when decode_splits is pinned), so tokens AND the
+    last step's logits must be bit-identical; batch 1 and a ragged batch of 3."""
+    spec = gar_small()
+    new_tokens = 12
+    _, _, eng, req_a = _setup(spec, 1, seed=51, new_tokens=new_tokens, extra_seq=512)
+    reqs = [req_a] + [make_request(spec, seed=52 + i, n_masks=1, max_num_tiles=4, dtype=bf, device=DEV) for i in range(1)]
+    eng.set_option("decode_splits", 5)
+    eng.set_option("mega_unit_warps", 4)  # same key partition per warp as gar_decode_attn (4-warp CTAs)
+    results = {}
+    for mega in (0, 1):
+        eng.set_option("decode_mega", mega)
+        for batch in (1, 2):
+            for slot, req in enumerate(reqs[:batch]):
+                with torch.cuda.stream(eng.stream):
+                    eng.request(slot, req["pixel_values"], req["global_mask_values"], req["input_ids"][0].contiguous(),
+                                req["bboxes"][0], req["aspect_ratios"][0].tolist())
+            toks = eng.generate(batch, new_tokens, None)
+            logits = eng.buffer("logits", (batch, eng.vocab_padded)).float().cpu()
+            results[(mega, batch)] = (toks, logits)
+    for batch in (1, 2):
+        t0, l0 = results[(0, batch)]
+        t1, l1 = results[(1, batch)]
+        assert t0 == t1, f"batch {batch}: tokens differ {t0} vs {t1}"
+        assert torch.equal(l0, l1), f"batch {batch}: logits differ by {(l0 - l1).abs().max().item()}"
+    # production setting: 2-warp attention units and the auto split count -- another (equally valid) fp32 summation
+    # order of the split-KV partials, so bf16 logits may move by an ulp or two
+    eng.set_option("mega_unit_warps", 2)
+    eng.set_option("decode_splits", 0)
+    for slot, req in enumerate(reqs[:2]):
+        with torch.cuda.stream(eng.stream):
+            eng.request(slot, req["pixel_values"], req["global_mask_values"], req["input_ids"][0].contiguous(),
+                        req["bboxes"][0], req["aspect_ratios"][0].tolist())
+    toks = eng.generate(2, new_tokens, None)
+    logits = eng.buffer("logits", (2, eng.vocab_padded)).float().cpu()
+    t0, l0 = results[(0, 2)]
+    if toks == t0:  # same greedy path -> the last step's logits are comparable
+        assert (logits - l0).abs().max().item() < 0.08
+    else:  # a near-tie flipped: the sequences must agree up to the first flip
+        k = next(i for i, (x, y) in enumerate(zip(toks[0] + toks[1], t0[0] + t0[1])) if x != y)
+        assert k > 0, "first generated token differs between the decode paths"
+    eng.close()
