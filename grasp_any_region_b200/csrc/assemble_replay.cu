@@ -44,6 +44,7 @@ struct AssembleParams {
 // plan word: kind in bits [30,32), payload in [0,30)
 __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant__ AssembleParams p,
                                  int* __restrict__ plan_all, int* __restrict__ status_all) {
+  pdl_launch_dependents();
   const RequestParams& rq = p.r[blockIdx.x];
   const long long* __restrict__ ids = rq.ids;
   int* __restrict__ plan = plan_all + static_cast<size_t>(blockIdx.x) * S;
@@ -157,6 +158,8 @@ __global__ void __launch_bounds__(128, 12)
 gather_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ table, const bf16* __restrict__ feats,
                    bf16* __restrict__ out, int S, int D, int vocab, int rows_per_req_feats,
                    const __grid_constant__ AssembleParams p) {
+  pdl_launch_dependents();  // the replay kernel may get resident while this one streams
+  pdl_wait();               // the row plan comes from plan_rows_kernel
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nvec = D / 8;
@@ -197,6 +200,7 @@ gather_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ table,
 __global__ void __launch_bounds__(256)
 replay_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ feats_all, bf16* __restrict__ out, int S, int D,
                    int rows_per_req_feats, const __grid_constant__ AssembleParams p) {
+  pdl_wait();  // (transitively) the row plan; replay rows are disjoint from the gather kernel's rows
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nvec = D / 8;
@@ -323,13 +327,14 @@ extern "C" int gar_assemble_embeds_batch(int nreq, const long long* const* input
     const int wpb = 4;
     // one row per warp; 4 vectors per lane in flight (2 passes over a 2048-wide row), 12 blocks/SM resident
     const long long gblocks = (rows + wpb - 1) / wpb;
-    gather_rows_kernel<4><<<static_cast<unsigned>(gblocks), wpb * 32, 0, stream>>>(
-        plan, static_cast<const bf16*>(embed_table), feats, o, S, D, vocab, n_image_rows, p);
-    GAR_CUDA_CHECK(cudaGetLastError());
+    // programmatic dependent launches: the next kernel's blocks are resident when its predecessor drains
+    GAR_CUDA_CHECK(gar_launch(gather_rows_kernel<4>, dim3(static_cast<unsigned>(gblocks)), dim3(wpb * 32), 0, stream, true,
+                              dim3(1, 1, 1), static_cast<const int*>(plan), static_cast<const bf16*>(embed_table), feats, o, S,
+                              D, vocab, n_image_rows, p));
     if (n_regions > 0) {
       const long long rblocks = (rows + 7) / 8;
-      replay_rows_kernel<<<static_cast<unsigned>(rblocks), 256, 0, stream>>>(plan, feats, o, S, D, n_image_rows, p);
-      GAR_CUDA_CHECK(cudaGetLastError());
+      GAR_CUDA_CHECK(gar_launch(replay_rows_kernel, dim3(static_cast<unsigned>(rblocks)), dim3(256), 0, stream, true,
+                                dim3(1, 1, 1), static_cast<const int*>(plan), feats, o, S, D, n_image_rows, p));
     }
   }
   return GAR_OK;

@@ -366,7 +366,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                      "r"(sbase + SMEM_Q + u * TILE_BYTES), "r"(p.o_col0 + h * p.q_head_cols + 64 * u), "r"(q0), "r"(b)
                      : "memory");
       tma_store_commit();
-      tma_store_wait<0>();
+      tma_store_wait_read<0>();  // the staging tile has been read: the CTA may retire while the write drains
     }
   }
   tc_fence_before();

@@ -41,6 +41,24 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-form (erf) GELU for the GEMM epilogue at a third of erff's instruction count: Abramowitz-Stegun 7.1.26,
+// erfc(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + p z), |error| <= 1.5e-7 -- two MUFU ops
+// (rcp, ex2) and a few FMAs.  The negative branch uses erfc directly (no 1 - erf cancellation in the tail).  Input and
+// output are bf16-rounded values: the approximation error is ~4 orders of magnitude below half a bf16 ulp.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float erfc_abs = poly * t * e;                       // erfc(|x| / sqrt 2)
+  const float one_plus_erf = x < 0.f ? erfc_abs : 2.0f - erfc_abs;
+  return 0.5f * x * one_plus_erf;
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
 // single-instruction MUFU.EX2 / FMNMX3 (the softmax inner loops are issue-bound)

@@ -144,6 +144,95 @@ __device__ __forceinline__ void norm_row(const uint4* __restrict__ xin, const bf
   }
 }
 
+// Fixed-width variant (d = 256 * NV): the row lives in NV registers-vectors per lane with no predication, and the next
+// row of the warp is already in flight while the current one is reduced and written (two rows = 2 * d * 2 bytes in
+// flight per warp).  Same operation order per row as norm_row.
+template <bool RMS, int NV>
+__device__ __forceinline__ void norm_row_regs(const uint4 (&cache)[NV], const bf16* __restrict__ w,
+                                              const bf16* __restrict__ b, uint4* __restrict__ yout, float eps, int lane) {
+  constexpr int d = NV * 256;
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const uint32_t* xw = reinterpret_cast<const uint32_t*>(&cache[j]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(xw[k]);
+      if (RMS) sum += f.x * f.x + f.y * f.y;
+      else sum += f.x + f.y;
+    }
+  }
+  sum = warp_sum(sum);
+  float mean = 0.f, rstd;
+  if (RMS) {
+    rstd = rsqrtf(sum / d + eps);
+  } else {
+    mean = sum / d;
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const uint32_t* xw = reinterpret_cast<const uint32_t*>(&cache[j]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(xw[k]);
+        var += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+      }
+    }
+    var = warp_sum(var);
+    rstd = rsqrtf(var / d + eps);
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int v = lane + j * 32;
+    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w) + v);
+    uint4 bv = make_uint4(0, 0, 0, 0);
+    if (!RMS) bv = __ldg(reinterpret_cast<const uint4*>(b) + v);
+    const uint32_t* xw = reinterpret_cast<const uint32_t*>(&cache[j]);
+    const uint32_t* ww = reinterpret_cast<const uint32_t*>(&wv);
+    const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bv);
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(xw[k]), g = unpack_bf16x2(ww[k]);
+      if (RMS) {
+        ow[k] = pack_bf16x2(g.x * bf16r(f.x * rstd), g.y * bf16r(f.y * rstd));
+      } else {
+        const float2 h = unpack_bf16x2(bw[k]);
+        ow[k] = pack_bf16x2((f.x - mean) * rstd * g.x + h.x, (f.y - mean) * rstd * g.y + h.y);
+      }
+    }
+    yout[v] = o;
+  }
+}
+
+template <bool RMS, int NV>
+__global__ void __launch_bounds__(128) norm_kernel_fixed(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ w,
+                                                         const bf16* __restrict__ b, bf16* __restrict__ y, int ldy,
+                                                         int rows, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * (blockDim.x >> 5);
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  uint4 cur[NV], nxt[NV];
+  if (row < rows) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) cur[j] = ld_nc_v4(reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ldx) + lane + j * 32);
+  }
+  while (row < rows) {
+    const int nrow = row + stride;
+    if (nrow < rows) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) nxt[j] = ld_nc_v4(reinterpret_cast<const uint4*>(x + static_cast<size_t>(nrow) * ldx) + lane + j * 32);
+    }
+    norm_row_regs<RMS, NV>(cur, w, b, reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * ldy), eps, lane);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) cur[j] = nxt[j];
+    row = nrow;
+  }
+}
+
 template <bool RMS>
 __global__ void norm_kernel(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ w,
                             const bf16* __restrict__ b, bf16* __restrict__ y, int ldy, int rows, int d, float eps) {
@@ -491,9 +580,14 @@ int gar_layernorm(const void* x, int ldx, const void* w, const void* b, void* y,
     gar_set_error("gar_layernorm: d=%d unsupported (need d%%8==0, d<=%d)", d, NORM_MAXV * 256);
     return GAR_ERR_SHAPE;
   }
-  norm_kernel<false><<<grid_for(static_cast<long long>(rows) * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), ldx, static_cast<const bf16*>(w), static_cast<const bf16*>(b),
-      static_cast<bf16*>(y), ldy, rows, d, eps);
+  const bf16 *xp = static_cast<const bf16*>(x), *wp = static_cast<const bf16*>(w), *bp = static_cast<const bf16*>(b);
+  bf16* yp = static_cast<bf16*>(y);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // x must not alias y for the streaming-load variant (the engine never normalises in place)
+  const int grid = grid_for(static_cast<long long>(rows) * 32, 128);
+  if (d == 1024 && x != y) norm_kernel_fixed<false, 4><<<grid, 128, 0, st>>>(xp, ldx, wp, bp, yp, ldy, rows, eps);
+  else if (d == 1536 && x != y) norm_kernel_fixed<false, 6><<<grid, 128, 0, st>>>(xp, ldx, wp, bp, yp, ldy, rows, eps);
+  else norm_kernel<false><<<grid, 128, 0, st>>>(xp, ldx, wp, bp, yp, ldy, rows, d, eps);
   GAR_CUDA_CHECK(cudaGetLastError());
   return GAR_OK;
 }
@@ -503,10 +597,19 @@ int gar_rmsnorm(const void* x, int ldx, const void* w, void* y, int ldy, int row
     gar_set_error("gar_rmsnorm: d=%d unsupported (need d%%8==0, d<=%d)", d, NORM_MAXV * 256);
     return GAR_ERR_SHAPE;
   }
-  GAR_CUDA_CHECK(gar_launch(norm_kernel<true>, dim3(grid_for(static_cast<long long>(rows) * 32, 128)), dim3(128), 0,
-                            static_cast<cudaStream_t>(stream), true, dim3(1, 1, 1), static_cast<const bf16*>(x), ldx,
-                            static_cast<const bf16*>(w), static_cast<const bf16*>(nullptr), static_cast<bf16*>(y), ldy,
-                            rows, d, eps));
+  const dim3 grid(grid_for(static_cast<long long>(rows) * 32, 128));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bf16 *xp = static_cast<const bf16*>(x), *wp = static_cast<const bf16*>(w), *nb = nullptr;
+  bf16* yp = static_cast<bf16*>(y);
+  if (d == 2048 && x != y && rows >= 64)
+    GAR_CUDA_CHECK(gar_launch(norm_kernel_fixed<true, 8>, grid, dim3(128), 0, st, true, dim3(1, 1, 1), xp, ldx, wp, nb, yp, ldy,
+                              rows, eps));
+  else if (d == 4096 && x != y && rows >= 64)
+    GAR_CUDA_CHECK(gar_launch(norm_kernel_fixed<true, 16>, grid, dim3(128), 0, st, true, dim3(1, 1, 1), xp, ldx, wp, nb, yp,
+                              ldy, rows, eps));
+  else
+    GAR_CUDA_CHECK(gar_launch(norm_kernel<true>, grid, dim3(128), 0, st, true, dim3(1, 1, 1), xp, ldx, wp, nb, yp, ldy, rows,
+                              d, eps));
   return GAR_OK;
 }
 

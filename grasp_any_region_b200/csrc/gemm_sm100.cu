@@ -266,7 +266,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
           }
           if (EPI == EPI_BIAS_ROPE2D) {
             const int tok = gm % ea.ntok;

@@ -179,6 +179,17 @@ def test_layernorm_rmsnorm():
     ref2 = w2 * (x32 * torch.rsqrt(x32.pow(2).mean(-1, keepdim=True) + 1e-5)).to(bf)
     assert (y2.float() - ref2.float()).abs().max().item() <= 2e-2
     assert (y2 != ref2).float().mean().item() < 0.01
+    # widths without a fixed-width kernel, the ViT-G width, and fewer rows than one warp sweep
+    for rows, d in ((3, 512), (1500, 1536), (70, 4096), (5, 2048)):
+        xa = rnd(rows, d, seed=16 + d)
+        wa, ba = (1 + rnd(d, scale=0.1, seed=17).float()).to(bf), rnd(d, scale=0.1, seed=18)
+        ya = ops.layernorm(xa, wa, ba, 1e-5)
+        ra = F.layer_norm(xa.float(), (d,), wa.float(), ba.float(), 1e-5).to(bf)
+        assert (ya.float() - ra.float()).abs().max().item() <= 3e-2, (rows, d)
+        yb = ops.rmsnorm(xa, wa, 1e-5)
+        x32 = xa.float()
+        rb = wa * (x32 * torch.rsqrt(x32.pow(2).mean(-1, keepdim=True) + 1e-5)).to(bf)
+        assert (yb.float() - rb.float()).abs().max().item() <= 3e-2, (rows, d)
 
 
 def test_patchify_and_mask_decode():
@@ -307,7 +318,9 @@ def attn_bkv(request):
 
 
 @pytest.mark.parametrize("hd", [64, 128])
-@pytest.mark.parametrize("T,ntok,heads", [(1, 128, 1), (2, 1025, 2), (1, 1024, 4), (3, 300, 2), (1, 65, 1), (2, 160, 2), (1, 289, 1)])
+# ragged lengths: 1025 = 8*128 + 1 (PE ViT with cls token), one-row / one-key tails, lengths past 2048
+@pytest.mark.parametrize("T,ntok,heads", [(1, 128, 1), (2, 1025, 2), (1, 1024, 4), (3, 300, 2), (1, 65, 1), (2, 160, 2),
+                                          (1, 289, 1), (2, 258, 2), (1, 131, 3), (1, 132, 1), (1, 133, 1), (1, 2049, 1), (2, 129, 2)])
 def test_attention_vit_layout(T, ntok, heads, hd, attn_bkv):
     qkv = rnd(T * ntok, 3 * heads * hd, seed=27)
     out = ops.attn_fwd_packed_qkv(qkv, T, ntok, heads, hd)
