@@ -11,7 +11,8 @@
 //   gather_rows  : one warp per output row of every request; text & image rows are 16-byte vector
 //                  copies with all of a lane's loads in flight before its first store (the kernel is a
 //                  pure HBM stream: few registers, full occupancy)
-//   replay_rows  : one warp per crop row: roi_align for its (ph,pw) bin evaluated directly on the
+//   replay_rows  : one warp per crop row (grid = requests x regions x 256 rows; the plan kernel publishes where each
+//                  region's run starts): roi_align for its (ph,pw) bin evaluated directly on the
 //                  channel-contiguous (T,256,D) feature tensor (no merged map, no fp32 copy) in the
 //                  operator's exact fp32 operation order (oracle/roi_align_ref.py), one bf16 rounding.
 // HBM-bound: ~2*S*D*2 bytes per request; no tensor cores on this path.
@@ -43,7 +44,8 @@ struct AssembleParams {
 
 // plan word: kind in bits [30,32), payload in [0,30)
 __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant__ AssembleParams p,
-                                 int* __restrict__ plan_all, int* __restrict__ status_all) {
+                                 int* __restrict__ plan_all, int* __restrict__ status_all,
+                                 int* __restrict__ region_start_all) {
   pdl_launch_dependents();
   const RequestParams& rq = p.r[blockIdx.x];
   const long long* __restrict__ ids = rq.ids;
@@ -119,6 +121,10 @@ __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant
     status[0] = st;
     status[1] = s_total;
   }
+  // first position of every region's crop-token run (-1: absent or no box): the replay kernel's row index
+  if (tid < MAX_REGIONS)
+    region_start_all[blockIdx.x * MAX_REGIONS + tid] =
+        (tid < p.n_regions && s_cnt[tid] > 0 && rq.has_roi[tid]) ? s_min[tid] : -1;
 }
 
 struct Sample {
@@ -158,8 +164,7 @@ __global__ void __launch_bounds__(128, 12)
 gather_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ table, const bf16* __restrict__ feats,
                    bf16* __restrict__ out, int S, int D, int vocab, int rows_per_req_feats,
                    const __grid_constant__ AssembleParams p) {
-  pdl_launch_dependents();  // the replay kernel may get resident while this one streams
-  pdl_wait();               // the row plan comes from plan_rows_kernel
+  pdl_wait();  // (transitively) the row plan from plan_rows_kernel; replay rows are disjoint from this kernel's rows
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nvec = D / 8;
@@ -198,23 +203,26 @@ gather_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ table,
 
 // RoI replay rows: bin (ph, pw) of region k of request req.  One warp per crop row (the plan says which rows).
 __global__ void __launch_bounds__(256)
-replay_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ feats_all, bf16* __restrict__ out, int S, int D,
-                   int rows_per_req_feats, const __grid_constant__ AssembleParams p) {
-  pdl_wait();  // (transitively) the row plan; replay rows are disjoint from the gather kernel's rows
+replay_rows_kernel(const int* __restrict__ region_start, const bf16* __restrict__ feats_all, bf16* __restrict__ out, int S,
+                   int D, int rows_per_req_feats, const __grid_constant__ AssembleParams p) {
+  // grid = (ceil(tpt^2 / warps per block), regions, requests): warp <-> (request, region k, bin offset)
+  pdl_launch_dependents();  // the gather kernel may get resident while the replay rows are computed
+  const int req = blockIdx.z, k = blockIdx.y;
+  const RequestParams& rq = p.r[req];
+  // every block waits for plan_rows_kernel (region_start comes from it) -- also the blocks with nothing to do: this
+  // grid must not complete before the plan does, because the gather kernel behind it only waits for THIS grid
+  pdl_wait();
+  if (!rq.has_roi[k]) return;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nvec = D / 8;
-  const long long total = static_cast<long long>(p.nreq) * S;
-  for (long long g = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); g < total;
-       g += static_cast<long long>(gridDim.x) * wpb) {
-    const int word = plan[g];
-    if (((word >> 30) & 3) != KIND_CROP) continue;
-    const int req = static_cast<int>(g / S);
-    const RequestParams& rq = p.r[req];
+  {
+    const int off = blockIdx.x * wpb + (threadIdx.x >> 5);
+    const int start = region_start[req * MAX_REGIONS + k];
+    if (off >= p.tpt * p.tpt || start < 0) return;
+    const long long g = static_cast<long long>(req) * S + start + off;
     const bf16* feats = feats_all + static_cast<size_t>(req) * rows_per_req_feats * D;
     uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(g) * D);
-    const int k = (word >> 16) & 0x3fff;
-    const int off = word & 0xffff;
     const int tpt = p.tpt;
     const int ph = off / tpt, pw = off % tpt;
     const int H = rq.nch * tpt, W = rq.ncw * tpt;
@@ -286,7 +294,7 @@ replay_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ feats_
 
 // Batched form: request r reads input_ids[r] (device pointers in a HOST array), features
 // image_features + r*n_image_rows*D, boxes rois[r][n_regions][5] / has_roi[r][n_regions] (host), tile grid
-// ncw[r] x nch[r]; writes rows [r*S, (r+1)*S) of out / plan_ws and status_dev[2r..2r+1].
+// ncw[r] x nch[r]; writes rows [r*S, (r+1)*S) of out / plan_ws and status_dev[2r..2r+1].  plan_ws: nreq*S + 8*nreq ints.
 extern "C" int gar_assemble_embeds_batch(int nreq, const long long* const* input_ids, int S, const void* embed_table,
                                          int vocab, const void* image_features, int n_image_rows, int D,
                                          const long long* crop_ids, const float* rois, const int* has_roi,
@@ -319,23 +327,24 @@ extern "C" int gar_assemble_embeds_batch(int nreq, const long long* const* input
       }
     }
     int* plan = plan_ws + static_cast<size_t>(r0) * S;
+    int* region_start = plan_ws + static_cast<size_t>(nreq) * S + r0 * MAX_REGIONS;
     const bf16* feats = static_cast<const bf16*>(image_features) + static_cast<size_t>(r0) * n_image_rows * D;
     bf16* o = static_cast<bf16*>(out) + static_cast<size_t>(r0) * S * D;
-    plan_rows_kernel<<<nr, 1024, 0, stream>>>(S, n_image_rows, p, plan, status_dev + 2 * r0);
+    plan_rows_kernel<<<nr, 1024, 0, stream>>>(S, n_image_rows, p, plan, status_dev + 2 * r0, region_start);
     GAR_CUDA_CHECK(cudaGetLastError());
+    // programmatic dependent launches: replay (short, latency-bound) first, then the HBM stream of the gather
+    if (n_regions > 0) {
+      GAR_CUDA_CHECK(gar_launch(replay_rows_kernel, dim3((tpt * tpt + 7) / 8, n_regions, nr), dim3(256), 0, stream, true,
+                                dim3(1, 1, 1), static_cast<const int*>(region_start), feats, o, S, D, n_image_rows, p));
+    }
     const long long rows = static_cast<long long>(nr) * S;
     const int wpb = 4;
     // one row per warp; 4 vectors per lane in flight (2 passes over a 2048-wide row), 12 blocks/SM resident
     const long long gblocks = (rows + wpb - 1) / wpb;
-    // programmatic dependent launches: the next kernel's blocks are resident when its predecessor drains
     GAR_CUDA_CHECK(gar_launch(gather_rows_kernel<4>, dim3(static_cast<unsigned>(gblocks)), dim3(wpb * 32), 0, stream, true,
                               dim3(1, 1, 1), static_cast<const int*>(plan), static_cast<const bf16*>(embed_table), feats, o, S,
                               D, vocab, n_image_rows, p));
-    if (n_regions > 0) {
-      const long long rblocks = (rows + 7) / 8;
-      GAR_CUDA_CHECK(gar_launch(replay_rows_kernel, dim3(static_cast<unsigned>(rblocks)), dim3(256), 0, stream, true,
-                                dim3(1, 1, 1), static_cast<const int*>(plan), feats, o, S, D, n_image_rows, p));
-    }
+
   }
   return GAR_OK;
 }

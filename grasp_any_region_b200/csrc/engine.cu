@@ -454,7 +454,7 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   rc |= dev_alloc(e, &e->vcache, kv_elems, true);
   rc |= dev_alloc(e, &e->o_part, B * d.llm_heads * 32 * d.llm_head_dim);
   rc |= dev_alloc(e, &e->ml_part, B * d.llm_heads * 32 * 2);
-  rc |= dev_alloc(e, &e->plan, PR);
+  rc |= dev_alloc(e, &e->plan, PR + 8 * (B + 1));  // row plan + the per-request region-start table
   rc |= dev_alloc(e, &e->status, 2 * B, true);
   rc |= dev_alloc(e, &e->next_tok, B, true);
   rc |= dev_alloc(e, &e->out_tokens, B * d.max_new_tokens, true);

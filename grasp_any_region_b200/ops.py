@@ -201,7 +201,7 @@ def assemble_embeds(input_ids, table, feats, crop_ids, rois, has_roi, spatial_sc
     D = table.shape[1]
     n = len(crop_ids)
     out = torch.empty((S, D), dtype=torch.bfloat16, device=table.device)
-    plan = torch.empty((S,), dtype=torch.int32, device=table.device)
+    plan = torch.empty((S + 8,), dtype=torch.int32, device=table.device)
     status = torch.zeros((2,), dtype=torch.int32, device=table.device)
     c_ids = (C.c_longlong * n)(*crop_ids)
     flat = [float(v) for r in rois for v in r]
@@ -223,7 +223,7 @@ def assemble_embeds_batch(input_ids_list, table, feats, crop_ids, rois, has_roi,
     D = table.shape[1]
     k = len(crop_ids)
     out = torch.empty((n, S, D), dtype=torch.bfloat16, device=table.device)
-    plan = torch.empty((n * S,), dtype=torch.int32, device=table.device)
+    plan = torch.empty((n * S + 8 * n,), dtype=torch.int32, device=table.device)
     status = torch.zeros((n, 2), dtype=torch.int32, device=table.device)
     c_ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in input_ids_list])
     c_ids = (C.c_longlong * k)(*crop_ids)

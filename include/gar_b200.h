@@ -129,7 +129,7 @@ int gar_bump_step(int* step, void* stream);
 
 /* Fused embed + image-feature scatter + RoI-aligned feature replay (modeling_gar.py:332-414).
  * rois: n_regions x [0,x1,y1,x2,y2] fp32 host array computed like modeling_gar.py:367-387;
- * plan_ws: S ints (device); status_dev: 2 ints (device): [status bits, n image tokens]. */
+ * plan_ws: S + 8 ints (device); status_dev: 2 ints (device): [status bits, n image tokens]. */
 int gar_assemble_embeds(const long long* input_ids_dev, int S, const void* embed_table, int vocab,
                         const void* image_features, int n_image_rows, int D, const long long* crop_ids,
                         const float* rois, const int* has_roi, int n_regions, float spatial_scale, int ncw, int nch,
@@ -138,7 +138,7 @@ int gar_assemble_embeds(const long long* input_ids_dev, int S, const void* embed
 /* The same for nreq equal-length requests in one plan / gather / replay launch triple (HBM stream over all requests).
  * input_ids_dev: HOST array of nreq device pointers; rois (nreq, n_regions, 5), has_roi (nreq, n_regions), ncw/nch
  * (nreq) host arrays; request r uses features image_features + r*n_image_rows*D and writes rows [r*S,(r+1)*S) of out
- * and plan_ws (nreq*S ints) and status_dev[2r..2r+1]. */
+ * and plan_ws (nreq*S + 8*nreq ints) and status_dev[2r..2r+1]. */
 int gar_assemble_embeds_batch(int nreq, const long long* const* input_ids_dev, int S, const void* embed_table,
                               int vocab, const void* image_features, int n_image_rows, int D,
                               const long long* crop_ids, const float* rois, const int* has_roi, int n_regions,

@@ -9,8 +9,9 @@ timeout 700 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --
 tail -1 gpurun_out/ncu_list.log | cut -c1-200
 timeout 500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:gemm_bf16_tn -c 400 --csv --log-file gpurun_out/gemm_traffic.csv $CMD > gpurun_out/ncu_traffic.log 2>&1
 tail -1 gpurun_out/ncu_traffic.log | cut -c1-200
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tn -s 12 -c 3 -f -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_full_gemm.log 2>&1
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 2 -c 1 -f -o gpurun_out/prof_attn $CMD > gpurun_out/ncu_full_attn.log 2>&1
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:gemv_decode -s 20 -c 4 -f -o gpurun_out/prof_gemv $CMD > gpurun_out/ncu_full_gemv.log 2>&1
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:assemble_kernel -c 2 -f -o gpurun_out/prof_assemble $CMD > gpurun_out/ncu_full_asm.log 2>&1
-ls -la gpurun_out | tail -12
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tn -s 12 -c 3 -f -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_full_gemm.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 2 -c 1 -f -o gpurun_out/prof_attn $CMD > gpurun_out/ncu_full_attn.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:gemv_decode -s 20 -c 4 -f -o gpurun_out/prof_gemv $CMD > gpurun_out/ncu_full_gemv.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k "regex:plan_rows|gather_rows|replay_rows" -c 3 -f -o gpurun_out/prof_assemble $CMD > gpurun_out/ncu_full_asm.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:norm_kernel_fixed -s 4 -c 2 -f -o gpurun_out/prof_norm $CMD > gpurun_out/ncu_full_norm.log 2>&1
+ls -la gpurun_out | tail -14

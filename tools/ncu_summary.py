@@ -3,6 +3,7 @@
 
   python tools/ncu_summary.py list  gpurun_out/launches.csv   > profiles/rNN_launches.txt
   python tools/ncu_summary.py full  gpurun_out/prof.ncu-rep   > profiles/rNN_<kernel>_full.txt
+  python tools/ncu_summary.py traffic gpurun_out/gemm_traffic.csv "<command>" > profiles/rNN_gemm_traffic.json
 """
 import collections
 import csv
@@ -51,6 +52,35 @@ def launch_list(path):
         print(f"{t:12.1f} {100*t/total:5.1f}% {c:6d} {t/c:9.1f}  {k[:100]}")
 
 
+def traffic(path, command):
+    """Mean DRAM bytes (read + write) and duration per launch, overall and per kernel variant (bench.py roofline.traffic)."""
+    import json
+
+    lines = open(path).readlines()
+    start = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
+    per_id = collections.OrderedDict()
+    for r in csv.DictReader(lines[start:]):
+        d = per_id.setdefault(r["ID"], {"k": clean(r["Kernel Name"]), "bytes": 0.0, "us": 0.0})
+        v = float(r["Metric Value"].replace(",", ""))
+        u = r["Metric Unit"]
+        if r["Metric Name"].startswith("dram__bytes"):
+            d["bytes"] += v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        elif r["Metric Name"] == "gpu__time_duration.sum":
+            d["us"] += v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
+    var = collections.OrderedDict()
+    for d in per_id.values():
+        a = var.setdefault(d["k"], [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += d["bytes"]
+        a[2] += d["us"]
+    n = len(per_id)
+    out = {"source": command, "launches": n,
+           "dram_bytes_per_launch": sum(d["bytes"] for d in per_id.values()) / max(1, n),
+           "per_variant": {k: {"launches": c, "dram_bytes_per_launch": b / c, "us_per_launch": t / c}
+                           for k, (c, b, t) in var.items()}}
+    print(json.dumps(out, indent=1))
+
+
 def full(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -63,6 +93,10 @@ def full(path):
                 print(f"  {k:75s} {d[k]:>16} {units[hdr.index(k)]}")
         print()
 
+
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[1] == "traffic":
+    traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
+    sys.exit(0)
 
 if __name__ == "__main__":
     {"list": launch_list, "full": full}[sys.argv[1]](sys.argv[2])
