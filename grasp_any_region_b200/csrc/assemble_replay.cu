@@ -59,15 +59,25 @@ __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant
   __syncthreads();
   const int per = (S + nthr - 1) / nthr;
   const int lo = tid * per, hi = min(S, lo + per);
+  // both passes read the thread's ids eight at a time (independent loads in flight before the first use)
+  constexpr int PU = 8;
   int cnt = 0;
-  for (int s = lo; s < hi; ++s) {
-    const long long id = ids[s];
-    if (id == p.image_token_id) ++cnt;
-    for (int k = 0; k < p.n_regions; ++k) {
-      if (id == p.crop_ids[k]) {
-        atomicMin(&s_min[k], s);
-        atomicMax(&s_max[k], s);
-        atomicAdd(&s_cnt[k], 1);
+  for (int s0 = lo; s0 < hi; s0 += PU) {
+    long long idr[PU];
+#pragma unroll
+    for (int u = 0; u < PU; ++u) idr[u] = s0 + u < hi ? ids[s0 + u] : -1;
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+      const int s = s0 + u;
+      if (s >= hi) break;
+      const long long id = idr[u];
+      if (id == p.image_token_id) ++cnt;
+      for (int k = 0; k < p.n_regions; ++k) {
+        if (id == p.crop_ids[k]) {
+          atomicMin(&s_min[k], s);
+          atomicMax(&s_max[k], s);
+          atomicAdd(&s_cnt[k], 1);
+        }
       }
     }
   }
@@ -93,20 +103,28 @@ __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant
   }
   __syncthreads();
   int ord = s_warp[tid >> 5] + incl - cnt;
-  for (int s = lo; s < hi; ++s) {
-    const long long id = ids[s];
-    int word = KIND_TEXT << 30;
-    if (id == p.image_token_id) {
-      word = (KIND_IMAGE << 30) | ord;
-      ++ord;
-    } else {
-      for (int k = 0; k < p.n_regions; ++k) {
-        if (id == p.crop_ids[k] && rq.has_roi[k]) {
-          word = (KIND_CROP << 30) | (k << 16) | ((s - s_min[k]) & 0xffff);
+  for (int s0 = lo; s0 < hi; s0 += PU) {
+    long long idr[PU];
+#pragma unroll
+    for (int u = 0; u < PU; ++u) idr[u] = s0 + u < hi ? ids[s0 + u] : -1;
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+      const int s = s0 + u;
+      if (s >= hi) break;
+      const long long id = idr[u];
+      int word = KIND_TEXT << 30;
+      if (id == p.image_token_id) {
+        word = (KIND_IMAGE << 30) | ord;
+        ++ord;
+      } else {
+        for (int k = 0; k < p.n_regions; ++k) {
+          if (id == p.crop_ids[k] && rq.has_roi[k]) {
+            word = (KIND_CROP << 30) | (k << 16) | ((s - s_min[k]) & 0xffff);
+          }
         }
       }
+      plan[s] = word;
     }
-    plan[s] = word;
   }
   if (tid == 0) {
     int st = 0;
@@ -258,6 +276,11 @@ replay_rows_kernel(const int* __restrict__ region_start, const bf16* __restrict_
       }
     }
     for (int v = lane; v < nvec; v += 32) {
+      // all 16 cell vectors of this output vector go out together (addresses of invalid samples are clamped, hence
+      // loadable; their values are never used) -- one L2 round trip per output vector instead of four
+      uint4 raws[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) raws[i] = __ldg(cell[i] + v);
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -267,7 +290,7 @@ replay_rows_kernel(const int* __restrict__ region_start, const bf16* __restrict_
         float val[8];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint4 raw = __ldg(cell[q * 4 + c] + v);
+          const uint4 raw = raws[q * 4 + c];
           const uint32_t* rw = reinterpret_cast<const uint32_t*>(&raw);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {

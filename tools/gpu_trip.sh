@@ -1,7 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -x 2>&1 | tail -3 | tee gpurun_out/kernel_tests.log
-timeout 400 python -m pytest tests/test_gpu_engine.py -q -m gpu -x 2>&1 | tail -3 | tee gpurun_out/engine_tests.log
-timeout 200 python tools/prof_kernels.py attn_vit 3 2>&1 | tail -2 | tee gpurun_out/attn_timing.log
-timeout 200 python tools/prof_kernels.py gemm 3 2>&1 | grep "epi=2\|N=4096" | tee gpurun_out/gemm_timing.log
-echo "== bench"; timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_a.log | cut -c1-200
-grep -o '"phases": {[^}]*}' gpurun_out/bench_a.log; grep -o '"stages": {.*}}, "phases' gpurun_out/bench_a.log; grep -o '"roofline": {[^}]*}' gpurun_out/bench_a.log
+timeout 200 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "regex:plan_rows|gather_rows|replay_rows" -c 6 --csv --log-file gpurun_out/assemble_list.csv python bench.py --steps 1 --warmup 0 --new-tokens 4 --no-e2e --no-cpu-baseline --no-profile > /dev/null 2>&1
+grep -E "plan_rows|gather_rows|replay_rows" gpurun_out/assemble_list.csv | grep time_duration | awk -F'","' '{print substr($5,1,40), $(NF-1), $NF}' | head -8
