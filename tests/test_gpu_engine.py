@@ -258,3 +258,47 @@ def test_decode_megakernel_matches_per_kernel_step():
         k = next(i for i, (x, y) in enumerate(zip(toks[0] + toks[1], t0[0] + t0[1])) if x != y)
         assert k > 0, "first generated token differs between the decode paths"
     eng.close()
+
+
+def test_engine_request_from_image_and_masks_non_square_canvas():
+    """A request built by the host-side builder (grasp_any_region_b200/preprocess.py: the reference's canvas choice,
+    bicubic tiling, NEAREST id map, inclusive-max boxes) for a 900x600 image lands on a 3x2 canvas; image features,
+    the RoI replay (bit-exact) and the prefill logits match the oracle like the synthetic square requests do."""
+    import numpy as np
+
+    from grasp_any_region_b200.preprocess import build_request
+
+    spec = gar_small()
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, size=(600, 900, 3), dtype=np.uint8)
+    m0 = np.zeros((600, 900), bool); m0[40:330, 60:420] = True
+    m1 = np.zeros((600, 900), bool); m1[300:590, 380:880] = True
+    req = build_request(spec, img, [m0, m1], text_ids=list(range(2000, 2040)), max_num_tiles=6, dtype=bf, device=DEV)
+    assert req["aspect_ratios"][0].tolist() == [3, 2]
+    oracle32 = build_oracle(spec, seed=0, dtype=torch.float32)
+    sd = {k: v.to(bf) for k, v in oracle32.state_dict().items()}
+    oracle32.load_state_dict({k: v.float() for k, v in sd.items()})
+    oracle32 = oracle32.to(DEV)
+    o16 = build_oracle(spec, seed=0, dtype=torch.float32)
+    o16.load_state_dict({k: v.float() for k, v in sd.items()})
+    o16 = o16.to(bf)
+    ids = req["input_ids"]
+    S, T, D = ids.shape[1], req["pixel_values"].shape[0], spec.text.hidden_size
+    eng = Engine(spec, sd, device=DEV, max_tiles=T, max_seq=S + 16, max_batch=1, max_new_tokens=4)
+    with torch.cuda.stream(eng.stream):
+        eng.request(0, req["pixel_values"], req["global_mask_values"], ids[0].contiguous(), req["bboxes"][0],
+                    req["aspect_ratios"][0].tolist())
+    eng.stream.synchronize()
+    assert eng.status(0) == 0
+    feats = eng.buffer("image_features", (T, spec.tokens_per_tile, D))
+    t32 = oracle32.prefill_embeds(req["pixel_values"].float(), req["global_mask_values"], req["aspect_ratios"],
+                                  req["bboxes"], ids)
+    scale = t32["image_features"].abs().max().item()
+    assert (feats.float() - t32["image_features"]).abs().max().item() <= 0.03 * scale
+    emb = eng.buffer("inputs_embeds", (S, D))
+    want = o16.assemble(ids.cpu(), feats.cpu(), req["aspect_ratios"].cpu(), req["bboxes"])[0]
+    assert torch.equal(emb.cpu(), want), "inputs_embeds (embed/scatter/RoI replay on a 3x2 canvas) must be bit-exact"
+    logits = eng.buffer("logits", (eng.vocab_padded,))[: spec.text.vocab_size].float()
+    _, lg32 = oracle32.greedy(emb.float()[None], 1)
+    assert (logits - lg32[0]).abs().max().item() <= 5e-2
+    eng.close()
