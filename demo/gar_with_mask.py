@@ -49,7 +49,18 @@ def main():
 
         spec = presets.PRESETS[args.synthetic]()
         model = GARModel(GARConfig.from_spec(spec)).random_init_(args.seed).to("cuda:0").eval()
-        sample = make_request(spec, seed=args.seed, n_masks=1)
+        if args.image_path and args.mask_path:
+            # a real image + mask through the repo's own request builder (no hub processor / tokenizer needed:
+            # the question's token ids are a fixed placeholder, so the printed ids are not a caption)
+            from PIL import Image
+
+            from grasp_any_region_b200.preprocess import build_request
+
+            img = np.array(Image.open(args.image_path).convert("RGB"))
+            mask = np.array(Image.open(args.mask_path).convert("L")).astype(bool)
+            sample = build_request(spec, img, [mask], text_ids=list(range(1000, 1040)), device="cuda:0")
+        else:
+            sample = make_request(spec, seed=args.seed, n_masks=1)
         eos = pad = None
         decode = lambda ids: " ".join(str(int(t)) for t in ids)  # noqa: E731  (no tokenizer offline)
     else:

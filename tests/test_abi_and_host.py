@@ -36,6 +36,26 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.gar_abi_version() == 1
 
 
+def test_ctypes_signatures_match_header_arity():
+    """Every binding in _lib.SIGNATURES passes exactly as many arguments as the prototype in gar_b200.h declares
+    (a mismatch would only show up as stack garbage on the GPU box)."""
+    header = open(os.path.join(ROOT, "include", "gar_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    seen = {}
+    for m in re.finditer(r"\b(gar_[a-z0-9_]+)\s*\(", header):
+        depth, i = 1, m.end()
+        while depth:
+            depth += {"(": 1, ")": -1}.get(header[i], 0)
+            i += 1
+        if header[i:].lstrip()[:1] != ";":
+            continue  # not a prototype (e.g. a mention inside a macro)
+        params = header[m.end():i - 1].strip()
+        seen[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    assert set(seen) == set(_lib.SIGNATURES)
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert len(argtypes) == seen[name], f"{name}: header declares {seen[name]} parameters, ctypes binds {len(argtypes)}"
+
+
 def test_desc_struct_layout_matches_header():
     # 9 ints/floats, 8 ints, float, int, (pad), int64, 8 x int64, 4 ints
     assert ctypes.sizeof(_lib.GarModelDesc) == 4 * 20 + 8 + 64 + 24  # 5 capacity ints + tail padding
