@@ -306,7 +306,7 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
                              e->sumsq_a, &rows, pf_ptr(pf), s));
     }
     n_part = D / rows;
-    e->launches += 7;
+    e->launches += 6;  // qkv, RoPE+KV append, attention (+combine by ticket), o-proj, gate/up, down (fused RoPE: one less)
   }
   NEEDW(wn, "llm.norm");
   NEEDW(wl, "llm.lm_head");
