@@ -52,11 +52,16 @@ SIGNATURES = {
     "gar_pool2x2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gar_embed_gather": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "gar_argmax_step": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "gar_argmax_step_eos": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, C.POINTER(_i), _i, _i, _i, _vp, _vp]),
     "gar_bump_step": (_i, [_vp, _vp]),
     "gar_assemble_embeds": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, C.POINTER(_ll), C.POINTER(_f), C.POINTER(_i), _i,
                                  _f, _i, _i, _i, _ll, _vp, _vp, _vp, _vp]),
     "gar_assemble_embeds_batch": (_i, [_i, C.POINTER(_vp), _i, _vp, _i, _vp, _i, _i, C.POINTER(_ll), C.POINTER(_f),
                                        C.POINTER(_i), _i, _f, C.POINTER(_i), C.POINTER(_i), _i, _ll, _vp, _vp, _vp, _vp]),
+    "gar_assemble_plan_batch": (_i, [_i, C.POINTER(_vp), _i, _i, C.POINTER(_ll), C.POINTER(_i), _i, _i, _ll, _vp, _vp,
+                                     _vp]),
+    "gar_assemble_rows_batch": (_i, [_i, C.POINTER(_vp), _i, _vp, _i, _vp, _i, _i, C.POINTER(_ll), C.POINTER(_f),
+                                     C.POINTER(_i), _i, _f, C.POINTER(_i), C.POINTER(_i), _i, _ll, _vp, _vp, _vp]),
     "gar_attn_fwd": (_i, [_vp, _ll, _ll, _i, _vp, _vp, _ll, _ll, _i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _i, _i, _i,
                           _i, _i, _i, _i, _i, _i, _f, _vp]),
     "gar_decode_attn_rope": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -68,15 +73,19 @@ SIGNATURES = {
     "gar_engine_set_weight": (_i, [_vp, C.c_char_p, _vp]),
     "gar_engine_get_buffer": (_i, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_ll)]),
     "gar_engine_vit_encode": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "gar_engine_patchify_at": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "gar_engine_vit_encode_patches": (_i, [_vp, _i, _i, _vp]),
     "gar_engine_assemble": (_i, [_vp, _i, _vp, _i, _i, C.POINTER(_f), C.POINTER(_i), _f, _i, _i, _vp]),
     "gar_engine_prefill": (_i, [_vp, _i, _i, _vp]),
     "gar_engine_assemble_at": (_i, [_vp, _i, _vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_i), _f, _i, _i, _vp]),
     "gar_engine_assemble_batch": (_i, [_vp, _i, _i, C.POINTER(_vp), _i, _i, C.POINTER(_f), C.POINTER(_i), _f,
                                        C.POINTER(_i), C.POINTER(_i), _vp]),
+    "gar_engine_plan_batch": (_i, [_vp, _i, _i, C.POINTER(_vp), _i, _i, C.POINTER(_i), C.POINTER(_i), _vp]),
     "gar_engine_prefill_batch": (_i, [_vp, _i, _i, _i, _vp]),
     "gar_engine_prefill_all_logits": (_i, [_vp, _i, _i, _vp, _vp]),
     "gar_engine_generate": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _vp]),
     "gar_engine_generate_group": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_i), _vp]),
+    "gar_engine_generate_eos": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _i, C.POINTER(_i), C.POINTER(_i), _vp]),
     "gar_engine_status": (_i, [_vp, _i, C.POINTER(_i)]),
     "gar_engine_launch_count": (_ll, [_vp]),
     "gar_engine_set_option": (_i, [_vp, C.c_char_p, _i]),

@@ -19,6 +19,10 @@ _TIMM_ARCH = {
 
 def _vision_spec(vc: dict, use_cls: Optional[bool]) -> VisionSpec:
     args = dict(vc.get("model_args") or {})
+    # PE-Core towers inside Perception-LM run without timm's post-transformer norm (`norm` = Identity, SURVEY.md
+    # Appendix A); a checkpoint that asks for it needs a kernel this path does not have.
+    if args.get("use_post_transformer_norm", False):
+        raise ValueError("vision_config.model_args.use_post_transformer_norm=True is not supported by the B200 path")
     base = dict(_TIMM_ARCH.get(vc.get("architecture", ""), {}))
     for k in ("embed_dim", "depth", "num_heads"):
         if k in args:

@@ -5,16 +5,15 @@
 //   :341-346  get_placeholder_mask + masked_scatter of image_features  (bool mask S*D + scatter)
 //   :348-414  per crop token: `in` scan + 2 .item() syncs, _merge permute+contiguous, .float() of the
 //             whole map, torchvision.ops.roi_align, permute/cast, 3-way torch.cat
-// with three launches for a whole batch of requests and no host synchronisation:
-//   plan_rows    : one block per request scans input_ids -> per-row source plan (text / image ordinal /
-//                  crop offset), validates counts and run shapes into a status word
-//   gather_rows  : one warp per output row of every request; text & image rows are 16-byte vector
-//                  copies with all of a lane's loads in flight before its first store (the kernel is a
-//                  pure HBM stream: few registers, full occupancy)
-//   replay_rows  : one warp per crop row (grid = requests x regions x 256 rows; the plan kernel publishes where each
-//                  region's run starts): roi_align for its (ph,pw) bin evaluated directly on the
-//                  channel-contiguous (T,256,D) feature tensor (no merged map, no fp32 copy) in the
-//                  operator's exact fp32 operation order (oracle/roi_align_ref.py), one bf16 rounding.
+// with two launches for a whole batch of requests and no host synchronisation on the data path:
+//   plan_rows     : one block per request scans input_ids -> per-row source plan (text / image ordinal /
+//                   crop region + bin), validates counts and run shapes into a status word.  Depends only on
+//                   input_ids, so the engine runs it BEFORE the ViT and the host reads the status early.
+//   assemble_rows : one warp per output row of every request, role by plan word.  Text & image rows are 16-byte
+//                   vector copies with all of a lane's loads in flight before its first store; crop rows evaluate
+//                   roi_align for their (ph,pw) bin directly on the channel-contiguous (T,256,D) feature tensor (no
+//                   merged map, no fp32 copy) in the operator's exact fp32 operation order
+//                   (oracle/roi_align_ref.py), one bf16 rounding.
 // HBM-bound: ~2*S*D*2 bytes per request; no tensor cores on this path.
 #include "common.cuh"
 
@@ -44,8 +43,7 @@ struct AssembleParams {
 
 // plan word: kind in bits [30,32), payload in [0,30)
 __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant__ AssembleParams p,
-                                 int* __restrict__ plan_all, int* __restrict__ status_all,
-                                 int* __restrict__ region_start_all) {
+                                 int* __restrict__ plan_all, int* __restrict__ status_all) {
   pdl_launch_dependents();
   const RequestParams& rq = p.r[blockIdx.x];
   const long long* __restrict__ ids = rq.ids;
@@ -139,10 +137,6 @@ __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant
     status[0] = st;
     status[1] = s_total;
   }
-  // first position of every region's crop-token run (-1: absent or no box): the replay kernel's row index
-  if (tid < MAX_REGIONS)
-    region_start_all[blockIdx.x * MAX_REGIONS + tid] =
-        (tid < p.n_regions && s_cnt[tid] > 0 && rq.has_roi[tid]) ? s_min[tid] : -1;
 }
 
 struct Sample {
@@ -175,73 +169,63 @@ __device__ __forceinline__ Sample make_sample(float y, float x, int H, int W) {
   return sm;
 }
 
-// Text and image rows of every request: out row <- one table / feature row.  CH 16-byte vectors per lane are loaded
-// before the first store, so a warp keeps CH*512 B in flight (12 resident blocks: ~100 KB per SM).
+// One warp per output row of every request, role chosen by the row's plan word:
+//   text / image rows : out row <- one table / feature row, CH 16-byte vectors per lane loaded before the first store
+//                       (a warp keeps CH*512 B in flight; 8 resident blocks of 4 warps per SM)
+//   crop rows         : roi_align bin (ph, pw) of region k evaluated in place on the channel-contiguous (T,256,D)
+//                       feature tensor in torchvision's exact fp32 operation order (oracle/roi_align_ref.py), one bf16
+//                       rounding.  The four sample points are accumulated one after the other (4 cell loads in flight
+//                       per lane) so the role fits the gather role's register budget.
+// Every row index comes from the loop bound (g < nreq*S) and every source index is clamped, so a malformed prompt
+// (status bits set by plan_rows_kernel) can never make this kernel touch memory outside its request.
 template <int CH>
-__global__ void __launch_bounds__(128, 12)
-gather_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ table, const bf16* __restrict__ feats,
-                   bf16* __restrict__ out, int S, int D, int vocab, int rows_per_req_feats,
-                   const __grid_constant__ AssembleParams p) {
-  pdl_wait();  // (transitively) the row plan from plan_rows_kernel; replay rows are disjoint from this kernel's rows
+__global__ void __launch_bounds__(128, 8)
+assemble_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ table, const bf16* __restrict__ feats_all,
+                     bf16* __restrict__ out, int S, int D, int vocab, int rows_per_req_feats,
+                     const __grid_constant__ AssembleParams p) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nvec = D / 8;
+  const int tpt = p.tpt;
   const long long total = static_cast<long long>(p.nreq) * S;
   for (long long g = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); g < total;
        g += static_cast<long long>(gridDim.x) * wpb) {
     const int word = plan[g];
-    const int kind = (word >> 30) & 3;
-    if (kind == KIND_CROP) continue;
+    int kind = (word >> 30) & 3;
     const int req = static_cast<int>(g / S), s = static_cast<int>(g - static_cast<long long>(req) * S);
-    const uint4* src;
-    if (kind == KIND_IMAGE) {
-      src = reinterpret_cast<const uint4*>(
-          feats + (static_cast<size_t>(req) * rows_per_req_feats + (word & 0x3fffffff)) * D);
-    } else {
-      long long id = p.r[req].ids[s];
-      id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-      src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * D);
-    }
-    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(g) * D);
-    for (int v0 = 0; v0 < nvec; v0 += 32 * CH) {
-      uint4 buf[CH];
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const int v = v0 + c * 32 + lane;
-        if (v < nvec) buf[c] = ld_nc_v4(src + v);
-      }
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        const int v = v0 + c * 32 + lane;
-        if (v < nvec) dst[v] = buf[c];
-      }
-    }
-  }
-}
-
-// RoI replay rows: bin (ph, pw) of region k of request req.  One warp per crop row (the plan says which rows).
-__global__ void __launch_bounds__(256)
-replay_rows_kernel(const int* __restrict__ region_start, const bf16* __restrict__ feats_all, bf16* __restrict__ out, int S,
-                   int D, int rows_per_req_feats, const __grid_constant__ AssembleParams p) {
-  // grid = (ceil(tpt^2 / warps per block), regions, requests): warp <-> (request, region k, bin offset)
-  pdl_launch_dependents();  // the gather kernel may get resident while the replay rows are computed
-  const int req = blockIdx.z, k = blockIdx.y;
-  const RequestParams& rq = p.r[req];
-  // every block waits for plan_rows_kernel (region_start comes from it) -- also the blocks with nothing to do: this
-  // grid must not complete before the plan does, because the gather kernel behind it only waits for THIS grid
-  pdl_wait();
-  if (!rq.has_roi[k]) return;
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  const int nvec = D / 8;
-  {
-    const int off = blockIdx.x * wpb + (threadIdx.x >> 5);
-    const int start = region_start[req * MAX_REGIONS + k];
-    if (off >= p.tpt * p.tpt || start < 0) return;
-    const long long g = static_cast<long long>(req) * S + start + off;
+    const RequestParams& rq = p.r[req];
     const bf16* feats = feats_all + static_cast<size_t>(req) * rows_per_req_feats * D;
     uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(g) * D);
-    const int tpt = p.tpt;
+    const int k = (word >> 16) & 0x3fff, off = word & 0xffff;
+    if (kind == KIND_CROP && off >= tpt * tpt) kind = KIND_TEXT;  // run longer than one crop (status bit 2 is set)
+    if (kind != KIND_CROP) {
+      const uint4* src;
+      if (kind == KIND_IMAGE) {
+        int ord = word & 0x3fffffff;
+        ord = ord < rows_per_req_feats ? ord : rows_per_req_feats - 1;  // more <image> tokens than features (status bit 1)
+        src = reinterpret_cast<const uint4*>(feats + static_cast<size_t>(ord) * D);
+      } else {
+        long long id = rq.ids[s];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * D);
+      }
+      for (int v0 = 0; v0 < nvec; v0 += 32 * CH) {
+        uint4 buf[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int v = v0 + c * 32 + lane;
+          if (v < nvec) buf[c] = ld_nc_v4(src + v);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int v = v0 + c * 32 + lane;
+          if (v < nvec) dst[v] = buf[c];
+        }
+      }
+      continue;
+    }
+    // ---- RoI replay row: bin (ph, pw) of region k
     const int ph = off / tpt, pw = off % tpt;
     const int H = rq.nch * tpt, W = rq.ncw * tpt;
     const float scale = p.spatial_scale;
@@ -251,51 +235,48 @@ replay_rows_kernel(const int* __restrict__ region_start, const bf16* __restrict_
     const float end_h = __fsub_rn(__fmul_rn(rq.rois[k][4], scale), 0.5f);
     const float bin_h = __fdiv_rn(__fsub_rn(end_h, start_h), static_cast<float>(tpt));
     const float bin_w = __fdiv_rn(__fsub_rn(end_w, start_w), static_cast<float>(tpt));
-    Sample sm[4];
-#pragma unroll
-    for (int iy = 0; iy < 2; ++iy) {
+    // lane q < 4 owns sample point q = iy*2+ix; the warp then broadcasts its weights / cell rows
+    Sample mine;
+    {
+      const int iy = (lane >> 1) & 1, ix = lane & 1;
       const float yy = __fadd_rn(__fadd_rn(start_h, __fmul_rn(static_cast<float>(ph), bin_h)),
                                  __fdiv_rn(__fmul_rn(iy + 0.5f, bin_h), 2.0f));
-#pragma unroll
-      for (int ix = 0; ix < 2; ++ix) {
-        const float xx = __fadd_rn(__fadd_rn(start_w, __fmul_rn(static_cast<float>(pw), bin_w)),
-                                   __fdiv_rn(__fmul_rn(ix + 0.5f, bin_w), 2.0f));
-        sm[iy * 2 + ix] = make_sample(yy, xx, H, W);
-      }
-    }
-    // feature cell (y,x) of the merged map lives at tile 1 + (y/tpt)*ncw + x/tpt, token (y%tpt)*tpt + x%tpt
-    const uint4* cell[16];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
+      const float xx = __fadd_rn(__fadd_rn(start_w, __fmul_rn(static_cast<float>(pw), bin_w)),
+                                 __fdiv_rn(__fmul_rn(ix + 0.5f, bin_w), 2.0f));
+      mine = make_sample(yy, xx, H, W);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int lin = sm[q].pos[c];
+        // feature cell (y,x) of the merged map lives at tile 1 + (y/tpt)*ncw + x/tpt, token (y%tpt)*tpt + x%tpt
+        const int lin = mine.pos[c];
         const int y = lin / W, x = lin % W;
-        const size_t row = (static_cast<size_t>(1 + (y / tpt) * rq.ncw + x / tpt) * tpt + (y % tpt)) * tpt + (x % tpt);
-        cell[q * 4 + c] = reinterpret_cast<const uint4*>(feats + row * D);
+        mine.pos[c] = ((1 + (y / tpt) * rq.ncw + x / tpt) * tpt + (y % tpt)) * tpt + (x % tpt);
       }
     }
     for (int v = lane; v < nvec; v += 32) {
-      // all 16 cell vectors of this output vector go out together (addresses of invalid samples are clamped, hence
-      // loadable; their values are never used) -- one L2 round trip per output vector instead of four
-      uint4 raws[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) raws[i] = __ldg(cell[i] + v);
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        if (!sm[q].valid) continue;
+        const int valid = __shfl_sync(0xffffffffu, mine.valid, q);
+        uint4 raws[4];
+        float w[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int row = __shfl_sync(0xffffffffu, mine.pos[c], q);
+          w[c] = __shfl_sync(0xffffffffu, mine.w[c], q);
+          // rows of invalid samples are clamped, hence loadable; their values are never used
+          raws[c] = __ldg(reinterpret_cast<const uint4*>(feats + static_cast<size_t>(row) * D) + v);
+        }
+        if (!valid) continue;
         float val[8];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint4 raw = raws[q * 4 + c];
-          const uint32_t* rw = reinterpret_cast<const uint32_t*>(&raw);
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(&raws[c]);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float2 f = unpack_bf16x2(rw[j]);
-            const float t0 = __fmul_rn(sm[q].w[c], f.x), t1 = __fmul_rn(sm[q].w[c], f.y);
+            const float t0 = __fmul_rn(w[c], f.x), t1 = __fmul_rn(w[c], f.y);
             val[2 * j] = c == 0 ? t0 : __fadd_rn(val[2 * j], t0);
             val[2 * j + 1] = c == 0 ? t1 : __fadd_rn(val[2 * j + 1], t1);
           }
@@ -315,61 +296,101 @@ replay_rows_kernel(const int* __restrict__ region_start, const bf16* __restrict_
 
 }  // namespace
 
+namespace {
+int fill_params(AssembleParams& p, int r0, int nr, const long long* const* input_ids, const long long* crop_ids,
+                const float* rois, const int* has_roi, int n_regions, float spatial_scale, const int* ncw, const int* nch,
+                int tpt, long long image_token_id) {
+  memset(&p, 0, sizeof(p));
+  p.n_regions = n_regions;
+  p.nreq = nr;
+  for (int k = 0; k < MAX_REGIONS; ++k) p.crop_ids[k] = k < n_regions ? crop_ids[k] : -1;
+  p.spatial_scale = spatial_scale;
+  p.tpt = tpt;
+  p.image_token_id = image_token_id;
+  for (int r = 0; r < nr; ++r) {
+    RequestParams& rq = p.r[r];
+    rq.ids = input_ids[r0 + r];
+    rq.ncw = ncw ? ncw[r0 + r] : 1;
+    rq.nch = nch ? nch[r0 + r] : 1;
+    for (int k = 0; k < n_regions; ++k) {
+      rq.has_roi[k] = has_roi[(r0 + r) * n_regions + k];
+      for (int j = 0; j < 5; ++j) rq.rois[k][j] = rois ? rois[((r0 + r) * n_regions + k) * 5 + j] : 0.f;
+    }
+  }
+  return GAR_OK;
+}
+}  // namespace
+
+// Row plan + validation only (depends on nothing but input_ids: callers run it before the ViT and read the status
+// word early, so a malformed prompt raises before any feature is computed, like the reference's ValueError).
+extern "C" int gar_assemble_plan_batch(int nreq, const long long* const* input_ids, int S, int n_image_rows,
+                                       const long long* crop_ids, const int* has_roi, int n_regions, int tpt,
+                                       long long image_token_id, int* plan_ws, int* status_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_regions > MAX_REGIONS || S <= 0 || nreq <= 0 || tpt * tpt > 0xffff) {
+    gar_set_error("gar_assemble_plan_batch: bad args nreq=%d S=%d n_regions=%d", nreq, S, n_regions);
+    return GAR_ERR_ARG;
+  }
+  for (int r0 = 0; r0 < nreq; r0 += MAX_REQS) {
+    const int nr = nreq - r0 < MAX_REQS ? nreq - r0 : MAX_REQS;
+    AssembleParams p;
+    fill_params(p, r0, nr, input_ids, crop_ids, nullptr, has_roi, n_regions, 1.f, nullptr, nullptr, tpt, image_token_id);
+    plan_rows_kernel<<<nr, 1024, 0, stream>>>(S, n_image_rows, p, plan_ws + static_cast<size_t>(r0) * S, status_dev + 2 * r0);
+    GAR_CUDA_CHECK(cudaGetLastError());
+  }
+  return GAR_OK;
+}
+
+// The HBM stream: every output row of every request in ONE launch (text / image gather rows and RoI replay rows by
+// warp role), reading the plan written by gar_assemble_plan_batch.
+extern "C" int gar_assemble_rows_batch(int nreq, const long long* const* input_ids, int S, const void* embed_table,
+                                       int vocab, const void* image_features, int n_image_rows, int D,
+                                       const long long* crop_ids, const float* rois, const int* has_roi, int n_regions,
+                                       float spatial_scale, const int* ncw, const int* nch, int tpt,
+                                       long long image_token_id, void* out, const int* plan_ws, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_regions > MAX_REGIONS || D % 8 || S <= 0 || nreq <= 0 || tpt * tpt > 0xffff || n_image_rows <= 0) {
+    gar_set_error("gar_assemble_rows_batch: bad args nreq=%d S=%d D=%d n_regions=%d", nreq, S, D, n_regions);
+    return GAR_ERR_ARG;
+  }
+  for (int r0 = 0; r0 < nreq; r0 += MAX_REQS) {
+    const int nr = nreq - r0 < MAX_REQS ? nreq - r0 : MAX_REQS;
+    AssembleParams p;
+    fill_params(p, r0, nr, input_ids, crop_ids, rois, has_roi, n_regions, spatial_scale, ncw, nch, tpt, image_token_id);
+    for (int r = 0; r < nr; ++r) {
+      // every merged-map cell the replay can address must exist: tiles 1..ncw*nch of this request's features
+      if ((1 + p.r[r].ncw * p.r[r].nch) * tpt * tpt > n_image_rows) {
+        gar_set_error("gar_assemble_rows_batch: grid %dx%d needs %d feature rows, got %d", p.r[r].ncw, p.r[r].nch,
+                      (1 + p.r[r].ncw * p.r[r].nch) * tpt * tpt, n_image_rows);
+        return GAR_ERR_SHAPE;
+      }
+    }
+    const bf16* feats = static_cast<const bf16*>(image_features) + static_cast<size_t>(r0) * n_image_rows * D;
+    bf16* o = static_cast<bf16*>(out) + static_cast<size_t>(r0) * S * D;
+    const long long rows = static_cast<long long>(nr) * S;
+    const int wpb = 4;
+    const long long gblocks = (rows + wpb - 1) / wpb;
+    GAR_CUDA_CHECK(gar_launch(assemble_rows_kernel<4>, dim3(static_cast<unsigned>(gblocks)), dim3(wpb * 32), 0, stream,
+                              false, dim3(1, 1, 1), plan_ws + static_cast<size_t>(r0) * S,
+                              static_cast<const bf16*>(embed_table), feats, o, S, D, vocab, n_image_rows, p));
+  }
+  return GAR_OK;
+}
+
 // Batched form: request r reads input_ids[r] (device pointers in a HOST array), features
 // image_features + r*n_image_rows*D, boxes rois[r][n_regions][5] / has_roi[r][n_regions] (host), tile grid
-// ncw[r] x nch[r]; writes rows [r*S, (r+1)*S) of out / plan_ws and status_dev[2r..2r+1].  plan_ws: nreq*S + 8*nreq ints.
+// ncw[r] x nch[r]; writes rows [r*S, (r+1)*S) of out / plan_ws and status_dev[2r..2r+1].  plan_ws: nreq*S ints.
 extern "C" int gar_assemble_embeds_batch(int nreq, const long long* const* input_ids, int S, const void* embed_table,
                                          int vocab, const void* image_features, int n_image_rows, int D,
                                          const long long* crop_ids, const float* rois, const int* has_roi,
                                          int n_regions, float spatial_scale, const int* ncw, const int* nch, int tpt,
                                          long long image_token_id, void* out, int* plan_ws, int* status_dev,
                                          void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (n_regions > MAX_REGIONS || D % 8 || S <= 0 || nreq <= 0 || tpt * tpt > 0xffff) {
-    gar_set_error("gar_assemble_embeds_batch: bad args nreq=%d S=%d D=%d n_regions=%d", nreq, S, D, n_regions);
-    return GAR_ERR_ARG;
-  }
-  for (int r0 = 0; r0 < nreq; r0 += MAX_REQS) {
-    const int nr = nreq - r0 < MAX_REQS ? nreq - r0 : MAX_REQS;
-    AssembleParams p;
-    memset(&p, 0, sizeof(p));
-    p.n_regions = n_regions;
-    p.nreq = nr;
-    for (int k = 0; k < MAX_REGIONS; ++k) p.crop_ids[k] = k < n_regions ? crop_ids[k] : -1;
-    p.spatial_scale = spatial_scale;
-    p.tpt = tpt;
-    p.image_token_id = image_token_id;
-    for (int r = 0; r < nr; ++r) {
-      RequestParams& rq = p.r[r];
-      rq.ids = input_ids[r0 + r];
-      rq.ncw = ncw[r0 + r];
-      rq.nch = nch[r0 + r];
-      for (int k = 0; k < n_regions; ++k) {
-        rq.has_roi[k] = has_roi[(r0 + r) * n_regions + k];
-        for (int j = 0; j < 5; ++j) rq.rois[k][j] = rois[((r0 + r) * n_regions + k) * 5 + j];
-      }
-    }
-    int* plan = plan_ws + static_cast<size_t>(r0) * S;
-    int* region_start = plan_ws + static_cast<size_t>(nreq) * S + r0 * MAX_REGIONS;
-    const bf16* feats = static_cast<const bf16*>(image_features) + static_cast<size_t>(r0) * n_image_rows * D;
-    bf16* o = static_cast<bf16*>(out) + static_cast<size_t>(r0) * S * D;
-    plan_rows_kernel<<<nr, 1024, 0, stream>>>(S, n_image_rows, p, plan, status_dev + 2 * r0, region_start);
-    GAR_CUDA_CHECK(cudaGetLastError());
-    // programmatic dependent launches: replay (short, latency-bound) first, then the HBM stream of the gather
-    if (n_regions > 0) {
-      GAR_CUDA_CHECK(gar_launch(replay_rows_kernel, dim3((tpt * tpt + 7) / 8, n_regions, nr), dim3(256), 0, stream, true,
-                                dim3(1, 1, 1), static_cast<const int*>(region_start), feats, o, S, D, n_image_rows, p));
-    }
-    const long long rows = static_cast<long long>(nr) * S;
-    const int wpb = 4;
-    // one row per warp; 4 vectors per lane in flight (2 passes over a 2048-wide row), 12 blocks/SM resident
-    const long long gblocks = (rows + wpb - 1) / wpb;
-    GAR_CUDA_CHECK(gar_launch(gather_rows_kernel<4>, dim3(static_cast<unsigned>(gblocks)), dim3(wpb * 32), 0, stream, true,
-                              dim3(1, 1, 1), static_cast<const int*>(plan), static_cast<const bf16*>(embed_table), feats, o, S,
-                              D, vocab, n_image_rows, p));
-
-  }
-  return GAR_OK;
+  int rc = gar_assemble_plan_batch(nreq, input_ids, S, n_image_rows, crop_ids, has_roi, n_regions, tpt, image_token_id,
+                                   plan_ws, status_dev, stream_);
+  if (rc) return rc;
+  return gar_assemble_rows_batch(nreq, input_ids, S, embed_table, vocab, image_features, n_image_rows, D, crop_ids, rois,
+                                 has_roi, n_regions, spatial_scale, ncw, nch, tpt, image_token_id, out, plan_ws, stream_);
 }
 
 // rois: n_regions x 5 fp32 host array; has_roi: n_regions ints; crop_ids: n_regions int64 (host)

@@ -508,7 +508,7 @@ __global__ void argmax_partial_kernel(const bf16* __restrict__ logits, int ld, i
 __global__ void argmax_step_kernel(const bf16* __restrict__ logits, int ld, int V, const float* __restrict__ pmax,
                                    const int* __restrict__ pidx, int chunks, int* __restrict__ next_tok,
                                    int* __restrict__ out_tokens, int out_ld, int* __restrict__ step_ptr,
-                                   int* __restrict__ pos, int* __restrict__ finished, int eos, int advance_pos,
+                                   int* __restrict__ pos, int* __restrict__ finished, int4 eos4, int advance_pos,
                                    int bump_step) {
   pdl_launch_dependents();
   pdl_wait();
@@ -528,10 +528,14 @@ __global__ void argmax_step_kernel(const bf16* __restrict__ logits, int ld, int 
   if (threadIdx.x == 0) {
     const int step = step_ptr ? *step_ptr : 0;
     const int fin = finished ? finished[b] : 0;
+    // eos4: up to four stop ids (-1 = unused); a finished sequence keeps feeding its first stop id (HF pads likewise)
+    const int eos = eos4.x;
     const int tok = fin ? (eos >= 0 ? eos : bidx) : bidx;
     next_tok[b] = tok;
     if (out_tokens) out_tokens[static_cast<size_t>(b) * out_ld + step] = fin ? -1 : tok;
-    if (finished && eos >= 0 && tok == eos) finished[b] = 1;
+    const bool stop = (eos4.x >= 0 && tok == eos4.x) || (eos4.y >= 0 && tok == eos4.y) || (eos4.z >= 0 && tok == eos4.z) ||
+                      (eos4.w >= 0 && tok == eos4.w);
+    if (finished && stop) finished[b] = 1;
     if (pos && advance_pos) pos[b] += 1;
   }
   // the last block to finish bumps the step counter (replaces a separate 1-thread launch)
@@ -671,10 +675,28 @@ int gar_embed_gather(const void* table, const long long* ids64, const int* ids32
   return GAR_OK;
 }
 
+int gar_argmax_step_eos(const void* logits, int ld, int V, int batch, int* next_tok, int* out_tokens, int out_ld,
+                        int* step_ptr, int* pos, int* finished, const int* eos_ids, int n_eos, int advance_pos,
+                        int bump_step, void* partial_ws, void* stream);
+
 int gar_argmax_step(const void* logits, int ld, int V, int batch, int* next_tok, int* out_tokens, int out_ld,
                     int* step_ptr, int* pos, int* finished, int eos, int advance_pos, int bump_step, void* partial_ws,
                     void* stream) {
+  const int ids[1] = {eos};
+  return gar_argmax_step_eos(logits, ld, V, batch, next_tok, out_tokens, out_ld, step_ptr, pos, finished, ids,
+                             eos >= 0 ? 1 : 0, advance_pos, bump_step, partial_ws, stream);
+}
+
+int gar_argmax_step_eos(const void* logits, int ld, int V, int batch, int* next_tok, int* out_tokens, int out_ld,
+                        int* step_ptr, int* pos, int* finished, const int* eos_ids, int n_eos, int advance_pos,
+                        int bump_step, void* partial_ws, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n_eos < 0 || n_eos > 4 || (n_eos > 0 && !eos_ids)) return GAR_ERR_ARG;
+  int4 eos = make_int4(-1, -1, -1, -1);
+  if (n_eos > 0) eos.x = eos_ids[0];
+  if (n_eos > 1) eos.y = eos_ids[1];
+  if (n_eos > 2) eos.z = eos_ids[2];
+  if (n_eos > 3) eos.w = eos_ids[3];
   const int chunks = (V + ARGMAX_CHUNK - 1) / ARGMAX_CHUNK;
   float* pmax = nullptr;
   int* pidx = nullptr;

@@ -50,7 +50,15 @@ struct gar_engine {
   float *sumsq_a, *sumsq_b;
   // decode graph
   std::map<long long, cudaGraphExec_t> graphs;  // decode-step graphs keyed by (slot0, batch)
-  std::map<long long, int> graph_eos;
+  std::map<long long, std::vector<int>> graph_eos;
+  int eos_ids[4] = {-1, -1, -1, -1};  // stop ids of the decode in flight (GenerationConfig.eos_token_id may be a list)
+  int n_eos = 0;
+  int eos_poll_steps = 8;   // decode steps per early-stop poll (0 = never poll: always run max_new_tokens steps)
+  int steps_run = 0;        // decode steps launched by the last generate call
+  int* fin_host = nullptr;  // pinned: 2 x max_batch finished flags
+  cudaEvent_t fin_ev[2] = {nullptr, nullptr};
+  // plan_rows already ran for this (slot0, nreq, S, T) (gar_engine_plan_batch): assemble_batch skips it
+  int plan_slot0 = -1, plan_nreq = 0, plan_S = 0, plan_T = 0;
   long long launches = 0;
   int launches_per_step = 0;
   // optional per-kernel-class timing (CUDA events on the launching stream; bench.py roofline)
@@ -187,19 +195,21 @@ int llm_layers(gar_engine* e, bf16* h, bf16* ln, int rows, bool decode, int slot
   return GAR_OK;
 }
 
-int lm_head(gar_engine* e, const bf16* hrows, int ldh, int rows, bf16* logits, void* s) {
+// `scratch`: rows x llm_dim normalised rows.  Prefill passes its own lnl, decode its private lndec: a decode group may
+// run on a second stream while another group's prefill is in flight, so the two must never share scratch.
+int lm_head(gar_engine* e, const bf16* hrows, int ldh, int rows, bf16* logits, bf16* scratch, void* s) {
   const gar_model_desc& d = e->d;
   NEEDW(wn, "llm.norm");
   NEEDW(wl, "llm.lm_head");
-  TRY(gar_rmsnorm(hrows, ldh, wn, e->lndec, d.llm_dim, rows, d.llm_dim, d.rms_eps, s));
+  TRY(gar_rmsnorm(hrows, ldh, wn, scratch, d.llm_dim, rows, d.llm_dim, d.rms_eps, s));
   e->launches += 1;
-  return gemm(e, e->lndec, d.llm_dim, wl, d.llm_dim, logits, d.vocab_padded, rows, d.vocab_padded, d.llm_dim,
+  return gemm(e, scratch, d.llm_dim, wl, d.llm_dim, logits, d.vocab_padded, rows, d.vocab_padded, d.llm_dim,
               GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s);
 }
 
 // Decode step on the latency-first GEMV kernels: RMSNorm, SwiGLU and residual adds live inside them, the
 // RMSNorm statistics travel as per-CTA partial sums of squares (7 launches per layer instead of 11).
-int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
+int decode_step_gemv(gar_engine* e, int batch, void* s) {
   const gar_model_desc& d = e->d;
   const int D = d.llm_dim, hq = d.llm_heads, hkv = d.llm_kv_heads, hd = d.llm_head_dim, I = d.llm_inter;
   const int qkv_w = (hq + 2 * hkv) * hd;
@@ -315,15 +325,16 @@ int decode_step_gemv(gar_engine* e, int batch, int eos, void* s) {
     TRY(gar_gemv_decode(e->hdec, D, wl, D, e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded, batch, d.vocab_padded, D, 0, nullptr, 0, wn,
                         e->sumsq_a, n_part, d.rms_eps, nullptr, nullptr, s));
   }
-  TRY(gar_argmax_step(e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded, d.vocab, batch,
-                      e->next_tok + e->slot_base, e->out_tokens + static_cast<size_t>(e->slot_base) * d.max_new_tokens,
-                      d.max_new_tokens, e->step, e->pos + e->slot_base, e->finished + e->slot_base, eos, 1, 1, e->argmax_ws, s));
+  TRY(gar_argmax_step_eos(e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded, d.vocab, batch,
+                          e->next_tok + e->slot_base, e->out_tokens + static_cast<size_t>(e->slot_base) * d.max_new_tokens,
+                          d.max_new_tokens, e->step, e->pos + e->slot_base, e->finished + e->slot_base, e->eos_ids, e->n_eos,
+                          1, 1, e->argmax_ws, s));
   e->launches += 3;
   return GAR_OK;
 }
 
 // Decode step as ONE persistent kernel + the argmax bookkeeping launch pair.
-int decode_step_mega(gar_engine* e, int batch, int eos, void* s) {
+int decode_step_mega(gar_engine* e, int batch, void* s) {
   const gar_model_desc& d = e->d;
   const int D = d.llm_dim, hq = d.llm_heads, hkv = d.llm_kv_heads, hd = d.llm_head_dim, I = d.llm_inter;
   NEEDW(table, "llm.embed");
@@ -362,29 +373,30 @@ int decode_step_mega(gar_engine* e, int batch, int eos, void* s) {
                              e->o_part, e->ml_part, e->tickets, e->gbar, batch, D, I, hq, hkv, hd, d.vocab_padded,
                              d.max_seq, splits, uw, d.rms_eps, 1.0f / sqrtf(static_cast<float>(hd)), s));
   }
-  TRY(gar_argmax_step(logits, d.vocab_padded, d.vocab, batch, e->next_tok + e->slot_base,
-                      e->out_tokens + static_cast<size_t>(e->slot_base) * d.max_new_tokens, d.max_new_tokens, e->step,
-                      e->pos + e->slot_base, e->finished + e->slot_base, eos, 1, 1, e->argmax_ws, s));
+  TRY(gar_argmax_step_eos(logits, d.vocab_padded, d.vocab, batch, e->next_tok + e->slot_base,
+                          e->out_tokens + static_cast<size_t>(e->slot_base) * d.max_new_tokens, d.max_new_tokens, e->step,
+                          e->pos + e->slot_base, e->finished + e->slot_base, e->eos_ids, e->n_eos, 1, 1, e->argmax_ws, s));
   e->launches += 3;
   return GAR_OK;
 }
 
-int decode_step(gar_engine* e, int batch, int eos, void* s) {
+int decode_step(gar_engine* e, int batch, void* s) {
   const gar_model_desc& d = e->d;
   if (e->decode_mega && d.llm_layers <= 32 && gar_decode_mega_supported(batch, d.llm_dim, d.llm_inter, d.llm_heads, d.llm_kv_heads,
                                                    d.llm_head_dim, d.vocab_padded))
-    return decode_step_mega(e, batch, eos, s);
+    return decode_step_mega(e, batch, s);
   if (e->use_gemv && batch <= 8 && d.llm_dim % 256 == 0 && d.llm_inter % 256 == 0 &&
       (d.llm_heads * d.llm_head_dim) % 256 == 0 && d.llm_inter % 32 == 0 && d.vocab_padded % 64 == 0)
-    return decode_step_gemv(e, batch, eos, s);
+    return decode_step_gemv(e, batch, s);
   NEEDW(table, "llm.embed");
   TRY(gar_embed_gather(table, nullptr, e->next_tok + e->slot_base, e->hdec, batch, d.llm_dim, s));
   e->launches += 1;
   TRY(llm_layers(e, e->hdec, e->lndec, batch, true, 0, s));
-  TRY(lm_head(e, e->hdec, d.llm_dim, batch, e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, s));
-  TRY(gar_argmax_step(e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded, d.vocab, batch,
-                      e->next_tok + e->slot_base, e->out_tokens + static_cast<size_t>(e->slot_base) * d.max_new_tokens,
-                      d.max_new_tokens, e->step, e->pos + e->slot_base, e->finished + e->slot_base, eos, 1, 1, e->argmax_ws, s));
+  TRY(lm_head(e, e->hdec, d.llm_dim, batch, e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, e->lndec, s));
+  TRY(gar_argmax_step_eos(e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded, d.vocab, batch,
+                          e->next_tok + e->slot_base, e->out_tokens + static_cast<size_t>(e->slot_base) * d.max_new_tokens,
+                          d.max_new_tokens, e->step, e->pos + e->slot_base, e->finished + e->slot_base, e->eos_ids, e->n_eos,
+                          1, 1, e->argmax_ws, s));
   e->launches += 2;
   return GAR_OK;
 }
@@ -467,6 +479,9 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   rc |= dev_alloc(e, &e->sumsq_a, (D / 16 + 1) * 8, true);
   rc |= dev_alloc(e, &e->sumsq_b, (D / 16 + 1) * 8, true);
   rc |= dev_alloc(e, &e->gbar, 2, true);
+  if (cudaMallocHost(reinterpret_cast<void**>(&e->fin_host), 2 * B * sizeof(int)) != cudaSuccess) rc |= GAR_ERR_CUDA;
+  for (int i = 0; i < 2 && !rc; ++i)
+    if (cudaEventCreateWithFlags(&e->fin_ev[i], cudaEventDisableTiming) != cudaSuccess) rc |= GAR_ERR_CUDA;
   if (rc) {
     gar_engine_destroy(e);
     return GAR_ERR_CUDA;
@@ -479,6 +494,9 @@ int gar_engine_destroy(gar_engine* e) {
   if (!e) return GAR_OK;
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   for (void* p : e->allocs) cudaFree(p);
+  if (e->fin_host) cudaFreeHost(e->fin_host);
+  for (int i = 0; i < 2; ++i)
+    if (e->fin_ev[i]) cudaEventDestroy(e->fin_ev[i]);
   delete e;
   return GAR_OK;
 }
@@ -514,9 +532,34 @@ int gar_engine_get_buffer(gar_engine* e, const char* name, void** dev_ptr, long 
   return GAR_OK;
 }
 
+// R2 + operand prep of R3/K1 for T tiles of ONE request, written at tile `tile0` of the im2col arenas: the requests of a
+// batched pass are patchified straight from their own tensors (no concatenated copy of the pixel data is ever made).
+int gar_engine_patchify_at(gar_engine* e, const void* pixel_values, const void* mask_values, int T, int tile0, void* s) {
+  if (!e || !pixel_values || T <= 0 || tile0 < 0 || tile0 + T > e->d.max_tiles) {
+    gar_set_error("gar_engine_patchify_at: tiles [%d,%d) outside [0,%d)", tile0, tile0 + T, e ? e->d.max_tiles : 0);
+    return GAR_ERR_ARG;
+  }
+  const gar_model_desc& d = e->d;
+  const size_t off = static_cast<size_t>(tile0) * e->grid * e->grid * e->kpad;
+  TRY(gar_patchify(pixel_values, mask_values, e->a_img + off, mask_values ? e->a_mask + off : nullptr, T, d.img_size,
+                   d.patch_size, e->kpad, d.prompt_numbers, s));
+  e->launches += 1;
+  return GAR_OK;
+}
+
 int gar_engine_vit_encode(gar_engine* e, const void* pixel_values, const void* mask_values, int T, void* s) {
   if (!e || !pixel_values || T <= 0 || T > e->d.max_tiles) {
     gar_set_error("gar_engine_vit_encode: T=%d outside [1,%d]", T, e ? e->d.max_tiles : 0);
+    return GAR_ERR_ARG;
+  }
+  TRY(gar_engine_patchify_at(e, pixel_values, mask_values, T, 0, s));
+  return gar_engine_vit_encode_patches(e, T, mask_values != nullptr, s);
+}
+
+// R3-R5 on the first T tiles of the im2col arenas (filled by gar_engine_patchify_at)
+int gar_engine_vit_encode_patches(gar_engine* e, int T, int with_mask, void* s) {
+  if (!e || T <= 0 || T > e->d.max_tiles) {
+    gar_set_error("gar_engine_vit_encode_patches: T=%d outside [1,%d]", T, e ? e->d.max_tiles : 0);
     return GAR_ERR_ARG;
   }
   const gar_model_desc& d = e->d;
@@ -528,13 +571,10 @@ int gar_engine_vit_encode(gar_engine* e, const void* pixel_values, const void* m
   NEEDW(rope, "vit.rope");
   const void* cls = e->npt ? W(e, "vit.cls") : nullptr;
   if (e->npt && !cls) return GAR_ERR_STATE;
-  // R2+R3 operand prep, then the two k=s=14 convs as GEMMs: x = bf16(conv(px)) ; x = bf16(x + bf16(conv(mask)))
-  TRY(gar_patchify(pixel_values, mask_values, e->a_img, e->a_mask, T, d.img_size, d.patch_size, e->kpad,
-                   d.prompt_numbers, s));
-  e->launches += 1;
+  // the two k=s=14 convs as GEMMs: x = bf16(conv(px)) ; x = bf16(x + bf16(conv(mask)))
   TRY(gemm(e, e->a_img, e->kpad, wp, e->kpad, e->pe, dv, T * NP, dv, e->kpad, GAR_EPI_NONE, nullptr, nullptr, nullptr,
            0, s));
-  if (mask_values) {
+  if (with_mask) {
     NEEDW(wm, "vit.mask_w");
     TRY(gemm(e, e->a_mask, e->kpad, wm, e->kpad, e->pe, dv, T * NP, dv, e->kpad, GAR_EPI_RES, nullptr, nullptr, e->pe,
              dv, s));
@@ -613,7 +653,8 @@ int gar_engine_assemble(gar_engine* e, int slot, const long long* input_ids_dev,
   }
   const gar_model_desc& d = e->d;
   NEEDW(table, "llm.embed");
-  e->launches += 3;
+  e->launches += 2;
+  e->plan_slot0 = -1;
   // algorithmic bytes: write S*D*2 + read one D-row per non-replay row + <=16 cells per region
   ProfScope ps(e, s, PK_ASSEMBLE, 2.0 * (2.0 * S - 0.0) * d.llm_dim);
   return gar_assemble_embeds(input_ids_dev, S, table, d.vocab, e->feats, T * e->tokens_per_tile, d.llm_dim,
@@ -637,7 +678,8 @@ int gar_engine_assemble_at(gar_engine* e, int slot, const long long* input_ids_d
     return GAR_ERR_SHAPE;
   }
   NEEDW(table, "llm.embed");
-  e->launches += 3;
+  e->launches += 2;
+  e->plan_slot0 = -1;
   ProfScope ps(e, s, PK_ASSEMBLE, 2.0 * (2.0 * S) * d.llm_dim);
   return gar_assemble_embeds(input_ids_dev, S, table, d.vocab,
                              e->feats + static_cast<size_t>(feat_tile0) * e->tokens_per_tile * d.llm_dim,
@@ -646,8 +688,39 @@ int gar_engine_assemble_at(gar_engine* e, int slot, const long long* input_ids_d
                              e->emb + static_cast<size_t>(emb_row0) * d.llm_dim, e->plan + emb_row0, e->status + 2 * slot, s);
 }
 
-// R6-R7 for nreq equal-shape requests of a batched pass in ONE plan/gather/replay launch triple: request r reads
-// features from tile r*T, writes inputs_embeds rows [r*S, (r+1)*S) and status slot slot0+r.
+// R6 row plan + validation for nreq equal-shape requests.  Depends only on input_ids / which boxes exist, so callers
+// run it FIRST (before the ViT): the status words come back to the host right away and a malformed prompt raises
+// before any feature is computed (the reference raises its ValueError before the language model runs,
+// modeling_perception_lm.py:309-315).  Synchronises `stream` (cheap when the plan is the first thing enqueued).
+// status_host: nreq status words (GAR_STATUS_* bits), may be NULL.
+int gar_engine_plan_batch(gar_engine* e, int slot0, int nreq, const long long* const* input_ids_dev, int S, int T,
+                          const int* has_roi, int* status_host, void* s) {
+  if (!e) return GAR_ERR_ARG;
+  const gar_model_desc& d = e->d;
+  const long long pr = d.max_prefill_rows > d.max_seq ? d.max_prefill_rows : d.max_seq;
+  if (nreq <= 0 || slot0 < 0 || slot0 + nreq > d.max_batch || S <= 0 || S > d.max_seq ||
+      static_cast<long long>(nreq) * S > pr || T <= 0 || static_cast<long long>(nreq) * T > d.max_tiles || !has_roi) {
+    gar_set_error("gar_engine_plan_batch: slot0=%d nreq=%d S=%d T=%d outside capacity", slot0, nreq, S, T);
+    return GAR_ERR_ARG;
+  }
+  ProfScope ps(e, s, PK_ASSEMBLE, 0.0);
+  TRY(gar_assemble_plan_batch(nreq, input_ids_dev, S, T * e->tokens_per_tile, d.crop_token_ids, has_roi,
+                              d.prompt_numbers, e->tpt, d.image_token_id, e->plan, e->status + 2 * slot0, s));
+  e->launches += (nreq + 7) / 8;
+  e->plan_slot0 = slot0; e->plan_nreq = nreq; e->plan_S = S; e->plan_T = T;
+  if (status_host) {
+    std::vector<int> st(2 * nreq);
+    GAR_CUDA_CHECK(cudaMemcpyAsync(st.data(), e->status + 2 * slot0, sizeof(int) * 2 * nreq, cudaMemcpyDeviceToHost,
+                                   static_cast<cudaStream_t>(s)));
+    GAR_CUDA_CHECK(cudaStreamSynchronize(static_cast<cudaStream_t>(s)));
+    for (int r = 0; r < nreq; ++r) status_host[r] = st[2 * r];
+  }
+  return GAR_OK;
+}
+
+// R6-R7 for nreq equal-shape requests of a batched pass: request r reads features from tile r*T, writes
+// inputs_embeds rows [r*S, (r+1)*S) and status slot slot0+r.  One row launch for everything; the plan launch is skipped
+// when gar_engine_plan_batch already ran for the same (slot0, nreq, S, T).
 int gar_engine_assemble_batch(gar_engine* e, int slot0, int nreq, const long long* const* input_ids_dev, int S, int T,
                               const float* rois, const int* has_roi, float spatial_scale, const int* ncw,
                               const int* nch, void* s) {
@@ -666,11 +739,19 @@ int gar_engine_assemble_batch(gar_engine* e, int slot0, int nreq, const long lon
     }
   }
   NEEDW(table, "llm.embed");
-  e->launches += 3 * ((nreq + 7) / 8);
+  const bool planned = e->plan_slot0 == slot0 && e->plan_nreq == nreq && e->plan_S == S && e->plan_T == T;
+  e->plan_slot0 = -1;
+  // algorithmic bytes: write S*D*2 + read one D-row per non-replay row + <=16 cells per region
   ProfScope ps(e, s, PK_ASSEMBLE, 2.0 * (2.0 * S) * d.llm_dim * nreq);
-  return gar_assemble_embeds_batch(nreq, input_ids_dev, S, table, d.vocab, e->feats, T * e->tokens_per_tile, d.llm_dim,
-                                   d.crop_token_ids, rois, has_roi, d.prompt_numbers, spatial_scale, ncw, nch, e->tpt,
-                                   d.image_token_id, e->emb, e->plan, e->status + 2 * slot0, s);
+  if (!planned) {
+    TRY(gar_assemble_plan_batch(nreq, input_ids_dev, S, T * e->tokens_per_tile, d.crop_token_ids, has_roi,
+                                d.prompt_numbers, e->tpt, d.image_token_id, e->plan, e->status + 2 * slot0, s));
+    e->launches += (nreq + 7) / 8;
+  }
+  e->launches += (nreq + 7) / 8;
+  return gar_assemble_rows_batch(nreq, input_ids_dev, S, table, d.vocab, e->feats, T * e->tokens_per_tile, d.llm_dim,
+                                 d.crop_token_ids, rois, has_roi, d.prompt_numbers, spatial_scale, ncw, nch, e->tpt,
+                                 d.image_token_id, e->emb, e->plan, s);
 }
 
 int gar_engine_prefill_batch(gar_engine* e, int slot0, int nreq, int S, void* s) {
@@ -688,7 +769,7 @@ int gar_engine_prefill_batch(gar_engine* e, int slot0, int nreq, int S, void* s)
   TRY(llm_layers(e, e->h, e->lnl, rows, false, slot0, s, nreq));
   // last position of every request: rows (r+1)*S-1, i.e. a strided row view of h
   TRY(lm_head(e, e->h + static_cast<size_t>(S - 1) * d.llm_dim, S * d.llm_dim, nreq,
-              e->logits + static_cast<size_t>(slot0) * d.vocab_padded, s));
+              e->logits + static_cast<size_t>(slot0) * d.vocab_padded, e->lnl, s));
   std::vector<int> pos(nreq, S);
   GAR_CUDA_CHECK(cudaMemcpyAsync(e->pos + slot0, pos.data(), sizeof(int) * nreq, cudaMemcpyHostToDevice,
                                  static_cast<cudaStream_t>(s)));
@@ -707,7 +788,7 @@ int gar_engine_prefill(gar_engine* e, int slot, int S, void* s) {
   TRY(llm_layers(e, e->h, e->lnl, S, false, slot, s));
   // logits only for the last position (logits_to_keep=1 in HF generate's prefill)
   TRY(lm_head(e, e->h + static_cast<size_t>(S - 1) * d.llm_dim, d.llm_dim, 1,
-              e->logits + static_cast<size_t>(slot) * d.vocab_padded, s));
+              e->logits + static_cast<size_t>(slot) * d.vocab_padded, e->lnl, s));
   const int pos = S;
   GAR_CUDA_CHECK(cudaMemcpyAsync(e->pos + slot, &pos, sizeof(int), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(s)));
   return GAR_OK;
@@ -730,38 +811,75 @@ int gar_engine_prefill_all_logits(gar_engine* e, int slot, int S, void* logits_o
 // Greedy decode of KV slots [slot0, slot0 + batch).  Only one decode runs at a time, but it may run on its own
 // stream while gar_engine_vit_encode / assemble / prefill for OTHER slots are in flight on another stream
 // (decode touches only decode-private scratch, its slots' KV / logits / counters, and the read-only weights).
-int gar_engine_generate_group(gar_engine* e, int slot0, int batch, int max_new_tokens, int eos, int* out_tokens_host,
-                              void* s_) {
+//
+// Stop ids: HF's greedy loop ends a sequence at the first token in GenerationConfig.eos_token_id (an int or a list,
+// demo/gar_with_mask.py:115-120).  Finished sequences are latched on the device; the host polls the latches every
+// `eos_poll_steps` graph replays (async copy + event, one chunk always in flight) and stops launching once every
+// sequence of the group has finished, so a 1024-token budget costs what the caption needs, not 1024 steps.
+int gar_engine_generate_eos(gar_engine* e, int slot0, int batch, int max_new_tokens, const int* eos_ids, int n_eos,
+                            int* out_tokens_host, int* steps_run, void* s_) {
   cudaStream_t s = static_cast<cudaStream_t>(s_);
   if (!e || batch <= 0 || slot0 < 0 || slot0 + batch > e->d.max_batch || max_new_tokens <= 0 ||
-      max_new_tokens > e->d.max_new_tokens || !out_tokens_host) {
-    gar_set_error("gar_engine_generate: slot0=%d batch=%d max_new_tokens=%d outside capacity", slot0, batch,
-                  max_new_tokens);
+      max_new_tokens > e->d.max_new_tokens || !out_tokens_host || n_eos < 0 || n_eos > 4 || (n_eos > 0 && !eos_ids)) {
+    gar_set_error("gar_engine_generate: slot0=%d batch=%d max_new_tokens=%d n_eos=%d outside capacity", slot0, batch,
+                  max_new_tokens, n_eos);
     return GAR_ERR_ARG;
   }
   const gar_model_desc& d = e->d;
   e->slot_base = slot0;
+  e->n_eos = 0;
+  for (int i = 0; i < 4; ++i) e->eos_ids[i] = -1;
+  for (int i = 0; i < n_eos; ++i)
+    if (eos_ids[i] >= 0) e->eos_ids[e->n_eos++] = eos_ids[i];
+  const std::vector<int> eos_key(e->eos_ids, e->eos_ids + 4);
   int* out_dev = e->out_tokens + static_cast<size_t>(slot0) * d.max_new_tokens;
   GAR_CUDA_CHECK(cudaMemsetAsync(e->step, 0, 2 * sizeof(int), s));
   GAR_CUDA_CHECK(cudaMemsetAsync(e->finished + slot0, 0, sizeof(int) * batch, s));
   GAR_CUDA_CHECK(cudaMemsetAsync(out_dev, 0xff, sizeof(int) * batch * d.max_new_tokens, s));
   // token 0 from the prefill logits (position bookkeeping already at S per slot)
-  TRY(gar_argmax_step(e->logits + static_cast<size_t>(slot0) * d.vocab_padded, d.vocab_padded, d.vocab, batch,
-                      e->next_tok + slot0, out_dev, d.max_new_tokens, e->step, e->pos + slot0, e->finished + slot0, eos, 0,
-                      1, e->argmax_ws, s));
+  TRY(gar_argmax_step_eos(e->logits + static_cast<size_t>(slot0) * d.vocab_padded, d.vocab_padded, d.vocab, batch,
+                          e->next_tok + slot0, out_dev, d.max_new_tokens, e->step, e->pos + slot0, e->finished + slot0,
+                          e->eos_ids, e->n_eos, 0, 1, e->argmax_ws, s));
   e->launches += 2;
   const int steps = max_new_tokens - 1;
+  int done = 0;  // decode steps launched
   if (steps > 0) {
-    // step 1 eagerly (also the warm-up that sets every kernel attribute), the rest as graph replays
-    const long long before = e->launches;
-    TRY(decode_step(e, batch, eos, s));
-    e->launches_per_step = static_cast<int>(e->launches - before);
-    if (steps > 1 && e->profiling) {
-      for (int i = 1; i < steps; ++i) TRY(decode_step(e, batch, eos, s));
-    } else if (steps > 1) {
-      const long long key = (static_cast<long long>(slot0) << 32) | (static_cast<long long>(batch) << 8) | (eos >= 0 ? 1 : 0);
+    const bool poll = e->n_eos > 0 && e->eos_poll_steps > 0;
+    int* fin[2] = {e->fin_host, e->fin_host + d.max_batch};
+    bool pending[2] = {false, false};
+    int cur = 0;
+    // returns true when every sequence of the group had finished at the time of poll buffer `c`
+    auto all_finished = [&](int c) -> bool {
+      if (!pending[c]) return false;
+      cudaEventSynchronize(e->fin_ev[c]);
+      pending[c] = false;
+      for (int b = 0; b < batch; ++b)
+        if (!fin[c][b]) return false;
+      return true;
+    };
+    auto post_poll = [&]() -> int {
+      GAR_CUDA_CHECK(cudaMemcpyAsync(fin[cur], e->finished + slot0, sizeof(int) * batch, cudaMemcpyDeviceToHost, s));
+      GAR_CUDA_CHECK(cudaEventRecord(e->fin_ev[cur], s));
+      pending[cur] = true;
+      cur ^= 1;
+      return GAR_OK;
+    };
+    bool stop = false;
+    if (poll) TRY(post_poll());  // the first token may already be a stop id: checked at the first chunk boundary
+    if (!stop) {
+      // step 1 eagerly (also the warm-up that sets every kernel attribute), the rest as graph replays
+      const long long before = e->launches;
+      TRY(decode_step(e, batch, s));
+      e->launches_per_step = static_cast<int>(e->launches - before);
+      done = 1;
+    }
+    if (!stop && steps > 1 && e->profiling) {
+      for (int i = 1; i < steps; ++i) TRY(decode_step(e, batch, s));
+      done = steps;
+    } else if (!stop && steps > 1) {
+      const long long key = (static_cast<long long>(slot0) << 32) | (static_cast<long long>(batch) << 8);
       auto it = e->graphs.find(key);
-      if (it == e->graphs.end() || e->graph_eos[key] != eos) {
+      if (it == e->graphs.end() || e->graph_eos[key] != eos_key) {
         if (s == nullptr || s == cudaStreamLegacy) {
           gar_set_error("gar_engine_generate: needs a non-default stream (CUDA graph capture)");
           return GAR_ERR_ARG;
@@ -771,7 +889,7 @@ int gar_engine_generate_group(gar_engine* e, int slot0, int batch, int max_new_t
         cudaGraphExec_t exec = nullptr;
         GAR_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         const long long keep = e->launches;
-        int rc = decode_step(e, batch, eos, s);
+        int rc = decode_step(e, batch, s);
         e->launches = keep;
         cudaError_t ce = cudaStreamEndCapture(s, &graph);
         if (rc) return rc;
@@ -779,14 +897,25 @@ int gar_engine_generate_group(gar_engine* e, int slot0, int batch, int max_new_t
         GAR_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
         cudaGraphDestroy(graph);
         e->graphs[key] = exec;
-        e->graph_eos[key] = eos;
+        e->graph_eos[key] = eos_key;
         it = e->graphs.find(key);
       }
-      // EOS is latched on the device; sequences that finished keep stepping (outputs masked to -1)
-      for (int i = 1; i < steps; ++i) GAR_CUDA_CHECK(cudaGraphLaunch(it->second, s));
-      e->launches += static_cast<long long>(e->launches_per_step) * (steps - 1);
+      int i = 1;
+      while (i < steps && !stop) {
+        const int n = poll ? (steps - i < e->eos_poll_steps ? steps - i : e->eos_poll_steps) : steps - i;
+        for (int j = 0; j < n; ++j) GAR_CUDA_CHECK(cudaGraphLaunch(it->second, s));
+        i += n;
+        done += n;
+        if (poll && i < steps) {
+          TRY(post_poll());
+          stop = all_finished(cur);  // the poll posted one chunk earlier: the newest chunk keeps the GPU busy meanwhile
+        }
+      }
+      e->launches += static_cast<long long>(e->launches_per_step) * (done - 1);
     }
   }
+  e->steps_run = done;
+  if (steps_run) *steps_run = done;
   std::vector<int> tmp(static_cast<size_t>(batch) * d.max_new_tokens);
   GAR_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), out_dev, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
   GAR_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -794,6 +923,11 @@ int gar_engine_generate_group(gar_engine* e, int slot0, int batch, int max_new_t
     for (int t = 0; t < max_new_tokens; ++t)
       out_tokens_host[b * max_new_tokens + t] = tmp[static_cast<size_t>(b) * d.max_new_tokens + t];
   return GAR_OK;
+}
+
+int gar_engine_generate_group(gar_engine* e, int slot0, int batch, int max_new_tokens, int eos, int* out_tokens_host,
+                              void* s) {
+  return gar_engine_generate_eos(e, slot0, batch, max_new_tokens, &eos, eos >= 0 ? 1 : 0, out_tokens_host, nullptr, s);
 }
 
 int gar_engine_generate(gar_engine* e, int batch, int max_new_tokens, int eos, int* out_tokens_host, void* s) {
@@ -821,6 +955,7 @@ int gar_engine_set_option(gar_engine* e, const char* name, int value) {
   else if (n == "decode_mega") e->decode_mega = value;
   else if (n == "mega_unit_warps" && (value == 2 || value == 4)) e->mega_unit_warps = value;
   else if (n == "decode_splits" && value >= 0 && value <= 32) e->dec_splits = value;
+  else if (n == "eos_poll_steps" && value >= 0) e->eos_poll_steps = value;
   else if (n == "pdl" || n == "decode_attn_mma" || n == "attn_bkv" || n == "gemm_2cta") {
     if (gar_set_global_option(name, value)) return GAR_ERR_ARG;
   }

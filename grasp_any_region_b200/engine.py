@@ -219,27 +219,42 @@ class Engine:
     def request(self, slot: int, pixel_values, global_mask_values, input_ids, bboxes, aspect_ratio):
         """ViT -> assemble -> prefill for one (image, mask-set, prompt) request into KV slot `slot`.
         Inputs must already be on the device in bf16 / int64; runs on the engine stream."""
-        ncw, nch = int(aspect_ratio[0]), int(aspect_ratio[1])
-        T = pixel_values.shape[0]
-        self.vit_encode(pixel_values, global_mask_values)
-        self.assemble(slot, input_ids, T, bboxes, ncw, nch)
-        self.prefill(slot, input_ids.numel())
+        self.request_batch(slot, [(pixel_values, global_mask_values, input_ids, bboxes, aspect_ratio)])
 
-    def request_batch(self, slot0: int, requests):
+    def plan_batch(self, slot0: int, requests) -> List[int]:
+        """R6 row plan + validation of `requests` (same tuples as request_batch) BEFORE anything else runs; returns
+        one GAR_STATUS_* word per request.  Synchronises the engine stream (idle at this point)."""
+        n = len(requests)
+        T, S = requests[0][0].shape[0], requests[0][2].numel()
+        has = []
+        for (_, _, _, bboxes, _) in requests:
+            has += [1 if (bboxes is not None and bboxes.get(str(c)) is not None) else 0
+                    for c in self.spec.crop_tokens_ids]
+        c_ids = (C.c_void_p * n)(*[r[2].data_ptr() for r in requests])
+        st = (C.c_int * n)()
+        check(self.lib.gar_engine_plan_batch(self._h, slot0, n, c_ids, S, T, (C.c_int * len(has))(*has), st, self._s()),
+              "gar_engine_plan_batch")
+        return list(st)
+
+    def request_batch(self, slot0: int, requests, planned: bool = False):
         """ViT -> assemble -> prefill for several requests in ONE pass (one GEMM / attention launch covers all of
         them): requires equal tile counts and prompt lengths.  `requests` = list of
         (pixel_values, global_mask_values, input_ids(S,), bboxes, (ncw, nch)) already on the device.
-        Per-request results are identical to request(); only the launch count and tile quantisation change."""
+        Per-request results are identical to a one-request pass; only the launch count and tile quantisation change.
+        Every request is patchified straight from its own tensors (no concatenated copy)."""
         n = len(requests)
         T = requests[0][0].shape[0]
         S = requests[0][2].numel()
         assert all(r[0].shape[0] == T and r[2].numel() == S for r in requests)
         assert n * T <= self.max_tiles and n * S <= self.max_prefill_rows and slot0 + n <= self.max_batch
         with_mask = requests[0][1] is not None
-        px = torch.cat([r[0] for r in requests], 0)
-        mv = torch.cat([r[1] for r in requests], 0) if with_mask else None
-        self.vit_encode(px, mv)
-        keep = [px, mv]
+        assert all((r[1] is not None) == with_mask for r in requests)
+        for i, r in enumerate(requests):
+            check(self.lib.gar_engine_patchify_at(self._h, C.c_void_p(r[0].data_ptr()),
+                                                  C.c_void_p(r[1].data_ptr()) if with_mask else None, T, i * T,
+                                                  self._s()), "gar_engine_patchify_at")
+        check(self.lib.gar_engine_vit_encode_patches(self._h, n * T, int(with_mask), self._s()),
+              "gar_engine_vit_encode_patches")
         flat_rois, flat_has, ncws, nchs, scale = [], [], [], [], 1.0
         for (_, _, ids, bboxes, (ncw, nch)) in requests:
             rois, has, scale = roi_boxes_f32(self.spec, bboxes, ncw, nch)
@@ -253,16 +268,26 @@ class Engine:
                                                  (C.c_int * n)(*ncws), (C.c_int * n)(*nchs), self._s()),
               "gar_engine_assemble_batch")
         check(self.lib.gar_engine_prefill_batch(self._h, slot0, n, S, self._s()), "gar_engine_prefill_batch")
-        return keep
 
-    def generate(self, batch: int, max_new_tokens: int, eos_token_id: Optional[int], slot0: int = 0,
+    def generate(self, batch: int, max_new_tokens: int, eos_token_id=None, slot0: int = 0,
                  stream: Optional[torch.cuda.Stream] = None) -> List[List[int]]:
-        """Greedy decode of KV slots [slot0, slot0+batch); blocks until the tokens are on the host."""
+        """Greedy decode of KV slots [slot0, slot0+batch); blocks until the tokens are on the host.
+        eos_token_id: None, an int, or a list of up to four stop ids (HF GenerationConfig.eos_token_id).
+        Decoding stops as soon as every sequence has emitted a stop id; `last_steps_run` = decode steps launched."""
+        if eos_token_id is None:
+            eos = []
+        elif isinstance(eos_token_id, (list, tuple)):
+            eos = [int(x) for x in eos_token_id]
+        else:
+            eos = [int(eos_token_id)]
+        if len(eos) > 4:
+            raise _lib.GarError(f"at most 4 eos_token_id values are supported, got {len(eos)}")
         buf = (C.c_int * (batch * max_new_tokens))()
+        steps = C.c_int(0)
         s = C.c_void_p((stream or self.stream).cuda_stream)
-        check(self.lib.gar_engine_generate_group(self._h, slot0, batch, max_new_tokens,
-                                                 -1 if eos_token_id is None else int(eos_token_id), buf, s),
-              "gar_engine_generate")
+        check(self.lib.gar_engine_generate_eos(self._h, slot0, batch, max_new_tokens, (C.c_int * max(1, len(eos)))(*eos),
+                                               len(eos), buf, C.byref(steps), s), "gar_engine_generate")
+        self.last_steps_run = steps.value
         out = []
         for b in range(batch):
             row = [buf[b * max_new_tokens + i] for i in range(max_new_tokens)]

@@ -128,6 +128,51 @@ class GARModel(_Base):
     def _init_weights(self, module):  # parameters always come from a checkpoint / random_init_
         pass
 
+    @classmethod
+    def from_pretrained(cls, *args, **kwargs):
+        """HF loader (the path every reference caller takes, demo/gar_with_mask.py:84-94).  A checkpoint that lacks
+        any parameter of the path is an error here: there is no initialiser to fall back to, and a silently
+        uninitialised tensor would only show up as garbage captions."""
+        want_info = kwargs.pop("output_loading_info", False)
+        # Every reference caller passes device_map="cuda:0".  A single-device map needs no dispatch machinery (and
+        # transformers would demand `accelerate` for it): load, then move the whole model -- the engine is one replica
+        # per GPU by design.  Anything that really shards a model across devices is refused.
+        device = None
+        dm = kwargs.pop("device_map", None)
+        if dm is not None:
+            if isinstance(dm, dict):
+                targets = set(dm.values())
+                if len(targets) != 1:
+                    raise ValueError(f"device_map must name ONE device (one full replica per GPU), got {dm}")
+                dm = targets.pop()
+            if dm in ("auto", "balanced", "balanced_low_0", "sequential"):
+                dm = "cuda:0" if torch.cuda.is_available() else "cpu"
+            device = torch.device(f"cuda:{dm}" if isinstance(dm, int) else dm)
+        out = super().from_pretrained(*args, output_loading_info=True, **kwargs)
+        model, info = out if isinstance(out, tuple) else (out, {})
+        if device is not None:
+            model = model.to(device)
+        missing = sorted(info.get("missing_keys", []) or [])
+        if missing:
+            raise ValueError(f"checkpoint is missing {len(missing)} parameter(s) of the GAR path, e.g. {missing[:4]}")
+        return (model, info) if want_info else model
+
+    # The engine holds fused / padded private copies of some weights: anything that changes or moves the parameters
+    # (load_state_dict, .to(), .cuda(), .half() ...) drops it, and the next call rebuilds it from the live tensors.
+    def _drop_engine(self):
+        eng = getattr(self, "_engine", None)
+        if eng is not None:
+            eng.close()
+            self._engine = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._drop_engine()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._drop_engine()
+        return super().load_state_dict(*args, **kwargs)
+
     @property
     def dtype(self):
         return torch.bfloat16
@@ -144,16 +189,14 @@ class GARModel(_Base):
                     p.copy_((1.0 + 0.05 * torch.randn(p.shape, generator=g)).to(p.dtype))
                 else:
                     p.copy_((0.02 * torch.randn(p.shape, generator=g)).to(p.dtype))
-        self._engine = None
+        self._drop_engine()
         return self
 
     def configure_engine(self, **caps) -> "GARModel":
         """Capacity of the device arenas: max_tiles, max_seq, max_batch, max_new_tokens, max_prefill_rows
         (max_tiles >= n*T and max_prefill_rows >= n*S let generate_batch encode n requests in one pass)."""
         self._engine_caps.update(caps)
-        if self._engine is not None:
-            self._engine.close()
-            self._engine = None
+        self._drop_engine()
         return self
 
     def engine(self) -> Engine:
@@ -169,49 +212,12 @@ class GARModel(_Base):
     # ------------------------------------------------------------------ request plumbing
     def _prepare_request(self, eng: Engine, pixel_values, global_mask_values, aspect_ratios, bboxes, input_ids,
                          batch_idx=0):
-        """Device-side copies of one request in the dtypes the engine reads (bf16 / int64)."""
+        """Device-side copies of one request in the dtypes the engine reads (bf16 / int64).  The (tiny) ids go
+        first so the row plan can validate the prompt while the pixel copies are still in flight."""
         dev = eng.device
         if input_ids.shape[0] != 1:
             raise AssertionError("Currently only support batch_size=1")
-        px = pixel_values.to(dev, non_blocking=True).to(torch.bfloat16)
-        if px.dim() == 5:
-            px = px.flatten(0, 1)
-        assert px.dim() == 4, (
-            f"pixel_values should be of shape (batch_size * num_tiles, channels, height, width). But got {px.shape}.")
-        mv = None
-        if global_mask_values is not None:
-            mv = global_mask_values.to(dev, non_blocking=True).to(torch.bfloat16).contiguous()
         ids = input_ids[batch_idx].to(dev, non_blocking=True).to(torch.long).contiguous()
-        ar = aspect_ratios[batch_idx]
-        return px.contiguous(), mv, ids, bboxes[batch_idx], (int(ar[0]), int(ar[1]))
-
-    def _stage_requests_batched(self, eng: Engine, slot0: int, requests: List[dict]) -> bool:
-        """One ViT/prefill pass for all requests when they share tile count and prompt length (and the engine
-        was sized for it); returns False when the caller must stage them one by one."""
-        prepared = [self._prepare_request(eng, r["pixel_values"], r.get("global_mask_values"), r["aspect_ratios"],
-                                          r["bboxes"], r["input_ids"]) for r in requests]
-        n, T, S = len(prepared), prepared[0][0].shape[0], prepared[0][2].numel()
-        uniform = all(p[0].shape[0] == T and p[2].numel() == S and (p[1] is None) == (prepared[0][1] is None)
-                      for p in prepared)
-        if not (uniform and n > 1 and n * T <= eng.max_tiles and n * S <= eng.max_prefill_rows):
-            return False
-        eng.stream.wait_stream(torch.cuda.current_stream(eng.device))
-        with torch.cuda.stream(eng.stream):
-            keep = eng.request_batch(slot0, prepared)
-        for p in prepared:
-            for t in (p[0], p[1], p[2]):
-                if t is not None:
-                    t.record_stream(eng.stream)
-        for t in keep:
-            if t is not None:
-                t.record_stream(eng.stream)
-        return True
-
-    def _stage_request(self, eng: Engine, slot, pixel_values, global_mask_values, aspect_ratios, bboxes, input_ids,
-                       batch_idx=0):
-        dev = eng.device
-        if input_ids.shape[0] != 1:
-            raise AssertionError("Currently only support batch_size=1")
         px = pixel_values.to(dev, non_blocking=True).to(torch.bfloat16)
         if px.dim() == 5:
             px = px.flatten(0, 1)
@@ -221,25 +227,60 @@ class GARModel(_Base):
         if global_mask_values is not None:
             # the reference decodes ids in the tensor's own dtype (bf16 after the dataset's cast, quirk 7)
             mv = global_mask_values.to(dev, non_blocking=True).to(torch.bfloat16).contiguous()
-        ids = input_ids[batch_idx].to(dev, non_blocking=True).to(torch.long).contiguous()
         ar = aspect_ratios[batch_idx]
-        ncw, nch = int(ar[0]), int(ar[1])
-        eng.stream.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(eng.stream):
-            eng.request(slot, px.contiguous(), mv, ids, bboxes[batch_idx], (ncw, nch))
-        for t in (px, mv, ids):
-            if t is not None:
-                t.record_stream(eng.stream)
-        return ids.numel()
+        return px.contiguous(), mv, ids, bboxes[batch_idx], (int(ar[0]), int(ar[1]))
 
-    def _raise_on_status(self, eng: Engine, slot: int, n_feats=None):
-        st = eng.status(slot)
+    @staticmethod
+    def _raise_on_status_word(st: int):
         if st & 1:
             raise ValueError("Image features and image tokens do not match")
         if st & 4:
             raise KeyError("bboxes has no entry for a crop token present in input_ids")
         if st & 2:
             raise AssertionError("each crop-token run must be 256 contiguous tokens")
+
+    def _stage(self, eng: Engine, slot0: int, requests: List[dict]) -> None:
+        """ViT -> assemble -> prefill of `requests` into KV slots slot0.. on the engine stream.  Consecutive requests
+        of equal shape (tile count, prompt length) share one ViT pass and one prefill pass as far as the engine's
+        arenas allow; the rest go one by one.  Each pass first runs the row plan and raises the reference's
+        exceptions (ValueError / KeyError / AssertionError) BEFORE any feature or logit of that pass is computed."""
+        prepared = [self._prepare_request(eng, r["pixel_values"], r.get("global_mask_values"), r["aspect_ratios"],
+                                          r["bboxes"], r["input_ids"]) for r in requests]
+        eng.stream.wait_stream(torch.cuda.current_stream(eng.device))
+        i = 0
+        with torch.cuda.stream(eng.stream):
+            while i < len(prepared):
+                T, S, masked = prepared[i][0].shape[0], prepared[i][2].numel(), prepared[i][1] is not None
+                fit = max(1, min(eng.max_tiles // T, eng.max_prefill_rows // S))
+                j = i + 1
+                while (j < len(prepared) and j - i < fit and prepared[j][0].shape[0] == T
+                       and prepared[j][2].numel() == S and (prepared[j][1] is not None) == masked):
+                    j += 1
+                run = prepared[i:j]
+                for st in eng.plan_batch(slot0 + i, run):
+                    self._raise_on_status_word(st)
+                eng.request_batch(slot0 + i, run)
+                i = j
+        for p in prepared:
+            for t in (p[0], p[1], p[2]):
+                if t is not None:
+                    t.record_stream(eng.stream)
+
+    @staticmethod
+    def _generation_args(generation_config, generate_kwargs):
+        max_new, eos, do_sample = 20, None, False
+        if generation_config is not None:
+            max_new = getattr(generation_config, "max_new_tokens", None) or max_new
+            eos = getattr(generation_config, "eos_token_id", None)
+            do_sample = bool(getattr(generation_config, "do_sample", False))
+        max_new = generate_kwargs.pop("max_new_tokens", max_new)
+        eos = generate_kwargs.pop("eos_token_id", eos)
+        if do_sample or generate_kwargs.pop("do_sample", False):
+            raise NotImplementedError(
+                "only greedy decoding (do_sample=False) is implemented, as every reference caller uses")
+        if isinstance(eos, (list, tuple)):
+            eos = [int(x) for x in eos]
+        return int(max_new), eos
 
     @torch.no_grad()
     def generate(self, pixel_values: Optional[torch.FloatTensor] = None,
@@ -250,45 +291,33 @@ class GARModel(_Base):
                  return_dict: Optional[bool] = None, **generate_kwargs) -> GenerateOutput:
         if pixel_values is None:
             raise NotImplementedError("text-only generate() is outside the region-captioning hot path")
-        max_new, eos, do_sample = 20, None, False
-        if generation_config is not None:
-            max_new = getattr(generation_config, "max_new_tokens", None) or max_new
-            eos = getattr(generation_config, "eos_token_id", None)
-            do_sample = bool(getattr(generation_config, "do_sample", False))
-        max_new = generate_kwargs.pop("max_new_tokens", max_new)
-        if do_sample:
-            raise NotImplementedError("only greedy decoding (do_sample=False) is implemented, as every reference caller uses")
-        if isinstance(eos, (list, tuple)):
-            eos = eos[0]
+        if attention_mask is not None and not bool((attention_mask != 0).all()):
+            # every reference caller passes all ones (eval_dataset.py:143); padding would change the prefill
+            raise NotImplementedError("attention_mask with padded positions is not supported (batch 1, no padding)")
+        max_new, eos = self._generation_args(generation_config, generate_kwargs)
         eng = self.engine()
         if max_new > eng.max_new_tokens:
-            self.configure_engine(max_new_tokens=int(max_new))
+            self.configure_engine(max_new_tokens=max_new)
             eng = self.engine()
-        self._stage_request(eng, 0, pixel_values, global_mask_values, aspect_ratios, bboxes, input_ids)
-        toks = eng.generate(1, int(max_new), eos)
-        self._raise_on_status(eng, 0)
+        self._stage(eng, 0, [dict(pixel_values=pixel_values, global_mask_values=global_mask_values,
+                                  aspect_ratios=aspect_ratios, bboxes=bboxes, input_ids=input_ids)])
+        toks = eng.generate(1, max_new, eos)
         seq = torch.tensor([toks[0]], dtype=torch.long, device=eng.device)
         return GenerateOutput(sequences=seq)
 
     @torch.no_grad()
-    def generate_batch(self, requests: List[dict], max_new_tokens: int = 128, eos_token_id: Optional[int] = None):
+    def generate_batch(self, requests: List[dict], max_new_tokens: int = 128, eos_token_id=None):
         """B200 scheduler extension: independent requests (each the dict the reference's dataset emits)
         share one batched decode.  Per-request results equal the batch-1 ``generate`` results."""
         eng = self.engine()
         if len(requests) > eng.max_batch:
             raise ValueError(f"{len(requests)} requests > engine max_batch {eng.max_batch}")
-        if not self._stage_requests_batched(eng, 0, requests):
-            for slot, r in enumerate(requests):
-                self._stage_request(eng, slot, r["pixel_values"], r.get("global_mask_values"), r["aspect_ratios"],
-                                    r["bboxes"], r["input_ids"])
-        toks = eng.generate(len(requests), int(max_new_tokens), eos_token_id)
-        for slot in range(len(requests)):
-            self._raise_on_status(eng, slot)
-        return toks
+        self._stage(eng, 0, requests)
+        return eng.generate(len(requests), int(max_new_tokens), eos_token_id)
 
     @torch.no_grad()
     def generate_batches(self, batches: List[List[dict]], max_new_tokens: int = 128,
-                         eos_token_id: Optional[int] = None) -> List[List[List[int]]]:
+                         eos_token_id=None) -> List[List[List[int]]]:
         """Throughput serving of a stream of request batches (B200 scheduler extension).
 
         Two KV-slot groups ping-pong: while group g decodes on the engine's decode stream, the next batch's
@@ -307,9 +336,7 @@ class GARModel(_Base):
 
         def stage(bi: int, group: int):
             torch.cuda.set_device(dev)
-            for j, r in enumerate(batches[bi]):
-                self._stage_request(eng, group * G + j, r["pixel_values"], r.get("global_mask_values"),
-                                    r["aspect_ratios"], r["bboxes"], r["input_ids"])
+            self._stage(eng, group * G, batches[bi])
             ev = torch.cuda.Event()
             ev.record(eng.stream)
             return ev
@@ -334,8 +361,6 @@ class GARModel(_Base):
                 if "err" in box:
                     raise box["err"]
                 ev = box["ev"]
-            for j in range(len(batch)):
-                self._raise_on_status(eng, g * G + j)
             out.append(toks)
         return out
 
@@ -358,11 +383,13 @@ class GARModel(_Base):
         ar = data["aspect_ratios"][0]
         eng.stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(eng.stream):
-            eng.vit_encode(px.contiguous(), mv)
+            req = (px.contiguous(), mv, ids, data["bboxes"][0], (int(ar[0]), int(ar[1])))
+            for st in eng.plan_batch(0, [req]):
+                self._raise_on_status_word(st)
+            eng.vit_encode(req[0], mv)
             eng.assemble(0, ids, px.shape[0], data["bboxes"][0], int(ar[0]), int(ar[1]))
             logits = eng.prefill_all_logits(0, ids.numel())
         torch.cuda.current_stream(dev).wait_stream(eng.stream)
-        self._raise_on_status(eng, 0)
         labels = data["labels"][0].to(dev).clone()
         for c in self.crop_tokens_ids:  # replayed rows carry no label (reference :180-191)
             labels[ids == c] = -100

@@ -130,34 +130,61 @@ def bbox_of(mask_hw: np.ndarray) -> Tuple[float, float, float, float]:
     return (xs.min() / w, ys.min() / h, xs.max() / w, ys.max() / h)
 
 
-def paint_id_map(masks: Sequence[np.ndarray], prompt_numbers: int) -> np.ndarray:
-    """background = prompt_numbers, region k = k where still background (first writer wins, eval_dataset.py:238-239)"""
+def paint_id_map(masks: Sequence[np.ndarray], prompt_numbers: int, prompt_ids: Optional[Sequence[int]] = None,
+                 order: Optional[Sequence[int]] = None) -> np.ndarray:
+    """background = prompt_numbers; mask i paints id prompt_ids[i] (default i) where still background -- first writer
+    wins (eval_dataset.py:62-69, 238-239).  `order`: the sequence in which the masks are visited (default 0..n-1; the
+    reference's multi-region builder visits a `set` of prompt strings, so its order varies with PYTHONHASHSEED)."""
     assert 1 <= len(masks) <= prompt_numbers
-    idmap = np.full(masks[0].shape, prompt_numbers, dtype=np.uint8)
-    for k, m in enumerate(masks):
-        idmap[(idmap == prompt_numbers) & m.astype(bool)] = k
+    prompt_ids = list(range(len(masks))) if prompt_ids is None else [int(k) for k in prompt_ids]
+    assert all(0 <= k < prompt_numbers for k in prompt_ids) and len(prompt_ids) == len(masks)
+    idmap = np.full(np.asarray(masks[0]).shape, prompt_numbers, dtype=np.uint8)
+    for i in (range(len(masks)) if order is None else order):
+        idmap[(idmap == prompt_numbers) & np.asarray(masks[i]).astype(bool)] = prompt_ids[i]
     return idmap
 
 
+def region_boxes(spec: GARSpec, masks: Sequence[np.ndarray], prompt_ids: Optional[Sequence[int]] = None,
+                 reference_quirks: bool = False) -> Dict[str, Tuple[float, float, float, float]]:
+    """bboxes dict keyed by str(crop token id) (modeling_gar.py:367).  reference_quirks=True reproduces what
+    `MultiRegionDataset._parse_annotations` really emits (eval_dataset.py:201-205, 241): the box of
+    EVERY region is computed from the last mask, because the loop reuses a stale `mask_id`."""
+    prompt_ids = list(range(len(masks))) if prompt_ids is None else [int(k) for k in prompt_ids]
+    out = {}
+    for i, k in enumerate(prompt_ids):
+        src = masks[-1] if reference_quirks else masks[i]
+        out[str(spec.crop_tokens_ids[k])] = bbox_of(np.asarray(src))
+    return out
+
+
 def build_request(spec: GARSpec, image_hwc_u8: np.ndarray, masks: Sequence[np.ndarray], text_ids: Sequence[int],
-                  max_num_tiles: int = 16, dtype: torch.dtype = torch.bfloat16, device: str = "cpu") -> Dict:
+                  max_num_tiles: int = 16, dtype: torch.dtype = torch.bfloat16, device: str = "cpu",
+                  prompt_ids: Optional[Sequence[int]] = None, reference_quirks: bool = False,
+                  prompt_order: Optional[Sequence[int]] = None) -> Dict:
     """The dict `GARModel.generate(**request)` takes, for one image and its region masks.  `text_ids` stands in for the
     tokenised question (no tokenizer ships with the repo): the prompt is
-    [BOS, header] + <|image|> * (T * 256) + per region k: text + crop_token_k * 256 + text + [eot, assistant header]."""
+    [BOS, header] + <|image|> * (T * 256) + per region k: text + crop_token_k * 256 + text + [eot, assistant header].
+
+    prompt_ids[i]: which <PromptK> mask i is (default i).  reference_quirks=True emits exactly what the reference's
+    `gar_relationship.py` request builder would (stale last-mask boxes; regions painted and listed in `prompt_order`,
+    the visiting order of its `set` of prompt strings -- pass the order observed there; default 0..n-1)."""
     from .synth import BOS, EH, EOT, SH
 
     tile = spec.vision.img_size
+    prompt_ids = list(range(len(masks))) if prompt_ids is None else [int(k) for k in prompt_ids]
+    order = list(range(len(masks))) if prompt_order is None else [int(i) for i in prompt_order]
+    assert sorted(order) == list(range(len(masks)))
     img = torch.from_numpy(np.ascontiguousarray(image_hwc_u8)).permute(2, 0, 1).contiguous()
     pixel_values, (ncw, nch) = tile_image(img, tile, max_num_tiles)
-    idmap = paint_id_map(masks, spec.prompt_numbers)
+    idmap = paint_id_map(masks, spec.prompt_numbers, prompt_ids, order if reference_quirks else None)
     mask_values = tile_id_map(torch.from_numpy(idmap), ncw, nch, tile)
-    bboxes = {str(spec.crop_tokens_ids[k]): bbox_of(np.asarray(m)) for k, m in enumerate(masks)}
+    bboxes = region_boxes(spec, masks, prompt_ids, reference_quirks)
     T = pixel_values.shape[0]
     text = [int(t) for t in text_ids]
     per = max(1, len(text) // (len(masks) + 1))
     seq: List[int] = [BOS, SH, 882, EH, 271] + [spec.image_token_id] * (T * spec.tokens_per_tile)
-    for k in range(len(masks)):
-        seq += text[k * per:(k + 1) * per] + [spec.crop_tokens_ids[k]] * spec.tokens_per_tile
+    for n, i in enumerate(order if reference_quirks else range(len(masks))):
+        seq += text[n * per:(n + 1) * per] + [spec.crop_tokens_ids[prompt_ids[i]]] * spec.tokens_per_tile
     seq += text[len(masks) * per:] + [EOT, SH, 78191, EH, 271]
     input_ids = torch.tensor(seq, dtype=torch.long)[None]
     return dict(

@@ -125,25 +125,40 @@ int gar_embed_gather(const void* table, const long long* ids64, const int* ids32
 int gar_argmax_step(const void* logits, int ld, int V, int batch, int* next_tok, int* out_tokens, int out_ld,
                     int* step_ptr, int* pos, int* finished, int eos, int advance_pos, int bump_step, void* partial_ws,
                     void* stream);
+/* same with up to four stop ids (GenerationConfig.eos_token_id may be a list); eos_ids is a HOST array */
+int gar_argmax_step_eos(const void* logits, int ld, int V, int batch, int* next_tok, int* out_tokens, int out_ld,
+                        int* step_ptr, int* pos, int* finished, const int* eos_ids, int n_eos, int advance_pos,
+                        int bump_step, void* partial_ws, void* stream);
 int gar_bump_step(int* step, void* stream);
 
 /* Fused embed + image-feature scatter + RoI-aligned feature replay (modeling_gar.py:332-414).
  * rois: n_regions x [0,x1,y1,x2,y2] fp32 host array computed like modeling_gar.py:367-387;
- * plan_ws: S + 8 ints (device); status_dev: 2 ints (device): [status bits, n image tokens]. */
+ * plan_ws: S ints (device); status_dev: 2 ints (device): [status bits, n image tokens]. */
 int gar_assemble_embeds(const long long* input_ids_dev, int S, const void* embed_table, int vocab,
                         const void* image_features, int n_image_rows, int D, const long long* crop_ids,
                         const float* rois, const int* has_roi, int n_regions, float spatial_scale, int ncw, int nch,
                         int tpt, long long image_token_id, void* out, int* plan_ws, int* status_dev, void* stream);
 
-/* The same for nreq equal-length requests in one plan / gather / replay launch triple (HBM stream over all requests).
+/* The same for nreq equal-length requests (one plan launch + ONE row launch: an HBM stream over all requests).
  * input_ids_dev: HOST array of nreq device pointers; rois (nreq, n_regions, 5), has_roi (nreq, n_regions), ncw/nch
  * (nreq) host arrays; request r uses features image_features + r*n_image_rows*D and writes rows [r*S,(r+1)*S) of out
- * and plan_ws (nreq*S + 8*nreq ints) and status_dev[2r..2r+1]. */
+ * and plan_ws (nreq*S ints) and status_dev[2r..2r+1]. */
 int gar_assemble_embeds_batch(int nreq, const long long* const* input_ids_dev, int S, const void* embed_table,
                               int vocab, const void* image_features, int n_image_rows, int D,
                               const long long* crop_ids, const float* rois, const int* has_roi, int n_regions,
                               float spatial_scale, const int* ncw, const int* nch, int tpt, long long image_token_id,
                               void* out, int* plan_ws, int* status_dev, void* stream);
+/* Its two halves.  The plan (row kinds, image ordinals, crop bins, status bits) depends only on input_ids, so it can run
+ * before the image features exist and its status word can be read early: the reference raises its ValueError
+ * (modeling_perception_lm.py:309-315) before the language model runs, and so does a caller of these two. */
+int gar_assemble_plan_batch(int nreq, const long long* const* input_ids_dev, int S, int n_image_rows,
+                            const long long* crop_ids, const int* has_roi, int n_regions, int tpt,
+                            long long image_token_id, int* plan_ws, int* status_dev, void* stream);
+int gar_assemble_rows_batch(int nreq, const long long* const* input_ids_dev, int S, const void* embed_table, int vocab,
+                            const void* image_features, int n_image_rows, int D, const long long* crop_ids,
+                            const float* rois, const int* has_roi, int n_regions, float spatial_scale, const int* ncw,
+                            const int* nch, int tpt, long long image_token_id, void* out, const int* plan_ws,
+                            void* stream);
 
 /* softmax(QK^T*scale)V, head_dim 64, tcgen05 + TMEM (timm SDPA non-causal; flash-attn 2 causal GQA prefill).
  * All strides/offsets in bf16 elements.  K/V batch coordinate = b*kv_batch_mul + kv_head*kv_batch_head_mul. */
@@ -222,6 +237,12 @@ int gar_engine_get_buffer(gar_engine* e, const char* name, void** dev_ptr, long 
 
 /* R2-R5: pixel_values/global_mask_values (T,3,img,img) -> image features (T, tokens_per_tile, llm_dim) */
 int gar_engine_vit_encode(gar_engine* e, const void* pixel_values, const void* mask_values, int T, void* stream);
+/* The same in two steps, so that the requests of a batched pass are read from their own tensors (no concatenated copy):
+ * patchify_at does R2 + the im2col of T tiles of one request into tiles [tile0, tile0+T) of the engine's operand arena;
+ * vit_encode_patches then runs R3-R5 over the first T_total tiles. */
+int gar_engine_patchify_at(gar_engine* e, const void* pixel_values, const void* mask_values, int T, int tile0,
+                           void* stream);
+int gar_engine_vit_encode_patches(gar_engine* e, int T_total, int with_mask, void* stream);
 /* R6-R7 on the engine's image features -> inputs_embeds (S, llm_dim) */
 int gar_engine_assemble(gar_engine* e, int slot, const long long* input_ids_dev, int S, int T, const float* rois,
                         const int* has_roi, float spatial_scale, int ncw, int nch, void* stream);
@@ -234,6 +255,12 @@ int gar_engine_assemble_at(gar_engine* e, int slot, const long long* input_ids_d
 int gar_engine_assemble_batch(gar_engine* e, int slot0, int nreq, const long long* const* input_ids_dev, int S, int T,
                               const float* rois, const int* has_roi, float spatial_scale, const int* ncw,
                               const int* nch, void* stream);
+/* R6 row plan + validation only, for the requests a following gar_engine_assemble_batch(slot0, nreq, S, T) will
+ * assemble.  Needs only input_ids and has_roi (nreq x prompt_numbers), so it runs BEFORE gar_engine_vit_encode;
+ * synchronises `stream` and returns one GAR_STATUS_* word per request in status_host (may be NULL): callers raise the
+ * reference's ValueError / KeyError before any feature or logit is computed. */
+int gar_engine_plan_batch(gar_engine* e, int slot0, int nreq, const long long* const* input_ids_dev, int S, int T,
+                          const int* has_roi, int* status_host, void* stream);
 /* R8 for nreq equal-length requests at once (rows = nreq*S of inputs_embeds, slots slot0..slot0+nreq-1): same math per
  * request as gar_engine_prefill, 1/nreq of the launches */
 int gar_engine_prefill_batch(gar_engine* e, int slot0, int nreq, int S, void* stream);
@@ -249,6 +276,11 @@ int gar_engine_generate(gar_engine* e, int batch, int max_new_tokens, int eos, i
  * ViT/assemble/prefill runs on a second stream (pipelined serving; bench.py) */
 int gar_engine_generate_group(gar_engine* e, int slot0, int batch, int max_new_tokens, int eos, int* out_tokens_host,
                               void* stream);
+/* R9 with HF's stop-id list: eos_ids (HOST array, n_eos <= 4; n_eos = 0 disables).  A sequence ends at the first stop id
+ * (which is emitted, like HF); once every sequence of the group has ended the engine stops launching decode steps (the
+ * device-side latches are polled every "eos_poll_steps" graph replays).  steps_run (may be NULL): decode steps launched. */
+int gar_engine_generate_eos(gar_engine* e, int slot0, int batch, int max_new_tokens, const int* eos_ids, int n_eos,
+                            int* out_tokens_host, int* steps_run, void* stream);
 int gar_engine_status(gar_engine* e, int slot, int* status_bits);
 long long gar_engine_launch_count(gar_engine* e);
 /* options: "skinny_gemm" (1 = decode GEMMs use gar_gemm_skinny_bf16, default 1), "decode_splits" */

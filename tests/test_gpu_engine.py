@@ -202,13 +202,16 @@ def test_batched_encode_matches_per_request():
     lg_seq = None
     model.configure_engine(max_tiles=15, max_seq=S + 32, max_batch=3, max_new_tokens=new_tokens, max_prefill_rows=3 * S)
     eng = model.engine()
-    assert model._stage_requests_batched(eng, 0, reqs)
+    l0 = eng.launch_count()
+    model._stage(eng, 0, reqs)                                          # one ViT pass + one prefill pass for all three
     eng.stream.synchronize()
+    batched_launches = eng.launch_count() - l0
     lg_bat = eng.buffer("logits", (3, eng.vocab_padded)).clone()
+    l0 = eng.launch_count()
     for slot, r in enumerate(reqs):
-        model._stage_request(eng, slot, r["pixel_values"], r["global_mask_values"], r["aspect_ratios"], r["bboxes"],
-                             r["input_ids"])
+        model._stage(eng, slot, [r])
     eng.stream.synchronize()
+    assert eng.launch_count() - l0 > 2 * batched_launches               # the batched pass really was one pass
     lg_seq = eng.buffer("logits", (3, eng.vocab_padded)).clone()
     assert torch.equal(lg_bat, lg_seq)
     bat = model.generate_batch(reqs, max_new_tokens=new_tokens)
@@ -302,3 +305,123 @@ def test_engine_request_from_image_and_masks_non_square_canvas():
     _, lg32 = oracle32.greedy(emb.float()[None], 1)
     assert (logits - lg32[0]).abs().max().item() <= 5e-2
     eng.close()
+
+
+def _small_model(max_batch=4, new_tokens=24, embed_std=1.0):
+    from grasp_any_region_b200 import GARConfig, GARModel
+
+    spec = gar_small()
+    oracle = build_oracle(spec, seed=0, dtype=torch.float32)
+    sd = {k: v.to(bf) for k, v in oracle.state_dict().items()}
+    # unit-scale embeddings: the next token depends on the current one, so greedy streams do not collapse
+    k = "mllm.model.language_model.embed_tokens.weight"
+    sd[k] = (sd[k].float() * (embed_std / 0.02)).to(bf)
+    model = GARModel(GARConfig.from_spec(spec))
+    model.load_state_dict(sd)
+    return spec, model.to(DEV)
+
+
+def test_eos_stops_each_sequence_and_the_decode_loop():
+    """HF greedy semantics on the device (demo/gar_with_mask.py:115-120 sets eos_token_id on every call): a sequence
+    ends AT its first stop id; the others keep going unchanged; once all have ended no further decode step is
+    launched; a list of stop ids behaves like HF's list-valued eos_token_id."""
+    new_tokens = 40
+    spec, model = _small_model()
+    reqs = [make_request(spec, seed=80 + i, n_masks=1 + i % 2, max_num_tiles=4, dtype=bf) for i in range(3)]
+    S = max(r["input_ids"].shape[1] for r in reqs)
+    model.configure_engine(max_tiles=5, max_seq=S + 64, max_batch=4, max_new_tokens=new_tokens)
+    eng = model.engine()
+    base = model.generate_batch(reqs, max_new_tokens=new_tokens)
+    assert eng.last_steps_run == new_tokens - 1
+    assert all(len(t) == new_tokens for t in base) and len(set(base[0])) > 8, base[0]
+    # a stop id that request 0 emits at step 10 (first occurrence may be earlier) and that may or may not occur elsewhere
+    eos = base[0][10]
+    want = []
+    for t in base:
+        want.append(t[: t.index(eos) + 1] if eos in t else t)
+    got = model.generate_batch(reqs, max_new_tokens=new_tokens, eos_token_id=eos)
+    assert got == want
+    # all three end early -> the loop stops early: stop ids = each sequence's own 6th token
+    stops = [base[i][5] for i in range(3)]
+    want = []
+    for t in base:
+        cut = min(t.index(s) for s in stops if s in t)
+        want.append(t[: cut + 1])
+    got = model.generate_batch(reqs, max_new_tokens=new_tokens, eos_token_id=stops)
+    assert got == want
+    assert eng.last_steps_run <= 5 + 2 * 8 + 1 < new_tokens - 1, eng.last_steps_run
+    # the reference-facing call: GenerationConfig-like object with a list-valued eos_token_id
+    class GC:
+        max_new_tokens, do_sample, eos_token_id, pad_token_id = new_tokens, False, [stops[0], 7], None
+
+    out = model.generate(**reqs[0], generation_config=GC())
+    t = base[0]
+    assert out.sequences[0].tolist() == t[: t.index(stops[0]) + 1]
+
+
+def test_malformed_prompt_raises_before_any_feature_is_computed():
+    """The reference raises ValueError (image-token / feature count mismatch, modeling_perception_lm.py:309-315) before
+    the language model runs; here the row plan validates the prompt BEFORE the ViT: only the plan kernel is launched,
+    and nothing is written out of bounds (a crop run cut short at the end of the prompt)."""
+    new_tokens = 4
+    spec, model = _small_model()
+    req = make_request(spec, seed=90, n_masks=2, max_num_tiles=4, dtype=bf)
+    S = req["input_ids"].shape[1]
+    model.configure_engine(max_tiles=5, max_seq=S + 64, max_batch=2, max_new_tokens=new_tokens)
+    eng = model.engine()
+    good = model.generate_batch([req], max_new_tokens=new_tokens)[0]
+    ids = req["input_ids"]
+    # (a) one <image> token too many
+    bad = dict(req, input_ids=torch.cat([ids[:, :5], torch.full((1, 1), spec.image_token_id), ids[:, 5:]], 1))
+    l0 = eng.launch_count()
+    with pytest.raises(ValueError, match="do not match"):
+        model.generate_batch([bad], max_new_tokens=new_tokens)
+    assert eng.launch_count() - l0 <= 1, "only the row plan may run before the error is raised"
+    # (b) a crop token without a box
+    bad = dict(req, bboxes=[{k: v for k, v in list(req["bboxes"][0].items())[:1]}])
+    with pytest.raises(KeyError):
+        model.generate_batch([bad], max_new_tokens=new_tokens)
+    # (c) a crop run that is not 256 contiguous tokens (cut short at the very end of the prompt)
+    crop = spec.crop_tokens_ids[1]
+    pos = (ids[0] == crop).nonzero().flatten()
+    short = torch.cat([ids[:, : int(pos.min())], ids[:, int(pos.max()) + 1:], ids[:, int(pos.min()): int(pos.min()) + 100]], 1)
+    with pytest.raises(AssertionError):
+        model.generate_batch([dict(req, input_ids=short)], max_new_tokens=new_tokens)
+    # the engine is still healthy and deterministic afterwards
+    assert model.generate_batch([req], max_new_tokens=new_tokens)[0] == good
+
+
+def test_auto_model_from_pretrained_on_cuda_generates(tmp_path):
+    """SURVEY §8(b) loader row on the GPU: AutoModel.from_pretrained(dir, trust_remote_code=True, torch_dtype=bf16,
+    device_map="cuda:0") (demo/gar_with_mask.py:84-94) returns the B200 GARModel and generate() equals the directly
+    constructed model's."""
+    from transformers import AutoModel
+
+    try:
+        from test_loader_auto_map import write_checkpoint_dir
+    except ImportError:
+        from tests.test_loader_auto_map import write_checkpoint_dir
+
+    spec = gar_small()
+    d = str(tmp_path / "ckpt")
+    src = write_checkpoint_dir(d, spec, seed=3).to(DEV)
+    model = AutoModel.from_pretrained(d, trust_remote_code=True, torch_dtype=bf, device_map="cuda:0")
+    assert type(model).__name__ == "GARModel" and next(model.parameters()).device.type == "cuda"
+    req = make_request(spec, seed=91, n_masks=2, max_num_tiles=4, dtype=bf)
+    S = req["input_ids"].shape[1]
+
+    class GC:
+        max_new_tokens, do_sample, eos_token_id, pad_token_id = 6, False, None, None
+
+    for m in (src, model):
+        m.configure_engine(max_tiles=5, max_seq=S + 32, max_batch=1, max_new_tokens=6)
+    a = src.generate(**req, generation_config=GC()).sequences
+    b = model.generate(**req, generation_config=GC()).sequences
+    assert a.shape == (1, 6) and torch.equal(a, b)
+    # load_state_dict after the first generate() must not leave a stale engine behind (fused private weight copies)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["mllm.lm_head.weight"] = sd["mllm.lm_head.weight"].flip(0).contiguous()
+    model.load_state_dict(sd)
+    c = model.generate(**req, generation_config=GC()).sequences
+    V = spec.text.vocab_size
+    assert int(c[0, 0]) == V - 1 - int(a[0, 0]), "engine was not rebuilt after load_state_dict"

@@ -76,3 +76,54 @@ def test_build_request_layout():
         assert pos.numel() == spec.tokens_per_tile and int(pos.max() - pos.min()) + 1 == spec.tokens_per_tile
         assert str(spec.crop_tokens_ids[k]) in req["bboxes"][0]
     assert float(req["pixel_values"].min()) >= -1.0 - 1e-6 and float(req["pixel_values"].max()) <= 1.0 + 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# id map + boxes against the reference's own request builders (oracle/gen_idmap_goldens.py executes
+# evaluation/eval_dataset.py `_parse_annotations` of both datasets unmodified)
+# ---------------------------------------------------------------------------------------------------------------
+IDGOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "idmap_goldens.json")))
+
+
+def _rect_masks(seed, h, w, n):
+    g = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        hh, ww = int(g.integers(h // 8, h // 2)), int(g.integers(w // 8, w // 2))
+        y0, x0 = int(g.integers(0, h - hh)), int(g.integers(0, w - ww))
+        m = np.zeros((h, w), dtype=bool)
+        m[y0:y0 + hh, x0:x0 + ww] = True
+        out.append(m)
+    return out
+
+
+@pytest.mark.parametrize("case", IDGOLD["single"], ids=lambda c: f"seed{c['seed']}")
+def test_single_region_id_map_and_box_match_reference(case):
+    spec = gar_tiny()
+    m = _rect_masks(case["seed"], case["h"], case["w"], 1)
+    idmap = pp.paint_id_map(m, spec.prompt_numbers, prompt_ids=[case["prompt"]])
+    assert hashlib.sha256(np.ascontiguousarray(idmap).tobytes()).hexdigest() == case["sha256"]
+    boxes = pp.region_boxes(spec, m, prompt_ids=[case["prompt"]])
+    assert {k: list(map(float, v)) for k, v in boxes.items()} == case["bboxes"]
+
+
+@pytest.mark.parametrize("case", IDGOLD["multi"], ids=lambda c: f"seed{c['seed']}")
+def test_multi_region_quirks_match_reference(case):
+    """the reference's multi-region builder gives EVERY region the last mask's box and paints in the
+    visiting order of a set of strings; reference_quirks=True reproduces both, the default does neither."""
+    spec = gar_tiny()
+    masks = _rect_masks(case["seed"], case["h"], case["w"], case["n"])
+    idmap = pp.paint_id_map(masks, spec.prompt_numbers, order=case["order"])
+    assert hashlib.sha256(np.ascontiguousarray(idmap).tobytes()).hexdigest() == case["sha256"]
+    boxes = pp.region_boxes(spec, masks, reference_quirks=True)
+    assert {k: list(map(float, v)) for k, v in boxes.items()} == {k: v for k, v in case["bboxes"].items()}
+    assert len(set(map(tuple, case["bboxes"].values()))) == 1          # the quirk itself: one box for all regions
+    clean = pp.region_boxes(spec, masks)
+    assert len(set(clean.values())) == case["n"]
+    img = np.zeros((case["h"], case["w"], 3), np.uint8)
+    req = pp.build_request(spec, img, masks, text_ids=list(range(100, 140)), max_num_tiles=4, dtype=torch.float32,
+                           reference_quirks=True, prompt_order=case["order"])
+    ids = req["input_ids"][0]
+    starts = [int((ids == spec.crop_tokens_ids[k]).nonzero().min()) for k in case["order"]]
+    assert starts == sorted(starts)                                     # crop runs listed in the reference's order
+    assert {k: list(map(float, v)) for k, v in req["bboxes"][0].items()} == case["bboxes"]
