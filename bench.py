@@ -3,19 +3,25 @@
 
 Workload (BASELINE.json configs[1]): 8 independent requests per GPU, each a synthetic 1024x1024 image
 (17 tiles of 448^2) + 1 mask, S = 4672 prompt positions, 128 greedy tokens, random-init GAR-1B.
-One "step" = that batch through the whole hot path: per request ViT encode -> assemble/RoI replay ->
-Llama prefill; then one batched 128-token decode.
+One "step" = that batch through the whole hot path: one ViT pass and one prefill pass over the 8 equal-shaped
+requests (row plan -> patchify -> PE-ViT -> projector -> assemble/RoI replay -> Llama prefill), then one batched
+128-token decode.
 
   value : captions/s with the requests already resident in HBM (CUDA-event timed, max over ranks)
   e2e   : same metric through GARModel.generate_batch() from pinned HOST buffers (H2D of every
           request and D2H of the tokens inside the timed region)
   roofline : dominant kernel = the tcgen05 GEMM (gemm_bf16_tn_kernel); achieved = summed algorithmic
-          2*M*N*K of every GEMM launch of one step / summed CUDA-event durations of those launches
-  cpu_baseline : the oracle port (fp32, all host cores) on a bounded sample of the same request
+          2*M*N*K of every GEMM launch of one step / summed CUDA-event durations of those launches.
+          `rooflines` carries the same object for the other kernels north_star names: tcgen05 attention (tensor),
+          the decode step in production mode (CUDA graph; HBM: weights + live KV per step / measured step time) and
+          the fused assemble + RoI replay (HBM).
+  cpu_baseline : the oracle port (fp32, all host cores) on ONE full request of the same workload, no extrapolation
+  gpu_lib_baseline : the oracle modules in bf16 on the same B200 (cuBLAS + SDPA + torchvision roi_align, batch 1 per
+          request like the reference) and per-kernel A/B against torch.matmul / F.scaled_dot_product_attention
 
-`--impl reference` times the reference's CPU implementation of the path (the oracle port; the
-reference itself is pure Python over timm/transformers and cannot be installed offline) on the same
-config and prints the same JSON line with "impl": "reference".
+`--impl reference` times the reference's CPU implementation of the path (the oracle port; the reference itself is
+pure Python over timm/transformers and cannot be installed offline): min(steps, 2) REAL full requests of config 1
+(T=17, S=4672, 128 tokens, fp32, all host cores), one request per step as the reference runs them.
 """
 from __future__ import annotations
 
@@ -47,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel-class event timing step")
+    ap.add_argument("--no-lib-baseline", action="store_true", help="skip the same-box torch/cuBLAS/SDPA baseline")
     ap.add_argument("--pipeline", action="store_true",
                     help="overlap decode of batch i with ViT+prefill of batch i+1 (pays off only for many steps)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (pdl, skinny_gemm, decode_splits)")
@@ -110,64 +117,76 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm (oracle port): bounded sample of one request, extrapolated to the full request
+# CPU arm (oracle port): REAL full requests, no extrapolation
 # ----------------------------------------------------------------------------------------------
-def cpu_request_seconds(spec, args, vit_tiles, prefill_tokens, decode_steps, repeat=1):
-    """Times the oracle (fp32, all cores) on: `vit_tiles` of the T tiles, the first `prefill_tokens` of the
-    S prompt positions, `decode_steps` decode steps; scales each linearly to the full request."""
+def cpu_full_requests(spec, args, n_requests, warmup=0):
+    """Runs the oracle (fp32, all host cores) on `warmup + n_requests` complete requests of the bench workload --
+    mask decode, both patch convs, the whole PE-ViT over all T tiles, projector, assemble + RoI replay, prefill over all
+    S positions, args.new_tokens greedy steps with a KV cache -- and returns the timed requests' phase seconds."""
     from grasp_any_region_b200.synth import make_request
     from oracle.gar_oracle import build_oracle
 
     torch.set_num_threads(os.cpu_count())
     oracle = build_oracle(spec, seed=0, dtype=torch.float32)
-    req = make_request(spec, seed=0, n_masks=args.masks, max_num_tiles=args.max_num_tiles, dtype=torch.float32)
-    T = req["pixel_values"].shape[0]
-    S = req["input_ids"].shape[1]
-    lm = oracle.mllm.model.language_model
     out = []
-    for _ in range(repeat):
+    for i in range(warmup + n_requests):
+        req = make_request(spec, seed=i, n_masks=args.masks, max_num_tiles=args.max_num_tiles, dtype=torch.float32)
         with torch.no_grad():
             t0 = time.perf_counter()
-            me = oracle.mask_embeds(req["global_mask_values"][:vit_tiles])
-            oracle.image_features(req["pixel_values"][:vit_tiles], me)
-            t_vit = (time.perf_counter() - t0) * T / vit_tiles
-            emb = lm.embed_tokens(req["input_ids"][:, :prefill_tokens])
+            taps = oracle.prefill_embeds(req["pixel_values"], req["global_mask_values"], req["aspect_ratios"],
+                                         req["bboxes"], req["input_ids"])
+            t1 = time.perf_counter()
+            # greedy() = prefill + (new_tokens - 1) decode steps; time the prefill separately through a 1-token call
+            lm = oracle.mllm.model.language_model
+            S = taps["inputs_embeds"].shape[1]
             caches = [dict() for _ in lm.layers]
-            t0 = time.perf_counter()
-            h = lm(emb, torch.arange(prefill_tokens), caches)
-            oracle.mllm.lm_head(h[:, -1:])
-            # linear layers scale with S, causal attention with S^2: extrapolate both parts
-            t_pref_sample = time.perf_counter() - t0
-            t_prefill = t_pref_sample * (S / prefill_tokens)
-            t0 = time.perf_counter()
-            for i in range(decode_steps):
-                e = lm.embed_tokens(torch.tensor([[1 + i]]))
-                h = lm(e, torch.tensor([prefill_tokens + i]), caches)
-                oracle.mllm.lm_head(h[:, -1:])
-            t_dec = (time.perf_counter() - t0) / decode_steps * args.new_tokens
-        out.append(t_vit + t_prefill + t_dec)
-    sample = (f"oracle port fp32: ViT on {vit_tiles}/{T} tiles, prefill of {prefill_tokens}/{S} positions "
-              f"(linear extrapolation; understates the S^2 attention share), {decode_steps} decode steps at "
-              f"context {prefill_tokens} -> scaled to one full request of {args.new_tokens} tokens")
-    return out, sample
+            h = lm(taps["inputs_embeds"], torch.arange(S), caches)
+            logits = oracle.mllm.lm_head(h[:, -1:, :])
+            t2 = time.perf_counter()
+            toks = []
+            for j in range(args.new_tokens):
+                nxt = logits[:, -1].argmax(-1)
+                toks.append(int(nxt))
+                if j == args.new_tokens - 1:
+                    break
+                e = lm.embed_tokens(nxt)[:, None, :]
+                h = lm(e, torch.tensor([S + j]), caches)
+                logits = oracle.mllm.lm_head(h[:, -1:, :])
+            t3 = time.perf_counter()
+        if i >= warmup:
+            out.append({"vit_assemble_s": t1 - t0, "prefill_s": t2 - t1, "decode_s": t3 - t2, "total_s": t3 - t0,
+                        "T": int(req["pixel_values"].shape[0]), "S": int(S), "tokens": len(toks)})
+    return out
+
+
+def cpu_sample_text(rows, args):
+    r = rows[0]
+    return (f"oracle port fp32, {len(rows)} full request(s), no extrapolation: ViT over all {r['T']} tiles + assemble, "
+            f"prefill of all {r['S']} positions, {r['tokens']} greedy tokens with KV cache "
+            f"(mean ViT {sum(x['vit_assemble_s'] for x in rows) / len(rows):.1f} s, prefill "
+            f"{sum(x['prefill_s'] for x in rows) / len(rows):.1f} s, decode {sum(x['decode_s'] for x in rows) / len(rows):.1f} s)")
 
 
 def run_reference(args, spec):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    times, sample = cpu_request_seconds(spec, args, vit_tiles=1, prefill_tokens=512, decode_steps=2,
-                                        repeat=args.warmup + args.steps)
-    timed = times[args.warmup:]
-    per_req = sum(timed) / len(timed)
+    # a full request is 45-90 s of fp32 CPU work: two timed requests, no warm-up (nothing is lazily compiled on this arm)
+    steps, warmup = max(1, min(args.steps, 2)), 0
+    rows = cpu_full_requests(spec, args, steps, warmup)
+    per_req = sum(r["total_s"] for r in rows) / len(rows)
     val = 1.0 / per_req
     line = {
         "impl": "reference", "metric": metric_name(args), "value": val,
-        "unit": "captions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "unit": "captions/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": per_req * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "model": args.model, "note": "CPU port of the reference path; each step = one bounded-sample request"},
-        "cpu_baseline": {"value": val, "unit": "captions/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args), "requests_per_step": 1,
+                   "note": (f"CPU port of the reference path, one full request per step (the reference is batch 1); "
+                            f"{steps} timed + {warmup} warm-up real requests (requested --steps {args.steps} --warmup "
+                            f"{args.warmup}, bounded so the run ends within minutes)")},
+        "cpu_baseline": {"value": val, "unit": "captions/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": cpu_sample_text(rows, args)},
         "e2e": {"value": val, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -180,8 +199,154 @@ def metric_name(args):
 
 
 def workload_name(args):
-    return (f"{args.model} bf16, batch={args.batch} x (1024x1024 image -> {args.max_num_tiles}+1 tiles, "
+    from grasp_any_region_b200.synth import tile_grid_for
+
+    tw, th = tile_grid_for((1024, 1024), args.max_num_tiles)
+    return (f"{args.model} bf16, batch={args.batch} x (1024x1024 image -> {tw * th}+1 tiles, "
             f"{args.masks} mask), {args.new_tokens}-token greedy decode")
+
+
+# ----------------------------------------------------------------------------------------------
+# Same-box GPU library baseline (BASELINE.md §3 "B-gpu-lib"): what every hand-written kernel must beat
+# ----------------------------------------------------------------------------------------------
+def _cuda_ms(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def gpu_lib_baseline(spec, args, model, reqs_dev, dev, n_requests=2):
+    """(1) The oracle modules with the bench's weights in bf16 on this GPU -- cuBLAS GEMMs, SDPA (flash) attention,
+    torchvision roi_align, torch.cat KV cache, one request at a time like the reference -- timed per phase.
+    (2) Kernel A/B at the production shapes: our tcgen05 GEMM vs torch.matmul, our attention vs
+    F.scaled_dot_product_attention (flash and cuDNN backends), our batched decode step vs one oracle decode step at
+    batch 8 (cuBLAS + SDPA over a torch.cat cache)."""
+    import torch.nn.functional as F
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    from grasp_any_region_b200 import ops
+    from oracle.gar_oracle import GAROracle
+
+    bf = torch.bfloat16
+    with torch.device(dev):
+        o = GAROracle(spec)
+    o.load_state_dict({k: v.float() for k, v in model.state_dict().items()})
+    o = o.to(bf).eval()
+    lm = o.mllm.model.language_model
+    NT = args.new_tokens
+    rows = []
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    with torch.no_grad():
+        for i in range(1 + n_requests):
+            r = reqs_dev[i % len(reqs_dev)]
+            e = [ev() for _ in range(4)]
+            torch.cuda.synchronize()
+            e[0].record()
+            taps = o.prefill_embeds(r["pixel_values"], r["global_mask_values"], r["aspect_ratios"], r["bboxes"],
+                                    r["input_ids"])
+            e[1].record()
+            S = taps["inputs_embeds"].shape[1]
+            caches = [dict() for _ in lm.layers]
+            h = lm(taps["inputs_embeds"], torch.arange(S, device=dev), caches)
+            logits = o.mllm.lm_head(h[:, -1:, :])
+            e[2].record()
+            for j in range(NT - 1):
+                nxt = logits[:, -1].argmax(-1)
+                h = lm(lm.embed_tokens(nxt)[:, None, :], torch.tensor([S + j], device=dev), caches)
+                logits = o.mllm.lm_head(h[:, -1:, :])
+            e[3].record()
+            torch.cuda.synchronize()
+            if i > 0:
+                rows.append([e[k].elapsed_time(e[k + 1]) for k in range(3)])
+    vit, pre, dec = (sum(r[k] for r in rows) / len(rows) for k in range(3))
+    out = {"what": "oracle modules, bf16, this GPU: cuBLAS + SDPA(flash) + torchvision roi_align + torch.cat KV cache, "
+                   "batch 1 per request (as the reference runs), eager PyTorch",
+           "requests_timed": len(rows), "vit_assemble_ms_per_request": vit, "prefill_ms_per_request": pre,
+           "decode_ms_per_token": dec / max(1, NT - 1), "captions_per_s": 1e3 / (vit + pre + dec)}
+
+    # ---- kernel A/B at production shapes
+    v, t = spec.vision, spec.text
+    B = len(reqs_dev)
+    T = reqs_dev[0]["pixel_values"].shape[0]
+    S = reqs_dev[0]["input_ids"].shape[1]
+    Mv, Ml = B * T * v.tokens, B * S
+    dq, qkvw = v.embed_dim, (t.num_heads + 2 * t.num_kv_heads) * t.head_dim
+    shapes = [("vit.qkv", Mv, 3 * dq, v.embed_dim), ("vit.proj", Mv, v.embed_dim, dq), ("vit.fc1", Mv, v.mlp_dim, v.embed_dim),
+              ("vit.fc2", Mv, v.embed_dim, v.mlp_dim), ("llm.qkv", Ml, qkvw, t.hidden_size),
+              ("llm.o", Ml, t.hidden_size, t.num_heads * t.head_dim), ("llm.gate_up", Ml, 2 * t.intermediate_size, t.hidden_size),
+              ("llm.down", Ml, t.hidden_size, t.intermediate_size)]
+    gemms = {}
+    for name, M, N, K in shapes:
+        if N % 32 or K % 64:
+            continue
+        a = torch.randn((M, K), device=dev, dtype=bf) * 0.05
+        w = torch.randn((N, K), device=dev, dtype=bf) * 0.05
+        c = torch.empty((M, N), device=dev, dtype=bf)
+        ours = _cuda_ms(lambda: ops.gemm(a, w, out=c), 4, 1)
+        lib = _cuda_ms(lambda: torch.matmul(a, w.t(), out=c), 4, 1)
+        fl = 2.0 * M * N * K / 1e9
+        gemms[name] = {"M": M, "N": N, "K": K, "ours_ms": ours, "torch_matmul_ms": lib, "ours_TFLOPs": fl / ours,
+                       "torch_TFLOPs": fl / lib}
+        del a, w, c
+    out["gemm_vs_torch_matmul"] = gemms
+
+    def sdpa_ms(q, k, vv, causal, backend):
+        try:
+            with sdpa_kernel(backend):
+                return _cuda_ms(lambda: F.scaled_dot_product_attention(q, k, vv, is_causal=causal), 4, 1)
+        except Exception as ex:  # a backend that refuses the shape is reported, not fatal
+            return f"unavailable: {type(ex).__name__}"
+
+    att = {}
+    if v.head_dim == 64:
+        nt, H = v.tokens, v.num_heads
+        qkv = torch.randn((B * T * nt, 3 * dq), device=dev, dtype=bf)
+        ours = _cuda_ms(lambda: ops.attn_fwd_packed_qkv(qkv, B * T, nt, H, v.head_dim), 4, 1)
+        q, k, vv = (x.contiguous() for x in qkv.view(B * T, nt, 3, H, v.head_dim).permute(2, 0, 3, 1, 4).unbind(0))
+        fl = 4.0 * B * T * nt * nt * dq / 1e9
+        att["vit"] = {"shape": [B * T, H, nt, v.head_dim], "ours_ms": ours, "ours_TFLOPs": fl / ours,
+                      "sdpa_flash_ms": sdpa_ms(q, k, vv, False, SDPBackend.FLASH_ATTENTION),
+                      "sdpa_cudnn_ms": sdpa_ms(q, k, vv, False, SDPBackend.CUDNN_ATTENTION)}
+        del qkv, q, k, vv
+    hq, hkv, hd = t.num_heads, t.num_kv_heads, t.head_dim
+    msq = ((S + 127) // 128) * 128
+    qb = torch.randn((S, qkvw), device=dev, dtype=bf)
+    kc = torch.randn((hkv, msq, hd), device=dev, dtype=bf)
+    vc = torch.randn((hkv, msq, hd), device=dev, dtype=bf)
+    ours = _cuda_ms(lambda: ops.attn_fwd_cache(qb, qkvw, kc, vc, hq, hkv, hd, S, msq), 4, 1)
+    q = qb[:, : hq * hd].reshape(S, hq, hd).transpose(0, 1)[None].contiguous()
+    k = kc[:, :S].repeat_interleave(hq // hkv, 0)[None].contiguous()
+    vv = vc[:, :S].repeat_interleave(hq // hkv, 0)[None].contiguous()
+    fl = 2.0 * S * S * hd * hq / 1e9
+    att["prefill_causal_one_request"] = {"shape": [1, hq, S, hd], "ours_ms": ours, "ours_TFLOPs": fl / ours,
+                                         "sdpa_flash_ms": sdpa_ms(q, k, vv, True, SDPBackend.FLASH_ATTENTION),
+                                         "sdpa_cudnn_ms": sdpa_ms(q, k, vv, True, SDPBackend.CUDNN_ATTENTION)}
+    del qb, kc, vc, q, k, vv
+    out["attention_vs_sdpa"] = att
+
+    # one oracle decode step at batch B over a context of S (torch.cat cache growth included, as DynamicCache does)
+    with torch.no_grad():
+        caches = [{"k": torch.randn((B, hkv, S, hd), device=dev, dtype=bf), "v": torch.randn((B, hkv, S, hd), device=dev, dtype=bf)}
+                  for _ in lm.layers]
+        tok = torch.randint(0, 1000, (B,), device=dev)
+
+        def step():
+            for c in caches:  # keep the context length fixed across timed iterations
+                c["k"], c["v"] = c["k"][:, :, :S], c["v"][:, :, :S]
+            h = lm(lm.embed_tokens(tok)[:, None, :], torch.tensor([S], device=dev), caches)
+            return o.mllm.lm_head(h[:, -1:, :]).argmax(-1)
+
+        out["decode_step_batch%d_ms" % B] = {"torch_cublas_sdpa_eager": _cuda_ms(step, 5, 2)}
+    del o, caches
+    torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -314,11 +479,7 @@ def main():
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         torch.cuda.synchronize()
         ev[0].record(eng.stream)
-        if not model._stage_requests_batched(eng, 0, reqs_dev):
-            with torch.cuda.stream(eng.stream):
-                for slot, r in enumerate(reqs_dev):
-                    eng.request(slot, r["pixel_values"], r["global_mask_values"], r["input_ids"][0], r["bboxes"][0],
-                                r["aspect_ratios"][0].tolist())
+        model._stage(eng, 0, reqs_dev)
         ev[1].record(eng.stream)
         eng.generate(B, NT, None)
         ev[2].record(eng.stream)
@@ -328,39 +489,73 @@ def main():
                   "decode_ms_per_token_step": dec / max(1, NT - 1), "batch": B}
 
     # ---- per-kernel-class timing of ONE more step (CUDA events around every launch of the class)
-    roof, stages = None, None
+    roof, rooflines, stages = None, None, None
     if rank == 0 and not args.no_profile:
         eng.profile(True)
-        run_steps(reqs_dev, 1, gather=False)
+        toks_prof = model.generate_batch(reqs_dev, max_new_tokens=NT, eos_token_id=None)
         prof = eng.profile_read()
         eng.profile(False)
+        del toks_prof
         g_ms, g_fl, g_n = prof["gemm"]
         a_ms, a_fl, a_n = prof["attn"]
         s_ms, s_by, s_n = prof["assemble"]
+        step_ms = ms / args.steps
         tf = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05)", "achieved": tf,
                 "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["tf_sustained"],
                 "peak_source": f"{peaks['source']} sustained bf16",
                 # the committed ncu pass is of the default workload only
                 "traffic": gemm_traffic_bytes() if (args.model, B, args.max_num_tiles) == ("gar-1b", 8, 16) else None,
-                "launches_per_step": g_n, "ms_per_step": g_ms, "share_of_step": g_ms / (ms / args.steps)}
+                "launches_per_step": g_n, "ms_per_step": g_ms, "share_of_step": g_ms / step_ms}
+        atf = a_fl / (a_ms * 1e-3) / 1e12 if a_ms > 0 else 0.0
+        # decode step in PRODUCTION mode (CUDA graph replay): algorithmic bytes = every weight once per step + the live
+        # K and V prefixes of every sequence; time = the event-timed decode phase above / steps
+        t = spec.text
+        w_bytes = 2.0 * (t.num_layers * ((t.num_heads + 2 * t.num_kv_heads) * t.head_dim * t.hidden_size
+                                         + t.hidden_size * t.num_heads * t.head_dim
+                                         + 3 * t.intermediate_size * t.hidden_size) + eng.vocab_padded * t.hidden_size)
+        kv_bytes = 2.0 * 2 * t.num_kv_heads * t.head_dim * t.num_layers * B * (S + NT / 2.0)
+        d_ms = phases["decode_ms_per_token_step"]
+        d_gbs = (w_bytes + kv_bytes) / (d_ms * 1e-3) / 1e9
+        asm_gbs = s_by / (s_ms * 1e-3) / 1e9 if s_ms > 0 else 0.0
+        rooflines = [
+            roof,
+            {"bound": "tensor", "kernel": "attn_fwd_kernel (tcgen05, ViT + causal prefill)", "achieved": atf,
+             "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": atf / peaks["tf_sustained"],
+             "launches_per_step": a_n, "ms_per_step": a_ms, "share_of_step": a_ms / step_ms, "traffic": None},
+            {"bound": "hbm", "kernel": "decode step (CUDA graph: gemv_decode + decode_attn + argmax kernels)",
+             "achieved": d_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": d_gbs / peaks["hbm"],
+             "bytes_per_step": w_bytes + kv_bytes, "ms_per_launch": d_ms, "launches_per_step": NT - 1,
+             "share_of_step": phases["decode_ms_total"] / step_ms, "traffic": None,
+             "mode": "production (graph replay), from phases.decode_ms_per_token_step"},
+            {"bound": "hbm", "kernel": "plan_rows + assemble_rows (embed gather + image scatter + RoI replay)",
+             "achieved": asm_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": asm_gbs / peaks["hbm"],
+             "bytes_per_step": s_by, "ms_per_step": s_ms, "launches_per_step": s_n, "share_of_step": s_ms / step_ms,
+             "traffic": None},
+        ]
         stages = {
-            "attn_tcgen05": {"ms": a_ms, "TFLOP/s": a_fl / (a_ms * 1e-3) / 1e12 if a_ms > 0 else 0.0, "launches": a_n},
-            "assemble_replay": {"ms": s_ms, "GB/s": s_by / (s_ms * 1e-3) / 1e9 if s_ms > 0 else 0.0,
-                                "frac_hbm": (s_by / (s_ms * 1e-3) / 1e9) / peaks["hbm"] if s_ms > 0 else 0.0,
-                                "launches": s_n},
-            "decode_attn": {"ms": prof["decode_attn"][0], "launches": prof["decode_attn"][2]},
-            "decode_gemv": {"ms": prof["gemv"][0], "launches": prof["gemv"][2],
-                            "GB/s": prof["gemv"][1] / (prof["gemv"][0] * 1e-3) / 1e9 if prof["gemv"][0] > 0 else 0.0,
-                            "frac_hbm": (prof["gemv"][1] / (prof["gemv"][0] * 1e-3) / 1e9) / peaks["hbm"] if prof["gemv"][0] > 0 else 0.0},
+            "attn_tcgen05": {"ms": a_ms, "TFLOP/s": atf, "launches": a_n},
+            "assemble_replay": {"ms": s_ms, "GB/s": asm_gbs, "frac_hbm": asm_gbs / peaks["hbm"], "launches": s_n},
+            "decode_attn_ungraphed": {"ms": prof["decode_attn"][0], "launches": prof["decode_attn"][2]},
+            "decode_gemv_ungraphed": {"ms": prof["gemv"][0], "launches": prof["gemv"][2]},
         }
+
+    lib = None
+    if rank == 0 and world == 1 and not args.no_lib_baseline:
+        try:
+            lib = gpu_lib_baseline(spec, args, model, reqs_dev, dev)
+            if phases is not None:
+                lib["decode_step_batch%d_ms" % B]["ours_graph"] = phases["decode_ms_per_token_step"]
+                lib["ours_vit_assemble_prefill_ms_per_request"] = phases["vit_assemble_prefill_ms_per_request"]
+        except Exception as ex:  # a baseline must not take the bench line down
+            lib = {"failed": f"{type(ex).__name__}: {ex}"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            times, sample = cpu_request_seconds(spec, args, vit_tiles=2, prefill_tokens=1024, decode_steps=3)
-            cpu = {"value": 1.0 / times[0], "unit": "captions/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": sample}
+            rows = cpu_full_requests(spec, args, 1)
+            cpu = {"value": 1.0 / rows[0]["total_s"], "unit": "captions/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": cpu_sample_text(rows, args)}
         except Exception as ex:  # the baseline must not take the bench line down
             cpu = {"value": None, "unit": "captions/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"failed: {ex}"}
@@ -376,8 +571,8 @@ def main():
                        "parallelism": f"dp{world} (independent requests per rank, one all-gather of token ids)",
                        "pipeline": bool(args.pipeline),
                        "encode": "the B requests of a step share one ViT pass and one prefill pass (equal shapes); decode batched"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "stages": stages, "phases": phases,
-            "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "rooflines": rooflines,
+            "stages": stages, "phases": phases, "cpu_baseline": cpu, "gpu_lib_baseline": lib,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

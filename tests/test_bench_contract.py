@@ -21,7 +21,8 @@ def test_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "captions/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and abs(d["value"] - 1e3 / d["ms_per_step"]) < 1e-6 * d["value"] + 1e-9
-    assert d["config"]["workload"] and "model" in d["config"]
+    assert d["config"]["workload"] and d["config"]["requests_per_step"] == 1
+    assert "no extrapolation" in d["cpu_baseline"]["sample"] and d["steps"] == 1 and d["warmup"] == 0
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
