@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--no-lib-baseline", action="store_true", help="skip the same-box torch/cuBLAS/SDPA baseline")
     ap.add_argument("--pipeline", action="store_true",
                     help="overlap decode of batch i with ViT+prefill of batch i+1 (pays off only for many steps)")
+    ap.add_argument("--decode-sms", type=int, default=0,
+                    help="with --pipeline: SMs of the decode partition (green contexts); 0 = no SM partitioning")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (pdl, skinny_gemm, decode_splits)")
     return ap.parse_args()
 
@@ -397,6 +399,10 @@ def main():
     for kv in args.opt:
         k, v = kv.split("=")
         eng.set_option(k, int(v))
+    partition = None
+    if args.pipeline and args.decode_sms > 0:
+        partition = ({"encode_sms": eng.partition_sms[0], "decode_sms": eng.partition_sms[1]}
+                     if eng.enable_partition(args.decode_sms) else {"unavailable": getattr(eng, "partition_error", "?")})
 
     def pin(r):
         o = dict(r)
@@ -569,7 +575,7 @@ def main():
             "config": {"workload": workload_name(args), "requests_per_gpu_per_step": B, "tiles": T, "prompt_len": S,
                        "l2": "inputs+weights per step (3.2 GB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"dp{world} (independent requests per rank, one all-gather of token ids)",
-                       "pipeline": bool(args.pipeline),
+                       "pipeline": bool(args.pipeline), "sm_partition": partition,
                        "encode": "the B requests of a step share one ViT pass and one prefill pass (equal shapes); decode batched"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "rooflines": rooflines,
             "stages": stages, "phases": phases, "cpu_baseline": cpu, "gpu_lib_baseline": lib,

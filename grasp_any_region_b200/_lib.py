@@ -88,6 +88,7 @@ SIGNATURES = {
     "gar_engine_generate_eos": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _i, C.POINTER(_i), C.POINTER(_i), _vp]),
     "gar_engine_status": (_i, [_vp, _i, C.POINTER(_i)]),
     "gar_engine_launch_count": (_ll, [_vp]),
+    "gar_engine_partition": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_vp), C.POINTER(_i)]),
     "gar_engine_set_option": (_i, [_vp, C.c_char_p, _i]),
     "gar_engine_profile": (_i, [_vp, _i]),
     "gar_engine_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),

@@ -372,7 +372,11 @@ int gar_make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 // 3-D bf16 tensor: dims {d0 (contiguous), d1, d2} with element pitches p1, p2
 int gar_make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t p1,
                      uint64_t p2, uint32_t b0, uint32_t b1, uint32_t b2, GarSwizzle sw);
-int gar_num_sms();
+int gar_num_sms();                // physical SM count: kernel-variant heuristics (results must not depend on partitions)
+int gar_grid_sms();               // SMs the calling thread's launches may occupy: persistent grid sizes
+void gar_set_sm_limit(int sms);   // thread-local; 0 = no limit
+int gar_make_sm_partition(int small_sms, cudaStream_t* small_stream, int* small_count, cudaStream_t* rest_stream,
+                          int* rest_count);
 int gar_pdl_enabled();
 int gar_global_option(const char* name);
 void gar_set_pdl(int on);

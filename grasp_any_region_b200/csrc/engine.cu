@@ -57,6 +57,9 @@ struct gar_engine {
   int steps_run = 0;        // decode steps launched by the last generate call
   int* fin_host = nullptr;  // pinned: 2 x max_batch finished flags
   cudaEvent_t fin_ev[2] = {nullptr, nullptr};
+  // SM partition (green contexts): launches into part_stream[i] may occupy part_sms[i] SMs (gar_engine_partition)
+  cudaStream_t part_stream[2] = {nullptr, nullptr};
+  int part_sms[2] = {0, 0};
   // plan_rows already ran for this (slot0, nreq, S, T) (gar_engine_plan_batch): assemble_batch skips it
   int plan_slot0 = -1, plan_nreq = 0, plan_S = 0, plan_T = 0;
   long long launches = 0;
@@ -96,6 +99,18 @@ const void* W(gar_engine* e, const std::string& name, bool required = true) {
 std::string L(const char* prefix, int i, const char* suffix) {
   return std::string(prefix) + "." + std::to_string(i) + "." + suffix;
 }
+
+// Thread-local SM budget for the duration of one engine call: persistent kernels launched into a partition's stream
+// size their grids to the partition (common.cuh gar_grid_sms).
+struct SmScope {
+  SmScope(gar_engine* e, void* s) {
+    int lim = 0;
+    for (int i = 0; i < 2; ++i)
+      if (e && e->part_stream[i] && e->part_stream[i] == static_cast<cudaStream_t>(s)) lim = e->part_sms[i];
+    gar_set_sm_limit(lim);
+  }
+  ~SmScope() { gar_set_sm_limit(0); }
+};
 
 struct ProfScope {
   gar_engine* e;
@@ -558,6 +573,7 @@ int gar_engine_vit_encode(gar_engine* e, const void* pixel_values, const void* m
 
 // R3-R5 on the first T tiles of the im2col arenas (filled by gar_engine_patchify_at)
 int gar_engine_vit_encode_patches(gar_engine* e, int T, int with_mask, void* s) {
+  SmScope sm_scope(e, s);
   if (!e || T <= 0 || T > e->d.max_tiles) {
     gar_set_error("gar_engine_vit_encode_patches: T=%d outside [1,%d]", T, e ? e->d.max_tiles : 0);
     return GAR_ERR_ARG;
@@ -755,6 +771,7 @@ int gar_engine_assemble_batch(gar_engine* e, int slot0, int nreq, const long lon
 }
 
 int gar_engine_prefill_batch(gar_engine* e, int slot0, int nreq, int S, void* s) {
+  SmScope sm_scope(e, s);
   const gar_model_desc& d = e->d;
   const long long pr = d.max_prefill_rows > d.max_seq ? d.max_prefill_rows : d.max_seq;
   if (!e || nreq <= 0 || slot0 < 0 || slot0 + nreq > d.max_batch || S <= 0 || S + d.max_new_tokens > d.max_seq ||
@@ -777,6 +794,7 @@ int gar_engine_prefill_batch(gar_engine* e, int slot0, int nreq, int S, void* s)
 }
 
 int gar_engine_prefill(gar_engine* e, int slot, int S, void* s) {
+  SmScope sm_scope(e, s);
   if (!e || slot < 0 || slot >= e->d.max_batch || S <= 0 || S + e->d.max_new_tokens > e->d.max_seq) {
     gar_set_error("gar_engine_prefill: slot=%d S=%d (+%d new) exceeds max_seq=%d", slot, S,
                   e ? e->d.max_new_tokens : 0, e ? e->d.max_seq : 0);
@@ -795,6 +813,7 @@ int gar_engine_prefill(gar_engine* e, int slot, int S, void* s) {
 }
 
 int gar_engine_prefill_all_logits(gar_engine* e, int slot, int S, void* logits_out, void* s) {
+  SmScope sm_scope(e, s);
   if (!e || !logits_out || slot < 0 || slot >= e->d.max_batch || S <= 0 || S > e->d.max_seq) return GAR_ERR_ARG;
   const gar_model_desc& d = e->d;
   GAR_CUDA_CHECK(cudaMemcpyAsync(e->h, e->emb, static_cast<size_t>(S) * d.llm_dim * 2, cudaMemcpyDeviceToDevice,
@@ -819,6 +838,7 @@ int gar_engine_prefill_all_logits(gar_engine* e, int slot, int S, void* logits_o
 int gar_engine_generate_eos(gar_engine* e, int slot0, int batch, int max_new_tokens, const int* eos_ids, int n_eos,
                             int* out_tokens_host, int* steps_run, void* s_) {
   cudaStream_t s = static_cast<cudaStream_t>(s_);
+  SmScope sm_scope(e, s_);
   if (!e || batch <= 0 || slot0 < 0 || slot0 + batch > e->d.max_batch || max_new_tokens <= 0 ||
       max_new_tokens > e->d.max_new_tokens || !out_tokens_host || n_eos < 0 || n_eos > 4 || (n_eos > 0 && !eos_ids)) {
     gar_set_error("gar_engine_generate: slot0=%d batch=%d max_new_tokens=%d n_eos=%d outside capacity", slot0, batch,
@@ -877,7 +897,9 @@ int gar_engine_generate_eos(gar_engine* e, int slot0, int batch, int max_new_tok
       for (int i = 1; i < steps; ++i) TRY(decode_step(e, batch, s));
       done = steps;
     } else if (!stop && steps > 1) {
-      const long long key = (static_cast<long long>(slot0) << 32) | (static_cast<long long>(batch) << 8);
+      // keyed by the stream too: a graph captured inside one SM partition is replayed only there
+      const long long key = (static_cast<long long>(slot0) << 32) | (static_cast<long long>(batch) << 8) |
+                            (static_cast<long long>(reinterpret_cast<uintptr_t>(s) >> 4 & 0xff) << 40);
       auto it = e->graphs.find(key);
       if (it == e->graphs.end() || e->graph_eos[key] != eos_key) {
         if (s == nullptr || s == cudaStreamLegacy) {
@@ -943,6 +965,25 @@ int gar_engine_status(gar_engine* e, int slot, int* status_bits) {
 }
 
 long long gar_engine_launch_count(gar_engine* e) { return e ? e->launches : 0; }
+
+// Splits the GPU's SMs into a decode partition (>= decode_sms SMs; the driver rounds to its granularity) and an encode
+// partition (the rest) with one stream each (CUDA green contexts).  Work enqueued on the two streams runs on disjoint
+// SMs, so the HBM-bound decode of one request group and the tensor-bound ViT + prefill of the next overlap for real
+// instead of interleaving at kernel boundaries.  Fails (GAR_ERR_CUDA) when the driver cannot partition.
+int gar_engine_partition(gar_engine* e, int decode_sms, void** encode_stream, int* encode_count, void** decode_stream,
+                         int* decode_count) {
+  if (!e || decode_sms <= 0 || !encode_stream || !decode_stream) return GAR_ERR_ARG;
+  cudaStream_t small = nullptr, rest = nullptr;
+  int ns = 0, nr = 0;
+  TRY(gar_make_sm_partition(decode_sms, &small, &ns, &rest, &nr));
+  e->part_stream[0] = rest; e->part_sms[0] = nr;
+  e->part_stream[1] = small; e->part_sms[1] = ns;
+  *encode_stream = rest;
+  *decode_stream = small;
+  if (encode_count) *encode_count = nr;
+  if (decode_count) *decode_count = ns;
+  return GAR_OK;
+}
 
 int gar_engine_set_option(gar_engine* e, const char* name, int value) {
   if (!e || !name) return GAR_ERR_ARG;

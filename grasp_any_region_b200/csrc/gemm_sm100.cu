@@ -373,12 +373,12 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   const int tile_m = CTA2 ? 2 * BLOCK_M : BLOCK_M;
   const int num_tiles = ((M + tile_m - 1) / tile_m) * ((N + BLOCK_N - 1) / BLOCK_N);
   if (CTA2) {
-    const int clusters = std::min(num_tiles, gar_num_sms() / 2);
+    const int clusters = std::min(num_tiles, gar_grid_sms() / 2);
     GAR_CUDA_CHECK(gar_launch(kern, dim3(2 * clusters), dim3(NUM_THREADS), C::SMEM_BYTES, stream, false, dim3(2, 1, 1), ta,
                               tb, tc, M, N, K, ea));
     return GAR_OK;
   }
-  const int grid = num_tiles < gar_num_sms() ? num_tiles : gar_num_sms();
+  const int grid = num_tiles < gar_grid_sms() ? num_tiles : gar_grid_sms();
   kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tc, M, N, K, ea);
   GAR_CUDA_CHECK(cudaGetLastError());
   return GAR_OK;

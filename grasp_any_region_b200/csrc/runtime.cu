@@ -61,6 +61,83 @@ int gar_num_sms() {
   return sms;
 }
 
+// SM budget of the calling thread's launches: persistent kernels size their grids with gar_grid_sms() so that a launch
+// into an SM partition (green context, gar_engine_partition) does not queue CTAs the partition cannot hold.  Kernel
+// VARIANT choices keep using the physical count (gar_num_sms), so results never depend on the partitioning.
+static thread_local int g_sm_limit = 0;
+void gar_set_sm_limit(int sms) { g_sm_limit = sms; }
+int gar_grid_sms() {
+  const int phys = gar_num_sms();
+  return (g_sm_limit > 0 && g_sm_limit < phys) ? g_sm_limit : phys;
+}
+
+// ---- SM partitions (CUDA green contexts) through runtime-resolved driver entry points ----
+namespace {
+template <typename Fn>
+Fn driver_fn(const char* name) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+  return reinterpret_cast<Fn>(p);
+}
+}  // namespace
+
+// Splits the device's SMs into a small partition of >= small_sms SMs and the rest, and creates one non-blocking stream
+// in each.  Returns GAR_ERR_CUDA (with the driver's message) when the driver cannot do it; callers then run unpartitioned.
+int gar_make_sm_partition(int small_sms, cudaStream_t* small_stream, int* small_count, cudaStream_t* rest_stream,
+                          int* rest_count) {
+  typedef CUresult (*GetDev)(CUdevice*, int);
+  typedef CUresult (*GetRes)(CUdevice, CUdevResource*, CUdevResourceType);
+  typedef CUresult (*Split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+  typedef CUresult (*GenDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+  typedef CUresult (*GreenCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+  typedef CUresult (*GreenStream)(CUstream*, CUgreenCtx, unsigned int, int);
+  auto get_dev = driver_fn<GetDev>("cuDeviceGet");
+  auto get_res = driver_fn<GetRes>("cuDeviceGetDevResource");
+  auto split = driver_fn<Split>("cuDevSmResourceSplitByCount");
+  auto gen = driver_fn<GenDesc>("cuDevResourceGenerateDesc");
+  auto create = driver_fn<GreenCreate>("cuGreenCtxCreate");
+  auto mkstream = driver_fn<GreenStream>("cuGreenCtxStreamCreate");
+  if (!get_dev || !get_res || !split || !gen || !create || !mkstream) {
+    gar_set_error("gar_make_sm_partition: this driver has no green-context entry points");
+    return GAR_ERR_CUDA;
+  }
+  int ordinal = 0;
+  GAR_CUDA_CHECK(cudaGetDevice(&ordinal));
+  GAR_CUDA_CHECK(cudaFree(nullptr));  // make sure the primary context exists
+  CUdevice dev;
+  CUdevResource all, small, rest;
+  unsigned int groups = 1;
+  CUdevResourceDesc d_small, d_rest;
+  CUgreenCtx g_small, g_rest;
+  CUstream s_small, s_rest;
+  CUresult r;
+#define GAR_DRV(call)                                                                 \
+  if ((r = (call)) != CUDA_SUCCESS) {                                                 \
+    gar_set_error("gar_make_sm_partition: %s failed with CUresult %d", #call, (int)r); \
+    return GAR_ERR_CUDA;                                                              \
+  }
+  GAR_DRV(get_dev(&dev, ordinal));
+  GAR_DRV(get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
+  GAR_DRV(split(&small, &groups, &all, &rest, 0, static_cast<unsigned int>(small_sms)));
+  if (groups != 1 || rest.sm.smCount == 0) {
+    gar_set_error("gar_make_sm_partition: cannot split %u SMs into %d + rest", all.sm.smCount, small_sms);
+    return GAR_ERR_CUDA;
+  }
+  GAR_DRV(gen(&d_small, &small, 1));
+  GAR_DRV(gen(&d_rest, &rest, 1));
+  GAR_DRV(create(&g_small, d_small, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+  GAR_DRV(create(&g_rest, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+  GAR_DRV(mkstream(&s_small, g_small, CU_STREAM_NON_BLOCKING, 0));
+  GAR_DRV(mkstream(&s_rest, g_rest, CU_STREAM_NON_BLOCKING, 0));
+#undef GAR_DRV
+  *small_stream = s_small;
+  *rest_stream = s_rest;
+  *small_count = static_cast<int>(small.sm.smCount);
+  *rest_count = static_cast<int>(rest.sm.smCount);
+  return GAR_OK;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -82,7 +82,30 @@ class Engine:
         self.stream = torch.cuda.Stream(device=self.device)
         # decode of one request group may overlap the next group's ViT+prefill (see GARModel.generate_batches)
         self.decode_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.enc_stream: Optional[torch.cuda.Stream] = None   # SM-partition streams (enable_partition)
+        self.dec_stream: Optional[torch.cuda.Stream] = None
+        self.partition_sms = None
+        self.last_steps_run = 0
         self._load_weights(state_dict)
+
+    def enable_partition(self, decode_sms: int) -> bool:
+        """Split the GPU's SMs into a decode partition (>= decode_sms, driver granularity) and an encode partition
+        (the rest); `enc_stream` / `dec_stream` then confine what is enqueued on them to their SM sets, so
+        GARModel.generate_batches overlaps decode(i) with ViT + prefill(i+1) on disjoint SMs.  decode_sms <= 0 turns it
+        off.  Returns False (and stays unpartitioned) when the driver cannot create green contexts."""
+        if decode_sms <= 0:
+            self.enc_stream = self.dec_stream = self.partition_sms = None
+            return False
+        es, ds, en, dn = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
+        rc = self.lib.gar_engine_partition(self._h, int(decode_sms), C.byref(es), C.byref(en), C.byref(ds), C.byref(dn))
+        if rc != 0:
+            self.partition_error = self.lib.gar_last_error().decode(errors="replace")
+            self.enc_stream = self.dec_stream = self.partition_sms = None
+            return False
+        self.enc_stream = torch.cuda.ExternalStream(es.value, device=self.device)
+        self.dec_stream = torch.cuda.ExternalStream(ds.value, device=self.device)
+        self.partition_sms = (en.value, dn.value)
+        return True
 
     # ------------------------------------------------------------------ weights
     def _set(self, name: str, tensor: torch.Tensor):

@@ -321,9 +321,11 @@ class GARModel(_Base):
         """Throughput serving of a stream of request batches (B200 scheduler extension).
 
         Two KV-slot groups ping-pong: while group g decodes on the engine's decode stream, the next batch's
-        ViT + assemble + prefill is enqueued (from a helper thread) on the main stream into group 1-g.  The
-        decode is a latency-bound weight stream and the encoder is tensor-bound, so they overlap well.  Every
-        request's result equals its batch-1 ``generate`` result."""
+        ViT + assemble + prefill is enqueued (from a helper thread) on the encode stream into group 1-g.  The decode
+        is an HBM-bound weight stream and the encoder is tensor-bound, so they are complementary; with
+        ``engine().enable_partition(k)`` the two streams own disjoint SM sets (k SMs decode, the rest encode) and
+        really run side by side instead of interleaving at kernel boundaries.  Every request's result equals its
+        batch-1 ``generate`` result."""
         import threading
 
         eng = self.engine()
@@ -333,6 +335,21 @@ class GARModel(_Base):
         if 2 * G > eng.max_batch:
             raise ValueError(f"pipelining needs engine max_batch >= 2 x batch ({2 * G}), got {eng.max_batch}")
         dev = eng.device
+        plain = (eng.stream, eng.decode_stream)
+        if eng.enc_stream is not None:
+            # the partition streams take over for the duration of the call (they see everything the plain ones did)
+            eng.enc_stream.wait_stream(eng.stream)
+            eng.dec_stream.wait_stream(eng.decode_stream)
+            eng.stream, eng.decode_stream = eng.enc_stream, eng.dec_stream
+        try:
+            return self._generate_batches(eng, batches, G, dev, max_new_tokens, eos_token_id, threading)
+        finally:
+            if eng.stream is not plain[0]:
+                plain[0].wait_stream(eng.stream)
+                plain[1].wait_stream(eng.decode_stream)
+            eng.stream, eng.decode_stream = plain
+
+    def _generate_batches(self, eng, batches, G, dev, max_new_tokens, eos_token_id, threading):
 
         def stage(bi: int, group: int):
             torch.cuda.set_device(dev)

@@ -283,6 +283,12 @@ int gar_engine_generate_eos(gar_engine* e, int slot0, int batch, int max_new_tok
                             int* out_tokens_host, int* steps_run, void* stream);
 int gar_engine_status(gar_engine* e, int slot, int* status_bits);
 long long gar_engine_launch_count(gar_engine* e);
+/* SM partitioning for pipelined serving: creates two streams bound to disjoint SM sets (CUDA green contexts) -- a decode
+ * partition of >= decode_sms SMs (driver granularity: multiples of 8) and an encode partition with the rest.  Passing
+ * these streams to the stage / generate entry points confines their kernels to the partition; persistent kernels size
+ * their grids to it.  Results are identical to the unpartitioned run.  GAR_ERR_CUDA if the driver cannot partition. */
+int gar_engine_partition(gar_engine* e, int decode_sms, void** encode_stream, int* encode_sms, void** decode_stream,
+                         int* decode_sms_out);
 /* options: "skinny_gemm" (1 = decode GEMMs use gar_gemm_skinny_bf16, default 1), "decode_splits" */
 int gar_engine_set_option(gar_engine* e, const char* name, int value);
 /* optional per-kernel-class CUDA-event timing for bench.py's roofline (decode runs ungraphed while on) */

@@ -140,6 +140,19 @@ def test_pipelined_batches_match_sequential():
     got = model.generate_batches(batches, max_new_tokens=new_tokens)
     want = [[singles[0], singles[1]], [singles[2], singles[3]], [singles[4]], [singles[1], singles[0]]]
     assert got == want
+    # the same with the two streams bound to disjoint SM partitions (green contexts): decode on >= 32 SMs, encode on
+    # the rest; persistent kernels size their grids to the partition, kernel variants (hence results) do not change
+    eng = model.engine()
+    if eng.enable_partition(32):
+        enc, dec = eng.partition_sms
+        print("SM partition: encode", enc, "decode", dec)
+        assert dec >= 32 and enc + dec <= 148 and enc >= 64
+        assert model.generate_batches(batches, max_new_tokens=new_tokens) == want
+        assert model.generate_batches(batches[:2], max_new_tokens=new_tokens, eos_token_id=singles[0][3]) == [
+            [t[: t.index(singles[0][3]) + 1] if singles[0][3] in t else t for t in b] for b in want[:2]]
+        assert [model.generate_batch([r], max_new_tokens=new_tokens)[0] for r in reqs] == singles   # plain streams again
+    else:
+        print("green contexts unavailable:", getattr(eng, "partition_error", "?"))
 
 
 def test_forward_loss_matches_oracle():
