@@ -41,6 +41,7 @@ SIGNATURES = {
     "gar_decode_mega_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
     "gar_decode_mega_step": (_i, [_vp] + [_i] + [_vp] * 5 + [_vp] * 2 + [_vp] * 5 + [_vp] * 4 + [_vp, _vp] +
                              [_i] * 10 + [_f, _f, _vp]),
+    "gar_gemv_debug_timeline": (_i, [_vp]),
     "gar_embed_gather_sumsq": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "gar_patchify": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "gar_vit_embed_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),

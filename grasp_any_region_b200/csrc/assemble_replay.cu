@@ -5,15 +5,16 @@
 //   :341-346  get_placeholder_mask + masked_scatter of image_features  (bool mask S*D + scatter)
 //   :348-414  per crop token: `in` scan + 2 .item() syncs, _merge permute+contiguous, .float() of the
 //             whole map, torchvision.ops.roi_align, permute/cast, 3-way torch.cat
-// with two launches for a whole batch of requests and no host synchronisation on the data path:
-//   plan_rows     : one block per request scans input_ids -> per-row source plan (text / image ordinal /
-//                   crop region + bin), validates counts and run shapes into a status word.  Depends only on
-//                   input_ids, so the engine runs it BEFORE the ViT and the host reads the status early.
-//   assemble_rows : one warp per output row of every request, role by plan word.  Text & image rows are 16-byte
-//                   vector copies with all of a lane's loads in flight before its first store; crop rows evaluate
-//                   roi_align for their (ph,pw) bin directly on the channel-contiguous (T,256,D) feature tensor (no
-//                   merged map, no fp32 copy) in the operator's exact fp32 operation order
-//                   (oracle/roi_align_ref.py), one bf16 rounding.
+// with three launches for a whole batch of requests and no host synchronisation on the data path:
+//   plan_rows    : one block per request scans input_ids -> per-row source plan (text / image ordinal / crop bin),
+//                  the start of every region's crop run, and a status word (counts and run shapes validated).
+//                  Depends only on input_ids, so the engine runs it BEFORE the ViT and the host reads the status early.
+//   replay_rows  : one warp per crop row (grid = bins x regions x requests): roi_align for its (ph,pw) bin evaluated
+//                  directly on the channel-contiguous (T,256,D) feature tensor (no merged map, no fp32 copy) in the
+//                  operator's exact fp32 operation order (oracle/roi_align_ref.py), one bf16 rounding; latency-bound.
+//   gather_rows  : one warp per text / image row of every request: 16-byte vector copies with all of a lane's loads in
+//                  flight before its first store -- the HBM stream.  It starts together with replay_rows (programmatic
+//                  dependent launch, dependency wait at its END): the two write disjoint rows.
 // HBM-bound: ~2*S*D*2 bytes per request; no tensor cores on this path.
 #include "common.cuh"
 
@@ -43,7 +44,8 @@ struct AssembleParams {
 
 // plan word: kind in bits [30,32), payload in [0,30)
 __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant__ AssembleParams p,
-                                 int* __restrict__ plan_all, int* __restrict__ status_all) {
+                                 int* __restrict__ plan_all, int* __restrict__ status_all,
+                                 int* __restrict__ region_start_all) {
   pdl_launch_dependents();
   const RequestParams& rq = p.r[blockIdx.x];
   const long long* __restrict__ ids = rq.ids;
@@ -137,6 +139,13 @@ __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant
     status[0] = st;
     status[1] = s_total;
   }
+  // first position of every region's crop-token run (-1: absent, no box, or not a clean 256-run that fits the prompt):
+  // the replay kernel's row index
+  if (tid < MAX_REGIONS) {
+    const int run = p.tpt * p.tpt;
+    const bool ok = tid < p.n_regions && s_cnt[tid] > 0 && rq.has_roi[tid] && s_min[tid] + run <= S;
+    region_start_all[blockIdx.x * MAX_REGIONS + tid] = ok ? s_min[tid] : -1;
+  }
 }
 
 struct Sample {
@@ -169,63 +178,82 @@ __device__ __forceinline__ Sample make_sample(float y, float x, int H, int W) {
   return sm;
 }
 
-// One warp per output row of every request, role chosen by the row's plan word:
-//   text / image rows : out row <- one table / feature row, CH 16-byte vectors per lane loaded before the first store
-//                       (a warp keeps CH*512 B in flight; 8 resident blocks of 4 warps per SM)
-//   crop rows         : roi_align bin (ph, pw) of region k evaluated in place on the channel-contiguous (T,256,D)
-//                       feature tensor in torchvision's exact fp32 operation order (oracle/roi_align_ref.py), one bf16
-//                       rounding.  The four sample points are accumulated one after the other (4 cell loads in flight
-//                       per lane) so the role fits the gather role's register budget.
-// Every row index comes from the loop bound (g < nreq*S) and every source index is clamped, so a malformed prompt
-// (status bits set by plan_rows_kernel) can never make this kernel touch memory outside its request.
+// Text and image rows of every request: out row <- one table / feature row.  CH 16-byte vectors per lane are loaded
+// before the first store, so a warp keeps CH*512 B in flight (12 resident blocks: ~100 KB per SM).  Launched as a
+// programmatic dependent of replay_rows_kernel and waits for it only at its END: the two grids write disjoint rows, so
+// the HBM stream runs next to the latency-bound replay instead of behind it, and whatever follows in the stream still
+// sees both complete.  Every source index is clamped, so a malformed prompt (status bits set by plan_rows_kernel) can
+// never make this kernel touch memory outside its request.
 template <int CH>
-__global__ void __launch_bounds__(128, 8)
-assemble_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ table, const bf16* __restrict__ feats_all,
-                     bf16* __restrict__ out, int S, int D, int vocab, int rows_per_req_feats,
-                     const __grid_constant__ AssembleParams p) {
-  pdl_wait();
+__global__ void __launch_bounds__(128, 12)
+gather_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ table, const bf16* __restrict__ feats,
+                   bf16* __restrict__ out, int S, int D, int vocab, int rows_per_req_feats,
+                   const __grid_constant__ AssembleParams p) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nvec = D / 8;
-  const int tpt = p.tpt;
+  const int run = p.tpt * p.tpt;
   const long long total = static_cast<long long>(p.nreq) * S;
   for (long long g = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); g < total;
        g += static_cast<long long>(gridDim.x) * wpb) {
     const int word = plan[g];
     int kind = (word >> 30) & 3;
     const int req = static_cast<int>(g / S), s = static_cast<int>(g - static_cast<long long>(req) * S);
-    const RequestParams& rq = p.r[req];
+    if (kind == KIND_CROP) {
+      // replay_rows_kernel owns the rows of a clean run; anything else marked CROP (run too long / cut off: status
+      // bit 2) is filled with its token embedding so no row of the output is ever left unwritten
+      const int off = word & 0xffff, start = s - off;
+      if (off < run && start + run <= S) continue;
+      kind = KIND_TEXT;
+    }
+    const uint4* src;
+    if (kind == KIND_IMAGE) {
+      int ord = word & 0x3fffffff;
+      ord = ord < rows_per_req_feats ? ord : rows_per_req_feats - 1;  // more <image> tokens than features (status bit 1)
+      src = reinterpret_cast<const uint4*>(feats + (static_cast<size_t>(req) * rows_per_req_feats + ord) * D);
+    } else {
+      long long id = p.r[req].ids[s];
+      id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+      src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * D);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(g) * D);
+    for (int v0 = 0; v0 < nvec; v0 += 32 * CH) {
+      uint4 buf[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int v = v0 + c * 32 + lane;
+        if (v < nvec) buf[c] = ld_nc_v4(src + v);
+      }
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int v = v0 + c * 32 + lane;
+        if (v < nvec) dst[v] = buf[c];
+      }
+    }
+  }
+  pdl_wait();  // replay_rows_kernel (the programmatic predecessor) is complete before this grid is
+}
+
+// RoI replay rows: bin (ph, pw) of region k of request req.  One warp per crop row (the plan says which rows).
+__global__ void __launch_bounds__(256)
+replay_rows_kernel(const int* __restrict__ region_start, const bf16* __restrict__ feats_all, bf16* __restrict__ out, int S,
+                   int D, int rows_per_req_feats, const __grid_constant__ AssembleParams p) {
+  // grid = (ceil(tpt^2 / warps per block), regions, requests): warp <-> (request, region k, bin offset)
+  pdl_launch_dependents();  // the gather kernel starts at once and streams next to this (latency-bound) grid
+  const int req = blockIdx.z, k = blockIdx.y;
+  const RequestParams& rq = p.r[req];
+  if (!rq.has_roi[k]) return;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = D / 8;
+  {
+    const int off = blockIdx.x * wpb + (threadIdx.x >> 5);
+    const int start = region_start[req * MAX_REGIONS + k];
+    if (off >= p.tpt * p.tpt || start < 0 || start + off >= S) return;  // never outside this request's rows
+    const long long g = static_cast<long long>(req) * S + start + off;
     const bf16* feats = feats_all + static_cast<size_t>(req) * rows_per_req_feats * D;
     uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(g) * D);
-    const int k = (word >> 16) & 0x3fff, off = word & 0xffff;
-    if (kind == KIND_CROP && off >= tpt * tpt) kind = KIND_TEXT;  // run longer than one crop (status bit 2 is set)
-    if (kind != KIND_CROP) {
-      const uint4* src;
-      if (kind == KIND_IMAGE) {
-        int ord = word & 0x3fffffff;
-        ord = ord < rows_per_req_feats ? ord : rows_per_req_feats - 1;  // more <image> tokens than features (status bit 1)
-        src = reinterpret_cast<const uint4*>(feats + static_cast<size_t>(ord) * D);
-      } else {
-        long long id = rq.ids[s];
-        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-        src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(id) * D);
-      }
-      for (int v0 = 0; v0 < nvec; v0 += 32 * CH) {
-        uint4 buf[CH];
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const int v = v0 + c * 32 + lane;
-          if (v < nvec) buf[c] = ld_nc_v4(src + v);
-        }
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const int v = v0 + c * 32 + lane;
-          if (v < nvec) dst[v] = buf[c];
-        }
-      }
-      continue;
-    }
-    // ---- RoI replay row: bin (ph, pw) of region k
+    const int tpt = p.tpt;
     const int ph = off / tpt, pw = off % tpt;
     const int H = rq.nch * tpt, W = rq.ncw * tpt;
     const float scale = p.spatial_scale;
@@ -235,48 +263,51 @@ assemble_rows_kernel(const int* __restrict__ plan, const bf16* __restrict__ tabl
     const float end_h = __fsub_rn(__fmul_rn(rq.rois[k][4], scale), 0.5f);
     const float bin_h = __fdiv_rn(__fsub_rn(end_h, start_h), static_cast<float>(tpt));
     const float bin_w = __fdiv_rn(__fsub_rn(end_w, start_w), static_cast<float>(tpt));
-    // lane q < 4 owns sample point q = iy*2+ix; the warp then broadcasts its weights / cell rows
-    Sample mine;
-    {
-      const int iy = (lane >> 1) & 1, ix = lane & 1;
+    Sample sm[4];
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy) {
       const float yy = __fadd_rn(__fadd_rn(start_h, __fmul_rn(static_cast<float>(ph), bin_h)),
                                  __fdiv_rn(__fmul_rn(iy + 0.5f, bin_h), 2.0f));
-      const float xx = __fadd_rn(__fadd_rn(start_w, __fmul_rn(static_cast<float>(pw), bin_w)),
-                                 __fdiv_rn(__fmul_rn(ix + 0.5f, bin_w), 2.0f));
-      mine = make_sample(yy, xx, H, W);
+#pragma unroll
+      for (int ix = 0; ix < 2; ++ix) {
+        const float xx = __fadd_rn(__fadd_rn(start_w, __fmul_rn(static_cast<float>(pw), bin_w)),
+                                   __fdiv_rn(__fmul_rn(ix + 0.5f, bin_w), 2.0f));
+        sm[iy * 2 + ix] = make_sample(yy, xx, H, W);
+      }
+    }
+    // feature cell (y,x) of the merged map lives at tile 1 + (y/tpt)*ncw + x/tpt, token (y%tpt)*tpt + x%tpt
+    const uint4* cell[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        // feature cell (y,x) of the merged map lives at tile 1 + (y/tpt)*ncw + x/tpt, token (y%tpt)*tpt + x%tpt
-        const int lin = mine.pos[c];
+        const int lin = sm[q].pos[c];
         const int y = lin / W, x = lin % W;
-        mine.pos[c] = ((1 + (y / tpt) * rq.ncw + x / tpt) * tpt + (y % tpt)) * tpt + (x % tpt);
+        const size_t row = (static_cast<size_t>(1 + (y / tpt) * rq.ncw + x / tpt) * tpt + (y % tpt)) * tpt + (x % tpt);
+        cell[q * 4 + c] = reinterpret_cast<const uint4*>(feats + row * D);
       }
     }
     for (int v = lane; v < nvec; v += 32) {
+      // all 16 cell vectors of this output vector go out together (addresses of invalid samples are clamped, hence
+      // loadable; their values are never used) -- one L2 round trip per output vector instead of four
+      uint4 raws[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) raws[i] = __ldg(cell[i] + v);
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int valid = __shfl_sync(0xffffffffu, mine.valid, q);
-        uint4 raws[4];
-        float w[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int row = __shfl_sync(0xffffffffu, mine.pos[c], q);
-          w[c] = __shfl_sync(0xffffffffu, mine.w[c], q);
-          // rows of invalid samples are clamped, hence loadable; their values are never used
-          raws[c] = __ldg(reinterpret_cast<const uint4*>(feats + static_cast<size_t>(row) * D) + v);
-        }
-        if (!valid) continue;
+        if (!sm[q].valid) continue;
         float val[8];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const uint32_t* rw = reinterpret_cast<const uint32_t*>(&raws[c]);
+          const uint4 raw = raws[q * 4 + c];
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(&raw);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float2 f = unpack_bf16x2(rw[j]);
-            const float t0 = __fmul_rn(w[c], f.x), t1 = __fmul_rn(w[c], f.y);
+            const float t0 = __fmul_rn(sm[q].w[c], f.x), t1 = __fmul_rn(sm[q].w[c], f.y);
             val[2 * j] = c == 0 ? t0 : __fadd_rn(val[2 * j], t0);
             val[2 * j + 1] = c == 0 ? t1 : __fadd_rn(val[2 * j + 1], t1);
           }
@@ -335,7 +366,8 @@ extern "C" int gar_assemble_plan_batch(int nreq, const long long* const* input_i
     const int nr = nreq - r0 < MAX_REQS ? nreq - r0 : MAX_REQS;
     AssembleParams p;
     fill_params(p, r0, nr, input_ids, crop_ids, nullptr, has_roi, n_regions, 1.f, nullptr, nullptr, tpt, image_token_id);
-    plan_rows_kernel<<<nr, 1024, 0, stream>>>(S, n_image_rows, p, plan_ws + static_cast<size_t>(r0) * S, status_dev + 2 * r0);
+    plan_rows_kernel<<<nr, 1024, 0, stream>>>(S, n_image_rows, p, plan_ws + static_cast<size_t>(r0) * S, status_dev + 2 * r0,
+                                              plan_ws + static_cast<size_t>(nreq) * S + r0 * MAX_REGIONS);
     GAR_CUDA_CHECK(cudaGetLastError());
   }
   return GAR_OK;
@@ -367,11 +399,19 @@ extern "C" int gar_assemble_rows_batch(int nreq, const long long* const* input_i
     }
     const bf16* feats = static_cast<const bf16*>(image_features) + static_cast<size_t>(r0) * n_image_rows * D;
     bf16* o = static_cast<bf16*>(out) + static_cast<size_t>(r0) * S * D;
+    const int* region_start = plan_ws + static_cast<size_t>(nreq) * S + r0 * MAX_REGIONS;
+    const bool replay = n_regions > 0;
+    if (replay) {
+      replay_rows_kernel<<<dim3((tpt * tpt + 7) / 8, n_regions, nr), 256, 0, stream>>>(region_start, feats, o, S, D,
+                                                                                       n_image_rows, p);
+      GAR_CUDA_CHECK(cudaGetLastError());
+    }
     const long long rows = static_cast<long long>(nr) * S;
     const int wpb = 4;
+    // one row per warp; 4 vectors per lane in flight (2 passes over a 2048-wide row), 12 blocks/SM resident
     const long long gblocks = (rows + wpb - 1) / wpb;
-    GAR_CUDA_CHECK(gar_launch(assemble_rows_kernel<4>, dim3(static_cast<unsigned>(gblocks)), dim3(wpb * 32), 0, stream,
-                              false, dim3(1, 1, 1), plan_ws + static_cast<size_t>(r0) * S,
+    GAR_CUDA_CHECK(gar_launch(gather_rows_kernel<4>, dim3(static_cast<unsigned>(gblocks)), dim3(wpb * 32), 0, stream,
+                              replay, dim3(1, 1, 1), plan_ws + static_cast<size_t>(r0) * S,
                               static_cast<const bf16*>(embed_table), feats, o, S, D, vocab, n_image_rows, p));
   }
   return GAR_OK;
@@ -379,7 +419,7 @@ extern "C" int gar_assemble_rows_batch(int nreq, const long long* const* input_i
 
 // Batched form: request r reads input_ids[r] (device pointers in a HOST array), features
 // image_features + r*n_image_rows*D, boxes rois[r][n_regions][5] / has_roi[r][n_regions] (host), tile grid
-// ncw[r] x nch[r]; writes rows [r*S, (r+1)*S) of out / plan_ws and status_dev[2r..2r+1].  plan_ws: nreq*S ints.
+// ncw[r] x nch[r]; writes rows [r*S, (r+1)*S) of out / plan_ws and status_dev[2r..2r+1].  plan_ws: nreq*S + 8*nreq ints.
 extern "C" int gar_assemble_embeds_batch(int nreq, const long long* const* input_ids, int S, const void* embed_table,
                                          int vocab, const void* image_features, int n_image_rows, int D,
                                          const long long* crop_ids, const float* rois, const int* has_roi,

@@ -719,9 +719,11 @@ int gar_engine_plan_batch(gar_engine* e, int slot0, int nreq, const long long* c
     gar_set_error("gar_engine_plan_batch: slot0=%d nreq=%d S=%d T=%d outside capacity", slot0, nreq, S, T);
     return GAR_ERR_ARG;
   }
-  ProfScope ps(e, s, PK_ASSEMBLE, 0.0);
-  TRY(gar_assemble_plan_batch(nreq, input_ids_dev, S, T * e->tokens_per_tile, d.crop_token_ids, has_roi,
-                              d.prompt_numbers, e->tpt, d.image_token_id, e->plan, e->status + 2 * slot0, s));
+  {
+    ProfScope ps(e, s, PK_ASSEMBLE, 0.0);  // the plan kernel only (the status read-back below is host plumbing)
+    TRY(gar_assemble_plan_batch(nreq, input_ids_dev, S, T * e->tokens_per_tile, d.crop_token_ids, has_roi,
+                                d.prompt_numbers, e->tpt, d.image_token_id, e->plan, e->status + 2 * slot0, s));
+  }
   e->launches += (nreq + 7) / 8;
   e->plan_slot0 = slot0; e->plan_nreq = nreq; e->plan_S = S; e->plan_T = T;
   if (status_host) {
@@ -764,7 +766,7 @@ int gar_engine_assemble_batch(gar_engine* e, int slot0, int nreq, const long lon
                                 d.prompt_numbers, e->tpt, d.image_token_id, e->plan, e->status + 2 * slot0, s));
     e->launches += (nreq + 7) / 8;
   }
-  e->launches += (nreq + 7) / 8;
+  e->launches += 2 * ((nreq + 7) / 8);
   return gar_assemble_rows_batch(nreq, input_ids_dev, S, table, d.vocab, e->feats, T * e->tokens_per_tile, d.llm_dim,
                                  d.crop_token_ids, rois, has_roi, d.prompt_numbers, spatial_scale, ncw, nch, e->tpt,
                                  d.image_token_id, e->emb, e->plan, s);

@@ -32,7 +32,15 @@ struct GvArgs {
   const float* sumsq_in; int n_part; const bf16* norm_w; float eps;  // NORM prologue
   float* sumsq_out;                                                   // EPI_RES: [gridDim.x][8]
   int has_pf; PfArgs pf;                                              // L2 prefetch duty for the following kernels
+  unsigned long long* timeline;  // optional debug: per-CTA globaltimer stamps [blockIdx.x][8] (NULL in production)
 };
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define GV_STAMP(i) if (a.timeline != nullptr && threadIdx.x == 0) a.timeline[static_cast<size_t>(blockIdx.x) * 8 + (i)] = gtime_ns()
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                uint32_t b0, uint32_t b1) {
@@ -57,6 +65,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32, 16 / GV_WARPS) gemv_decode_kern
   constexpr int GV_THREADS = GV_WARPS * 32;
   constexpr int U = 8 / R;  // k-steps (32 k each) whose weight loads are in flight together
   pdl_launch_dependents();
+  GV_STAMP(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tig = lane & 3;
   const int row0 = blockIdx.x * 16 * R;
@@ -94,7 +103,9 @@ __global__ void __launch_bounds__(GV_WARPS * 32, 16 / GV_WARPS) gemv_decode_kern
   // this kernel's own first weight bytes are in flight: now pull the NEXT kernels' streams into L2
   const unsigned pf_tid = blockIdx.x * GV_THREADS + threadIdx.x, pf_n = gridDim.x * GV_THREADS;
   if (a.has_pf) pf_issue_plain(a.pf, pf_tid, pf_n);
+  GV_STAMP(1);
   pdl_wait();
+  GV_STAMP(2);
   if (a.has_pf) pf_issue_kv(a.pf, pf_tid, pf_n);
 
   // activations of the first chunk go in flight before the RMSNorm statistics are reduced
@@ -130,6 +141,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32, 16 / GV_WARPS) gemv_decode_kern
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     rstd = rsqrtf(s / static_cast<float>(a.K) + a.eps);
   }
+  GV_STAMP(3);
 
   for (int s0 = 0; s0 < steps; s0 += U) {
     if (NORM) {
@@ -173,6 +185,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32, 16 / GV_WARPS) gemv_decode_kern
   }
 
   // ---- reduce the 8 K-slices (fixed order), then the fused epilogue ----
+  GV_STAMP(4);
   __shared__ float part[GV_WARPS][16 * R][9];  // [warp][feature][batch], +1 pad
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -183,6 +196,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32, 16 / GV_WARPS) gemv_decode_kern
     part[warp][r * 16 + g + 8][2 * tig + 1] = acc[r][3];
   }
   __syncthreads();
+  GV_STAMP(5);
   constexpr int FEATS = 16 * R;
   constexpr int OUT_FEATS = EPI == GV_EPI_SWIGLU ? FEATS / 2 : FEATS;
   for (int idx = threadIdx.x; idx < OUT_FEATS * 8; idx += GV_THREADS) {
@@ -219,6 +233,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32, 16 / GV_WARPS) gemv_decode_kern
       if (f == 0) a.sumsq_out[static_cast<size_t>(blockIdx.x) * 8 + b] = q;
     }
   }
+  GV_STAMP(6);
 }
 
 // h[b] = table[tok[b]] and the row's sum of squares (the first layer's RMSNorm statistics)
@@ -273,6 +288,15 @@ int launch_gv(const GvArgs& a, bool norm, cudaStream_t s) {
 // epi: 0 none, 1 residual (+ optional sumsq_out[(N/rows_per_cta)][8]), 2 swiglu (W rows interleaved, out is [M, N/2]).
 // norm_w != NULL enables the RMSNorm prologue with sumsq_in[n_part][8].  Returns GAR_ERR_SHAPE when the shape does
 // not fit this kernel (callers then use gar_gemm_skinny_bf16 / gar_rmsnorm / gar_swiglu).
+static unsigned long long* g_gemv_timeline = nullptr;
+// debug hook: device buffer of >= 8 * grid int64 receiving per-CTA globaltimer stamps of the NEXT gemv launches
+// (0 entry, 1 first weights issued, 2 dependency wait done, 3 norm statistics ready, 4 weight stream consumed,
+//  5 K-slice partials in shared memory, 6 epilogue stored); NULL disables
+extern "C" int gar_gemv_debug_timeline(void* dev_buf) {
+  g_gemv_timeline = static_cast<unsigned long long*>(dev_buf);
+  return GAR_OK;
+}
+
 void gar_pf_to_args(const gar_prefetch* pf, PfArgs* o) {
   for (int r = 0; r < 2; ++r) {
     o->p[r] = static_cast<const char*>(pf->ptr[r]);
@@ -312,6 +336,7 @@ extern "C" int gar_gemv_decode_pf(const void* X, int ldx, const void* W, int ldw
   a.M = M; a.N = N; a.K = K;
   a.sumsq_in = sumsq_in; a.n_part = n_part; a.norm_w = static_cast<const bf16*>(norm_w); a.eps = eps;
   a.sumsq_out = sumsq_out;
+  a.timeline = g_gemv_timeline;
   a.has_pf = pf != nullptr;
   memset(&a.pf, 0, sizeof(a.pf));
   if (pf) gar_pf_to_args(pf, &a.pf);

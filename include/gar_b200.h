@@ -93,6 +93,8 @@ int gar_gemv_decode(const void* X, int ldx, const void* W, int ldw, void* out, i
 int gar_gemv_decode_pf(const void* X, int ldx, const void* W, int ldw, void* out, int ldo, int M, int N, int K, int epi,
                        const void* res, int ldres, const void* norm_w, const float* sumsq_in, int n_part, float eps,
                        float* sumsq_out, int* rows_per_cta, const gar_prefetch* pf, void* stream);
+/* debug: per-CTA globaltimer stamps of the following gar_gemv_decode launches into dev_buf (int64[8 * grid]); NULL disables */
+int gar_gemv_debug_timeline(void* dev_buf);
 int gar_embed_gather_sumsq(const void* table, const int* ids32, void* out, float* sumsq, int rows, int D, void* stream);
 
 /* mask-id decode + im2col of both stride-14 convs (modeling_gar.py:315-328; timm PatchEmbed) */
@@ -133,16 +135,17 @@ int gar_bump_step(int* step, void* stream);
 
 /* Fused embed + image-feature scatter + RoI-aligned feature replay (modeling_gar.py:332-414).
  * rois: n_regions x [0,x1,y1,x2,y2] fp32 host array computed like modeling_gar.py:367-387;
- * plan_ws: S ints (device); status_dev: 2 ints (device): [status bits, n image tokens]. */
+ * plan_ws: S + 8 ints (device); status_dev: 2 ints (device): [status bits, n image tokens]. */
 int gar_assemble_embeds(const long long* input_ids_dev, int S, const void* embed_table, int vocab,
                         const void* image_features, int n_image_rows, int D, const long long* crop_ids,
                         const float* rois, const int* has_roi, int n_regions, float spatial_scale, int ncw, int nch,
                         int tpt, long long image_token_id, void* out, int* plan_ws, int* status_dev, void* stream);
 
-/* The same for nreq equal-length requests (one plan launch + ONE row launch: an HBM stream over all requests).
+/* The same for nreq equal-length requests (one plan launch, then the replay and gather launches side by side: an HBM
+ * stream over all requests).
  * input_ids_dev: HOST array of nreq device pointers; rois (nreq, n_regions, 5), has_roi (nreq, n_regions), ncw/nch
  * (nreq) host arrays; request r uses features image_features + r*n_image_rows*D and writes rows [r*S,(r+1)*S) of out
- * and plan_ws (nreq*S ints) and status_dev[2r..2r+1]. */
+ * and plan_ws (nreq*S + 8*nreq ints) and status_dev[2r..2r+1]. */
 int gar_assemble_embeds_batch(int nreq, const long long* const* input_ids_dev, int S, const void* embed_table,
                               int vocab, const void* image_features, int n_image_rows, int D,
                               const long long* crop_ids, const float* rois, const int* has_roi, int n_regions,

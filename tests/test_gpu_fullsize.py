@@ -121,11 +121,16 @@ def _run_config(tag, spec, o32, o16, sd, n_masks, max_num_tiles, new_tokens, see
     assert torch.equal(emb[~crop_rows], want[~crop_rows]), "embed gather / image scatter rows must be bit-exact"
     # replay rows: the oracle evaluates torchvision's CUDA roi_align here (different FMA contraction than the CPU
     # operator the kernel is pinned to bit-for-bit in test_gpu_kernels / test_roi_replay_ref): allow one bf16 ulp
-    diff = (emb[crop_rows].float() - want[crop_rows].float()).abs()
-    ulp = _ulp_bf16(want[crop_rows].float())
+    # (where the four bilinear terms nearly cancel, an fp32-ulp difference of the sum is many ulps of the tiny bf16
+    # result: hence the absolute floor of 1e-5 of the feature scale)
+    ours_r, want_r = emb[crop_rows].float(), want[crop_rows].float()
+    diff = (ours_r - want_r).abs()
+    tol = torch.maximum(_ulp_bf16(torch.maximum(ours_r.abs(), want_r.abs())),
+                        torch.full_like(diff, 1e-5 * want_r.abs().max().item()))
     n_off = int((diff > 0).sum())
-    _report(f"  replay rows vs torchvision CUDA roi_align: {n_off} of {diff.numel()} elements differ, max {diff.max().item():.3g}")
-    assert bool((diff <= ulp).all())
+    _report(f"  replay rows vs torchvision CUDA roi_align: {n_off} of {diff.numel()} elements differ, max {diff.max().item():.3g},"
+            f" beyond 1 bf16 ulp: {int((diff > tol).sum())}")
+    assert bool((diff <= tol).all())
     want_cpu = o16.to("cpu").assemble(ids.cpu(), feats.cpu(), req["aspect_ratios"].cpu(), req["bboxes"])[0]
     o16.to(DEV)
     assert torch.equal(emb.cpu(), want_cpu), "inputs_embeds must be bit-exact vs the CPU roi_align the reference's CPU path runs"
