@@ -35,6 +35,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# The pipelined mode keeps a decode stream and an encode stream busy at the same time; with the default 8 hardware
+# work queues the two can land on the same queue and serialise behind each other's pre-enqueued launches.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import torch  # noqa: E402
 
@@ -52,6 +55,9 @@ def parse_args():
     ap.add_argument("--max-num-tiles", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-inputs", default="raw", choices=["raw", "tiles"],
+                    help="what the e2e arm ships from pinned host memory: raw = uint8 image + id map (preprocessing on "
+                         "the device), tiles = host-preprocessed bf16 tile tensors")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel-class event timing step")
     ap.add_argument("--no-lib-baseline", action="store_true", help="skip the same-box torch/cuBLAS/SDPA baseline")
     ap.add_argument("--pipeline", action="store_true",
@@ -378,7 +384,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(dev), timeout=datetime.timedelta(seconds=240))
 
     from grasp_any_region_b200 import GARConfig, GARModel
-    from grasp_any_region_b200.synth import make_request
+    from grasp_any_region_b200.synth import make_raw_request, make_request
 
     def note(msg):
         if os.environ.get("GAR_BENCH_VERBOSE") or world > 1:
@@ -410,15 +416,21 @@ def main():
             o[k] = r[k].pin_memory()
         return o
 
-    reqs_pinned = [pin(r) for r in reqs_host]
+    if args.e2e_inputs == "raw":
+        reqs_pinned = [make_raw_request(spec, seed=1000 * rank + i, n_masks=args.masks, max_num_tiles=args.max_num_tiles)
+                       for i in range(B)]
+        assert reqs_pinned[0]["input_ids"].shape[1] == S
+        e2e_keys = ("image_u8", "idmap_u8", "input_ids")
+    else:
+        reqs_pinned = [pin(r) for r in reqs_host]
+        e2e_keys = ("pixel_values", "global_mask_values", "input_ids")
     reqs_dev = []
     for r in reqs_host:
         o = dict(r)
         for k in ("pixel_values", "global_mask_values", "input_ids"):
             o[k] = r[k].to(dev)
         reqs_dev.append(o)
-    h2d = sum(r[k].numel() * r[k].element_size() for r in reqs_host
-              for k in ("pixel_values", "global_mask_values", "input_ids"))
+    h2d = sum(r[k].numel() * r[k].element_size() for r in reqs_pinned for k in e2e_keys)
     d2h = B * NT * 4
 
     def run_steps(batch_list, steps, gather=True):
@@ -469,6 +481,13 @@ def main():
     ms = timed(step_resident, args.steps)
     launches = eng.launch_count() - l0
     clocks = sampler.stop()
+    pipe_stats = getattr(eng, "pipeline_stats", None) if args.pipeline else None
+    if os.environ.get("GAR_BENCH_TRACE"):
+        eng.trace = []
+        timed(step_resident, 3)
+        pipe_stats = dict(pipe_stats or {}, trace=[(l, round(v, 1)) for l, v in eng.trace_ms()],
+                          pipeline_stats_traced=getattr(eng, "pipeline_stats", None))
+        eng.trace = None
     note(f"timed region done: {ms:.1f} ms")
     value = world * B * args.steps / (ms / 1e3)
 
@@ -477,7 +496,10 @@ def main():
         step_e2e(2)
         ms_e = timed(step_e2e, args.steps)
         e2e = {"value": world * B * args.steps / (ms_e / 1e3), "unit": "captions/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps,
+               "inputs": ("uint8 image + uint8 region-id map from pinned host memory; resize / tiling / normalisation on "
+                          "the device inside the timed region" if args.e2e_inputs == "raw" else
+                          "host-preprocessed bf16 tile tensors from pinned host memory")}
 
     # ---- phase split of one more step (events on the engine stream between the phases)
     phases = None
@@ -578,7 +600,7 @@ def main():
                        "pipeline": bool(args.pipeline), "sm_partition": partition,
                        "encode": "the B requests of a step share one ViT pass and one prefill pass (equal shapes); decode batched"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "rooflines": rooflines,
-            "stages": stages, "phases": phases, "cpu_baseline": cpu, "gpu_lib_baseline": lib,
+            "stages": stages, "phases": phases, "pipeline_stats": pipe_stats, "cpu_baseline": cpu, "gpu_lib_baseline": lib,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

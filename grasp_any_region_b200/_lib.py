@@ -37,10 +37,6 @@ SIGNATURES = {
     "gar_gemv_decode_pf": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
     "gar_decode_attn_rope_pf": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _i, _vp, _vp]),
-    "gar_decode_mega_debug_timeline": (_i, [_vp]),
-    "gar_decode_mega_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
-    "gar_decode_mega_step": (_i, [_vp] + [_i] + [_vp] * 5 + [_vp] * 2 + [_vp] * 5 + [_vp] * 4 + [_vp, _vp] +
-                             [_i] * 10 + [_f, _f, _vp]),
     "gar_gemv_debug_timeline": (_i, [_vp]),
     "gar_embed_gather_sumsq": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "gar_patchify": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -63,6 +59,9 @@ SIGNATURES = {
                                      _vp]),
     "gar_assemble_rows_batch": (_i, [_i, C.POINTER(_vp), _i, _vp, _i, _vp, _i, _i, C.POINTER(_ll), C.POINTER(_f),
                                      C.POINTER(_i), _i, _f, C.POINTER(_i), C.POINTER(_i), _i, _ll, _vp, _vp, _vp]),
+    "gar_resize_aa_u8_pass": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "gar_u8_to_tiles": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "gar_idmap_to_tiles": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "gar_attn_fwd": (_i, [_vp, _ll, _ll, _i, _vp, _vp, _ll, _ll, _i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _i, _i, _i,
                           _i, _i, _i, _i, _i, _i, _f, _vp]),
     "gar_decode_attn_rope": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -14,8 +14,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgar_b200.so")
-SOURCES = ["runtime.cu", "gemm_sm100.cu", "gemm_skinny_sm100.cu", "gemv_decode.cu", "attention_sm100.cu", "decode_attn.cu", "decode_mega.cu", "elementwise.cu",
-           "assemble_replay.cu", "engine.cu"]
+SOURCES = ["runtime.cu", "gemm_sm100.cu", "gemm_skinny_sm100.cu", "gemv_decode.cu", "attention_sm100.cu", "decode_attn.cu", "elementwise.cu",
+           "assemble_replay.cu", "preprocess_u8.cu", "engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

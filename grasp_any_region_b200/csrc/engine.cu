@@ -42,10 +42,6 @@ struct gar_engine {
   int fuse_rope = 1;
   int use_gemv = 1;
   int fuse_decode_rope = 1;
-  int mega_unit_warps = 2;  // warps per attention unit of the persistent kernel (4 = key partition of gar_decode_attn)
-  int decode_mega = 0;      // opt-in: whole decode step as one persistent kernel (decode_mega.cu); measured 1.15 vs 1.09 ms/step
-  std::map<int, std::vector<gar_mega_layer>> mega_layers;  // per slot_base: layer pointer table
-  unsigned* gbar = nullptr;
   int decode_prefetch = 0;  // decode kernels pull the following kernels' weight / KV streams into L2 (gar_prefetch)
   float *sumsq_a, *sumsq_b;
   // decode graph
@@ -56,6 +52,11 @@ struct gar_engine {
   int eos_poll_steps = 8;   // decode steps per early-stop poll (0 = never poll: always run max_new_tokens steps)
   int steps_run = 0;        // decode steps launched by the last generate call
   int* fin_host = nullptr;  // pinned: 2 x max_batch finished flags
+  // Host copies go through pinned memory and event waits only: a pageable cudaMemcpyAsync is host-synchronous and was
+  // measured to block the staging thread until the OTHER stream's decode had drained (pipelined serving).
+  int* status_host = nullptr;  // pinned: 2 x max_batch status words
+  int* out_host = nullptr;     // pinned: max_batch x max_new_tokens decoded ids
+  cudaEvent_t plan_ev = nullptr, out_ev = nullptr;
   cudaEvent_t fin_ev[2] = {nullptr, nullptr};
   // SM partition (green contexts): launches into part_stream[i] may occupy part_sms[i] SMs (gar_engine_partition)
   cudaStream_t part_stream[2] = {nullptr, nullptr};
@@ -73,6 +74,10 @@ struct gar_engine {
 enum ProfKind { PK_GEMM = 0, PK_ATTN = 1, PK_ASSEMBLE = 2, PK_DECODE_ATTN = 3, PK_GEMV = 4, PK_COUNT = 5 };
 
 namespace {
+
+__global__ void fill_int_kernel(int* dst, int value, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = value;
+}
 
 template <typename T>
 int dev_alloc(gar_engine* e, T** p, size_t count, bool zero = false) {
@@ -337,8 +342,9 @@ int decode_step_gemv(gar_engine* e, int batch, void* s) {
   NEEDW(wl, "llm.lm_head");
   {
     ProfScope ps(e, s, PK_GEMV, 2.0 * d.vocab_padded * static_cast<double>(D));
-    TRY(gar_gemv_decode(e->hdec, D, wl, D, e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded, batch, d.vocab_padded, D, 0, nullptr, 0, wn,
-                        e->sumsq_a, n_part, d.rms_eps, nullptr, nullptr, s));
+    TRY(gar_gemv_decode_pf(e->hdec, D, wl, D, e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded,
+                      batch, d.vocab_padded, D, 0, nullptr, 0, wn, e->sumsq_a, n_part, d.rms_eps, nullptr, nullptr, nullptr,
+                      s));
   }
   TRY(gar_argmax_step_eos(e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded, d.vocab, batch,
                           e->next_tok + e->slot_base, e->out_tokens + static_cast<size_t>(e->slot_base) * d.max_new_tokens,
@@ -348,58 +354,8 @@ int decode_step_gemv(gar_engine* e, int batch, void* s) {
   return GAR_OK;
 }
 
-// Decode step as ONE persistent kernel + the argmax bookkeeping launch pair.
-int decode_step_mega(gar_engine* e, int batch, void* s) {
-  const gar_model_desc& d = e->d;
-  const int D = d.llm_dim, hq = d.llm_heads, hkv = d.llm_kv_heads, hd = d.llm_head_dim, I = d.llm_inter;
-  NEEDW(table, "llm.embed");
-  NEEDW(cos_t, "llm.cos");
-  NEEDW(sin_t, "llm.sin");
-  NEEDW(wn, "llm.norm");
-  NEEDW(wl, "llm.lm_head");
-  auto it = e->mega_layers.find(e->slot_base);
-  if (it == e->mega_layers.end()) {
-    std::vector<gar_mega_layer> host(d.llm_layers);
-    const size_t slot_elems = static_cast<size_t>(hkv) * d.max_seq * hd;
-    for (int i = 0; i < d.llm_layers; ++i) {
-      NEEDW(ln1, L("llm", i, "ln1"));
-      NEEDW(wqkv, L("llm", i, "qkv.w"));
-      NEEDW(wo, L("llm", i, "o.w"));
-      NEEDW(ln2, L("llm", i, "ln2"));
-      NEEDW(wgu, L("llm", i, "gu.w"));
-      NEEDW(wdown, L("llm", i, "down.w"));
-      host[i] = {wqkv, wo, wgu, wdown, ln1, ln2,
-                 e->kcache + (static_cast<size_t>(i) * d.max_batch + e->slot_base) * slot_elems,
-                 e->vcache + (static_cast<size_t>(i) * d.max_batch + e->slot_base) * slot_elems};
-    }
-    it = e->mega_layers.emplace(e->slot_base, host).first;
-  }
-  const int uw = e->mega_unit_warps == 4 ? 4 : 2;
-  int splits = e->dec_splits;
-  if (splits <= 0) {  // one round of items over the attention units (8 / uw per CTA)
-    splits = ((8 / uw) * gar_num_sms()) / (batch * hkv);
-    splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
-  }
-  bf16* logits = e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded;
-  {
-    ProfScope ps(e, s, PK_GEMV, 0.0);
-    TRY(gar_decode_mega_step(it->second.data(), d.llm_layers, table, wl, wn, cos_t, sin_t, e->next_tok + e->slot_base,
-                             e->pos + e->slot_base, e->hdec, e->d_qkv, e->d_att, e->d_act, logits, e->sumsq_a, e->sumsq_b,
-                             e->o_part, e->ml_part, e->tickets, e->gbar, batch, D, I, hq, hkv, hd, d.vocab_padded,
-                             d.max_seq, splits, uw, d.rms_eps, 1.0f / sqrtf(static_cast<float>(hd)), s));
-  }
-  TRY(gar_argmax_step_eos(logits, d.vocab_padded, d.vocab, batch, e->next_tok + e->slot_base,
-                          e->out_tokens + static_cast<size_t>(e->slot_base) * d.max_new_tokens, d.max_new_tokens, e->step,
-                          e->pos + e->slot_base, e->finished + e->slot_base, e->eos_ids, e->n_eos, 1, 1, e->argmax_ws, s));
-  e->launches += 3;
-  return GAR_OK;
-}
-
 int decode_step(gar_engine* e, int batch, void* s) {
   const gar_model_desc& d = e->d;
-  if (e->decode_mega && d.llm_layers <= 32 && gar_decode_mega_supported(batch, d.llm_dim, d.llm_inter, d.llm_heads, d.llm_kv_heads,
-                                                   d.llm_head_dim, d.vocab_padded))
-    return decode_step_mega(e, batch, s);
   if (e->use_gemv && batch <= 8 && d.llm_dim % 256 == 0 && d.llm_inter % 256 == 0 &&
       (d.llm_heads * d.llm_head_dim) % 256 == 0 && d.llm_inter % 32 == 0 && d.vocab_padded % 64 == 0)
     return decode_step_gemv(e, batch, s);
@@ -493,8 +449,13 @@ int gar_engine_create(const gar_model_desc* desc, gar_engine** out) {
   rc |= dev_alloc(e, &e->ids_scratch, S);
   rc |= dev_alloc(e, &e->sumsq_a, (D / 16 + 1) * 8, true);
   rc |= dev_alloc(e, &e->sumsq_b, (D / 16 + 1) * 8, true);
-  rc |= dev_alloc(e, &e->gbar, 2, true);
   if (cudaMallocHost(reinterpret_cast<void**>(&e->fin_host), 2 * B * sizeof(int)) != cudaSuccess) rc |= GAR_ERR_CUDA;
+  if (cudaMallocHost(reinterpret_cast<void**>(&e->status_host), 2 * B * sizeof(int)) != cudaSuccess) rc |= GAR_ERR_CUDA;
+  if (cudaMallocHost(reinterpret_cast<void**>(&e->out_host), B * static_cast<size_t>(d.max_new_tokens) * sizeof(int)) !=
+      cudaSuccess)
+    rc |= GAR_ERR_CUDA;
+  if (cudaEventCreateWithFlags(&e->plan_ev, cudaEventDisableTiming) != cudaSuccess) rc |= GAR_ERR_CUDA;
+  if (cudaEventCreateWithFlags(&e->out_ev, cudaEventDisableTiming) != cudaSuccess) rc |= GAR_ERR_CUDA;
   for (int i = 0; i < 2 && !rc; ++i)
     if (cudaEventCreateWithFlags(&e->fin_ev[i], cudaEventDisableTiming) != cudaSuccess) rc |= GAR_ERR_CUDA;
   if (rc) {
@@ -510,6 +471,10 @@ int gar_engine_destroy(gar_engine* e) {
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   for (void* p : e->allocs) cudaFree(p);
   if (e->fin_host) cudaFreeHost(e->fin_host);
+  if (e->status_host) cudaFreeHost(e->status_host);
+  if (e->out_host) cudaFreeHost(e->out_host);
+  if (e->plan_ev) cudaEventDestroy(e->plan_ev);
+  if (e->out_ev) cudaEventDestroy(e->out_ev);
   for (int i = 0; i < 2; ++i)
     if (e->fin_ev[i]) cudaEventDestroy(e->fin_ev[i]);
   delete e;
@@ -727,10 +692,11 @@ int gar_engine_plan_batch(gar_engine* e, int slot0, int nreq, const long long* c
   e->launches += (nreq + 7) / 8;
   e->plan_slot0 = slot0; e->plan_nreq = nreq; e->plan_S = S; e->plan_T = T;
   if (status_host) {
-    std::vector<int> st(2 * nreq);
-    GAR_CUDA_CHECK(cudaMemcpyAsync(st.data(), e->status + 2 * slot0, sizeof(int) * 2 * nreq, cudaMemcpyDeviceToHost,
+    int* st = e->status_host + 2 * slot0;
+    GAR_CUDA_CHECK(cudaMemcpyAsync(st, e->status + 2 * slot0, sizeof(int) * 2 * nreq, cudaMemcpyDeviceToHost,
                                    static_cast<cudaStream_t>(s)));
-    GAR_CUDA_CHECK(cudaStreamSynchronize(static_cast<cudaStream_t>(s)));
+    GAR_CUDA_CHECK(cudaEventRecord(e->plan_ev, static_cast<cudaStream_t>(s)));
+    GAR_CUDA_CHECK(cudaEventSynchronize(e->plan_ev));
     for (int r = 0; r < nreq; ++r) status_host[r] = st[2 * r];
   }
   return GAR_OK;
@@ -789,9 +755,8 @@ int gar_engine_prefill_batch(gar_engine* e, int slot0, int nreq, int S, void* s)
   // last position of every request: rows (r+1)*S-1, i.e. a strided row view of h
   TRY(lm_head(e, e->h + static_cast<size_t>(S - 1) * d.llm_dim, S * d.llm_dim, nreq,
               e->logits + static_cast<size_t>(slot0) * d.vocab_padded, e->lnl, s));
-  std::vector<int> pos(nreq, S);
-  GAR_CUDA_CHECK(cudaMemcpyAsync(e->pos + slot0, pos.data(), sizeof(int) * nreq, cudaMemcpyHostToDevice,
-                                 static_cast<cudaStream_t>(s)));
+  fill_int_kernel<<<1, 64, 0, static_cast<cudaStream_t>(s)>>>(e->pos + slot0, S, nreq);
+  GAR_CUDA_CHECK(cudaGetLastError());
   return GAR_OK;
 }
 
@@ -809,8 +774,8 @@ int gar_engine_prefill(gar_engine* e, int slot, int S, void* s) {
   // logits only for the last position (logits_to_keep=1 in HF generate's prefill)
   TRY(lm_head(e, e->h + static_cast<size_t>(S - 1) * d.llm_dim, d.llm_dim, 1,
               e->logits + static_cast<size_t>(slot) * d.vocab_padded, e->lnl, s));
-  const int pos = S;
-  GAR_CUDA_CHECK(cudaMemcpyAsync(e->pos + slot, &pos, sizeof(int), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(s)));
+  fill_int_kernel<<<1, 64, 0, static_cast<cudaStream_t>(s)>>>(e->pos + slot, S, 1);
+  GAR_CUDA_CHECK(cudaGetLastError());
   return GAR_OK;
 }
 
@@ -940,9 +905,11 @@ int gar_engine_generate_eos(gar_engine* e, int slot0, int batch, int max_new_tok
   }
   e->steps_run = done;
   if (steps_run) *steps_run = done;
-  std::vector<int> tmp(static_cast<size_t>(batch) * d.max_new_tokens);
-  GAR_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), out_dev, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
-  GAR_CUDA_CHECK(cudaStreamSynchronize(s));
+  int* tmp = e->out_host + static_cast<size_t>(slot0) * d.max_new_tokens;
+  GAR_CUDA_CHECK(cudaMemcpyAsync(tmp, out_dev, static_cast<size_t>(batch) * d.max_new_tokens * sizeof(int),
+                                 cudaMemcpyDeviceToHost, s));
+  GAR_CUDA_CHECK(cudaEventRecord(e->out_ev, s));
+  GAR_CUDA_CHECK(cudaEventSynchronize(e->out_ev));
   for (int b = 0; b < batch; ++b)
     for (int t = 0; t < max_new_tokens; ++t)
       out_tokens_host[b * max_new_tokens + t] = tmp[static_cast<size_t>(b) * d.max_new_tokens + t];
@@ -995,8 +962,6 @@ int gar_engine_set_option(gar_engine* e, const char* name, int value) {
   else if (n == "gemv_decode") e->use_gemv = value;
   else if (n == "fuse_decode_rope") e->fuse_decode_rope = value;
   else if (n == "decode_prefetch") e->decode_prefetch = value;
-  else if (n == "decode_mega") e->decode_mega = value;
-  else if (n == "mega_unit_warps" && (value == 2 || value == 4)) e->mega_unit_warps = value;
   else if (n == "decode_splits" && value >= 0 && value <= 32) e->dec_splits = value;
   else if (n == "eos_poll_steps" && value >= 0) e->eos_poll_steps = value;
   else if (n == "pdl" || n == "decode_attn_mma" || n == "attn_bkv" || n == "gemm_2cta") {

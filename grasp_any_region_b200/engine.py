@@ -86,6 +86,7 @@ class Engine:
         self.dec_stream: Optional[torch.cuda.Stream] = None
         self.partition_sms = None
         self.last_steps_run = 0
+        self.trace = None  # debug: set to [] to collect (label, CUDA event) marks between the stage entry points
         self._load_weights(state_dict)
 
     def enable_partition(self, decode_sms: int) -> bool:
@@ -272,12 +273,14 @@ class Engine:
         assert n * T <= self.max_tiles and n * S <= self.max_prefill_rows and slot0 + n <= self.max_batch
         with_mask = requests[0][1] is not None
         assert all((r[1] is not None) == with_mask for r in requests)
+        self._mark("stage_begin")
         for i, r in enumerate(requests):
             check(self.lib.gar_engine_patchify_at(self._h, C.c_void_p(r[0].data_ptr()),
                                                   C.c_void_p(r[1].data_ptr()) if with_mask else None, T, i * T,
                                                   self._s()), "gar_engine_patchify_at")
         check(self.lib.gar_engine_vit_encode_patches(self._h, n * T, int(with_mask), self._s()),
               "gar_engine_vit_encode_patches")
+        self._mark("vit_done")
         flat_rois, flat_has, ncws, nchs, scale = [], [], [], [], 1.0
         for (_, _, ids, bboxes, (ncw, nch)) in requests:
             rois, has, scale = roi_boxes_f32(self.spec, bboxes, ncw, nch)
@@ -290,7 +293,24 @@ class Engine:
                                                  (C.c_int * len(flat_has))(*flat_has), float(scale),
                                                  (C.c_int * n)(*ncws), (C.c_int * n)(*nchs), self._s()),
               "gar_engine_assemble_batch")
+        self._mark("assemble_done")
         check(self.lib.gar_engine_prefill_batch(self._h, slot0, n, S, self._s()), "gar_engine_prefill_batch")
+        self._mark("prefill_done")
+
+    def _mark(self, label: str):
+        if self.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(self.stream)
+            self.trace.append((label, ev))
+
+    def trace_ms(self):
+        """[(label, ms since the previous mark)] of the marks collected so far (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        out, prev = [], None
+        for label, ev in self.trace or []:
+            out.append((label, 0.0 if prev is None or label == "stage_begin" else prev.elapsed_time(ev)))
+            prev = ev
+        return out
 
     def generate(self, batch: int, max_new_tokens: int, eos_token_id=None, slot0: int = 0,
                  stream: Optional[torch.cuda.Stream] = None) -> List[List[int]]:

@@ -96,3 +96,26 @@ def make_request(spec: GARSpec, seed: int = 0, n_masks: int = 1, image_size: int
         bboxes=[bboxes],
         aspect_ratios=torch.tensor([[tw, th]], dtype=torch.long, device=device),
     )
+
+
+def make_raw_request(spec: GARSpec, seed: int = 0, n_masks: int = 1, image_size: int = 1024, max_num_tiles: int = 16,
+                     text_tokens: int = 64, pin: bool = True) -> Dict:
+    """The same kind of request before preprocessing: a seeded uint8 image, rectangle masks and random text ids, as the
+    host half of the device-preprocessing path (preprocess_device.build_raw_request).  Same prompt length as
+    make_request for equal arguments."""
+    from .preprocess_device import build_raw_request
+
+    g = np.random.default_rng(seed)
+    image = g.integers(0, 256, size=(image_size, image_size, 3), dtype=np.uint8)
+    masks = []
+    for _ in range(n_masks):
+        side_w = int(g.integers(image_size // 16, 3 * image_size // 4))
+        side_h = int(g.integers(image_size // 16, 3 * image_size // 4))
+        x0 = int(g.integers(0, image_size - side_w))
+        y0 = int(g.integers(0, image_size - side_h))
+        m = np.zeros((image_size, image_size), dtype=bool)
+        m[y0:y0 + side_h, x0:x0 + side_w] = True
+        masks.append(m)
+    n_text = n_masks * (max(text_tokens - 10, n_masks * 4) // n_masks)
+    text = [int(v) for v in g.integers(0, 128000, size=n_text)]
+    return build_raw_request(spec, image, masks, text, max_num_tiles=max_num_tiles, pin=pin)

@@ -163,6 +163,23 @@ int gar_assemble_rows_batch(int nreq, const long long* const* input_ids_dev, int
                             const int* nch, int tpt, long long image_token_id, void* out, const int* plan_ws,
                             void* stream);
 
+/* ---- request preprocessing on the device: uint8 image + uint8 region-id map -> bf16 tile tensors ----
+ * One separable pass of ATen's native uint8 antialiased bicubic resize (what torchvision v2 `resize(..., BICUBIC)` runs on
+ * uint8 CPU tensors; image_processing_perception_lm_fast.py:254-277, 296-340): out = clamp((2^(precision-1) +
+ * sum_j weights[o][j] * src[idx_min[o] + j]) >> precision, 0, 255).  horizontal != 0 resizes x (dst (planes, in_h,
+ * out_size)), else y (dst (planes, out_size, in_w)).  idx_min / idx_size (out_size ints) and weights (out_size x max_interp
+ * int16) are DEVICE tables built on the host in double precision (preprocess_device.aa_tables). */
+int gar_resize_aa_u8_pass(const void* src_u8, int planes, int in_h, int in_w, int horizontal, int out_size,
+                          const int* idx_min, const int* idx_size, const short* weights, int max_interp, int precision,
+                          void* dst_u8, void* stream);
+/* uint8 canvas (3, nch*tile, ncw*tile) -> bf16 tiles (nch*ncw, 3, tile, tile), row-major over (tile row, tile column),
+ * values ((v * fl(1/255)) - 0.5) / 0.5 in torch's fp32 op order (`_split` + rescale + normalise, :316-372) */
+int gar_u8_to_tiles(const void* canvas_u8, int ncw, int nch, int tile, void* tiles_out, void* stream);
+/* uint8 id map (H, W) -> global_mask_values (1 + ncw*nch, 3, tile, tile) bf16 = 2 v / 255 - 1, thumbnail first, NEAREST
+ * through host-built DEVICE index tables (ys/xs of the thumbnail: `tile` ints each; of the canvas: nch*tile / ncw*tile) */
+int gar_idmap_to_tiles(const void* idmap_u8, int H, int W, const int* ys_thumb, const int* xs_thumb, const int* ys_canvas,
+                       const int* xs_canvas, int ncw, int nch, int tile, void* mask_values_out, void* stream);
+
 /* softmax(QK^T*scale)V, head_dim 64, tcgen05 + TMEM (timm SDPA non-causal; flash-attn 2 causal GQA prefill).
  * All strides/offsets in bf16 elements.  K/V batch coordinate = b*kv_batch_mul + kv_head*kv_batch_head_mul. */
 int gar_attn_fwd(const void* q, long long q_row_stride, long long q_batch_stride, int q_col0, const void* k,
@@ -188,25 +205,6 @@ int gar_decode_attn_rope_pf(const void* qkv, int ldq, void* kcache, void* vcache
                             const int* slot_dev, int batch, int hq, int hkv, int head_dim, int max_seq, int splits,
                             float scale, const void* cos_t, const void* sin_t, void* o_part_ws, void* ml_part_ws,
                             int* tickets, void* out, int ldo, const gar_prefetch* pf, void* stream);
-
-/* One persistent kernel for a whole greedy decode step (embedding gather, every Llama layer, lm_head): one CTA per
- * SM, weight tiles streamed ahead through a shared-memory ring by a producer warp, grid barriers between the
- * dependent phases (decode_mega.cu).  layers: n_layers (<= 32) x gar_mega_layer in HOST memory (copied into the kernel
- * parameters); gbar: 8 zero-initialised, 8-byte aligned bytes; sumsq_a/sumsq_b: (D/16 + 1) * 8 floats; next_tok/pos/h/qkv/att/act/logits/tickets/o_part/ml_part as
- * in the per-kernel decode step.  unit_warps: warps per attention unit, 2 (fastest) or 4 (the key partition of
- * gar_decode_attn: bit-identical results for equal `splits`).  The caller runs gar_argmax_step on `logits` afterwards. */
-typedef struct gar_mega_layer {
-  const void *wqkv, *wo, *wgu, *wdown, *ln1, *ln2;
-  void *kcache, *vcache; /* this layer's cache at the first slot of the decode group */
-} gar_mega_layer;
-int gar_decode_mega_debug_timeline(void* dev_buf); /* debug: CTA 0's per-phase globaltimer stamps; NULL disables */
-int gar_decode_mega_supported(int batch, int D, int I, int hq, int hkv, int head_dim, int vocab_padded);
-int gar_decode_mega_step(const gar_mega_layer* layers, int n_layers, const void* table, const void* lm_head,
-                         const void* final_norm, const void* cos_t, const void* sin_t, const int* next_tok,
-                         const int* pos, void* h, void* qkv, void* att, void* act, void* logits, float* sumsq_a,
-                         float* sumsq_b, float* o_part, float* ml_part, int* tickets, unsigned* gbar, int batch, int D,
-                         int I, int hq, int hkv, int head_dim, int vocab_padded, int max_seq, int splits, int unit_warps,
-                         float eps, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Engine: GARModel.generate() (modeling_gar.py:295-428) as a device-resident pipeline

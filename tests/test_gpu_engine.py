@@ -231,51 +231,6 @@ def test_batched_encode_matches_per_request():
     assert bat == seq
 
 
-def test_decode_megakernel_matches_per_kernel_step():
-    """The persistent decode-step kernel (decode_mega.cu) keeps the arithmetic and the summation order of the
-    per-kernel decode step (same k-slices, same split-KV partition when decode_splits is pinned), so tokens AND the
-    last step's logits must be bit-identical; batch 1 and a ragged batch of 3."""
-    spec = gar_small()
-    new_tokens = 12
-    _, _, eng, req_a = _setup(spec, 1, seed=51, new_tokens=new_tokens, extra_seq=512)
-    reqs = [req_a] + [make_request(spec, seed=52 + i, n_masks=1, max_num_tiles=4, dtype=bf, device=DEV) for i in range(1)]
-    eng.set_option("decode_splits", 5)
-    eng.set_option("mega_unit_warps", 4)  # same key partition per warp as gar_decode_attn (4-warp CTAs)
-    results = {}
-    for mega in (0, 1):
-        eng.set_option("decode_mega", mega)
-        for batch in (1, 2):
-            for slot, req in enumerate(reqs[:batch]):
-                with torch.cuda.stream(eng.stream):
-                    eng.request(slot, req["pixel_values"], req["global_mask_values"], req["input_ids"][0].contiguous(),
-                                req["bboxes"][0], req["aspect_ratios"][0].tolist())
-            toks = eng.generate(batch, new_tokens, None)
-            logits = eng.buffer("logits", (batch, eng.vocab_padded)).float().cpu()
-            results[(mega, batch)] = (toks, logits)
-    for batch in (1, 2):
-        t0, l0 = results[(0, batch)]
-        t1, l1 = results[(1, batch)]
-        assert t0 == t1, f"batch {batch}: tokens differ {t0} vs {t1}"
-        assert torch.equal(l0, l1), f"batch {batch}: logits differ by {(l0 - l1).abs().max().item()}"
-    # production setting: 2-warp attention units and the auto split count -- another (equally valid) fp32 summation
-    # order of the split-KV partials, so bf16 logits may move by an ulp or two
-    eng.set_option("mega_unit_warps", 2)
-    eng.set_option("decode_splits", 0)
-    for slot, req in enumerate(reqs[:2]):
-        with torch.cuda.stream(eng.stream):
-            eng.request(slot, req["pixel_values"], req["global_mask_values"], req["input_ids"][0].contiguous(),
-                        req["bboxes"][0], req["aspect_ratios"][0].tolist())
-    toks = eng.generate(2, new_tokens, None)
-    logits = eng.buffer("logits", (2, eng.vocab_padded)).float().cpu()
-    t0, l0 = results[(0, 2)]
-    if toks == t0:  # same greedy path -> the last step's logits are comparable
-        assert (logits - l0).abs().max().item() < 0.08
-    else:  # a near-tie flipped: the sequences must agree up to the first flip
-        k = next(i for i, (x, y) in enumerate(zip(toks[0] + toks[1], t0[0] + t0[1])) if x != y)
-        assert k > 0, "first generated token differs between the decode paths"
-    eng.close()
-
-
 def test_engine_request_from_image_and_masks_non_square_canvas():
     """A request built by the host-side builder (grasp_any_region_b200/preprocess.py: the reference's canvas choice,
     bicubic tiling, NEAREST id map, inclusive-max boxes) for a 900x600 image lands on a 3x2 canvas; image features,
@@ -438,3 +393,35 @@ def test_auto_model_from_pretrained_on_cuda_generates(tmp_path):
     c = model.generate(**req, generation_config=GC()).sequences
     V = spec.text.vocab_size
     assert int(c[0, 0]) == V - 1 - int(a[0, 0]), "engine was not rebuilt after load_state_dict"
+
+
+def test_raw_uint8_requests_match_preprocessed_requests():
+    """N1 end to end: generate_batch on requests that still carry the uint8 image + id map (4 MB over PCIe, preprocessing
+    on the device) returns exactly the tokens of the same requests preprocessed on the host (41 MB of bf16 tiles)."""
+    import numpy as np
+
+    from grasp_any_region_b200.preprocess import build_request
+    from grasp_any_region_b200.preprocess_device import build_raw_request
+
+    new_tokens = 8
+    spec, model = _small_model()
+    rng = np.random.default_rng(3)
+    raws, cooked = [], []
+    for i in range(2):
+        img = rng.integers(0, 256, size=(640, 640, 3), dtype=np.uint8)
+        m0 = np.zeros((640, 640), bool); m0[50 + 40 * i: 300, 60: 420] = True
+        m1 = np.zeros((640, 640), bool); m1[320: 600, 200 + 30 * i: 610] = True
+        text = list(range(3000 + i, 3040 + i))
+        raws.append(build_raw_request(spec, img, [m0, m1], text, max_num_tiles=4))
+        cooked.append(build_request(spec, img, [m0, m1], text, max_num_tiles=4, dtype=bf))
+    S = cooked[0]["input_ids"].shape[1]
+    assert raws[0]["input_ids"].shape[1] == S and torch.equal(raws[0]["input_ids"], cooked[0]["input_ids"])
+    assert raws[0]["bboxes"] == cooked[0]["bboxes"]
+    T = cooked[0]["pixel_values"].shape[0]
+    model.configure_engine(max_tiles=2 * T, max_seq=S + 32, max_batch=2, max_new_tokens=new_tokens, max_prefill_rows=2 * S)
+    want = model.generate_batch(cooked, max_new_tokens=new_tokens)
+    got = model.generate_batch(raws, max_new_tokens=new_tokens)
+    assert got == want
+    raw_bytes = sum(r[k].numel() * r[k].element_size() for r in raws for k in ("image_u8", "idmap_u8", "input_ids"))
+    cooked_bytes = sum(r[k].numel() * r[k].element_size() for r in cooked for k in ("pixel_values", "global_mask_values", "input_ids"))
+    assert raw_bytes * 3 < cooked_bytes

@@ -146,23 +146,53 @@ def test_gemv_decode_chain(M):
     h2 = gemm_ref(act, wd, ops.EPI_RES, res=h1).to(bf)
     logits = r(rms(h2, lnf).float() @ wl.float().t())
 
-    g1, sq1 = ops.gemv_decode(att, wo, epi=1, res=h, want_sumsq=True)
+    gemv = ops.gemv_decode
+    g1, sq1 = gemv(att, wo, epi=1, res=h, want_sumsq=True)
     assert (g1.float() - h1.float()).abs().max().item() <= 4e-2
     assert torch.allclose(sq1.sum(0)[:M], g1.float().pow(2).sum(-1), rtol=1e-4)
-    gact, _ = ops.gemv_decode(g1, ops.interleave_gate_up(wg, wu), epi=2, norm_w=ln2, sumsq_in=sq1)
+    gact, _ = gemv(g1, ops.interleave_gate_up(wg, wu), epi=2, norm_w=ln2, sumsq_in=sq1)
     n2g = rms(g1, ln2)
     actg = (F.silu(r(n2g.float() @ wg.float().t()).to(bf)) * r(n2g.float() @ wu.float().t()).to(bf))
     assert (gact.float() - actg.float()).abs().max().item() <= 3e-2 * max(1.0, actg.float().abs().max().item())
     assert (gact != actg).float().mean().item() < 0.03
-    g2, sq2 = ops.gemv_decode(gact, wd, epi=1, res=g1, want_sumsq=True)
-    gl, _ = ops.gemv_decode(g2, wl, epi=0, norm_w=lnf, sumsq_in=sq2)
+    g2, sq2 = gemv(gact, wd, epi=1, res=g1, want_sumsq=True)
+    gl, _ = gemv(g2, wl, epi=0, norm_w=lnf, sumsq_in=sq2)
     torch.cuda.synchronize()
     ref_l = r(rms(g2, lnf).float() @ wl.float().t())
     assert (gl.float() - ref_l).abs().max().item() <= 4e-2 * max(1.0, ref_l.abs().max().item())
     assert (gl.float() - logits).abs().max().item() <= 0.15 * max(1.0, logits.abs().max().item())
     # bitwise repeatable
-    gl2, _ = ops.gemv_decode(g2, wl, epi=0, norm_w=lnf, sumsq_in=sq2)
+    gl2, _ = gemv(g2, wl, epi=0, norm_w=lnf, sumsq_in=sq2)
     assert torch.equal(gl, gl2)
+
+
+@pytest.mark.parametrize("N,K,epi", [(3072, 2048, 0), (2048, 8192, 1), (16384, 2048, 2), (4096, 14336, 1), (128512, 2048, 0)])
+def test_gemv_decode_production_shapes(N, K, epi):
+    """GAR-1B / GAR-8B decode shapes against fp32 torch."""
+    M = 8
+    x, w = rnd(M, K, seed=90), rnd(N, K, scale=0.02, seed=91)
+    res = rnd(M, N, seed=92) if epi == 1 else None
+    nw = (1 + rnd(K, scale=0.1, seed=93).float()).to(bf) if epi != 1 else None
+    sq = None
+    xin = x
+    if nw is not None:
+        sq = torch.zeros((K // 16, 8), dtype=torch.float32, device=DEV)
+        sq[0, :M] = x.float().pow(2).sum(-1)
+        x32 = x.float()
+        xin = nw * (x32 * torch.rsqrt(x32.pow(2).mean(-1, keepdim=True) + 1e-5)).to(bf)
+    out, osq = ops.gemv_decode(x, w, epi=epi, res=res, norm_w=nw, sumsq_in=sq, want_sumsq=epi == 1)
+    acc = xin.float() @ w.float().t()
+    if epi == 2:
+        a3 = acc.reshape(M, N // 64, 2, 32)
+        ref = (F.silu(r(a3[:, :, 0]).to(bf).float()).to(bf).float() * r(a3[:, :, 1])).reshape(M, N // 2)
+    elif epi == 1:
+        ref = r(acc) + res.float()
+    else:
+        ref = acc
+    scale = max(1.0, ref.abs().max().item())
+    assert (out.float() - ref).abs().max().item() <= 2e-2 * scale
+    if epi == 1:
+        assert torch.allclose(osq.sum(0)[:M], out.float().pow(2).sum(-1), rtol=1e-4)
 
 
 def test_layernorm_rmsnorm():
@@ -446,3 +476,30 @@ def test_assemble_replay_batched_bit_exact(nreq, ncw, nch, n_masks):
         one, st1 = ops.assemble_embeds(ids_dev[i], table, feats[i], list(spec.crop_tokens_ids), rois[i], has[i], scale,
                                        ncw, nch, tpt, spec.image_token_id)
         assert torch.equal(one, out[i]) and int(st1[0]) == 0
+
+
+@pytest.mark.parametrize("h,w,max_tiles", [(1024, 1024, 16), (600, 900, 6), (300, 520, 8), (448, 448, 4), (2000, 700, 16)])
+def test_device_preprocessing_is_bit_identical_to_the_host_builder(h, w, max_tiles):
+    """SURVEY §8f N1 device half: uint8 image + uint8 id map -> bf16 tiles on the GPU (ATen's uint8 antialiased bicubic
+    passes, `_split`, rescale + normalise; NEAREST id-map tiling) equal the host builder's tensors -- which come from the
+    same torchvision call the reference's image processor makes -- bit for bit."""
+    import numpy as np
+
+    from grasp_any_region_b200 import preprocess as pp
+    from grasp_any_region_b200.config import gar_tiny
+    from grasp_any_region_b200.preprocess_device import DevicePreprocessor
+
+    spec = gar_tiny()
+    rng = np.random.default_rng(h + w)
+    img = torch.from_numpy(rng.integers(0, 256, size=(3, h, w), dtype=np.uint8))
+    m0 = np.zeros((h, w), bool); m0[h // 10: h // 2, w // 8: w // 2] = True
+    m1 = np.zeros((h, w), bool); m1[h // 3: h - 5, w // 3: w - 7] = True
+    idmap = torch.from_numpy(pp.paint_id_map([m0, m1], spec.prompt_numbers))
+    want_px, (ncw, nch) = pp.tile_image(img, spec.vision.img_size, max_tiles)
+    want_mv = pp.tile_id_map(idmap, ncw, nch, spec.vision.img_size)
+    pre = DevicePreprocessor(spec, DEV)
+    px, mv, grid = pre(img.to(DEV), idmap.to(DEV), max_tiles)
+    torch.cuda.synchronize()
+    assert grid == (ncw, nch) and px.dtype == bf and px.shape == want_px.shape and mv.shape == want_mv.shape
+    assert torch.equal(px.cpu(), want_px.to(bf)), "pixel tiles differ from the host (torchvision) path"
+    assert torch.equal(mv.cpu(), want_mv.to(bf)), "id-map tiles differ from the host path"

@@ -127,3 +127,43 @@ def test_multi_region_quirks_match_reference(case):
     starts = [int((ids == spec.crop_tokens_ids[k]).nonzero().min()) for k in case["order"]]
     assert starts == sorted(starts)                                     # crop runs listed in the reference's order
     assert {k: list(map(float, v)) for k, v in req["bboxes"][0].items()} == case["bboxes"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# N1 device half, host tables: the int16 antialias weight tables the GPU resize passes consume reproduce torchvision's
+# uint8 bicubic resize bit for bit when applied with plain integer arithmetic (horizontal pass first)
+# ---------------------------------------------------------------------------------------------------------------
+def _resize_with_tables(img_chw, oh, ow):
+    from grasp_any_region_b200.preprocess_device import aa_tables
+
+    def one_axis(a, out_size, axis):
+        if a.shape[axis] == out_size:
+            return a
+        lo, size, w, prec = aa_tables(a.shape[axis], out_size)
+        a = np.moveaxis(a, axis, -1).astype(np.int64)
+        out = np.zeros(a.shape[:-1] + (out_size,), np.int64)
+        for i in range(out_size):
+            out[..., i] = (1 << (prec - 1)) + (a[..., lo[i]:lo[i] + size[i]] * w[i, :size[i]].astype(np.int64)).sum(-1)
+        return np.moveaxis(np.clip(out >> prec, 0, 255).astype(np.uint8), -1, axis)
+
+    return one_axis(one_axis(img_chw, ow, 2), oh, 1)
+
+
+@pytest.mark.parametrize("h,w,oh,ow", [(100, 130, 56, 56), (64, 64, 112, 168), (300, 200, 448, 448), (1024, 1024, 448, 448),
+                                       (200, 333, 224, 112), (77, 500, 448, 896), (448, 300, 448, 448), (61, 61, 61, 61)])
+def test_aa_tables_reproduce_torchvision_uint8_bicubic(h, w, oh, ow):
+    from torchvision.transforms import InterpolationMode
+    from torchvision.transforms.v2 import functional as F
+
+    g = torch.Generator().manual_seed(h * 31 + w)
+    img = torch.randint(0, 256, (3, h, w), generator=g, dtype=torch.uint8)
+    want = F.resize(img[None], (oh, ow), interpolation=InterpolationMode.BICUBIC)[0].numpy()
+    assert np.array_equal(_resize_with_tables(img.numpy(), oh, ow), want)
+
+
+def test_nearest_table_is_the_host_builders_expression():
+    from grasp_any_region_b200.preprocess_device import nearest_table
+
+    for n_in, n_out in ((1024, 448), (600, 1792), (333, 448), (448, 448), (5, 448)):
+        a = torch.arange(n_in * 3).reshape(n_in, 3)
+        assert torch.equal(pp._nearest(a, n_out, 3)[:, 0] // 3, nearest_table(n_in, n_out).long())
