@@ -438,13 +438,17 @@ def main():
         gather=False for the rank-0-only diagnostic passes: a collective there would wait for ranks that never come."""
         if args.pipeline:
             toks = model.generate_batches([batch_list] * steps, max_new_tokens=NT, eos_token_id=None)
+            if world > 1 and gather:  # the path's one collective: all-gather of the decoded ids (north_star)
+                from grasp_any_region_b200.parallel import gather_tokens, pack_tokens
+
+                for step_toks in toks:
+                    gather_tokens(pack_tokens(step_toks, B, NT, dev), world * B)
+        elif world > 1 and gather:
+            # public sharded API: this rank's shard in, every rank's captions out (one NCCL all-gather per step)
+            toks = [model.generate_sharded(batch_list, max_new_tokens=NT, eos_token_id=None, already_sharded=True)
+                    for _ in range(steps)]
         else:
             toks = [model.generate_batch(batch_list, max_new_tokens=NT, eos_token_id=None) for _ in range(steps)]
-        if world > 1 and gather:  # the path's one collective: all-gather of the decoded ids (north_star)
-            flat = [t + [-1] * (NT - len(t)) for step_toks in toks for t in step_toks]
-            t = torch.tensor(flat, dtype=torch.int32, device=dev)
-            buf = torch.empty((world * t.shape[0], NT), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(buf, t)
         return toks
 
     def step_resident(steps=1):

@@ -26,6 +26,9 @@ def parse_args():
     p.add_argument("--synthetic", default=None, choices=sorted(presets.PRESETS))
     p.add_argument("--num_masks", type=int, default=3, help="--synthetic only")
     p.add_argument("--max_new_tokens", type=int, default=1024)
+    p.add_argument("--max_num_tiles", type=int, default=36, help="tile budget of the image processor (PLM default 36)")
+    p.add_argument("--no_reference_quirks", action="store_true",
+                   help="give every region its own box (the reference's builder gives all regions the LAST mask's box)")
     return p.parse_args()
 
 
@@ -49,22 +52,20 @@ def main():
         decode = lambda ids: " ".join(str(int(t)) for t in ids)  # noqa: E731
     else:
         from PIL import Image
-        from transformers import AutoProcessor
+        from transformers import AutoTokenizer
 
-        from evaluation.eval_dataset import MultiRegionDataset  # the reference's request builder
+        from grasp_any_region_b200.request import multi_region_request  # == MultiRegionDataset(...)[0], quirks included
 
-        model = GARModel.from_pretrained(args.model_name_or_path, torch_dtype=torch.bfloat16).to("cuda:0").eval()
-        processor = AutoProcessor.from_pretrained(args.model_name_or_path, trust_remote_code=True)
-        img = Image.open(args.image_path)
+        model = GARModel.from_pretrained(args.model_name_or_path, torch_dtype=torch.bfloat16,
+                                         device_map="cuda:0").eval()
+        tokenizer = AutoTokenizer.from_pretrained(args.model_name_or_path)
+        img = np.array(Image.open(args.image_path).convert("RGB"))
         masks = [np.array(Image.open(m).convert("L")).astype(bool) for m in ast.literal_eval(args.mask_paths)]
-        n = model.config.prompt_numbers
-        prompt_tokens = [f"<Prompt{i}>" for i in range(n)] + ["<NO_Prompt>"]
         question = args.question_str + "\nAnswer with the correct option's letter directly."
-        sample = MultiRegionDataset(image=img, masks=masks, question_str=question, processor=processor,
-                                    prompt_number=n, visual_prompt_tokens=prompt_tokens,
-                                    data_dtype=torch.bfloat16)[0]
-        eos, pad = processor.tokenizer.eos_token_id, processor.tokenizer.pad_token_id
-        decode = lambda ids: processor.tokenizer.decode(ids, skip_special_tokens=True).strip()  # noqa: E731
+        sample = multi_region_request(model.spec, tokenizer, img, masks, question, max_num_tiles=args.max_num_tiles,
+                                      device="cuda:0", reference_quirks=not args.no_reference_quirks)
+        eos, pad = tokenizer.eos_token_id, tokenizer.pad_token_id
+        decode = lambda ids: tokenizer.decode(ids, skip_special_tokens=True).strip()  # noqa: E731
 
     with torch.no_grad():
         out = model.generate(**sample, generation_config=GenerationConfig(

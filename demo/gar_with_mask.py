@@ -30,6 +30,7 @@ def parse_args():
     p.add_argument("--synthetic", default=None, choices=sorted(presets.PRESETS),
                    help="no checkpoint: random-init weights of this architecture + a synthetic request")
     p.add_argument("--max_new_tokens", type=int, default=1024)
+    p.add_argument("--max_num_tiles", type=int, default=36, help="tile budget of the image processor (PLM default 36)")
     return p.parse_args()
 
 
@@ -65,26 +66,29 @@ def main():
         decode = lambda ids: " ".join(str(int(t)) for t in ids)  # noqa: E731  (no tokenizer offline)
     else:
         from PIL import Image
-        from transformers import AutoProcessor
+        from transformers import AutoTokenizer
 
-        from evaluation.eval_dataset import SingleRegionCaptionDataset  # the reference's request builder
+        from grasp_any_region_b200.request import single_region_request  # == SingleRegionCaptionDataset(...)[0]
 
-        model = GARModel.from_pretrained(args.model_name_or_path, torch_dtype=torch.bfloat16).to("cuda:0").eval()
-        processor = AutoProcessor.from_pretrained(args.model_name_or_path, trust_remote_code=True)
-        img = Image.open(args.image_path)
+        model = GARModel.from_pretrained(args.model_name_or_path, torch_dtype=torch.bfloat16,
+                                         device_map="cuda:0").eval()
+        tokenizer = AutoTokenizer.from_pretrained(args.model_name_or_path)
+        img = np.array(Image.open(args.image_path).convert("RGB"))
         mask = np.array(Image.open(args.mask_path).convert("L")).astype(bool)
-        n = model.config.prompt_numbers
-        prompt_tokens = [f"<Prompt{i}>" for i in range(n)] + ["<NO_Prompt>"]
-        sample = SingleRegionCaptionDataset(image=img, mask=mask, processor=processor, prompt_number=n,
-                                            visual_prompt_tokens=prompt_tokens, data_dtype=torch.bfloat16)[0]
-        eos, pad = processor.tokenizer.eos_token_id, processor.tokenizer.pad_token_id
-        decode = lambda ids: processor.tokenizer.decode(ids, skip_special_tokens=True).strip()  # noqa: E731
+        # raw=True: the uint8 image and id map go to the GPU, resize / tiling / normalisation run there
+        sample = single_region_request(model.spec, tokenizer, img, mask, prompt_token="<Prompt0>",
+                                       max_num_tiles=args.max_num_tiles, raw=True)
+        eos, pad = tokenizer.eos_token_id, tokenizer.pad_token_id
+        decode = lambda ids: tokenizer.decode(ids, skip_special_tokens=True).strip()  # noqa: E731
 
+    gen = GenerationConfig(max_new_tokens=args.max_new_tokens, do_sample=False, eos_token_id=eos, pad_token_id=pad)
     with torch.no_grad():
-        out = model.generate(**sample, generation_config=GenerationConfig(
-            max_new_tokens=args.max_new_tokens, do_sample=False, eos_token_id=eos, pad_token_id=pad),
-            return_dict=True)
-    print(decode(out.sequences[0]))
+        if "image_u8" in sample:   # device-preprocessing request (B200 extension of the same call)
+            model.configure_engine(max_new_tokens=args.max_new_tokens)
+            ids = model.generate_batch([sample], max_new_tokens=args.max_new_tokens, eos_token_id=eos)[0]
+        else:
+            ids = model.generate(**sample, generation_config=gen, return_dict=True).sequences[0]
+    print(decode(ids))
 
 
 if __name__ == "__main__":

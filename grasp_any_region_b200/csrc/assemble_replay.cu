@@ -23,6 +23,7 @@ namespace {
 constexpr int MAX_REGIONS = 8;
 constexpr int KIND_TEXT = 0, KIND_IMAGE = 1, KIND_CROP = 2;
 
+constexpr int REPLAY_PARTS = 4;  // warps per RoI replay row
 constexpr int MAX_REQS = 8;  // requests per launch (kernel-parameter space); larger batches are chunked
 
 struct RequestParams {
@@ -247,7 +248,10 @@ replay_rows_kernel(const int* __restrict__ region_start, const bf16* __restrict_
   const int wpb = blockDim.x >> 5;
   const int nvec = D / 8;
   {
-    const int off = blockIdx.x * wpb + (threadIdx.x >> 5);
+    // a crop row is shared by REPLAY_PARTS warps (each takes every REPLAY_PARTS-th 16-byte vector column): four times
+    // the warps, a quarter of the dependent L2 round trips per warp -- the grid is latency-bound, not bandwidth-bound
+    const int wid = blockIdx.x * wpb + (threadIdx.x >> 5);
+    const int off = wid / REPLAY_PARTS, part = wid % REPLAY_PARTS;
     const int start = region_start[req * MAX_REGIONS + k];
     if (off >= p.tpt * p.tpt || start < 0 || start + off >= S) return;  // never outside this request's rows
     const long long g = static_cast<long long>(req) * S + start + off;
@@ -287,7 +291,7 @@ replay_rows_kernel(const int* __restrict__ region_start, const bf16* __restrict_
         cell[q * 4 + c] = reinterpret_cast<const uint4*>(feats + row * D);
       }
     }
-    for (int v = lane; v < nvec; v += 32) {
+    for (int v = lane + 32 * part; v < nvec; v += 32 * REPLAY_PARTS) {
       // all 16 cell vectors of this output vector go out together (addresses of invalid samples are clamped, hence
       // loadable; their values are never used) -- one L2 round trip per output vector instead of four
       uint4 raws[16];
@@ -402,7 +406,7 @@ extern "C" int gar_assemble_rows_batch(int nreq, const long long* const* input_i
     const int* region_start = plan_ws + static_cast<size_t>(nreq) * S + r0 * MAX_REGIONS;
     const bool replay = n_regions > 0;
     if (replay) {
-      replay_rows_kernel<<<dim3((tpt * tpt + 7) / 8, n_regions, nr), 256, 0, stream>>>(region_start, feats, o, S, D,
+      replay_rows_kernel<<<dim3((tpt * tpt * REPLAY_PARTS + 7) / 8, n_regions, nr), 256, 0, stream>>>(region_start, feats, o, S, D,
                                                                                        n_image_rows, p);
       GAR_CUDA_CHECK(cudaGetLastError());
     }

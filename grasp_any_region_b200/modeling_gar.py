@@ -335,6 +335,29 @@ class GARModel(_Base):
         return eng.generate(len(requests), int(max_new_tokens), eos_token_id)
 
     @torch.no_grad()
+    def generate_sharded(self, requests: List[dict], max_new_tokens: int = 128, eos_token_id=None,
+                         already_sharded: bool = False) -> List[List[int]]:
+        """Data-parallel serving over the process group (one process per GPU, a full replica each): every
+        rank passes the SAME global request list and decodes its contiguous shard -- or, with already_sharded=True, each
+        rank passes only its own shard (equal sizes) -- and the path's single collective, an all-gather of the fixed-shape
+        token buffer (NCCL over NVLink), returns every caption's ids in global request order on every rank.  Without an
+        initialised process group this is generate_batch."""
+        import torch.distributed as dist
+
+        from .parallel import gather_tokens, pack_tokens, shard_range
+
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        n_global = len(requests) * world if already_sharded else len(requests)
+        lo, hi = (0, len(requests)) if already_sharded else shard_range(n_global, rank, world)
+        eng = self.engine()
+        local: List[List[int]] = []
+        for i in range(lo, hi, eng.max_batch):
+            local += self.generate_batch(requests[i:min(hi, i + eng.max_batch)], max_new_tokens, eos_token_id)
+        rows = (n_global + world - 1) // world
+        return gather_tokens(pack_tokens(local, rows, int(max_new_tokens), eng.device), n_global)
+
+    @torch.no_grad()
     def generate_batches(self, batches: List[List[dict]], max_new_tokens: int = 128,
                          eos_token_id=None) -> List[List[List[int]]]:
         """Throughput serving of a stream of request batches (B200 scheduler extension).
