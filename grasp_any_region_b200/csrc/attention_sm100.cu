@@ -29,10 +29,9 @@ constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: 128 rows of 128 B (one 64-wi
 constexpr uint32_t TM_S = 0;
 
 // Tile configurations (BKV = keys per block):
-//   HD 64,  BKV 64 : 56 KB smem, 128 TMEM columns, three CTAs per SM -- the softmax is MUFU.EX2-bound, and a third
-//                    co-resident CTA keeps that pipe busy while the others wait on MMAs / barriers
-//   HD 64,  BKV 128: 96 KB smem, 256 TMEM columns, two CTAs per SM
-//   HD 128, BKV 128: 160 KB smem, one CTA per SM (GAR-8B Llama; PE-G's 96-wide heads are zero-padded to 128)
+//   HD 64,  BKV 64 : 64 KB smem, 128 TMEM columns, three CTAs per SM
+//   HD 64,  BKV 128: 112 KB smem, 256 TMEM columns, two CTAs per SM
+//   HD 128, BKV 128: 192 KB smem, one CTA per SM (GAR-8B Llama; PE-G's 96-wide heads are zero-padded to 128)
 template <int HD, int BKV>
 struct AttCfg {
   static constexpr int NSUB = HD / 64;
@@ -41,10 +40,12 @@ struct AttCfg {
   static constexpr int KV_BYTES = NSUB * KV_TILE;
   static constexpr int SMEM_Q = 0;
   static constexpr int SMEM_K = Q_BYTES;                      // 2 stages
-  static constexpr int SMEM_V = SMEM_K + 2 * KV_BYTES;        // 1 stage
-  static constexpr int SMEM_P = SMEM_V + KV_BYTES;            // BKV/64 sub-tiles [128 x 64]
+  static constexpr int SMEM_V = SMEM_K + 2 * KV_BYTES;        // 2 stages: the load of V(j+1) no longer waits for PV(j)
+  static constexpr int SMEM_P = SMEM_V + 2 * KV_BYTES;        // BKV/64 sub-tiles [128 x 64]
   static constexpr int SMEM_TOTAL = SMEM_P + (BKV / 64) * TILE_BYTES;
-  static constexpr int SMEM_BYTES = SMEM_TOTAL + 1024;
+  // no alignment slack: the dynamic segment is declared 1024-byte aligned (checked at run time), so two CTAs of the
+  // HD 64 / BKV 128 configuration (112 KB each) still fit the SM's 228 KB
+  static constexpr int SMEM_BYTES = SMEM_TOTAL;
   static constexpr int CTAS_PER_SM = HD == 64 ? (BKV == 64 ? 3 : 2) : 1;
   // 64K regs / (256 thr * CTAs), multiple of 8; control warpgroup keeps REG_CTRL, the softmax warpgroup gets the rest
   static constexpr int MAXREG = CTAS_PER_SM == 3 ? 80 : (CTAS_PER_SM == 2 ? 128 : 255);
@@ -89,6 +90,87 @@ __device__ __forceinline__ float row_max_n(const uint32_t (&s)[NCOLS], int kv0, 
   return fmaxf(fmax3(mx[0], mx[1], mx[2]), fmax3(fmax3(mx[3], mx[4], mx[5]), mx[6], mx[7]));
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2: two elements per FMA-pipe issue slot) and exp2 on the FMA pipe ----
+// The timeline of the row-per-thread softmax (tools/prof_kernels.py attn_timeline) puts ~60 % of a KV block into the
+// exp phase, and that phase is MUFU.EX2-bound: 16 lanes/clk/SM against 16 384 exponentials per 128 x 128 block.  A share
+// of the exponentials (POLY pairs out of every 8 column pairs) is therefore evaluated on the FMA pipe instead:
+// 2^x = 2^n * p(f), n = round(x) by the magic-number add, f = x - n in [-0.5, 0.5], p a degree-3 minimax polynomial
+// (max relative error 7.5e-5, far below the bf16 rounding P gets anyway), 2^n applied as an integer add on the exponent.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 exp2_poly2(f32x2 x2) {
+  float x0, x1;
+  upk2(x2, x0, x1);
+  x2 = pk2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));  // keep 2^n a normal number
+  const f32x2 j = add2(x2, pk2(12582912.0f, 12582912.0f));         // 1.5 * 2^23: the low mantissa bits now hold round(x)
+  const f32x2 n = add2(j, pk2(-12582912.0f, -12582912.0f));
+  const f32x2 f = fma2(n, pk2(-1.0f, -1.0f), x2);
+  f32x2 pl = fma2(pk2(0.0551716685f, 0.0551716685f), f, pk2(0.2426111251f, 0.2426111251f));
+  pl = fma2(pl, f, pk2(0.6932609677f, 0.6932609677f));
+  pl = fma2(pl, f, pk2(0.9999280572f, 0.9999280572f));
+  float j0, j1, p0, p1;
+  upk2(j, j0, j1);
+  upk2(pl, p0, p1);
+  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(j0) << 23));
+  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(j1) << 23));
+  return pk2(p0, p1);
+}
+
+// which of every 8 column pairs take the polynomial: POLY = 0 none (all MUFU), 1 -> 2/8, 2 -> 3/8, 3 -> 4/8
+__host__ __device__ constexpr uint32_t poly_mask(int poly) { return poly == 0 ? 0x00u : (poly == 1 ? 0x11u : (poly == 2 ? 0x49u : 0x55u)); }
+
+// unmasked block: P = exp2(S * scale - m) -> bf16 -> swizzled smem; returns the row sum of the fp32 P values
+template <int NCOLS, int POLY>
+__device__ __forceinline__ float exp_pack_store_fast(const uint32_t (&s)[NCOLS], float scale_log2, float neg_m,
+                                                     uint32_t rbase, uint32_t sw) {
+  const f32x2 sc2 = pk2(scale_log2, scale_log2), nm2 = pk2(neg_m, neg_m);
+  f32x2 rs2[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+  for (int c = 0; c < NCOLS / 8; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const f32x2 x2 = fma2(pk2(__uint_as_float(s[c * 8 + 2 * i]), __uint_as_float(s[c * 8 + 2 * i + 1])), sc2, nm2);
+      f32x2 p2;
+      if ((poly_mask(POLY) >> ((c * 4 + i) & 7)) & 1u) {
+        p2 = exp2_poly2(x2);
+      } else {
+        float x0, x1;
+        upk2(x2, x0, x1);
+        p2 = pk2(ex2_approx(x0), ex2_approx(x1));
+      }
+      rs2[i] = add2(rs2[i], p2);
+      float p0, p1;
+      upk2(p2, p0, p1);
+      w[i] = pack_bf16x2(p0, p1);
+    }
+    const uint32_t addr = rbase + (c >> 3) * TILE_BYTES + (((c & 7) ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                 : "memory");
+  }
+  float a0, a1, b0, b1, c0, c1, d0, d1;
+  upk2(rs2[0], a0, a1);
+  upk2(rs2[1], b0, b1);
+  upk2(rs2[2], c0, c1);
+  upk2(rs2[3], d0, d1);
+  return ((a0 + a1) + (b0 + b1)) + ((c0 + c1) + (d0 + d1));
+}
+
 template <bool MASKED, int NCOLS>
 __device__ __forceinline__ float exp_pack_store_n(const uint32_t (&s)[NCOLS], int kv0, int lim, float scale_log2,
                                                   float neg_m, uint32_t rbase, uint32_t sw) {
@@ -114,7 +196,7 @@ __device__ __forceinline__ float exp_pack_store_n(const uint32_t (&s)[NCOLS], in
   return (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
 }
 
-template <int HD, int BKV>
+template <int HD, int BKV, int POLY>
 __global__ void __launch_bounds__(ATT_THREADS) __maxnreg__((AttCfg<HD, BKV>::MAXREG))
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
@@ -123,14 +205,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   constexpr int NSUB = Cfg::NSUB, SMEM_Q = Cfg::SMEM_Q, SMEM_K = Cfg::SMEM_K, SMEM_V = Cfg::SMEM_V, SMEM_P = Cfg::SMEM_P;
   constexpr int Q_BYTES = Cfg::Q_BYTES, KV_BYTES = Cfg::KV_BYTES, KV_TILE = Cfg::KV_TILE;
   constexpr uint32_t TM_O = Cfg::TM_O;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[12];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[14];
   __shared__ uint32_t tmem_ptr_sh;
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sbase = smem_u32(smem_raw);
+  if (sbase & 1023u) __trap();  // the 128B-swizzled tiles need the 1024-byte alignment the declaration asks for
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t B_QFULL = bar0, B_KFULL0 = bar0 + 8, B_KEMPTY0 = bar0 + 24, B_VFULL = bar0 + 40,
-                 B_VEMPTY = bar0 + 48, B_SFULL = bar0 + 56, B_PFULL = bar0 + 64, B_PVDONE = bar0 + 72,
-                 B_SCONS = bar0 + 80;
+  const uint32_t B_QFULL = bar0, B_KFULL0 = bar0 + 8, B_KEMPTY0 = bar0 + 24, B_VFULL0 = bar0 + 40,
+                 B_VEMPTY0 = bar0 + 56, B_SFULL = bar0 + 72, B_PFULL = bar0 + 80, B_PVDONE = bar0 + 88,
+                 B_SCONS = bar0 + 96;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_qb = (p.q_len + BQ - 1) / BQ;
@@ -149,8 +232,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_init(B_KFULL0 + 8, 1);
     mbar_init(B_KEMPTY0, 1);
     mbar_init(B_KEMPTY0 + 8, 1);
-    mbar_init(B_VFULL, 1);
-    mbar_init(B_VEMPTY, 1);
+    mbar_init(B_VFULL0, 1);
+    mbar_init(B_VFULL0 + 8, 1);
+    mbar_init(B_VEMPTY0, 1);
+    mbar_init(B_VEMPTY0 + 8, 1);
     mbar_init(B_SFULL, 1);
     mbar_init(B_PFULL, 128);
     mbar_init(B_PVDONE, 1);
@@ -187,12 +272,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int u = 0; u < NSUB; ++u)
           tma_load_3d(sbase + SMEM_K + st * KV_BYTES + u * KV_TILE, &tmap_k, p.k_col0 + kvh * p.kv_head_cols + 64 * u,
                       j * BKV, kb_coord, B_KFULL0 + 8 * st);
-        mbar_wait(B_VEMPTY, (j & 1) ^ 1u);
-        mbar_expect_tx(B_VFULL, KV_BYTES);
+        mbar_wait(B_VEMPTY0 + 8 * st, ((j >> 1) & 1) ^ 1u);
+        mbar_expect_tx(B_VFULL0 + 8 * st, KV_BYTES);
 #pragma unroll
         for (int u = 0; u < NSUB; ++u)
-          tma_load_3d(sbase + SMEM_V + u * KV_TILE, &tmap_v, p.v_col0 + kvh * p.kv_head_cols + 64 * u, j * BKV, kb_coord,
-                      B_VFULL);
+          tma_load_3d(sbase + SMEM_V + st * KV_BYTES + u * KV_TILE, &tmap_v, p.v_col0 + kvh * p.kv_head_cols + 64 * u,
+                      j * BKV, kb_coord, B_VFULL0 + 8 * st);
       }
     }
   } else if (warp == 1) {
@@ -216,18 +301,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       };
       // Pipeline per KV block j:   S(j) -> [softmax loads S(j) into registers] -> S(j+1) issued at once
       // (overlaps the softmax math of block j) -> P(j) ready -> O += P(j) V(j).
+      const bool tlm = p.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 3 && blockIdx.z == 2;
+#define TLM_STAMP(i) if (tlm) p.timeline[512 + j * 8 + (i)] = clock64()
       issue_s(0);
       for (int j = 0; j < num_kvb; ++j) {
+        TLM_STAMP(0);
         if (j + 1 < num_kvb) {
           mbar_wait(B_SCONS, j & 1);  // every softmax thread holds S(j) in registers: TMEM S is free
+          TLM_STAMP(1);
           issue_s(j + 1);
         }
+        TLM_STAMP(2);
         mbar_wait(B_PFULL, j & 1);  // P(j) in smem, O rescaled
-        mbar_wait(B_VFULL, j & 1);
+        TLM_STAMP(3);
+        mbar_wait(B_VFULL0 + 8 * (j & 1), (j >> 1) & 1);
+        TLM_STAMP(4);
         tc_fence_after();
         // V tile: NSUB sub-tiles [kv rows][64 hd] of 128B rows => MN-major B operand (N = HD): LBO = stride
         // between 64-wide N blocks (one sub-tile), SBO = 8 kv rows; 16 kv rows per MMA = 2048 B
-        const uint64_t vdesc = umma_desc_sw128(sbase + SMEM_V, KV_TILE, 1024);
+        const uint64_t vdesc = umma_desc_sw128(sbase + SMEM_V + (j & 1) * KV_BYTES, KV_TILE, 1024);
         const int nk = (BKV > 32 && kv_end - j * BKV <= 32) ? 2 : BKV / 16;  // short tail: 32 keys of P/V only
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
@@ -236,8 +328,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             umma_bf16_ss(tmem + TM_O, pdesc, vdesc + 128u * k, idesc_o, (j | k) != 0);
           }
         }
-        umma_commit(B_VEMPTY);
+        umma_commit(B_VEMPTY0 + 8 * (j & 1));
         umma_commit(B_PVDONE);
+        TLM_STAMP(5);
       }
     }
   }
@@ -249,12 +342,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const int q_pos = q0 + row + shift;  // last key this row may see (causal)
     float m_run = -INFINITY, l_run = 0.f;
-#ifdef GAR_ATTN_TIMELINE  // debug build only: per-phase clock64 stamps of CTA (0,0,0), first softmax thread
-    const bool tl = p.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+    // debug: per-phase clock64 stamps of one mid-grid CTA's first softmax thread (p.timeline is NULL in production)
+    const bool tl = p.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 3 && blockIdx.z == 2 && threadIdx.x == 128;
 #define TL_STAMP(i) if (tl) p.timeline[j * 8 + (i)] = clock64()
-#else
-#define TL_STAMP(i)
-#endif
     // Tails cost what they hold, not a full tile: a softmax warp whose 32 query rows all lie past q_len only keeps the
     // barrier protocol in step (the ViT's 1025-token tiles leave a 1-row last query block), and a last KV block with
     // <= 32 live keys is handled on 32 score columns (and 2 of the BKV/16 PV MMAs) instead of BKV.
@@ -317,7 +407,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // P = exp2(S*scale - m) -> bf16 -> smem, canonical K-major 128B-swizzled layout:
         // row r, 16B chunk c at r*128 + ((c ^ (r&7))<<4); two [128 x 64] sub-tiles
         const float rs = need_mask ? exp_pack_store_n<true, NC>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7)
-                                   : exp_pack_store_n<false, NC>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7);
+                                   : exp_pack_store_fast<NC, POLY>(s, p.scale_log2, -m_use, p_rbase, row & 7);
         l_run = l_run * alpha + rs;
         m_run = m_new;
       };
@@ -388,7 +478,7 @@ extern "C" int gar_attn_debug_timeline(void* dev_buf) {
 
 // Generic strided description (all in bf16 elements):
 //   Q/O: [batch][q_len rows][row width], K/V: [kv_batches][kv rows][row width]
-template <int HD, int BKV>
+template <int HD, int BKV, int POLY>
 static int launch_attn(const void* q, long long q_row_stride, long long q_batch_stride, const void* k, const void* v,
                        long long kv_row_stride, long long kv_batch_stride, int kv_batches, void* o,
                        long long o_row_stride, long long o_batch_stride, int batch, int heads, int q_len,
@@ -406,12 +496,12 @@ static int launch_attn(const void* q, long long q_row_stride, long long q_batch_
   using Cfg = AttCfg<HD, BKV>;
   static bool attr_set = false;
   if (!attr_set) {
-    GAR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<HD, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GAR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<HD, BKV, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     attr_set = true;
   }
   dim3 grid((q_len + BQ - 1) / BQ, heads, batch);
-  attn_fwd_kernel<HD, BKV><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  attn_fwd_kernel<HD, BKV, POLY><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
   GAR_CUDA_CHECK(cudaGetLastError());
   return GAR_OK;
 }
@@ -443,13 +533,19 @@ extern "C" int gar_attn_fwd(const void* q, long long q_row_stride, long long q_b
   p.kv_batch_head_mul = kv_batch_head_mul;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.timeline = g_attn_timeline;
-  if (head_dim == 128)
-    return launch_attn<128, 128>(q, q_row_stride, q_batch_stride, k, v, kv_row_stride, kv_batch_stride, kv_batches, o,
-                                 o_row_stride, o_batch_stride, batch, heads, q_len, kv_rows_alloc, p, stream);
-  if (gar_global_option("attn_bkv") == 128)
-    return launch_attn<64, 128>(q, q_row_stride, q_batch_stride, k, v, kv_row_stride, kv_batch_stride, kv_batches, o,
-                                o_row_stride, o_batch_stride, batch, heads, q_len, kv_rows_alloc, p, stream);
-  return launch_attn<64, 64>(q, q_row_stride, q_batch_stride, k, v, kv_row_stride, kv_batch_stride, kv_batches, o,
-                             o_row_stride, o_batch_stride, batch, heads, q_len, kv_rows_alloc, p, stream);
+#define GAR_ATTN_ARGS q, q_row_stride, q_batch_stride, k, v, kv_row_stride, kv_batch_stride, kv_batches, o, o_row_stride, \
+                      o_batch_stride, batch, heads, q_len, kv_rows_alloc, p, stream
+  const int poly = gar_global_option("attn_poly");  // exponentials on the FMA pipe: 0 none (default), 1 2/8, 2 3/8, 3 4/8
+  if (head_dim == 128) return poly == 0 ? launch_attn<128, 128, 0>(GAR_ATTN_ARGS) : launch_attn<128, 128, 2>(GAR_ATTN_ARGS);
+  if (gar_global_option("attn_bkv") == 128) {
+    switch (poly) {
+      case 0: return launch_attn<64, 128, 0>(GAR_ATTN_ARGS);
+      case 1: return launch_attn<64, 128, 1>(GAR_ATTN_ARGS);
+      case 3: return launch_attn<64, 128, 3>(GAR_ATTN_ARGS);
+      default: return launch_attn<64, 128, 2>(GAR_ATTN_ARGS);
+    }
+  }
+  return poly == 0 ? launch_attn<64, 64, 0>(GAR_ATTN_ARGS) : launch_attn<64, 64, 2>(GAR_ATTN_ARGS);
+#undef GAR_ATTN_ARGS
   return GAR_OK;
 }

@@ -26,6 +26,7 @@ extern "C" int gar_copy_d2d(void* dst, const void* src, long long bytes, void* s
 static int g_pdl = 1;
 static int g_decode_attn_mma = 1;
 static int g_gemm_2cta = 1;
+static int g_attn_poly = 0;  // share of the softmax exponentials evaluated on the FMA pipe: 0 none (fastest measured), 1 2/8, 2 3/8, 3 4/8
 static int g_attn_bkv = 128;  // measured: 128 (2 CTAs/SM) beats 64 (3 CTAs/SM) on both ViT and prefill shapes
 int gar_pdl_enabled() { return g_pdl; }
 void gar_set_pdl(int on) { g_pdl = on; }
@@ -33,6 +34,7 @@ int gar_global_option(const char* name) {
   if (!strcmp(name, "decode_attn_mma")) return g_decode_attn_mma;
   if (!strcmp(name, "pdl")) return g_pdl;
   if (!strcmp(name, "attn_bkv")) return g_attn_bkv;
+  if (!strcmp(name, "attn_poly")) return g_attn_poly;
   if (!strcmp(name, "gemm_2cta")) return g_gemm_2cta;
   return 0;
 }
@@ -43,6 +45,7 @@ extern "C" int gar_set_global_option(const char* name, int value) {
   else if (!strcmp(name, "pdl")) g_pdl = value;
   else if (!strcmp(name, "gemm_2cta")) g_gemm_2cta = value;
   else if (!strcmp(name, "attn_bkv") && (value == 64 || value == 128)) g_attn_bkv = value;
+  else if (!strcmp(name, "attn_poly") && value >= 0 && value <= 3) g_attn_poly = value;
   else {
     gar_set_error("gar_set_global_option: unknown option '%s'", name);
     return GAR_ERR_ARG;

@@ -63,22 +63,30 @@ if which in ("all", "gemm"):
 
 if which == "attn_timeline":
     from grasp_any_region_b200 import _lib
-    T, ntok, H, hd = 17, 1025, 16, 64
+    T, ntok, H, hd = 136, 1025, 16, 64
     qkv = torch.randn(T * ntok, 3 * H * hd, device=dev).to(bf)
-    buf = torch.zeros(8 * 16, dtype=torch.int64, device=dev)
+    buf = torch.zeros(1024, dtype=torch.int64, device=dev)
     ops.attn_fwd_packed_qkv(qkv, T, ntok, H, hd); torch.cuda.synchronize()
     _lib.load().gar_attn_debug_timeline(buf.data_ptr())
     ops.attn_fwd_packed_qkv(qkv, T, ntok, H, hd); torch.cuda.synchronize()
     _lib.load().gar_attn_debug_timeline(None)
-    t = buf.view(16, 8).cpu()
-    t0 = int(t[0, 0])
-    print("per KV block (cycles): wait_S | tmem_ld | max | wait_PV | exp+store | fence+arrive | block total")
+    t = buf[:128].view(16, 8).cpu()
+    m = buf[512:640].view(16, 8).cpu()
+    print("softmax thread, per KV block (cycles): wait_S | tmem_ld | max | wait_PV | exp+store | fence+arrive | block total | start-to-start")
     for j in range(9):
         r = [int(x) for x in t[j]]
         nxt = int(t[j + 1, 0]) if j < 8 else r[6]
         wpv = (r[4] - r[3]) if j > 0 else 0
         exp0 = r[4] if j > 0 else r[3]
-        print(f"j={j}: {r[1]-r[0]:6d} | {r[2]-r[1]:6d} | {r[3]-r[2]:6d} | {wpv:6d} | {r[5]-exp0:6d} | {r[6]-r[5]:6d} | {r[6]-r[0]:6d}")
+        print(f"j={j}: {r[1]-r[0]:6d} | {r[2]-r[1]:6d} | {r[3]-r[2]:6d} | {wpv:6d} | {r[5]-exp0:6d} | {r[6]-r[5]:6d} | {r[6]-r[0]:6d} | {nxt-r[0]:6d}")
+    print("MMA thread, per KV block (cycles): wait_SCONS | issue_S(j+1) (incl. wait K) | wait_PFULL | wait_V | issue_PV | iteration")
+    for j in range(9):
+        r = [int(x) for x in m[j]]
+        if j < 8:
+            print(f"j={j}: {r[1]-r[0]:6d} | {r[2]-r[1]:6d} | {r[3]-r[2]:6d} | {r[4]-r[3]:6d} | {r[5]-r[4]:6d} | {r[5]-r[0]:6d}")
+        else:
+            print(f"j={j}:      - |      - | {r[3]-r[2]:6d} | {r[4]-r[3]:6d} | {r[5]-r[4]:6d} | {r[5]-r[0]:6d}")
+    print("softmax first stamp -> last stamp:", int(t[8, 6]) - int(t[0, 0]), "cycles; MMA thread:", int(m[8, 5]) - int(m[0, 0]))
 
 if which == "gemm_big":
     from grasp_any_region_b200 import _lib as _l2
