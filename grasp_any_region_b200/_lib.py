@@ -34,9 +34,6 @@ SIGNATURES = {
     "gar_gemm_bf16_rope2d": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gar_gemv_decode": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _f, _vp,
                              C.POINTER(_i), _vp]),
-    "gar_gemv_decode_pf": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp]),
-    "gar_decode_attn_rope_pf": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp,
-                                     _i, _vp, _vp]),
     "gar_gemv_debug_timeline": (_i, [_vp]),
     "gar_embed_gather_sumsq": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "gar_patchify": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -75,54 +75,6 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
                : "l"(p));
   return v;
 }
-// ---- L2 prefetch duty of the decode-step kernels (gar_prefetch in gar_b200.h) ----
-struct PfArgs {
-  const char* p[2];
-  unsigned long long n[2];
-  const char* kv[2];
-  const int* pos;
-  int pairs, hkv, row_bytes, max_rows;
-  long long pair_stride;
-  int lo[2], hi[2];
-};
-constexpr unsigned PF_CHUNK = 4096;
-__device__ __forceinline__ void l2_prefetch(const char* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-// plain ranges: independent of every earlier kernel, may be issued before the dependency wait
-__device__ __forceinline__ void pf_issue_plain(const PfArgs& a, unsigned tid, unsigned nthr) {
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    if (a.p[r] == nullptr) continue;
-    const unsigned long long chunks = (a.n[r] + PF_CHUNK - 1) / PF_CHUNK;
-    for (unsigned long long c = tid; c < chunks; c += nthr) {
-      const unsigned long long off = c * PF_CHUNK;
-      const unsigned long long left = a.n[r] - off;
-      const uint32_t sz = static_cast<uint32_t>(left < PF_CHUNK ? (left & ~15ull) : PF_CHUNK);
-      if (sz) l2_prefetch(a.p[r] + off, sz);
-    }
-  }
-}
-// live KV prefixes: lengths come from the device-side position counters (issue after the dependency wait)
-__device__ __forceinline__ void pf_issue_kv(const PfArgs& a, unsigned tid, unsigned nthr) {
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    if (a.kv[r] == nullptr) continue;
-    const unsigned cpp = (static_cast<unsigned>(a.max_rows) * a.row_bytes + PF_CHUNK - 1) / PF_CHUNK;
-    for (unsigned idx = tid; idx < static_cast<unsigned>(a.pairs) * cpp; idx += nthr) {
-      const unsigned pair = idx / cpp, c = idx % cpp;
-      const long long len = static_cast<long long>(a.pos[pair / a.hkv] + 1) * a.row_bytes;
-      const long long beg = (len * a.lo[r] / 256) & ~static_cast<long long>(PF_CHUNK - 1);
-      const long long end = len * a.hi[r] / 256;
-      const long long off = beg + static_cast<long long>(c) * PF_CHUNK;
-      if (off < end) {
-        const long long left = end - off;
-        l2_prefetch(a.kv[r] + pair * a.pair_stride + off,
-                    static_cast<uint32_t>(left < PF_CHUNK ? ((left + 15) & ~15ll) : PF_CHUNK));
-      }
-    }
-  }
-}
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>

@@ -10,8 +10,6 @@
 #include "../../include/gar_b200.h"
 #include "common.cuh"
 
-void gar_pf_to_args(const gar_prefetch* pf, PfArgs* o);
-
 namespace {
 
 constexpr int DEC_THREADS = 128;
@@ -274,14 +272,9 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, int ldq, bf16* __restrict__
                        const int* __restrict__ pos_dev, const int* __restrict__ slot_dev, int hq, int hkv, int max_seq,
                        int splits, float scale_log2, float* __restrict__ o_part, float* __restrict__ ml_part,
                        int* __restrict__ tickets, bf16* __restrict__ out, int ldo, const bf16* __restrict__ cos_t,
-                       const bf16* __restrict__ sin_t, int has_pf, PfArgs pf) {
+                       const bf16* __restrict__ sin_t) {
   constexpr int HD = 64;
   pdl_launch_dependents();
-  if (has_pf) {  // the following kernels' weight streams go to L2 while this kernel reads the KV cache
-    const unsigned nthr = gridDim.x * gridDim.y * gridDim.z * DEC_THREADS;
-    const unsigned tid = ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * DEC_THREADS + threadIdx.x;
-    pf_issue_plain(pf, tid, nthr);
-  }
   pdl_wait();
   const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   const int len = pos_dev[b] + 1;
@@ -487,12 +480,8 @@ __global__ void decode_attn_combine_kernel(const float* __restrict__ o_part, con
 static int decode_attn_impl(const void* qkv, int ldq, void* kcache, void* vcache, const int* pos_dev,
                             const int* slot_dev, int batch, int hq, int hkv, int head_dim, int max_seq, int splits,
                             float scale, void* o_part_ws, void* ml_part_ws, int* tickets, void* out, int ldo,
-                            const void* cos_t, const void* sin_t, void* stream_, const gar_prefetch* pf_in = nullptr) {
+                            const void* cos_t, const void* sin_t, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  PfArgs pfa;
-  memset(&pfa, 0, sizeof(pfa));
-  const int has_pf = pf_in != nullptr;
-  if (pf_in) gar_pf_to_args(pf_in, &pfa);
   const bool rope = cos_t != nullptr;
   bf16* kc_w = static_cast<bf16*>(kcache);
   bf16* vc_w = static_cast<bf16*>(vcache);
@@ -517,13 +506,13 @@ static int decode_attn_impl(const void* qkv, int ldq, void* kcache, void* vcache
                                 dim3(1, 1, 1), static_cast<const bf16*>(qkv), ldq, kc_w, vc_w, pos_dev, slot_dev, hq,  \
                                 hkv, max_seq, splits, sl2, static_cast<float*>(o_part_ws),                          \
                                 static_cast<float*>(ml_part_ws), tickets, static_cast<bf16*>(out), ldo,             \
-                                static_cast<const bf16*>(cos_t), static_cast<const bf16*>(sin_t), has_pf, pfa));    \
+                                static_cast<const bf16*>(cos_t), static_cast<const bf16*>(sin_t)));                 \
     else                                                                                                            \
       GAR_CUDA_CHECK(gar_launch(decode_attn_mma_kernel<G_, false>, grid, dim3(DEC_THREADS), 0, stream, true,        \
                                 dim3(1, 1, 1), static_cast<const bf16*>(qkv), ldq, kc_w, vc_w, pos_dev, slot_dev, hq,  \
                                 hkv, max_seq, splits, sl2, static_cast<float*>(o_part_ws),                          \
                                 static_cast<float*>(ml_part_ws), tickets, static_cast<bf16*>(out), ldo,             \
-                                static_cast<const bf16*>(nullptr), static_cast<const bf16*>(nullptr), has_pf, pfa)); \
+                                static_cast<const bf16*>(nullptr), static_cast<const bf16*>(nullptr)));             \
   } while (0)
   if (head_dim == 64 && (rope || gar_global_option("decode_attn_mma")) && (group == 4 || group == 2 || group == 1 || group == 8)) {
     if (group == 4) LAUNCH_MMA(4);
@@ -572,14 +561,4 @@ extern "C" int gar_decode_attn_rope(const void* qkv, int ldq, void* kcache, void
   if (!cos_t || !sin_t) return GAR_ERR_ARG;
   return decode_attn_impl(qkv, ldq, kcache, vcache, pos_dev, slot_dev, batch, hq, hkv, head_dim, max_seq, splits, scale,
                           o_part_ws, ml_part_ws, tickets, out, ldo, cos_t, sin_t, stream);
-}
-
-extern "C" int gar_decode_attn_rope_pf(const void* qkv, int ldq, void* kcache, void* vcache, const int* pos_dev,
-                                       const int* slot_dev, int batch, int hq, int hkv, int head_dim, int max_seq,
-                                       int splits, float scale, const void* cos_t, const void* sin_t, void* o_part_ws,
-                                       void* ml_part_ws, int* tickets, void* out, int ldo, const gar_prefetch* pf,
-                                       void* stream) {
-  if (!cos_t || !sin_t) return GAR_ERR_ARG;
-  return decode_attn_impl(qkv, ldq, kcache, vcache, pos_dev, slot_dev, batch, hq, hkv, head_dim, max_seq, splits, scale,
-                          o_part_ws, ml_part_ws, tickets, out, ldo, cos_t, sin_t, stream, pf);
 }

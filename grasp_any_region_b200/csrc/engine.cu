@@ -42,7 +42,6 @@ struct gar_engine {
   int fuse_rope = 1;
   int use_gemv = 1;
   int fuse_decode_rope = 1;
-  int decode_prefetch = 0;  // decode kernels pull the following kernels' weight / KV streams into L2 (gar_prefetch)
   float *sumsq_a, *sumsq_b;
   // decode graph
   std::map<long long, cudaGraphExec_t> graphs;  // decode-step graphs keyed by (slot0, batch)
@@ -227,6 +226,16 @@ int lm_head(gar_engine* e, const bf16* hrows, int ldh, int rows, bf16* logits, b
               GAR_EPI_NONE, nullptr, nullptr, nullptr, 0, s);
 }
 
+// KV splits of the decode attention: one resident wave of ~3 CTAs per SM across (split, kv head, sequence)
+int decode_splits(const gar_engine* e, int batch) {
+  int splits = e->dec_splits;
+  if (splits <= 0) {
+    splits = (3 * gar_num_sms()) / (batch * e->d.llm_kv_heads);
+    splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
+  }
+  return splits;
+}
+
 // Decode step on the latency-first GEMV kernels: RMSNorm, SwiGLU and residual adds live inside them, the
 // RMSNorm statistics travel as per-CTA partial sums of squares (7 launches per layer instead of 11).
 int decode_step_gemv(gar_engine* e, int batch, void* s) {
@@ -240,32 +249,7 @@ int decode_step_gemv(gar_engine* e, int batch, void* s) {
   TRY(gar_embed_gather_sumsq(table, e->next_tok + e->slot_base, e->hdec, e->sumsq_a, batch, D, s));
   e->launches += 1;
   int n_part = 1, rows = 0;
-  // L2 prefetch schedule: every kernel of the step pulls the stream that is needed ~1.5 kernels later, so HBM keeps
-  // streaming while the short dependent kernels are latency-bound (stream order per layer: wqkv, K, V, wo, wgu, wdown)
-  const size_t slot_elems0 = static_cast<size_t>(hkv) * d.max_seq * hd;
-  // decode_prefetch is a bit mask of duties (see the option table in DESIGN.md):
-  //   1 qkv->K(i)  2 qkv->V(i)  4 attn->wo(i)  8 attn->wgu(i)  16 o->first half of wgu(i)  32 o->wdown(i)
-  //   64 gu->wqkv(i+1)  128 down->wqkv(i+1)  256 down->K(i+1)  512 last layer: gu/down -> head of lm_head
-  const int pfm = e->decode_prefetch;
-  auto pf_ptr = [](gar_prefetch& pf) -> const gar_prefetch* {
-    return (pf.ptr[0] || pf.ptr[1] || pf.kv_ptr[0]) ? &pf : nullptr;
-  };
-  auto pf_plain = [&](const void* p0, size_t b0, const void* p1 = nullptr, size_t b1 = 0) {
-    gar_prefetch pf;
-    memset(&pf, 0, sizeof(pf));
-    pf.ptr[0] = p0; pf.bytes[0] = b0; pf.ptr[1] = p1; pf.bytes[1] = b1;
-    return pf;
-  };
-  auto pf_add_kv = [&](gar_prefetch& pf, int layer, bool k, int lo, int hi) {
-    const bf16* base = (k ? e->kcache : e->vcache) + (static_cast<size_t>(layer) * d.max_batch + e->slot_base) * slot_elems0;
-    const int r = pf.kv_ptr[0] ? 1 : 0;
-    pf.kv_ptr[r] = base; pf.kv_lo[r] = lo; pf.kv_hi[r] = hi;
-    pf.pos_dev = e->pos + e->slot_base;
-    pf.kv_pairs = batch * hkv; pf.kv_hkv = hkv; pf.kv_row_bytes = hd * 2; pf.kv_max_rows = d.max_seq;
-    pf.kv_pair_stride_bytes = static_cast<long long>(d.max_seq) * hd * 2;
-  };
-  const size_t b_qkv = static_cast<size_t>(qkv_w) * D * 2, b_o = static_cast<size_t>(D) * hq * hd * 2,
-               b_gu = static_cast<size_t>(2) * I * D * 2, b_down = static_cast<size_t>(D) * I * 2;
+  const int splits = decode_splits(e, batch);
   for (int i = 0; i < d.llm_layers; ++i) {
     NEEDW(ln1, L("llm", i, "ln1"));
     NEEDW(wqkv, L("llm", i, "qkv.w"));
@@ -278,25 +262,15 @@ int decode_step_gemv(gar_engine* e, int batch, void* s) {
     bf16* vc = e->vcache + (static_cast<size_t>(i) * d.max_batch + e->slot_base) * slot_elems;
     {
       ProfScope ps(e, s, PK_GEMV, 2.0 * qkv_w * static_cast<double>(D));
-      gar_prefetch pf = pf_plain(nullptr, 0);
-      if ((pfm & 1) && (i == 0 || !(pfm & 256))) pf_add_kv(pf, i, true, 0, 256);
-      if (pfm & 2) pf_add_kv(pf, i, false, 0, 256);
-      TRY(gar_gemv_decode_pf(e->hdec, D, wqkv, D, e->d_qkv, qkv_w, batch, qkv_w, D, 0, nullptr, 0, ln1, e->sumsq_a,
-                             n_part, d.rms_eps, nullptr, nullptr, pf_ptr(pf), s));
+      TRY(gar_gemv_decode(e->hdec, D, wqkv, D, e->d_qkv, qkv_w, batch, qkv_w, D, 0, nullptr, 0, ln1, e->sumsq_a, n_part,
+                          d.rms_eps, nullptr, nullptr, s));
     }
     {
       ProfScope ps(e, s, PK_DECODE_ATTN, 0.0);
-      int splits = e->dec_splits;
-      if (splits <= 0) {
-        splits = (3 * gar_num_sms()) / (batch * hkv);  // one resident wave of 3 CTAs per SM
-        splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
-      }
       if (e->fuse_decode_rope && hd == 64) {
         // RoPE of q and of the new K row, the KV append and the attention in one launch
-        gar_prefetch pf = pf_plain((pfm & 4) ? wo : nullptr, b_o, (pfm & 8) ? wgu : nullptr, b_gu);
-        TRY(gar_decode_attn_rope_pf(e->d_qkv, qkv_w, kc, vc, e->pos + e->slot_base, nullptr, batch, hq, hkv, hd,
-                                    d.max_seq, splits, scale, cos_t, sin_t, e->o_part, e->ml_part, e->tickets, e->d_att,
-                                    hq * hd, pf_ptr(pf), s));
+        TRY(gar_decode_attn_rope(e->d_qkv, qkv_w, kc, vc, e->pos + e->slot_base, nullptr, batch, hq, hkv, hd, d.max_seq,
+                                 splits, scale, cos_t, sin_t, e->o_part, e->ml_part, e->tickets, e->d_att, hq * hd, s));
         e->launches -= 1;
       } else {
         TRY(gar_llama_rope_kv(e->d_qkv, batch, hq, hkv, hd, cos_t, sin_t, 0, e->pos + e->slot_base, nullptr, -1, kc, vc,
@@ -307,33 +281,18 @@ int decode_step_gemv(gar_engine* e, int batch, void* s) {
     }
     {
       ProfScope ps(e, s, PK_GEMV, 2.0 * D * static_cast<double>(hq * hd));
-      gar_prefetch pf = pf_plain((pfm & 16) && !(pfm & 8) ? wgu : nullptr, b_gu / 2, (pfm & 32) ? wdown : nullptr, b_down);
-      TRY(gar_gemv_decode_pf(e->d_att, hq * hd, wo, hq * hd, e->hdec, D, batch, D, hq * hd, 1, e->hdec, D, nullptr, nullptr,
-                             0, 0.f, e->sumsq_b, &rows, pf_ptr(pf), s));
+      TRY(gar_gemv_decode(e->d_att, hq * hd, wo, hq * hd, e->hdec, D, batch, D, hq * hd, 1, e->hdec, D, nullptr, nullptr, 0,
+                          0.f, e->sumsq_b, &rows, s));
     }
     {
       ProfScope ps(e, s, PK_GEMV, 2.0 * 2.0 * I * D);
-      gar_prefetch pf = pf_plain(nullptr, 0);
-      if (i + 1 < d.llm_layers) {
-        if (pfm & 64) pf = pf_plain(W(e, L("llm", i + 1, "qkv.w")), b_qkv);
-      } else if (pfm & 512) {
-        pf = pf_plain(W(e, "llm.lm_head"), static_cast<size_t>(48) << 20);
-      }
-      TRY(gar_gemv_decode_pf(e->hdec, D, wgu, D, e->d_act, I, batch, 2 * I, D, 2, nullptr, 0, ln2, e->sumsq_b, D / rows,
-                             d.rms_eps, nullptr, nullptr, pf_ptr(pf), s));
+      TRY(gar_gemv_decode(e->hdec, D, wgu, D, e->d_act, I, batch, 2 * I, D, 2, nullptr, 0, ln2, e->sumsq_b, D / rows,
+                          d.rms_eps, nullptr, nullptr, s));
     }
     {
       ProfScope ps(e, s, PK_GEMV, 2.0 * D * static_cast<double>(I));
-      gar_prefetch pf = pf_plain(nullptr, 0);
-      if (i + 1 < d.llm_layers) {
-        if ((pfm & 128) && !(pfm & 64)) pf = pf_plain(W(e, L("llm", i + 1, "qkv.w")), b_qkv);
-        if (pfm & 256) pf_add_kv(pf, i + 1, true, 0, 256);
-      } else if (pfm & 512) {
-        pf = pf_plain(static_cast<const char*>(W(e, "llm.lm_head")) + (static_cast<size_t>(48) << 20),
-                      static_cast<size_t>(48) << 20);
-      }
-      TRY(gar_gemv_decode_pf(e->d_act, I, wdown, I, e->hdec, D, batch, D, I, 1, e->hdec, D, nullptr, nullptr, 0, 0.f,
-                             e->sumsq_a, &rows, pf_ptr(pf), s));
+      TRY(gar_gemv_decode(e->d_act, I, wdown, I, e->hdec, D, batch, D, I, 1, e->hdec, D, nullptr, nullptr, 0, 0.f,
+                          e->sumsq_a, &rows, s));
     }
     n_part = D / rows;
     e->launches += 6;  // qkv, RoPE+KV append, attention (+combine by ticket), o-proj, gate/up, down (fused RoPE: one less)
@@ -342,9 +301,8 @@ int decode_step_gemv(gar_engine* e, int batch, void* s) {
   NEEDW(wl, "llm.lm_head");
   {
     ProfScope ps(e, s, PK_GEMV, 2.0 * d.vocab_padded * static_cast<double>(D));
-    TRY(gar_gemv_decode_pf(e->hdec, D, wl, D, e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded,
-                      batch, d.vocab_padded, D, 0, nullptr, 0, wn, e->sumsq_a, n_part, d.rms_eps, nullptr, nullptr, nullptr,
-                      s));
+    TRY(gar_gemv_decode(e->hdec, D, wl, D, e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded,
+                        batch, d.vocab_padded, D, 0, nullptr, 0, wn, e->sumsq_a, n_part, d.rms_eps, nullptr, nullptr, s));
   }
   TRY(gar_argmax_step_eos(e->logits + static_cast<size_t>(e->slot_base) * d.vocab_padded, d.vocab_padded, d.vocab, batch,
                           e->next_tok + e->slot_base, e->out_tokens + static_cast<size_t>(e->slot_base) * d.max_new_tokens,
@@ -961,10 +919,10 @@ int gar_engine_set_option(gar_engine* e, const char* name, int value) {
   else if (n == "fuse_rope") e->fuse_rope = value;
   else if (n == "gemv_decode") e->use_gemv = value;
   else if (n == "fuse_decode_rope") e->fuse_decode_rope = value;
-  else if (n == "decode_prefetch") e->decode_prefetch = value;
   else if (n == "decode_splits" && value >= 0 && value <= 32) e->dec_splits = value;
   else if (n == "eos_poll_steps" && value >= 0) e->eos_poll_steps = value;
-  else if (n == "pdl" || n == "decode_attn_mma" || n == "attn_bkv" || n == "attn_poly" || n == "gemm_2cta") {
+  else if (n == "pdl" || n == "decode_attn_mma" || n == "attn_bkv" || n == "attn_poly" || n == "gemm_2cta" ||
+           n == "gemv_norm_smem") {
     if (gar_set_global_option(name, value)) return GAR_ERR_ARG;
   }
   else {

@@ -22,6 +22,8 @@
 namespace {
 
 enum { GV_EPI_NONE = 0, GV_EPI_RES = 1, GV_EPI_SWIGLU = 2 };
+constexpr int GV_NW_MAX = 4096;   // RMSNorm weights staged in shared memory up to this K (8 KB); longer rows read them from L2
+constexpr int GV_PART_MAX = 256;  // producer partial sums of squares staged in shared memory up to this many CTAs (8 KB)
 
 struct GvArgs {
   const bf16* W; int ldw;
@@ -31,7 +33,7 @@ struct GvArgs {
   int M, N, K;
   const float* sumsq_in; int n_part; const bf16* norm_w; float eps;  // NORM prologue
   float* sumsq_out;                                                   // EPI_RES: [gridDim.x][8]
-  int has_pf; PfArgs pf;                                              // L2 prefetch duty for the following kernels
+  int stage_norm;                                                     // NORM operands through shared memory
   unsigned long long* timeline;  // optional debug: per-CTA globaltimer stamps [blockIdx.x][8] (NULL in production)
 };
 
@@ -100,15 +102,31 @@ __global__ void __launch_bounds__(GV_WARPS * 32, 16 / GV_WARPS) gemv_decode_kern
         wh[u][r] = ldg_stream(whi[r] + u * 32);
       }
     }
-  // this kernel's own first weight bytes are in flight: now pull the NEXT kernels' streams into L2
-  const unsigned pf_tid = blockIdx.x * GV_THREADS + threadIdx.x, pf_n = gridDim.x * GV_THREADS;
-  if (a.has_pf) pf_issue_plain(a.pf, pf_tid, pf_n);
+  // The RMSNorm weight vector never depends on the previous kernel: it is staged into shared memory by cp.async
+  // BEFORE the dependency wait (no registers held, no round trip left on the critical path after the wait).
+  __shared__ __align__(16) bf16 s_nw[NORM ? GV_NW_MAX : 8];
+  __shared__ __align__(16) float s_ss[NORM ? GV_PART_MAX * 8 : 4];
+  const bool nw_smem = NORM && a.stage_norm && a.K <= GV_NW_MAX;
+  const bool ss_smem = NORM && a.stage_norm && a.n_part <= GV_PART_MAX;
+  if (nw_smem) {
+    for (int i = threadIdx.x; i < a.K / 8; i += GV_THREADS)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_nw + 8 * i)), "l"(a.norm_w + 8 * i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   GV_STAMP(1);
   pdl_wait();
   GV_STAMP(2);
-  if (a.has_pf) pf_issue_kv(a.pf, pf_tid, pf_n);
 
-  // activations of the first chunk go in flight before the RMSNorm statistics are reduced
+  // ONE round trip after the wait: the producer's partial sums of squares (every thread fetches one 16-byte piece
+  // of the [n_part][8] table) leave together with the activations of the first chunk
+  float4 ssv[GV_PART_MAX * 2 / GV_THREADS > 0 ? GV_PART_MAX * 2 / GV_THREADS : 1];
+  if (ss_smem) {
+#pragma unroll
+    for (int i = 0; i < static_cast<int>(sizeof(ssv) / sizeof(ssv[0])); ++i) {
+      const int q = threadIdx.x + i * GV_THREADS;
+      if (q < a.n_part * 2) ssv[i] = *reinterpret_cast<const float4*>(a.sumsq_in + 4 * q);
+    }
+  }
   uint4 xv[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
@@ -118,8 +136,16 @@ __global__ void __launch_bounds__(GV_WARPS * 32, 16 / GV_WARPS) gemv_decode_kern
 
   float rstd = 0.f;
   if (NORM) {
-    // fixed-order sum of the producer's partial sums of squares for batch row g; 16 independent loads in
-    // flight per lane so the whole reduction costs about one L2 round trip
+    if (ss_smem) {
+#pragma unroll
+      for (int i = 0; i < static_cast<int>(sizeof(ssv) / sizeof(ssv[0])); ++i) {
+        const int q = threadIdx.x + i * GV_THREADS;
+        if (q < a.n_part * 2) *reinterpret_cast<float4*>(s_ss + 4 * q) = ssv[i];
+      }
+    }
+    if (nw_smem) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (ss_smem || nw_smem) __syncthreads();
+    // fixed-order sum of the partial sums of squares for batch row g (same order on every path and in every CTA)
     float acc16[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc16[j] = 0.f;
@@ -128,7 +154,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32, 16 / GV_WARPS) gemv_decode_kern
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int p = p0 + 4 * j;
-          if (p < a.n_part) acc16[j] += a.sumsq_in[static_cast<size_t>(p) * 8 + g];
+          if (p < a.n_part) acc16[j] += ss_smem ? s_ss[p * 8 + g] : a.sumsq_in[static_cast<size_t>(p) * 8 + g];
         }
       }
     }
@@ -148,7 +174,8 @@ __global__ void __launch_bounds__(GV_WARPS * 32, 16 / GV_WARPS) gemv_decode_kern
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (s0 + u < steps) {
-          const uint4 nw = __ldg(reinterpret_cast<const uint4*>(a.norm_w + kbeg + 8 * tig + (s0 + u) * 32));
+          const int nwo = kbeg + 8 * tig + (s0 + u) * 32;
+          const uint4 nw = nw_smem ? *reinterpret_cast<const uint4*>(s_nw + nwo) : __ldg(reinterpret_cast<const uint4*>(a.norm_w + nwo));
           uint32_t* xw = reinterpret_cast<uint32_t*>(&xv[u]);
           const uint32_t* ww = reinterpret_cast<const uint32_t*>(&nw);
 #pragma unroll
@@ -273,13 +300,16 @@ int launch_gv(const GvArgs& a, bool norm, cudaStream_t s) {
   dim3 grid(n_out / out_feats);
   // 16 K-slices when K is long and the grid alone cannot fill the machine (R == 1 only: register budget)
   const bool wide = R == 1 && a.K % 512 == 0 && a.K >= 4096 && static_cast<int>(grid.x) < 2 * gar_num_sms();
-  if (wide) {
-    if (norm) GAR_CUDA_CHECK(gar_launch(gemv_decode_kernel<R, EPI, true, 16>, grid, dim3(512), 0, s, true, dim3(1, 1, 1), a));
-    else GAR_CUDA_CHECK(gar_launch(gemv_decode_kernel<R, EPI, false, 16>, grid, dim3(512), 0, s, true, dim3(1, 1, 1), a));
+#define GV_LAUNCH(NORM_, W_) \
+  GAR_CUDA_CHECK(gar_launch(gemv_decode_kernel<R, EPI, NORM_, W_>, grid, dim3(W_ * 32), 0, s, true, dim3(1, 1, 1), a))
+  if constexpr (R == 1) if (wide) {
+    if (norm) GV_LAUNCH(true, 16);
+    else GV_LAUNCH(false, 16);
     return GAR_OK;
   }
-  if (norm) GAR_CUDA_CHECK(gar_launch(gemv_decode_kernel<R, EPI, true, 8>, grid, dim3(256), 0, s, true, dim3(1, 1, 1), a));
-  else GAR_CUDA_CHECK(gar_launch(gemv_decode_kernel<R, EPI, false, 8>, grid, dim3(256), 0, s, true, dim3(1, 1, 1), a));
+  if (norm) GV_LAUNCH(true, 8);
+  else GV_LAUNCH(false, 8);
+#undef GV_LAUNCH
   return GAR_OK;
 }
 
@@ -297,34 +327,9 @@ extern "C" int gar_gemv_debug_timeline(void* dev_buf) {
   return GAR_OK;
 }
 
-void gar_pf_to_args(const gar_prefetch* pf, PfArgs* o) {
-  for (int r = 0; r < 2; ++r) {
-    o->p[r] = static_cast<const char*>(pf->ptr[r]);
-    o->n[r] = pf->bytes[r];
-    o->kv[r] = static_cast<const char*>(pf->kv_ptr[r]);
-    o->lo[r] = pf->kv_lo[r];
-    o->hi[r] = pf->kv_hi[r];
-  }
-  o->pos = pf->pos_dev;
-  o->pairs = pf->kv_pairs;
-  o->hkv = pf->kv_hkv > 0 ? pf->kv_hkv : 1;
-  o->row_bytes = pf->kv_row_bytes;
-  o->max_rows = pf->kv_max_rows;
-  o->pair_stride = pf->kv_pair_stride_bytes;
-  if (o->pos == nullptr || o->pairs <= 0) o->kv[0] = o->kv[1] = nullptr;
-}
-
 extern "C" int gar_gemv_decode(const void* X, int ldx, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
                                int epi, const void* res, int ldres, const void* norm_w, const float* sumsq_in,
                                int n_part, float eps, float* sumsq_out, int* rows_per_cta, void* stream_) {
-  return gar_gemv_decode_pf(X, ldx, W, ldw, out, ldo, M, N, K, epi, res, ldres, norm_w, sumsq_in, n_part, eps, sumsq_out,
-                            rows_per_cta, nullptr, stream_);
-}
-
-extern "C" int gar_gemv_decode_pf(const void* X, int ldx, const void* W, int ldw, void* out, int ldo, int M, int N,
-                                  int K, int epi, const void* res, int ldres, const void* norm_w,
-                                  const float* sumsq_in, int n_part, float eps, float* sumsq_out, int* rows_per_cta,
-                                  const gar_prefetch* pf, void* stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   if (M <= 0 || M > 8 || K % 256 || (ldx % 8) || (ldw % 8) || epi < 0 || epi > 2) return GAR_ERR_SHAPE;
   if (norm_w != nullptr && (sumsq_in == nullptr || n_part <= 0)) return GAR_ERR_ARG;
@@ -337,9 +342,7 @@ extern "C" int gar_gemv_decode_pf(const void* X, int ldx, const void* W, int ldw
   a.sumsq_in = sumsq_in; a.n_part = n_part; a.norm_w = static_cast<const bf16*>(norm_w); a.eps = eps;
   a.sumsq_out = sumsq_out;
   a.timeline = g_gemv_timeline;
-  a.has_pf = pf != nullptr;
-  memset(&a.pf, 0, sizeof(a.pf));
-  if (pf) gar_pf_to_args(pf, &a.pf);
+  a.stage_norm = gar_global_option("gemv_norm_smem");
   const bool norm = norm_w != nullptr;
   if (epi == GV_EPI_SWIGLU) {
     if (N % 64) return GAR_ERR_SHAPE;

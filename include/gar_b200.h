@@ -65,22 +65,6 @@ int gar_gemm_bf16_rope2d(const void* A, int lda, const void* B, int ldb, void* C
 int gar_gemm_skinny_bf16(const void* X, int ldx, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
                          int epi, const void* res, int ldres, void* stream);
 
-/* Optional duty of a decode-step kernel: pull the bytes the NEXT kernels of the step will stream (their weights, the
- * layer's KV cache) from HBM into the 126 MB L2 with cp.async.bulk.prefetch.L2 while this kernel is latency-bound, so
- * the HBM stream never idles between the step's short dependent launches.  Hints only: results never depend on it.
- *   ptr/bytes : up to two plain ranges
- *   kv_ptr    : K and/or V cache base of the (layer, slot group) the next attention reads; per (sequence, kv head)
- *               pair the live prefix (pos_dev[b]+1 rows of kv_row_bytes) is cut to [kv_lo, kv_hi) / 256 of its length */
-typedef struct gar_prefetch {
-  const void* ptr[2];
-  unsigned long long bytes[2];
-  const void* kv_ptr[2];
-  const int* pos_dev;
-  int kv_pairs, kv_hkv, kv_row_bytes, kv_max_rows;
-  long long kv_pair_stride_bytes;
-  int kv_lo[2], kv_hi[2];
-} gar_prefetch;
-
 /* Decode-step linear layer, latency-first (mma.sync weight stream, no TMEM/cluster/TMA setup):
  * out[M<=8,N] = epi(norm?(X) W^T).  epi 0 none | 1 out = bf16(res + bf16(acc)), optionally emitting per-CTA sums of
  * squares of out into sumsq_out[N/rows_per_cta][8] | 2 SwiGLU on W rows interleaved [32 gate | 32 up], out [M,N/2].
@@ -89,10 +73,6 @@ typedef struct gar_prefetch {
 int gar_gemv_decode(const void* X, int ldx, const void* W, int ldw, void* out, int ldo, int M, int N, int K, int epi,
                     const void* res, int ldres, const void* norm_w, const float* sumsq_in, int n_part, float eps,
                     float* sumsq_out, int* rows_per_cta, void* stream);
-/* same, with an L2 prefetch duty for the following kernels (pf may be NULL) */
-int gar_gemv_decode_pf(const void* X, int ldx, const void* W, int ldw, void* out, int ldo, int M, int N, int K, int epi,
-                       const void* res, int ldres, const void* norm_w, const float* sumsq_in, int n_part, float eps,
-                       float* sumsq_out, int* rows_per_cta, const gar_prefetch* pf, void* stream);
 /* debug: per-CTA globaltimer stamps of the following gar_gemv_decode launches into dev_buf (int64[8 * grid]); NULL disables */
 int gar_gemv_debug_timeline(void* dev_buf);
 int gar_embed_gather_sumsq(const void* table, const int* ids32, void* out, float* sumsq, int rows, int D, void* stream);
@@ -200,11 +180,6 @@ int gar_decode_attn_rope(const void* qkv, int ldq, void* kcache, void* vcache, c
                          int batch, int hq, int hkv, int head_dim, int max_seq, int splits, float scale,
                          const void* cos_t, const void* sin_t, void* o_part_ws, void* ml_part_ws, int* tickets,
                          void* out, int ldo, void* stream);
-
-int gar_decode_attn_rope_pf(const void* qkv, int ldq, void* kcache, void* vcache, const int* pos_dev,
-                            const int* slot_dev, int batch, int hq, int hkv, int head_dim, int max_seq, int splits,
-                            float scale, const void* cos_t, const void* sin_t, void* o_part_ws, void* ml_part_ws,
-                            int* tickets, void* out, int ldo, const gar_prefetch* pf, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Engine: GARModel.generate() (modeling_gar.py:295-428) as a device-resident pipeline

@@ -425,6 +425,39 @@ def test_decode_attention_fused_rope_matches_unfused():
         assert torch.equal(got, want)
 
 
+def test_decode_attention_long_context_and_poisoned_tail():
+    """Fused RoPE + append + decode attention at the bench's context (~4.7k keys, GAR-1B head layout, batch 8) against
+    fp32 SDPA over the rotated cache; cache rows PAST every live length are poisoned with NaN (never-written memory)
+    and must not reach the output; the appended rows must be bit-identical to the unfused RoPE + append kernel."""
+    from grasp_any_region_b200.config import TextSpec
+    from grasp_any_region_b200.rope import llama_cos_sin
+
+    B, hq, hkv, hd, max_seq, splits = 8, 32, 8, 64, 4864, 6
+    cos, sin = llama_cos_sin(TextSpec(), max_seq)
+    cos, sin = cos.to(bf).to(DEV), sin.to(bf).to(DEV)
+    qkv = rnd(B, (hq + 2 * hkv) * hd, seed=95)
+    kc0, vc0 = rnd(B, hkv, max_seq, hd, seed=96), rnd(B, hkv, max_seq, hd, seed=97)
+    pos = torch.tensor([4672, 4673, 4700, 4799, 15, 16, 0, 3000], dtype=torch.int32, device=DEV)
+    for b in range(B):
+        kc0[b, :, int(pos[b]) + 1:] = float("nan")
+        vc0[b, :, int(pos[b]) + 1:] = float("nan")
+    kc1, vc1, q1 = kc0.clone(), vc0.clone(), qkv.clone()
+    ops.llama_rope_kv_(q1, hq, hkv, hd, cos, sin, kc1, vc1, max_seq, pos_dev=pos, slot0=-1)
+    kc2, vc2 = kc0.clone(), vc0.clone()
+    got = ops.decode_attn_rope(qkv.clone(), kc2, vc2, pos, hq, hkv, hd, max_seq, cos, sin, splits=splits)
+    torch.cuda.synchronize()
+    assert torch.equal(kc1.nan_to_num(7.0), kc2.nan_to_num(7.0)) and torch.equal(vc1.nan_to_num(7.0), vc2.nan_to_num(7.0))
+    assert bool(torch.isfinite(got.float()).all())
+    for b in range(B):
+        n = int(pos[b]) + 1
+        q = q1[b, :hq * hd].view(hq, 1, hd).float()[None]
+        k = kc1[b, :, :n].float().repeat_interleave(hq // hkv, 0)[None]
+        v = vc1[b, :, :n].float().repeat_interleave(hq // hkv, 0)[None]
+        ref = F.scaled_dot_product_attention(q, k, v)[0, :, 0].reshape(hq * hd)
+        err = (got[b].float() - ref).abs().max().item()
+        assert err <= 2e-2, (b, err)
+
+
 # ---- R6+R7: assemble (embed + image scatter) and RoI replay, single and batched launch, bit-exact vs the oracle ----
 def _assemble_case(spec, g, ncw, nch, n_masks, text=9):
     import numpy as np
