@@ -49,13 +49,14 @@ SIGNATURES = {
     "gar_argmax_step_eos": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, C.POINTER(_i), _i, _i, _i, _vp, _vp]),
     "gar_bump_step": (_i, [_vp, _vp]),
     "gar_assemble_embeds": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, C.POINTER(_ll), C.POINTER(_f), C.POINTER(_i), _i,
-                                 _f, _i, _i, _i, _ll, _vp, _vp, _vp, _vp]),
+                                 _f, _i, _i, _i, _ll, _i, _vp, _vp, _vp, _vp]),
     "gar_assemble_embeds_batch": (_i, [_i, C.POINTER(_vp), _i, _vp, _i, _vp, _i, _i, C.POINTER(_ll), C.POINTER(_f),
-                                       C.POINTER(_i), _i, _f, C.POINTER(_i), C.POINTER(_i), _i, _ll, _vp, _vp, _vp, _vp]),
-    "gar_assemble_plan_batch": (_i, [_i, C.POINTER(_vp), _i, _i, C.POINTER(_ll), C.POINTER(_i), _i, _i, _ll, _vp, _vp,
-                                     _vp]),
+                                       C.POINTER(_i), _i, _f, C.POINTER(_i), C.POINTER(_i), _i, _ll, _i, _vp, _vp, _vp,
+                                       _vp]),
+    "gar_assemble_plan_batch": (_i, [_i, C.POINTER(_vp), _i, _i, C.POINTER(_ll), C.POINTER(_i), _i, _i, _ll, _i, _vp,
+                                     _vp, _vp]),
     "gar_assemble_rows_batch": (_i, [_i, C.POINTER(_vp), _i, _vp, _i, _vp, _i, _i, C.POINTER(_ll), C.POINTER(_f),
-                                     C.POINTER(_i), _i, _f, C.POINTER(_i), C.POINTER(_i), _i, _ll, _vp, _vp, _vp]),
+                                     C.POINTER(_i), _i, _f, C.POINTER(_i), C.POINTER(_i), _i, _ll, _i, _vp, _vp, _vp]),
     "gar_resize_aa_u8_pass": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "gar_u8_to_tiles": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "gar_idmap_to_tiles": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
@@ -87,6 +88,7 @@ SIGNATURES = {
     "gar_engine_launch_count": (_ll, [_vp]),
     "gar_engine_partition": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_i), C.POINTER(_vp), C.POINTER(_i)]),
     "gar_engine_set_option": (_i, [_vp, C.c_char_p, _i]),
+    "gar_engine_set_replay": (_i, [_vp, _i, C.POINTER(_ll), _i]),
     "gar_engine_profile": (_i, [_vp, _i]),
     "gar_engine_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
 }

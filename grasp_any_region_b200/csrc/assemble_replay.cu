@@ -12,10 +12,15 @@
 //   replay_rows  : one warp per crop row (grid = bins x regions x requests): roi_align for its (ph,pw) bin evaluated
 //                  directly on the channel-contiguous (T,256,D) feature tensor (no merged map, no fp32 copy) in the
 //                  operator's exact fp32 operation order (oracle/roi_align_ref.py), one bf16 rounding; latency-bound.
+//   (replay_mode selects which reference loop is reproduced: GAR_REPLAY_MERGED = GARModel.generate; the two replay
+//    branches of the vendored PLM's prepare_inputs_for_generation, modeling_perception_lm.py:648-852, are
+//    GAR_REPLAY_MERGED_LAST -- same map, but only the last crop token present keeps its replay, the reference splices
+//    every replay into the ORIGINAL embeddings -- and GAR_REPLAY_FRAME -- region k replays from tile k's own map.)
 //   gather_rows  : one warp per text / image row of every request: 16-byte vector copies with all of a lane's loads in
 //                  flight before its first store -- the HBM stream.  It starts together with replay_rows (programmatic
 //                  dependent launch, dependency wait at its END): the two write disjoint rows.
 // HBM-bound: ~2*S*D*2 bytes per request; no tensor cores on this path.
+#include "../../include/gar_b200.h"
 #include "common.cuh"
 
 namespace {
@@ -30,7 +35,8 @@ struct RequestParams {
   const long long* ids;          // (S,) int64 device
   float rois[MAX_REGIONS][5];    // [0, x1, y1, x2, y2] already in "feature coords" (reference quirk 1)
   int has_roi[MAX_REGIONS];      // bbox supplied for this crop id
-  int ncw, nch;                  // tile grid (w,h)
+  int ncw, nch;                  // tile grid (w,h) of the map a region is replayed from
+  int tile0[MAX_REGIONS];        // first tile of region k's map: 1 (thumbnail dropped) or, per-frame replay, k
 };
 
 struct AssembleParams {
@@ -40,6 +46,7 @@ struct AssembleParams {
   float spatial_scale;           // applied AGAIN inside roi_align, as the reference does
   int tpt;                       // tokens per tile side (16)
   long long image_token_id;
+  int mode;                      // GAR_REPLAY_*
   RequestParams r[MAX_REQS];
 };
 
@@ -104,6 +111,12 @@ __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant
   }
   __syncthreads();
   int ord = s_warp[tid >> 5] + incl - cnt;
+  // GAR_REPLAY_MERGED_LAST: only the last crop token (in crop-id order) present in the prompt is replayed; the runs of
+  // the others stay what embed_tokens made of them (KIND_TEXT rows)
+  int only = -1;
+  if (p.mode == GAR_REPLAY_MERGED_LAST)
+    for (int k = 0; k < p.n_regions; ++k)
+      if (s_cnt[k] > 0) only = k;
   for (int s0 = lo; s0 < hi; s0 += PU) {
     long long idr[PU];
 #pragma unroll
@@ -119,7 +132,7 @@ __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant
         ++ord;
       } else {
         for (int k = 0; k < p.n_regions; ++k) {
-          if (id == p.crop_ids[k] && rq.has_roi[k]) {
+          if (id == p.crop_ids[k] && rq.has_roi[k] && (p.mode != GAR_REPLAY_MERGED_LAST || k == only)) {
             word = (KIND_CROP << 30) | (k << 16) | ((s - s_min[k]) & 0xffff);
           }
         }
@@ -144,7 +157,8 @@ __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant
   // the replay kernel's row index
   if (tid < MAX_REGIONS) {
     const int run = p.tpt * p.tpt;
-    const bool ok = tid < p.n_regions && s_cnt[tid] > 0 && rq.has_roi[tid] && s_min[tid] + run <= S;
+    const bool ok = tid < p.n_regions && s_cnt[tid] > 0 && rq.has_roi[tid] && s_min[tid] + run <= S &&
+                    (p.mode != GAR_REPLAY_MERGED_LAST || tid == only);
     region_start_all[blockIdx.x * MAX_REGIONS + tid] = ok ? s_min[tid] : -1;
   }
 }
@@ -279,7 +293,7 @@ replay_rows_kernel(const int* __restrict__ region_start, const bf16* __restrict_
         sm[iy * 2 + ix] = make_sample(yy, xx, H, W);
       }
     }
-    // feature cell (y,x) of the merged map lives at tile 1 + (y/tpt)*ncw + x/tpt, token (y%tpt)*tpt + x%tpt
+    // feature cell (y,x) of the region's map lives at tile tile0 + (y/tpt)*ncw + x/tpt, token (y%tpt)*tpt + x%tpt
     const uint4* cell[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -287,7 +301,7 @@ replay_rows_kernel(const int* __restrict__ region_start, const bf16* __restrict_
       for (int c = 0; c < 4; ++c) {
         const int lin = sm[q].pos[c];
         const int y = lin / W, x = lin % W;
-        const size_t row = (static_cast<size_t>(1 + (y / tpt) * rq.ncw + x / tpt) * tpt + (y % tpt)) * tpt + (x % tpt);
+        const size_t row = (static_cast<size_t>(rq.tile0[k] + (y / tpt) * rq.ncw + x / tpt) * tpt + (y % tpt)) * tpt + (x % tpt);
         cell[q * 4 + c] = reinterpret_cast<const uint4*>(feats + row * D);
       }
     }
@@ -335,8 +349,9 @@ replay_rows_kernel(const int* __restrict__ region_start, const bf16* __restrict_
 namespace {
 int fill_params(AssembleParams& p, int r0, int nr, const long long* const* input_ids, const long long* crop_ids,
                 const float* rois, const int* has_roi, int n_regions, float spatial_scale, const int* ncw, const int* nch,
-                int tpt, long long image_token_id) {
+                int tpt, long long image_token_id, int mode) {
   memset(&p, 0, sizeof(p));
+  p.mode = mode;
   p.n_regions = n_regions;
   p.nreq = nr;
   for (int k = 0; k < MAX_REGIONS; ++k) p.crop_ids[k] = k < n_regions ? crop_ids[k] : -1;
@@ -346,8 +361,10 @@ int fill_params(AssembleParams& p, int r0, int nr, const long long* const* input
   for (int r = 0; r < nr; ++r) {
     RequestParams& rq = p.r[r];
     rq.ids = input_ids[r0 + r];
-    rq.ncw = ncw ? ncw[r0 + r] : 1;
-    rq.nch = nch ? nch[r0 + r] : 1;
+    // per-frame replay: every region's map is ONE tile (its frame)
+    rq.ncw = (ncw && mode != GAR_REPLAY_FRAME) ? ncw[r0 + r] : 1;
+    rq.nch = (nch && mode != GAR_REPLAY_FRAME) ? nch[r0 + r] : 1;
+    for (int k = 0; k < MAX_REGIONS; ++k) rq.tile0[k] = mode == GAR_REPLAY_FRAME ? k : 1;
     for (int k = 0; k < n_regions; ++k) {
       rq.has_roi[k] = has_roi[(r0 + r) * n_regions + k];
       for (int j = 0; j < 5; ++j) rq.rois[k][j] = rois ? rois[((r0 + r) * n_regions + k) * 5 + j] : 0.f;
@@ -361,16 +378,18 @@ int fill_params(AssembleParams& p, int r0, int nr, const long long* const* input
 // word early, so a malformed prompt raises before any feature is computed, like the reference's ValueError).
 extern "C" int gar_assemble_plan_batch(int nreq, const long long* const* input_ids, int S, int n_image_rows,
                                        const long long* crop_ids, const int* has_roi, int n_regions, int tpt,
-                                       long long image_token_id, int* plan_ws, int* status_dev, void* stream_) {
+                                       long long image_token_id, int replay_mode, int* plan_ws, int* status_dev,
+                                       void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (n_regions > MAX_REGIONS || S <= 0 || nreq <= 0 || tpt * tpt > 0xffff) {
+  if (n_regions > MAX_REGIONS || S <= 0 || nreq <= 0 || tpt * tpt > 0xffff || replay_mode < 0 || replay_mode > 2) {
     gar_set_error("gar_assemble_plan_batch: bad args nreq=%d S=%d n_regions=%d", nreq, S, n_regions);
     return GAR_ERR_ARG;
   }
   for (int r0 = 0; r0 < nreq; r0 += MAX_REQS) {
     const int nr = nreq - r0 < MAX_REQS ? nreq - r0 : MAX_REQS;
     AssembleParams p;
-    fill_params(p, r0, nr, input_ids, crop_ids, nullptr, has_roi, n_regions, 1.f, nullptr, nullptr, tpt, image_token_id);
+    fill_params(p, r0, nr, input_ids, crop_ids, nullptr, has_roi, n_regions, 1.f, nullptr, nullptr, tpt, image_token_id,
+                replay_mode);
     plan_rows_kernel<<<nr, 1024, 0, stream>>>(S, n_image_rows, p, plan_ws + static_cast<size_t>(r0) * S, status_dev + 2 * r0,
                                               plan_ws + static_cast<size_t>(nreq) * S + r0 * MAX_REGIONS);
     GAR_CUDA_CHECK(cudaGetLastError());
@@ -384,22 +403,28 @@ extern "C" int gar_assemble_rows_batch(int nreq, const long long* const* input_i
                                        int vocab, const void* image_features, int n_image_rows, int D,
                                        const long long* crop_ids, const float* rois, const int* has_roi, int n_regions,
                                        float spatial_scale, const int* ncw, const int* nch, int tpt,
-                                       long long image_token_id, void* out, const int* plan_ws, void* stream_) {
+                                       long long image_token_id, int replay_mode, void* out, const int* plan_ws,
+                                       void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (n_regions > MAX_REGIONS || D % 8 || S <= 0 || nreq <= 0 || tpt * tpt > 0xffff || n_image_rows <= 0) {
+  if (n_regions > MAX_REGIONS || D % 8 || S <= 0 || nreq <= 0 || tpt * tpt > 0xffff || n_image_rows <= 0 ||
+      replay_mode < 0 || replay_mode > 2) {
     gar_set_error("gar_assemble_rows_batch: bad args nreq=%d S=%d D=%d n_regions=%d", nreq, S, D, n_regions);
     return GAR_ERR_ARG;
   }
   for (int r0 = 0; r0 < nreq; r0 += MAX_REQS) {
     const int nr = nreq - r0 < MAX_REQS ? nreq - r0 : MAX_REQS;
     AssembleParams p;
-    fill_params(p, r0, nr, input_ids, crop_ids, rois, has_roi, n_regions, spatial_scale, ncw, nch, tpt, image_token_id);
+    fill_params(p, r0, nr, input_ids, crop_ids, rois, has_roi, n_regions, spatial_scale, ncw, nch, tpt, image_token_id,
+                replay_mode);
     for (int r = 0; r < nr; ++r) {
-      // every merged-map cell the replay can address must exist: tiles 1..ncw*nch of this request's features
-      if ((1 + p.r[r].ncw * p.r[r].nch) * tpt * tpt > n_image_rows) {
-        gar_set_error("gar_assemble_rows_batch: grid %dx%d needs %d feature rows, got %d", p.r[r].ncw, p.r[r].nch,
-                      (1 + p.r[r].ncw * p.r[r].nch) * tpt * tpt, n_image_rows);
-        return GAR_ERR_SHAPE;
+      // every map cell a replay can address must exist: tiles tile0 .. tile0 + ncw*nch - 1 of this request's features
+      for (int k = 0; k < n_regions; ++k) {
+        const int need = (p.r[r].tile0[k] + p.r[r].ncw * p.r[r].nch) * tpt * tpt;
+        if (p.r[r].has_roi[k] && need > n_image_rows) {
+          gar_set_error("gar_assemble_rows_batch: region %d (grid %dx%d from tile %d) needs %d feature rows, got %d", k,
+                        p.r[r].ncw, p.r[r].nch, p.r[r].tile0[k], need, n_image_rows);
+          return GAR_ERR_SHAPE;
+        }
       }
     }
     const bf16* feats = static_cast<const bf16*>(image_features) + static_cast<size_t>(r0) * n_image_rows * D;
@@ -429,22 +454,23 @@ extern "C" int gar_assemble_embeds_batch(int nreq, const long long* const* input
                                          int vocab, const void* image_features, int n_image_rows, int D,
                                          const long long* crop_ids, const float* rois, const int* has_roi,
                                          int n_regions, float spatial_scale, const int* ncw, const int* nch, int tpt,
-                                         long long image_token_id, void* out, int* plan_ws, int* status_dev,
-                                         void* stream_) {
+                                         long long image_token_id, int replay_mode, void* out, int* plan_ws,
+                                         int* status_dev, void* stream_) {
   int rc = gar_assemble_plan_batch(nreq, input_ids, S, n_image_rows, crop_ids, has_roi, n_regions, tpt, image_token_id,
-                                   plan_ws, status_dev, stream_);
+                                   replay_mode, plan_ws, status_dev, stream_);
   if (rc) return rc;
   return gar_assemble_rows_batch(nreq, input_ids, S, embed_table, vocab, image_features, n_image_rows, D, crop_ids, rois,
-                                 has_roi, n_regions, spatial_scale, ncw, nch, tpt, image_token_id, out, plan_ws, stream_);
+                                 has_roi, n_regions, spatial_scale, ncw, nch, tpt, image_token_id, replay_mode, out,
+                                 plan_ws, stream_);
 }
 
 // rois: n_regions x 5 fp32 host array; has_roi: n_regions ints; crop_ids: n_regions int64 (host)
 extern "C" int gar_assemble_embeds(const long long* input_ids, int S, const void* embed_table, int vocab,
                                    const void* image_features, int n_image_rows, int D, const long long* crop_ids,
                                    const float* rois, const int* has_roi, int n_regions, float spatial_scale, int ncw,
-                                   int nch, int tpt, long long image_token_id, void* out, int* plan_ws,
+                                   int nch, int tpt, long long image_token_id, int replay_mode, void* out, int* plan_ws,
                                    int* status_dev, void* stream_) {
   return gar_assemble_embeds_batch(1, &input_ids, S, embed_table, vocab, image_features, n_image_rows, D, crop_ids, rois,
-                                   has_roi, n_regions, spatial_scale, &ncw, &nch, tpt, image_token_id, out, plan_ws,
-                                   status_dev, stream_);
+                                   has_roi, n_regions, spatial_scale, &ncw, &nch, tpt, image_token_id, replay_mode, out,
+                                   plan_ws, status_dev, stream_);
 }

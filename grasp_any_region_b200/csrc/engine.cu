@@ -43,6 +43,12 @@ struct gar_engine {
   int use_gemv = 1;
   int fuse_decode_rope = 1;
   float *sumsq_a, *sumsq_b;
+  // replay loop reproduced by plan / assemble (gar_engine_set_replay): mode + the crop-token ids the boxes are indexed by
+  int replay_mode = GAR_REPLAY_MERGED;
+  long long replay_ids[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+  int replay_n = 0;  // 0: the model's own crop_tokens_ids / prompt_numbers
+  const long long* crop_ids() const { return replay_n > 0 ? replay_ids : d.crop_token_ids; }
+  int n_regions() const { return replay_n > 0 ? replay_n : d.prompt_numbers; }
   // decode graph
   std::map<long long, cudaGraphExec_t> graphs;  // decode-step graphs keyed by (slot0, batch)
   std::map<long long, std::vector<int>> graph_eos;
@@ -586,7 +592,7 @@ int gar_engine_assemble(gar_engine* e, int slot, const long long* input_ids_dev,
                   e ? e->d.max_batch : 0, e ? e->d.max_seq : 0);
     return GAR_ERR_ARG;
   }
-  if (ncw * nch != T - 1) {  // reference assert in _merge, modeling_gar.py:250
+  if (e->replay_mode != GAR_REPLAY_FRAME && ncw * nch != T - 1) {  // reference assert in _merge, modeling_gar.py:250
     gar_set_error("%d != %d", ncw * nch, T - 1);
     return GAR_ERR_SHAPE;
   }
@@ -597,8 +603,8 @@ int gar_engine_assemble(gar_engine* e, int slot, const long long* input_ids_dev,
   // algorithmic bytes: write S*D*2 + read one D-row per non-replay row + <=16 cells per region
   ProfScope ps(e, s, PK_ASSEMBLE, 2.0 * (2.0 * S - 0.0) * d.llm_dim);
   return gar_assemble_embeds(input_ids_dev, S, table, d.vocab, e->feats, T * e->tokens_per_tile, d.llm_dim,
-                             d.crop_token_ids, rois, has_roi, d.prompt_numbers, spatial_scale, ncw, nch, e->tpt,
-                             d.image_token_id, e->emb, e->plan, e->status + 2 * slot, s);
+                             e->crop_ids(), rois, has_roi, e->n_regions(), spatial_scale, ncw, nch, e->tpt,
+                             d.image_token_id, e->replay_mode, e->emb, e->plan, e->status + 2 * slot, s);
 }
 
 int gar_engine_assemble_at(gar_engine* e, int slot, const long long* input_ids_dev, int S, int T, int feat_tile0,
@@ -612,7 +618,7 @@ int gar_engine_assemble_at(gar_engine* e, int slot, const long long* input_ids_d
                   emb_row0);
     return GAR_ERR_ARG;
   }
-  if (ncw * nch != T - 1) {  // reference assert in _merge, modeling_gar.py:250
+  if (e->replay_mode != GAR_REPLAY_FRAME && ncw * nch != T - 1) {  // reference assert in _merge, modeling_gar.py:250
     gar_set_error("%d != %d", ncw * nch, T - 1);
     return GAR_ERR_SHAPE;
   }
@@ -622,8 +628,8 @@ int gar_engine_assemble_at(gar_engine* e, int slot, const long long* input_ids_d
   ProfScope ps(e, s, PK_ASSEMBLE, 2.0 * (2.0 * S) * d.llm_dim);
   return gar_assemble_embeds(input_ids_dev, S, table, d.vocab,
                              e->feats + static_cast<size_t>(feat_tile0) * e->tokens_per_tile * d.llm_dim,
-                             T * e->tokens_per_tile, d.llm_dim, d.crop_token_ids, rois, has_roi, d.prompt_numbers,
-                             spatial_scale, ncw, nch, e->tpt, d.image_token_id,
+                             T * e->tokens_per_tile, d.llm_dim, e->crop_ids(), rois, has_roi, e->n_regions(),
+                             spatial_scale, ncw, nch, e->tpt, d.image_token_id, e->replay_mode,
                              e->emb + static_cast<size_t>(emb_row0) * d.llm_dim, e->plan + emb_row0, e->status + 2 * slot, s);
 }
 
@@ -644,8 +650,8 @@ int gar_engine_plan_batch(gar_engine* e, int slot0, int nreq, const long long* c
   }
   {
     ProfScope ps(e, s, PK_ASSEMBLE, 0.0);  // the plan kernel only (the status read-back below is host plumbing)
-    TRY(gar_assemble_plan_batch(nreq, input_ids_dev, S, T * e->tokens_per_tile, d.crop_token_ids, has_roi,
-                                d.prompt_numbers, e->tpt, d.image_token_id, e->plan, e->status + 2 * slot0, s));
+    TRY(gar_assemble_plan_batch(nreq, input_ids_dev, S, T * e->tokens_per_tile, e->crop_ids(), has_roi, e->n_regions(),
+                                e->tpt, d.image_token_id, e->replay_mode, e->plan, e->status + 2 * slot0, s));
   }
   e->launches += (nreq + 7) / 8;
   e->plan_slot0 = slot0; e->plan_nreq = nreq; e->plan_S = S; e->plan_T = T;
@@ -675,7 +681,7 @@ int gar_engine_assemble_batch(gar_engine* e, int slot0, int nreq, const long lon
     return GAR_ERR_ARG;
   }
   for (int r = 0; r < nreq; ++r) {
-    if (ncw[r] * nch[r] != T - 1) {  // reference assert in _merge, modeling_gar.py:250
+    if (e->replay_mode != GAR_REPLAY_FRAME && ncw[r] * nch[r] != T - 1) {  // reference assert in _merge, modeling_gar.py:250
       gar_set_error("%d != %d", ncw[r] * nch[r], T - 1);
       return GAR_ERR_SHAPE;
     }
@@ -686,14 +692,14 @@ int gar_engine_assemble_batch(gar_engine* e, int slot0, int nreq, const long lon
   // algorithmic bytes: write S*D*2 + read one D-row per non-replay row + <=16 cells per region
   ProfScope ps(e, s, PK_ASSEMBLE, 2.0 * (2.0 * S) * d.llm_dim * nreq);
   if (!planned) {
-    TRY(gar_assemble_plan_batch(nreq, input_ids_dev, S, T * e->tokens_per_tile, d.crop_token_ids, has_roi,
-                                d.prompt_numbers, e->tpt, d.image_token_id, e->plan, e->status + 2 * slot0, s));
+    TRY(gar_assemble_plan_batch(nreq, input_ids_dev, S, T * e->tokens_per_tile, e->crop_ids(), has_roi, e->n_regions(),
+                                e->tpt, d.image_token_id, e->replay_mode, e->plan, e->status + 2 * slot0, s));
     e->launches += (nreq + 7) / 8;
   }
   e->launches += 2 * ((nreq + 7) / 8);
   return gar_assemble_rows_batch(nreq, input_ids_dev, S, table, d.vocab, e->feats, T * e->tokens_per_tile, d.llm_dim,
-                                 d.crop_token_ids, rois, has_roi, d.prompt_numbers, spatial_scale, ncw, nch, e->tpt,
-                                 d.image_token_id, e->emb, e->plan, s);
+                                 e->crop_ids(), rois, has_roi, e->n_regions(), spatial_scale, ncw, nch, e->tpt,
+                                 d.image_token_id, e->replay_mode, e->emb, e->plan, s);
 }
 
 int gar_engine_prefill_batch(gar_engine* e, int slot0, int nreq, int S, void* s) {
@@ -909,6 +915,18 @@ int gar_engine_partition(gar_engine* e, int decode_sms, void** encode_stream, in
   *decode_stream = small;
   if (encode_count) *encode_count = nr;
   if (decode_count) *decode_count = ns;
+  return GAR_OK;
+}
+
+int gar_engine_set_replay(gar_engine* e, int replay_mode, const long long* crop_ids, int n) {
+  if (!e || replay_mode < GAR_REPLAY_MERGED || replay_mode > GAR_REPLAY_FRAME || n < 0 || n > 8 || (n > 0 && !crop_ids)) {
+    gar_set_error("gar_engine_set_replay: mode=%d n=%d (at most 8 crop-token ids)", replay_mode, n);
+    return GAR_ERR_ARG;
+  }
+  e->replay_mode = replay_mode;
+  e->replay_n = n;
+  for (int i = 0; i < 8; ++i) e->replay_ids[i] = i < n ? crop_ids[i] : -1;
+  e->plan_slot0 = -1;  // a plan made under another mode is not reusable
   return GAR_OK;
 }
 

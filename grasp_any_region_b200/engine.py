@@ -25,15 +25,22 @@ PJ = "mllm.model.multi_modal_projector."
 LM = "mllm.model.language_model."
 
 
-def roi_boxes_f32(spec: GARSpec, bboxes: Dict[str, Sequence[float]], ncw: int, nch: int):
+REPLAY_MERGED, REPLAY_MERGED_LAST, REPLAY_FRAME = 0, 1, 2  # include/gar_b200.h GAR_REPLAY_*
+
+
+def roi_boxes_f32(spec: GARSpec, bboxes: Dict[str, Sequence[float]], ncw: int, nch: int, crop_ids=None,
+                  per_frame: bool = False):
     """Box arithmetic exactly as modeling_gar.py:366-387 does it on the host: python doubles, then one
-    rounding to fp32 (torch.tensor(..., dtype=float32)).  Returns (rois flat list, has list, scale)."""
+    rounding to fp32 (torch.tensor(..., dtype=float32)).  Returns (rois flat list, has list, scale).
+    per_frame: the map is one tile (modeling_perception_lm.py:787-801, feat_h = feat_w = 16)."""
     tpt = int(math.isqrt(spec.tokens_per_tile))
+    if per_frame:
+        ncw = nch = 1
     feat_h, feat_w = nch * tpt, ncw * tpt
     orig_h, orig_w = feat_h * 28, feat_w * 28
     spatial_scale = feat_w / orig_w
     rois, has = [], []
-    for cid in spec.crop_tokens_ids:
+    for cid in (spec.crop_tokens_ids if crop_ids is None else crop_ids):
         box = bboxes.get(str(cid)) if bboxes is not None else None
         if box is None:
             rois.append([0.0] * 5)
@@ -86,6 +93,7 @@ class Engine:
         self.dec_stream: Optional[torch.cuda.Stream] = None
         self.partition_sms = None
         self.last_steps_run = 0
+        self.replay_mode, self.crop_ids = REPLAY_MERGED, list(spec.crop_tokens_ids)
         self.trace = None  # debug: set to [] to collect (label, CUDA event) marks between the stage entry points
         self._load_weights(state_dict)
 
@@ -107,6 +115,17 @@ class Engine:
         self.dec_stream = torch.cuda.ExternalStream(ds.value, device=self.device)
         self.partition_sms = (en.value, dn.value)
         return True
+
+    def set_replay(self, mode: int = REPLAY_MERGED, crop_ids=None):
+        """Which reference replay loop the following plan / assemble calls reproduce (gar_engine_set_replay) and which
+        crop-token ids index the boxes; the defaults restore GARModel.generate's loop over spec.crop_tokens_ids."""
+        ids = list(self.spec.crop_tokens_ids) if crop_ids is None else [int(c) for c in crop_ids]
+        if not ids:
+            ids = [-2]  # no replay at all: an id no token can have
+        arr = (C.c_longlong * len(ids))(*ids)
+        check(self.lib.gar_engine_set_replay(self._h, int(mode), None if crop_ids is None else arr,
+                                             0 if crop_ids is None else len(ids)), "gar_engine_set_replay")
+        self.replay_mode, self.crop_ids = int(mode), ids
 
     # ------------------------------------------------------------------ weights
     def _set(self, name: str, tensor: torch.Tensor):
@@ -223,7 +242,7 @@ class Engine:
                                              T, self._s()), "gar_engine_vit_encode")
 
     def assemble(self, slot: int, input_ids: torch.Tensor, T: int, bboxes, ncw: int, nch: int):
-        rois, has, scale = roi_boxes_f32(self.spec, bboxes, ncw, nch)
+        rois, has, scale = roi_boxes_f32(self.spec, bboxes, ncw, nch, self.crop_ids, self.replay_mode == REPLAY_FRAME)
         n = len(has)
         c_rois = (C.c_float * (5 * n))(*[x for r in rois for x in r])
         c_has = (C.c_int * n)(*has)
@@ -252,8 +271,7 @@ class Engine:
         T, S = requests[0][0].shape[0], requests[0][2].numel()
         has = []
         for (_, _, _, bboxes, _) in requests:
-            has += [1 if (bboxes is not None and bboxes.get(str(c)) is not None) else 0
-                    for c in self.spec.crop_tokens_ids]
+            has += [1 if (bboxes is not None and bboxes.get(str(c)) is not None) else 0 for c in self.crop_ids]
         c_ids = (C.c_void_p * n)(*[r[2].data_ptr() for r in requests])
         st = (C.c_int * n)()
         check(self.lib.gar_engine_plan_batch(self._h, slot0, n, c_ids, S, T, (C.c_int * len(has))(*has), st, self._s()),
@@ -283,7 +301,8 @@ class Engine:
         self._mark("vit_done")
         flat_rois, flat_has, ncws, nchs, scale = [], [], [], [], 1.0
         for (_, _, ids, bboxes, (ncw, nch)) in requests:
-            rois, has, scale = roi_boxes_f32(self.spec, bboxes, ncw, nch)
+            rois, has, scale = roi_boxes_f32(self.spec, bboxes, ncw, nch, self.crop_ids,
+                                             self.replay_mode == REPLAY_FRAME)
             flat_rois += [x for r in rois for x in r]
             flat_has += list(has)
             ncws.append(int(ncw))

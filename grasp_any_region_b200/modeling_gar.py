@@ -12,6 +12,7 @@ torch ops or the CPU.
 from __future__ import annotations
 
 import dataclasses
+import weakref
 from typing import Dict, List, Optional
 
 import torch
@@ -20,7 +21,7 @@ from torch import nn
 from . import _lib
 from .config import GARSpec
 from .configuration_gar import GARConfig
-from .engine import LM, PJ, VT, Engine
+from .engine import LM, PJ, REPLAY_FRAME, REPLAY_MERGED, REPLAY_MERGED_LAST, VT, Engine
 
 try:  # same base class as the reference when transformers is importable
     from transformers.modeling_utils import PreTrainedModel as _Base
@@ -66,6 +67,14 @@ class _Node(nn.Module):
     """Parameter container reproducing the reference's module paths (no forward of its own)."""
 
 
+class _MLLMNode(_Node):
+    """``model.mllm``: the parameters of the vendored PerceptionLMForConditionalGeneration plus its ``generate`` with the
+    replay branches of ``prepare_inputs_for_generation`` (GARModel._mllm_generate)."""
+
+    def generate(self, *args, **kwargs):
+        return self._owner()._mllm_generate(*args, **kwargs)
+
+
 def _attach(root: nn.Module, dotted: str, shape, dtype):
     parts = dotted.split(".")
     mod = root
@@ -99,6 +108,9 @@ class GARModel(_Base):
         self.prompt_numbers = config.prompt_numbers
         self.crop_tokens_ids = config.crop_tokens_ids
         self.spec = config.spec
+        node = _MLLMNode()
+        object.__setattr__(node, "_owner", weakref.ref(self))  # not a submodule link: no cycle in .modules()
+        self.add_module("mllm", node)
         for name, shape in parameter_shapes(self.spec).items():
             _attach(self, name, shape, torch.bfloat16)
         if mllm is not None or mask_patch_embedding is not None:
@@ -323,6 +335,66 @@ class GARModel(_Base):
         toks = eng.generate(1, max_new, eos)
         seq = torch.tensor([toks[0]], dtype=torch.long, device=eng.device)
         return GenerateOutput(sequences=seq)
+
+    @torch.no_grad()
+    def _mllm_generate(self, input_ids=None, pixel_values=None, mask_embeds=None, attention_mask=None,
+                       feature_replay=None, feature_replay_video=None, crop_tokens=(128004,), bboxes=None,
+                       aspect_ratios=None, processor=None, generation_config=None, global_mask_values=None,
+                       pixel_values_videos=None, **generate_kwargs) -> GenerateOutput:
+        """``model.mllm.generate(...)`` with the replay branches of the vendored PLM's ``prepare_inputs_for_generation``
+        (models/modeling/modeling_perception_lm.py:574-860), same keyword names:
+
+        * ``feature_replay=True``: merged-map RoI replay over ``crop_tokens`` -- reproducing the reference's splice into
+          the ORIGINAL embeddings (:736-742): only the last crop token present keeps its replay;
+        * ``feature_replay_video=True``: the tiles of ``pixel_values`` are frames; frame f's crop token
+          ``processor.tokenizer.convert_tokens_to_ids("<|reserved_special_token_{2+f}|>")`` is replayed from frame f's
+          own 16x16 map (:765-852);
+        * neither: image-token scatter only.
+        Returns HF's decoder-only ``.sequences`` for a call that passed ``input_ids``: prompt ids followed by the new ones.
+        ``global_mask_values`` (B200 extension) feeds the engine's mask conv; a precomputed ``mask_embeds`` tensor is not
+        accepted (the engine fuses that conv into the patch embedding)."""
+        assert not (feature_replay and feature_replay_video)
+        if pixel_values is None or input_ids is None:
+            raise NotImplementedError("mllm.generate needs input_ids and pixel_values on this path")
+        if mask_embeds is not None:
+            raise NotImplementedError("pass global_mask_values=...; a precomputed mask_embeds tensor is not supported")
+        if pixel_values_videos is not None:
+            raise NotImplementedError("pixel_values_videos: frames go in as pixel_values (what the replay branch reads, :772)")
+        if attention_mask is not None and not bool((attention_mask != 0).all()):
+            raise NotImplementedError("attention_mask with padded positions is not supported (batch 1, no padding)")
+        assert input_ids.shape[0] == 1, "Currently only support batch_size=1 for feature replay"
+        T = pixel_values.shape[0] if pixel_values.dim() == 4 else pixel_values.shape[0] * pixel_values.shape[1]
+        if feature_replay_video:
+            assert processor is not None, "Need processor"
+            if T > 8:
+                raise NotImplementedError(f"per-frame replay supports at most 8 frames per request, got {T}")
+            ids = [int(processor.tokenizer.convert_tokens_to_ids(f"<|reserved_special_token_{2 + f}|>")) for f in range(T)]
+            mode = REPLAY_FRAME
+            if aspect_ratios is None or aspect_ratios is True:
+                aspect_ratios = [[1, 1]]
+        elif feature_replay:
+            ids, mode = [int(c) for c in crop_tokens], REPLAY_MERGED_LAST
+        else:
+            ids, mode = [], REPLAY_MERGED
+            if aspect_ratios is None or aspect_ratios is True:
+                aspect_ratios = [[1, 1]]
+            bboxes = bboxes if bboxes is not None else [{}]
+        if len(ids) > 8:
+            raise NotImplementedError(f"at most 8 crop tokens per request, got {len(ids)}")
+        max_new, eos = self._generation_args(generation_config, generate_kwargs)
+        eng = self.engine()
+        if max_new > eng.max_new_tokens:
+            self.configure_engine(max_new_tokens=max_new)
+            eng = self.engine()
+        eng.set_replay(mode, ids)
+        try:
+            self._stage(eng, 0, [dict(pixel_values=pixel_values, global_mask_values=global_mask_values,
+                                      aspect_ratios=aspect_ratios, bboxes=bboxes, input_ids=input_ids)])
+            toks = eng.generate(1, max_new, eos)
+        finally:
+            eng.set_replay()
+        new = torch.tensor([toks[0]], dtype=torch.long, device=eng.device)
+        return GenerateOutput(sequences=torch.cat([input_ids.to(eng.device).to(torch.long), new], dim=1))
 
     @torch.no_grad()
     def generate_batch(self, requests: List[dict], max_new_tokens: int = 128, eos_token_id=None):

@@ -195,7 +195,11 @@ def decode_attn_rope(qkv, kcache, vcache, pos_dev, hq, hkv, hd, max_seq, cos_t, 
     return out
 
 
-def assemble_embeds(input_ids, table, feats, crop_ids, rois, has_roi, spatial_scale, ncw, nch, tpt, image_token_id):
+REPLAY_MERGED, REPLAY_MERGED_LAST, REPLAY_FRAME = 0, 1, 2  # include/gar_b200.h GAR_REPLAY_*
+
+
+def assemble_embeds(input_ids, table, feats, crop_ids, rois, has_roi, spatial_scale, ncw, nch, tpt, image_token_id,
+                    replay_mode=REPLAY_MERGED):
     """input_ids (S,) int64 cuda; feats (T, tpt*tpt, D); rois list of 5-float lists (one per crop id)."""
     S = input_ids.numel()
     D = table.shape[1]
@@ -209,13 +213,13 @@ def assemble_embeds(input_ids, table, feats, crop_ids, rois, has_roi, spatial_sc
     c_has = (C.c_int * n)(*[int(h) for h in has_roi])
     check(_lib.load().gar_assemble_embeds(_p(input_ids), S, _p(table), table.shape[0], _p(feats),
                                           feats.shape[0] * feats.shape[1], D, c_ids, c_rois, c_has, n,
-                                          float(spatial_scale), ncw, nch, tpt, image_token_id, _p(out), _p(plan),
-                                          _p(status), _stream()), "gar_assemble_embeds")
+                                          float(spatial_scale), ncw, nch, tpt, image_token_id, int(replay_mode), _p(out),
+                                          _p(plan), _p(status), _stream()), "gar_assemble_embeds")
     return out, status
 
 
 def assemble_embeds_batch(input_ids_list, table, feats, crop_ids, rois, has_roi, spatial_scale, grids, tpt,
-                          image_token_id):
+                          image_token_id, replay_mode=REPLAY_MERGED):
     """Batched form: input_ids_list = nreq (S,) int64 cuda tensors; feats (nreq, T, tpt*tpt, D); rois[r][k] 5 floats;
     has_roi[r][k]; grids[r] = (ncw, nch).  Returns out (nreq, S, D), status (nreq, 2)."""
     n = len(input_ids_list)
@@ -233,8 +237,8 @@ def assemble_embeds_batch(input_ids_list, table, feats, crop_ids, rois, has_roi,
     c_h = (C.c_int * n)(*[int(g[1]) for g in grids])
     check(_lib.load().gar_assemble_embeds_batch(n, c_ptrs, S, _p(table), table.shape[0], _p(feats),
                                                 feats.shape[1] * feats.shape[2], D, c_ids, c_rois, c_has, k,
-                                                float(spatial_scale), c_w, c_h, tpt, image_token_id, _p(out), _p(plan),
-                                                _p(status), _stream()), "gar_assemble_embeds_batch")
+                                                float(spatial_scale), c_w, c_h, tpt, image_token_id, int(replay_mode),
+                                                _p(out), _p(plan), _p(status), _stream()), "gar_assemble_embeds_batch")
     return out, status
 
 

@@ -113,13 +113,25 @@ int gar_argmax_step_eos(const void* logits, int ld, int V, int batch, int* next_
                         int bump_step, void* partial_ws, void* stream);
 int gar_bump_step(int* step, void* stream);
 
+/* Which reference replay loop the assemble kernels reproduce (replay_mode):
+ *   GAR_REPLAY_MERGED      GARModel.generate, hf_models/modeling_gar.py:348-414: every crop token present is replayed
+ *                          from the merged map of tiles 1..T-1 (thumbnail dropped), on the running tensor
+ *   GAR_REPLAY_MERGED_LAST the vendored PLM's prepare_inputs_for_generation(feature_replay=True),
+ *                          models/modeling/modeling_perception_lm.py:648-763: same map and boxes, but each replay is
+ *                          spliced into the ORIGINAL embeddings (:736-742), so only the LAST crop token present keeps
+ *                          its replay; the other runs keep embed_tokens(crop id)
+ *   GAR_REPLAY_FRAME       prepare_inputs_for_generation(feature_replay_video=True), :765-852: crop id k is replayed
+ *                          from tile (frame) k's own tpt x tpt map, no thumbnail drop, running tensor; ncw/nch ignored */
+enum { GAR_REPLAY_MERGED = 0, GAR_REPLAY_MERGED_LAST = 1, GAR_REPLAY_FRAME = 2 };
+
 /* Fused embed + image-feature scatter + RoI-aligned feature replay (modeling_gar.py:332-414).
  * rois: n_regions x [0,x1,y1,x2,y2] fp32 host array computed like modeling_gar.py:367-387;
  * plan_ws: S + 8 ints (device); status_dev: 2 ints (device): [status bits, n image tokens]. */
 int gar_assemble_embeds(const long long* input_ids_dev, int S, const void* embed_table, int vocab,
                         const void* image_features, int n_image_rows, int D, const long long* crop_ids,
                         const float* rois, const int* has_roi, int n_regions, float spatial_scale, int ncw, int nch,
-                        int tpt, long long image_token_id, void* out, int* plan_ws, int* status_dev, void* stream);
+                        int tpt, long long image_token_id, int replay_mode, void* out, int* plan_ws, int* status_dev,
+                        void* stream);
 
 /* The same for nreq equal-length requests (one plan launch, then the replay and gather launches side by side: an HBM
  * stream over all requests).
@@ -130,18 +142,18 @@ int gar_assemble_embeds_batch(int nreq, const long long* const* input_ids_dev, i
                               int vocab, const void* image_features, int n_image_rows, int D,
                               const long long* crop_ids, const float* rois, const int* has_roi, int n_regions,
                               float spatial_scale, const int* ncw, const int* nch, int tpt, long long image_token_id,
-                              void* out, int* plan_ws, int* status_dev, void* stream);
+                              int replay_mode, void* out, int* plan_ws, int* status_dev, void* stream);
 /* Its two halves.  The plan (row kinds, image ordinals, crop bins, status bits) depends only on input_ids, so it can run
  * before the image features exist and its status word can be read early: the reference raises its ValueError
  * (modeling_perception_lm.py:309-315) before the language model runs, and so does a caller of these two. */
 int gar_assemble_plan_batch(int nreq, const long long* const* input_ids_dev, int S, int n_image_rows,
                             const long long* crop_ids, const int* has_roi, int n_regions, int tpt,
-                            long long image_token_id, int* plan_ws, int* status_dev, void* stream);
+                            long long image_token_id, int replay_mode, int* plan_ws, int* status_dev, void* stream);
 int gar_assemble_rows_batch(int nreq, const long long* const* input_ids_dev, int S, const void* embed_table, int vocab,
                             const void* image_features, int n_image_rows, int D, const long long* crop_ids,
                             const float* rois, const int* has_roi, int n_regions, float spatial_scale, const int* ncw,
-                            const int* nch, int tpt, long long image_token_id, void* out, const int* plan_ws,
-                            void* stream);
+                            const int* nch, int tpt, long long image_token_id, int replay_mode, void* out,
+                            const int* plan_ws, void* stream);
 
 /* ---- request preprocessing on the device: uint8 image + uint8 region-id map -> bf16 tile tensors ----
  * One separable pass of ATen's native uint8 antialiased bicubic resize (what torchvision v2 `resize(..., BICUBIC)` runs on
@@ -265,6 +277,11 @@ long long gar_engine_launch_count(gar_engine* e);
  * their grids to it.  Results are identical to the unpartitioned run.  GAR_ERR_CUDA if the driver cannot partition. */
 int gar_engine_partition(gar_engine* e, int decode_sms, void** encode_stream, int* encode_sms, void** decode_stream,
                          int* decode_sms_out);
+/* Which replay loop (GAR_REPLAY_*) and which crop-token ids (HOST array, n <= 8; NULL = the model's crop_tokens_ids)
+ * the following plan / assemble calls use; (GAR_REPLAY_MERGED, NULL, 0) restores GARModel.generate's behaviour.  The
+ * rois / has_roi arrays of those calls are indexed by this id list.  In GAR_REPLAY_FRAME the T tiles are T frames:
+ * crop id k replays from tile k and the ncw x nch == T-1 check of the merged map does not apply. */
+int gar_engine_set_replay(gar_engine* e, int replay_mode, const long long* crop_ids, int n);
 /* options: "skinny_gemm" (1 = decode GEMMs use gar_gemm_skinny_bf16, default 1), "decode_splits" */
 int gar_engine_set_option(gar_engine* e, const char* name, int value);
 /* optional per-kernel-class CUDA-event timing for bench.py's roofline (decode runs ungraphed while on) */

@@ -389,6 +389,64 @@ class GAROracle(nn.Module):
             out.append(cur.unsqueeze(0))
         return torch.cat(out, 0)
 
+    def assemble_plm(self, input_ids, image_features, aspect_ratios, bboxes, crop_tokens=(128004,), video=False,
+                     frame_crop_ids=None):
+        """The replay branches of the vendored PLM's ``prepare_inputs_for_generation``
+        (models/modeling/modeling_perception_lm.py:608-858), batch 1.  Returns inputs_embeds (1,S,D).
+
+        video=False (``feature_replay``, :648-763): same merged-map RoI replay as GARModel.generate, over ``crop_tokens``
+        in list order -- but every replay is spliced into the ORIGINAL scattered embeddings (``inputs_embeds[batch_idx]``,
+        :736-742), so only the LAST crop token present in the prompt keeps its replay; the others keep the embedding of
+        their crop-token id.
+        video=True (``feature_replay_video``, :765-852): frame f's crop token (``frame_crop_ids[f]`` = the id of
+        ``<|reserved_special_token_{2+f}|>``) is replayed from frame f's OWN 16x16 map (no thumbnail drop, no merge),
+        on the running tensor."""
+        spec = self.spec
+        emb = self.mllm.model.language_model.embed_tokens(input_ids)
+        img_mask = input_ids == spec.image_token_id
+        if int(img_mask.sum()) * emb.shape[-1] != image_features.numel():
+            raise ValueError(
+                f"Image features and image tokens do not match: tokens: {int(img_mask.sum())}, "
+                f"features {image_features.shape[:-1].numel()}")
+        emb = emb.masked_scatter(img_mask.unsqueeze(-1).expand_as(emb), image_features.to(emb.dtype))
+        import torchvision
+
+        tpt = int(math.isqrt(spec.tokens_per_tile))
+        D = image_features.shape[-1]
+        assert emb.shape[0] == 1, "Currently only support batch_size=1 for feature replay"
+        b = 0
+        cur = emb[b]
+
+        def replay_rows(fmap, bbox):
+            roi, scale = roi_box_f32(bbox, fmap.shape[2], fmap.shape[3])
+            feats = torchvision.ops.roi_align(fmap.float(), roi.unsqueeze(0).to(fmap.device), (tpt, tpt),
+                                              spatial_scale=scale, sampling_ratio=2, aligned=True)
+            return feats.permute(0, 2, 3, 1).flatten(1, 2).to(fmap.dtype).squeeze(0)
+
+        if not video:
+            ncw, nch = int(aspect_ratios[b][0]), int(aspect_ratios[b][1])
+            for crop_token in crop_tokens:
+                pos = (input_ids[b] == crop_token).nonzero().flatten()
+                if pos.numel() == 0:
+                    continue
+                head, tail = int(pos.min()), int(pos.max())
+                T1 = image_features.shape[0] - 1
+                assert T1 == ncw * nch, f"{ncw * nch} != {T1}"
+                tiles = image_features[1:].reshape(nch, ncw, tpt, tpt, D)
+                fmap = tiles.permute(4, 0, 2, 1, 3).reshape(1, D, nch * tpt, ncw * tpt)
+                # :736-742 -- spliced into emb[b], NOT into `cur`: earlier replays are discarded
+                cur = torch.cat([emb[b][:head], replay_rows(fmap, bboxes[b][str(crop_token)]), emb[b][tail + 1:]])
+        else:
+            for f in range(image_features.shape[0]):
+                crop_token = frame_crop_ids[f]
+                pos = (input_ids[b] == crop_token).nonzero().flatten()
+                if pos.numel() == 0:
+                    continue
+                head, tail = int(pos.min()), int(pos.max())
+                fmap = image_features[f].reshape(tpt, tpt, D).permute(2, 0, 1).unsqueeze(0)
+                cur = torch.cat([cur[:head], replay_rows(fmap, bboxes[b][str(crop_token)]), cur[tail + 1:]])
+        return cur.unsqueeze(0)
+
     # -- full path -----------------------------------------------------------------
     @torch.no_grad()
     def prefill_embeds(self, pixel_values, global_mask_values, aspect_ratios, bboxes, input_ids):

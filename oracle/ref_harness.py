@@ -13,8 +13,11 @@ with the shims listed in SURVEY.md §8(c):
   (iv)  ``mllm.generate`` is intercepted to capture ``inputs_embeds`` (HF generate is
         API-incompatible with transformers 5.5) and a manual greedy loop drives the vendored
         forward with ``past_key_values``.
+  (v)   for the PLM replay fixtures (SURVEY §8f N4) the vendored ``prepare_inputs_for_generation`` is called directly;
+        transformers 5.5's ``GenerationMixin.prepare_inputs_for_generation`` omits the ``inputs_embeds`` key the
+        vendored code indexes (:609; the pinned 4.56.2 returns it as None), so the key is defaulted to None.
 
-``python -m oracle.ref_harness`` regenerates tests/golden/ref_*.npz.
+``python -m oracle.ref_harness [case ...]`` regenerates tests/golden/ref_*.npz (all, or the named cases).
 """
 from __future__ import annotations
 
@@ -205,6 +208,81 @@ def compact(taps, request, spec):
     )
 
 
+def frame_crop_token_id(frame_idx: int) -> int:
+    """Llama-3 tokenizer id of ``<|reserved_special_token_{2 + frame_idx}|>`` (modeling_perception_lm.py:778-780):
+    the reserved tokens are numbered around the named specials 128006/128007/128009."""
+    k = 2 + frame_idx
+    return {0: 128002, 1: 128003, 2: 128004, 3: 128005, 4: 128008}.get(k, 128005 + k)
+
+
+class _FrameTokenizer:
+    def convert_tokens_to_ids(self, tok: str) -> int:
+        return frame_crop_token_id(int(tok.split("_")[-1].rstrip("|>")) - 2)
+
+
+class _FrameProcessor:
+    tokenizer = _FrameTokenizer()
+
+
+@torch.no_grad()
+def run_reference_plm_replay(model, request, video: bool, crop_tokens=None):
+    """inputs_embeds produced by the UNMODIFIED vendored ``prepare_inputs_for_generation`` replay branches
+    (feature_replay / feature_replay_video) for one request, plus the image features they were built from."""
+    from transformers.generation.utils import GenerationMixin
+
+    mllm = model.mllm
+    orig = GenerationMixin.prepare_inputs_for_generation
+
+    def shim(self, *a, **k):
+        out = orig(self, *a, **k)
+        out.setdefault("inputs_embeds", None)
+        return out
+
+    taps = {}
+    real_gif = mllm.get_image_features
+
+    def tap_gif(pixel_values=None, mask_embeds=None, **kw):
+        out = real_gif(pixel_values=pixel_values, mask_embeds=mask_embeds, **kw)
+        taps["image_features"] = out
+        return out
+
+    ids = request["input_ids"]
+    S = ids.shape[1]
+    GenerationMixin.prepare_inputs_for_generation = shim
+    mllm.get_image_features = tap_gif
+    try:
+        kw = dict(feature_replay_video=True, processor=_FrameProcessor()) if video else \
+            dict(feature_replay=True, crop_tokens=list(crop_tokens))
+        mi = mllm.prepare_inputs_for_generation(
+            ids, past_key_values=None, inputs_embeds=None, pixel_values=request["pixel_values"], mask_embeds=None,
+            attention_mask=torch.ones(1, S, dtype=torch.long), cache_position=torch.arange(S), logits_to_keep=1,
+            bboxes=request["bboxes"], aspect_ratios=request["aspect_ratios"].tolist(), **kw)
+    finally:
+        GenerationMixin.prepare_inputs_for_generation = orig
+        del mllm.get_image_features
+    taps["inputs_embeds"] = mi["inputs_embeds"]
+    return taps
+
+
+def compact_plm(taps, request, spec):
+    ids = request["input_ids"][0]
+    crop_ids = torch.tensor([frame_crop_token_id(f) for f in range(8)])
+    crop_rows = torch.isin(ids, crop_ids).nonzero().flatten()
+    text_rows = ((ids != spec.image_token_id) & ~torch.isin(ids, crop_ids)).nonzero().flatten()
+    img_rows = (ids == spec.image_token_id).nonzero().flatten()[::37]
+    rows = torch.cat([crop_rows, text_rows, img_rows]).sort().values
+    return dict(image_features=taps["image_features"][:, ::3, ::2].float().numpy(), embed_rows=rows.numpy(),
+                inputs_embeds=taps["inputs_embeds"][0, rows].float().numpy())
+
+
+PLM_CASES = {
+    # name: (video, n_masks, max_num_tiles, seed) -- 3 regions on a 2x2+1 tile request: the image branch keeps only the
+    # last crop token's replay; the video branch treats the 5 tiles as 5 frames and replays frames 0..2 from their own map
+    "ref_tiny_plm_replay": (False, 3, 4, 21),
+    "ref_tiny_plm_video": (True, 3, 4, 22),
+}
+
+
 CASES = {
     # name: (n_masks, max_num_tiles, image_size, new_tokens, seed)
     "ref_tiny_1mask": (1, 4, 1024, 12, 11),
@@ -223,12 +301,22 @@ def main():
     ref = build_reference_model(spec, oracle)
     outdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
+    only = set(sys.argv[1:])  # `python -m oracle.ref_harness [case names]`: regenerate just those fixtures
     for name, (n_masks, mnt, isz, ntok, seed) in CASES.items():
+        if only and name not in only:
+            continue
         req = make_request(spec, seed=seed, n_masks=n_masks, image_size=isz, max_num_tiles=mnt,
                            dtype=torch.float32)
         taps = run_reference(ref, req, ntok)
         np.savez_compressed(os.path.join(outdir, name + ".npz"), **compact(taps, req, spec))
         print(name, "S =", req["input_ids"].shape[1], "tokens:", taps["sequences"].tolist())
+    for name, (video, n_masks, mnt, seed) in PLM_CASES.items():
+        if only and name not in only:
+            continue
+        req = make_request(spec, seed=seed, n_masks=n_masks, image_size=1024, max_num_tiles=mnt, dtype=torch.float32)
+        taps = run_reference_plm_replay(ref, req, video, crop_tokens=spec.crop_tokens_ids)
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), **compact_plm(taps, req, spec))
+        print(name, "S =", req["input_ids"].shape[1])
 
 
 if __name__ == "__main__":

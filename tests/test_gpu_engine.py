@@ -425,3 +425,54 @@ def test_raw_uint8_requests_match_preprocessed_requests():
     raw_bytes = sum(r[k].numel() * r[k].element_size() for r in raws for k in ("image_u8", "idmap_u8", "input_ids"))
     cooked_bytes = sum(r[k].numel() * r[k].element_size() for r in cooked for k in ("pixel_values", "global_mask_values", "input_ids"))
     assert raw_bytes * 3 < cooked_bytes
+
+
+@pytest.mark.parametrize("video", [False, True])
+def test_mllm_generate_plm_replay_branches(video):
+    """SURVEY §8f N4 through the public surface: ``model.mllm.generate(feature_replay=... | feature_replay_video=...)``
+    (the keyword names of the vendored PLM's prepare_inputs_for_generation, modeling_perception_lm.py:574-860).
+    inputs_embeds must be bit-exact against the oracle restatement pinned to the reference's own run (incl. the
+    reference's last-crop-only splice in the image branch); the returned sequences carry the prompt ids in front, like
+    HF generate called with input_ids."""
+    from grasp_any_region_b200 import GARConfig, GARModel
+    from oracle.ref_harness import _FrameProcessor, frame_crop_token_id
+
+    spec = gar_small()
+    new_tokens = 6
+    o32, o16, eng0, req = _setup(spec, 3, seed=41 + video, new_tokens=new_tokens)
+    eng0.close()
+    model = GARModel(GARConfig.from_spec(spec))
+    model.load_state_dict({k: v.to(bf) for k, v in o16.state_dict().items()}, strict=False)
+    model = model.to(DEV)
+    ids = req["input_ids"]
+    S, T, D = ids.shape[1], req["pixel_values"].shape[0], spec.text.hidden_size
+    model.configure_engine(max_tiles=T, max_seq=S + new_tokens + 8, max_batch=1, max_new_tokens=new_tokens)
+    kw = dict(feature_replay_video=True, processor=_FrameProcessor()) if video else \
+        dict(feature_replay=True, crop_tokens=list(spec.crop_tokens_ids))
+    out = model.mllm.generate(input_ids=ids, pixel_values=req["pixel_values"], attention_mask=torch.ones_like(ids),
+                              bboxes=req["bboxes"], aspect_ratios=req["aspect_ratios"], max_new_tokens=new_tokens, **kw)
+    seq = out.sequences
+    assert seq.shape == (1, S + new_tokens) and torch.equal(seq[:, :S].cpu(), ids.cpu())
+    eng = model.engine()
+    assert eng.replay_mode == 0 and eng.crop_ids == list(spec.crop_tokens_ids), "the replay mode must not leak"
+    feats = eng.buffer("image_features", (T, spec.tokens_per_tile, D))
+    emb = eng.buffer("inputs_embeds", (S, D))
+    want = o16.to("cpu").assemble_plm(ids.cpu(), feats.cpu(), req["aspect_ratios"].cpu(), req["bboxes"],
+                                      crop_tokens=list(spec.crop_tokens_ids), video=video,
+                                      frame_crop_ids=[frame_crop_token_id(f) for f in range(T)])[0]
+    o16.to(DEV)
+    assert torch.equal(emb.cpu(), want), "inputs_embeds of the PLM replay branch must be bit-exact"
+    # and they differ from GARModel.generate's loop on the same request (3 regions: image branch drops two replays,
+    # video branch reads other tiles)
+    plain = o16.to("cpu").assemble(ids.cpu(), feats.cpu(), req["aspect_ratios"].cpu(), req["bboxes"])[0]
+    o16.to(DEV)
+    assert not torch.equal(plain, want)
+    # tokens: greedy on the same embeddings
+    seq32, lg32, all32 = o32.greedy(emb.float()[None], new_tokens, None, return_logits=True)
+    toks = seq[0, S:].tolist()
+    for i, (a, b) in enumerate(zip(toks, seq32[0].tolist())):
+        if a == b:
+            continue
+        top2 = all32[i][0].topk(2).values
+        assert (top2[0] - top2[1]).item() <= 8e-2, f"token {i}: {a} != {b}"
+        break

@@ -511,6 +511,51 @@ def test_assemble_replay_batched_bit_exact(nreq, ncw, nch, n_masks):
         assert torch.equal(one, out[i]) and int(st1[0]) == 0
 
 
+@pytest.mark.parametrize("video,nreq,ncw,nch,n_masks", [(False, 1, 2, 2, 3), (False, 3, 3, 2, 2), (False, 2, 4, 4, 5),
+                                                         (True, 1, 2, 2, 3), (True, 3, 2, 1, 3), (True, 2, 4, 2, 5)])
+def test_assemble_plm_replay_modes_bit_exact(video, nreq, ncw, nch, n_masks):
+    """the two replay branches of the vendored PLM's prepare_inputs_for_generation
+    (modeling_perception_lm.py:648-852) as replay modes of the same kernels, bit-exact against the oracle restatement
+    that tests/test_oracle_vs_reference.py pins to the reference's own run: GAR_REPLAY_MERGED_LAST keeps only the
+    last crop token's replay, GAR_REPLAY_FRAME replays crop id k from tile (frame) k's own map."""
+    import numpy as np
+
+    from grasp_any_region_b200.config import gar_tiny
+    from grasp_any_region_b200.engine import roi_boxes_f32
+    from oracle.gar_oracle import build_oracle
+
+    spec = gar_tiny()
+    oracle = build_oracle(spec, seed=0, dtype=torch.float32).to(bf)
+    table = oracle.mllm.model.language_model.embed_tokens.weight.detach().to(DEV).contiguous()
+    D = table.shape[1]
+    tpt = int(math.isqrt(spec.tokens_per_tile))
+    T = ncw * nch + 1
+    crop_ids = list(spec.crop_tokens_ids)  # frame f <-> crop id f in the per-frame mode (T >= n_masks here)
+    g = np.random.default_rng(nreq * 100 + ncw * 10 + n_masks + 7 * video)
+    cases = [_assemble_case(spec, g, ncw, nch, n_masks) for _ in range(nreq)]
+    feats = rnd(nreq, T, spec.tokens_per_tile, D, seed=5)
+    rois, has, grids = [], [], []
+    for _, boxes in cases:
+        rr, hh, scale = roi_boxes_f32(spec, boxes, ncw, nch, crop_ids, per_frame=video)
+        rois.append(rr)
+        has.append(hh)
+        grids.append((ncw, nch))
+    ids_dev = [c[0].to(DEV) for c in cases]
+    mode = ops.REPLAY_FRAME if video else ops.REPLAY_MERGED_LAST
+    out, status = ops.assemble_embeds_batch(ids_dev, table, feats, crop_ids, rois, has, scale, grids, tpt,
+                                            spec.image_token_id, replay_mode=mode)
+    plain, _ = ops.assemble_embeds_batch(ids_dev, table, feats, crop_ids, rois, has, scale, grids, tpt,
+                                         spec.image_token_id)
+    torch.cuda.synchronize()
+    assert status[:, 0].tolist() == [0] * nreq
+    for i, (ids, boxes) in enumerate(cases):
+        want = oracle.assemble_plm(ids[None], feats[i].cpu(), torch.tensor([[ncw, nch]]), [boxes], crop_tokens=crop_ids,
+                                   video=video, frame_crop_ids=crop_ids + [-1] * T)[0]
+        assert torch.equal(out[i].cpu(), want), f"request {i}: rows differ from the reference's replay branch"
+        if n_masks > 1:
+            assert not torch.equal(out[i], plain[i]), "the mode must change the result when several regions are present"
+
+
 @pytest.mark.parametrize("h,w,max_tiles", [(1024, 1024, 16), (600, 900, 6), (300, 520, 8), (448, 448, 4), (2000, 700, 16)])
 def test_device_preprocessing_is_bit_identical_to_the_host_builder(h, w, max_tiles):
     """SURVEY §8f N1 device half: uint8 image + uint8 id map -> bf16 tiles on the GPU (ATen's uint8 antialiased bicubic
