@@ -560,14 +560,18 @@ def main():
              "bytes_per_step": w_bytes + kv_bytes, "ms_per_launch": d_ms, "launches_per_step": NT - 1,
              "share_of_step": phases["decode_ms_total"] / step_ms, "traffic": None,
              "mode": "production (graph replay), from phases.decode_ms_per_token_step"},
-            {"bound": "hbm", "kernel": "plan_rows + assemble_rows (embed gather + image scatter + RoI replay)",
+            {"bound": "hbm", "kernel": "replay_rows + gather_rows (embed gather + image scatter + RoI replay; one call, "
+                                       "the two grids side by side)",
              "achieved": asm_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": asm_gbs / peaks["hbm"],
              "bytes_per_step": s_by, "ms_per_step": s_ms, "launches_per_step": s_n, "share_of_step": s_ms / step_ms,
-             "traffic": None},
+             "traffic": None,
+             "note": "the row plan (plan_rows_kernel: ids only, no feature bytes) runs before the ViT so that a malformed "
+                     f"prompt raises first; timed separately: {prof['plan'][0] * 1e3:.1f} us per step"},
         ]
         stages = {
             "attn_tcgen05": {"ms": a_ms, "TFLOP/s": atf, "launches": a_n},
-            "assemble_replay": {"ms": s_ms, "GB/s": asm_gbs, "frac_hbm": asm_gbs / peaks["hbm"], "launches": s_n},
+            "assemble_replay": {"ms": s_ms, "GB/s": asm_gbs, "frac_hbm": asm_gbs / peaks["hbm"], "launches": s_n,
+                                "plan_ms": prof["plan"][0]},
             "decode_attn_ungraphed": {"ms": prof["decode_attn"][0], "launches": prof["decode_attn"][2]},
             "decode_gemv_ungraphed": {"ms": prof["gemv"][0], "launches": prof["gemv"][2]},
         }

@@ -51,7 +51,7 @@ struct AssembleParams {
 };
 
 // plan word: kind in bits [30,32), payload in [0,30)
-__global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant__ AssembleParams p,
+__global__ void __launch_bounds__(1024) plan_rows_kernel(int S, int n_image_feats, const __grid_constant__ AssembleParams p,
                                  int* __restrict__ plan_all, int* __restrict__ status_all,
                                  int* __restrict__ region_start_all) {
   pdl_launch_dependents();
@@ -70,6 +70,11 @@ __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant
   // both passes read the thread's ids eight at a time (independent loads in flight before the first use)
   constexpr int PU = 8;
   int cnt = 0;
+  // crop-token positions: per-thread min / max / count per region, reduced by warp shuffles, then ONE shared-memory
+  // atomic per warp and region (a 256-token run hitting one shared address with 768 atomics serialised for ~8 us)
+  int lmin[MAX_REGIONS], lmax[MAX_REGIONS], lcnt[MAX_REGIONS];
+#pragma unroll
+  for (int k = 0; k < MAX_REGIONS; ++k) { lmin[k] = 0x7fffffff; lmax[k] = -1; lcnt[k] = 0; }
   for (int s0 = lo; s0 < hi; s0 += PU) {
     long long idr[PU];
 #pragma unroll
@@ -80,12 +85,27 @@ __global__ void plan_rows_kernel(int S, int n_image_feats, const __grid_constant
       if (s >= hi) break;
       const long long id = idr[u];
       if (id == p.image_token_id) ++cnt;
-      for (int k = 0; k < p.n_regions; ++k) {
-        if (id == p.crop_ids[k]) {
-          atomicMin(&s_min[k], s);
-          atomicMax(&s_max[k], s);
-          atomicAdd(&s_cnt[k], 1);
+#pragma unroll
+      for (int k = 0; k < MAX_REGIONS; ++k) {
+        if (k < p.n_regions && id == p.crop_ids[k]) {
+          lmin[k] = min(lmin[k], s);
+          lmax[k] = max(lmax[k], s);
+          ++lcnt[k];
         }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MAX_REGIONS; ++k) {
+    if (k >= p.n_regions) break;
+    const int wc = __reduce_add_sync(0xffffffffu, lcnt[k]);
+    if (wc > 0) {  // warp-uniform
+      const int wmin = __reduce_min_sync(0xffffffffu, lmin[k]);
+      const int wmax = __reduce_max_sync(0xffffffffu, lmax[k]);
+      if ((tid & 31) == 0) {
+        atomicMin(&s_min[k], wmin);
+        atomicMax(&s_max[k], wmax);
+        atomicAdd(&s_cnt[k], wc);
       }
     }
   }

@@ -76,7 +76,7 @@ struct gar_engine {
   std::vector<ProfRec> prof;
 };
 
-enum ProfKind { PK_GEMM = 0, PK_ATTN = 1, PK_ASSEMBLE = 2, PK_DECODE_ATTN = 3, PK_GEMV = 4, PK_COUNT = 5 };
+enum ProfKind { PK_GEMM = 0, PK_ATTN = 1, PK_ASSEMBLE = 2, PK_DECODE_ATTN = 3, PK_GEMV = 4, PK_PLAN = 5, PK_COUNT = 6 };
 
 namespace {
 
@@ -649,7 +649,7 @@ int gar_engine_plan_batch(gar_engine* e, int slot0, int nreq, const long long* c
     return GAR_ERR_ARG;
   }
   {
-    ProfScope ps(e, s, PK_ASSEMBLE, 0.0);  // the plan kernel only (the status read-back below is host plumbing)
+    ProfScope ps(e, s, PK_PLAN, 0.0);  // the plan kernel only (the status read-back below is host plumbing)
     TRY(gar_assemble_plan_batch(nreq, input_ids_dev, S, T * e->tokens_per_tile, e->crop_ids(), has_roi, e->n_regions(),
                                 e->tpt, d.image_token_id, e->replay_mode, e->plan, e->status + 2 * slot0, s));
   }

@@ -372,10 +372,10 @@ class Engine:
 
     def profile_read(self):
         """{class: (ms, work, launches)} summed over the launches recorded since profile(True)."""
-        n = 5
+        n = 6
         ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_longlong * n)()
         check(self.lib.gar_engine_profile_read(self._h, ms, work, cnt), "gar_engine_profile_read")
-        names = ["gemm", "attn", "assemble", "decode_attn", "gemv"]
+        names = ["gemm", "attn", "assemble", "decode_attn", "gemv", "plan"]
         return {names[i]: (ms[i], work[i], cnt[i]) for i in range(n)}
 
     def close(self):

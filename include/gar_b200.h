@@ -290,7 +290,8 @@ int gar_engine_set_option(gar_engine* e, const char* name, int value);
 #define GAR_PROF_ASSEMBLE 2
 #define GAR_PROF_DECODE_ATTN 3
 #define GAR_PROF_GEMV 4 /* decode weight-stream kernels; work = weight bytes */
-#define GAR_PROF_COUNT 5
+#define GAR_PROF_PLAN 5 /* row plan + validation of the prompts (runs before the ViT) */
+#define GAR_PROF_COUNT 6
 int gar_engine_profile(gar_engine* e, int enable);
 int gar_engine_profile_read(gar_engine* e, double* ms, double* work, long long* count);
 
