@@ -299,7 +299,8 @@ int launch_gv(const GvArgs& a, bool norm, cudaStream_t s) {
   const int n_out = EPI == GV_EPI_SWIGLU ? a.N / 2 : a.N;
   dim3 grid(n_out / out_feats);
   // 16 K-slices when K is long and the grid alone cannot fill the machine (R == 1 only: register budget)
-  const bool wide = R == 1 && a.K % 512 == 0 && a.K >= 4096 && static_cast<int>(grid.x) < 2 * gar_num_sms();
+  const bool wide = R == 1 && a.K % 512 == 0 && a.K >= 4096 && static_cast<int>(grid.x) < 2 * gar_num_sms() &&
+                    gar_global_option("gemv_wide");
 #define GV_LAUNCH(NORM_, W_) \
   GAR_CUDA_CHECK(gar_launch(gemv_decode_kernel<R, EPI, NORM_, W_>, grid, dim3(W_ * 32), 0, s, true, dim3(1, 1, 1), a))
   if constexpr (R == 1) if (wide) {
