@@ -455,6 +455,232 @@ decode_attn_mma_kernel(const bf16* __restrict__ qkv, int ldq, bf16* __restrict__
   if (tickets != nullptr) fused_combine_tail<HD, GROUP>(tickets, o_part, ml_part, out, ldo, b, kvh, hq, hkv, splits);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same flash-decoding step for any head_dim that is a multiple of 32 (instantiated for 128: Llama-3.1-8B), on a
+// tighter register budget: K blocks stay double-buffered in registers, V blocks go HBM -> shared memory by cp.async
+// into a two-stage per-warp ring (no registers), and the dead half of every accumulator tile (rows 8..15 of the
+// 16-row MMA tile never hold a query head) is ONE shared pair of always-zero registers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma16816_top(float& d0, float& d1, float& z0, float& z1, uint32_t a0, uint32_t a2,
+                                             uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d0), "+f"(d1), "+f"(z0), "+f"(z1)
+      : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int HD, int GROUP, bool ROPE>
+__global__ void __launch_bounds__(DEC_THREADS)
+decode_attn_mma_wide_kernel(const bf16* __restrict__ qkv, int ldq, bf16* __restrict__ kcache, bf16* __restrict__ vcache,
+                            const int* __restrict__ pos_dev, const int* __restrict__ slot_dev, int hq, int hkv,
+                            int max_seq, int splits, float scale_log2, float* __restrict__ o_part,
+                            float* __restrict__ ml_part, int* __restrict__ tickets, bf16* __restrict__ out, int ldo,
+                            const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t) {
+  constexpr int NC = HD / 32;    // 16-byte chunks per lane per K row: dims [32c + 8tig, +8), c < NC
+  constexpr int CPR = HD / 8;    // 16-byte chunks per V row
+  constexpr int VCH = 16 * CPR / 32;  // V chunks per lane per 16-key block
+  static_assert(HD % 64 == 0 && GROUP <= 8, "rotate-half pairs chunk c with chunk c + NC/2");
+  pdl_launch_dependents();
+  pdl_wait();
+  const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int len = pos_dev[b] + 1;
+  const int slot = slot_dev ? slot_dev[b] : b;
+  int chunk = (len + splits - 1) / splits;
+  chunk = (chunk + 15) & ~15;
+  const int k_begin = split * chunk;
+  const int k_end = min(len, k_begin + chunk);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+  constexpr int NW = DEC_THREADS / 32;
+
+  // per-warp V ring: 2 stages x 16 keys x HD; 16-byte chunk c of row `key` at (c & ~7) | ((c ^ key) & 7) (conflict-free
+  // ldmatrix.trans); after the key loop the warp's own stages hold its partial output rows for the cross-warp merge
+  __shared__ __align__(16) bf16 vstage[NW][2][16 * HD];
+  __shared__ float s_m[NW][8], s_l[NW][8];
+  static_assert(sizeof(float) * 8 * HD <= sizeof(bf16) * 2 * 16 * HD, "partial output rows must fit the warp's ring");
+
+  const bf16* cos_q = ROPE ? cos_t + static_cast<size_t>(len - 1) * (HD / 2) : nullptr;
+  const bf16* sin_q = ROPE ? sin_t + static_cast<size_t>(len - 1) * (HD / 2) : nullptr;
+  // q fragments (A operand rows = heads; rows >= GROUP and rows 8..15 are zero)
+  uint4 qf[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) qf[c] = make_uint4(0, 0, 0, 0);
+  if (g < GROUP) {
+    const bf16* qp = qkv + static_cast<size_t>(b) * ldq + static_cast<size_t>(kvh * GROUP + g) * HD;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) qf[c] = *reinterpret_cast<const uint4*>(qp + 32 * c + 8 * tig);
+    if (ROPE) {
+#pragma unroll
+      for (int c = 0; c < NC / 2; ++c) rope_lo_hi(qf[c], qf[c + NC / 2], cos_q + 32 * c, sin_q + 32 * c, tig);
+    }
+  }
+  bf16* kbase = kcache + (static_cast<size_t>(slot) * hkv + kvh) * max_seq * HD;
+  bf16* vbase = vcache + (static_cast<size_t>(slot) * hkv + kvh) * max_seq * HD;
+  const int new_pos = len - 1;  // ROPE: this row is not in the cache yet
+  const bf16* knew = qkv + static_cast<size_t>(b) * ldq + static_cast<size_t>(hq + kvh) * HD;
+  const bf16* vnew = qkv + static_cast<size_t>(b) * ldq + static_cast<size_t>(hq + hkv + kvh) * HD;
+
+  float o[HD / 8][2];
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) o[n][0] = o[n][1] = 0.f;
+  float z0 = 0.f, z1 = 0.f;              // rows 8..15 of every accumulator tile: always zero
+  float m_run = -INFINITY, l_run = 0.f;  // per (lane row g): partial over this lane's key columns
+
+  struct KStep { uint4 k0[NC], k1[NC]; };  // key kb+g and kb+8+g
+  auto load_k = [&](KStep& st, int kb) {
+    auto one = [&](int key, uint4 (&kr)[NC]) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) kr[c] = make_uint4(0, 0, 0, 0);
+      if (key >= k_end) return;
+      if (ROPE && key == new_pos) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) kr[c] = *reinterpret_cast<const uint4*>(knew + 32 * c + 8 * tig);
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c)
+          rope_lo_hi(kr[c], kr[c + NC / 2], cos_t + static_cast<size_t>(new_pos) * (HD / 2) + 32 * c,
+                     sin_t + static_cast<size_t>(new_pos) * (HD / 2) + 32 * c, tig);
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          *reinterpret_cast<uint4*>(kbase + static_cast<size_t>(key) * HD + 32 * c + 8 * tig) = kr[c];
+      } else {
+        const bf16* kp = kbase + static_cast<size_t>(key) * HD;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) kr[c] = *reinterpret_cast<const uint4*>(kp + 32 * c + 8 * tig);
+      }
+    };
+    one(kb + g, st.k0);
+    one(kb + 8 + g, st.k1);
+  };
+  // V block of one step into ring stage `stg`: cp.async for cache rows, a direct store for the step's own row (taken
+  // from `qkv`, also appended to the cache) and zeros past the key range
+  auto issue_v = [&](int stg, int kb) {
+#pragma unroll
+    for (int i = 0; i < VCH; ++i) {
+      const int id = lane + 32 * i, key = id / CPR, c = id % CPR;
+      bf16* dst = &vstage[warp][stg][key * HD + (((c & ~7) | ((c ^ key) & 7)) << 3)];
+      if (kb + key >= k_end) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      } else if (ROPE && kb + key == new_pos) {
+        const uint4 v = *reinterpret_cast<const uint4*>(vnew + 8 * c);
+        *reinterpret_cast<uint4*>(vbase + static_cast<size_t>(kb + key) * HD + 8 * c) = v;
+        *reinterpret_cast<uint4*>(dst) = v;
+      } else {
+        cp_async16(smem_u32(dst), vbase + static_cast<size_t>(kb + key) * HD + 8 * c);
+      }
+    }
+    cp_async_commit();
+  };
+
+  KStep cur, nxt;
+  const int kb_first = k_begin + warp * 16;
+  if (kb_first < k_end) {
+    load_k(cur, kb_first);
+    issue_v(0, kb_first);
+  }
+  int it = 0;
+  for (int kb = kb_first; kb < k_end; kb += NW * 16, ++it) {
+    __syncwarp();  // the ldmatrix reads of the previous step are done: its ring stage may be refilled
+    if (kb + NW * 16 < k_end) {
+      load_k(nxt, kb + NW * 16);
+      issue_v((it + 1) & 1, kb + NW * 16);
+    } else {
+      cp_async_commit();  // keeps the group count uniform for the wait below
+    }
+    // ---- S = q K^T for two 8-key groups
+    float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      mma16816_top(s00, s01, z0, z1, qf[c].x, qf[c].y, cur.k0[c].x, cur.k0[c].y);
+      mma16816_top(s00, s01, z0, z1, qf[c].z, qf[c].w, cur.k0[c].z, cur.k0[c].w);
+      mma16816_top(s10, s11, z0, z1, qf[c].x, qf[c].y, cur.k1[c].x, cur.k1[c].y);
+      mma16816_top(s10, s11, z0, z1, qf[c].z, qf[c].w, cur.k1[c].z, cur.k1[c].w);
+    }
+    // lane holds row g (head), keys kb + 2tig, +1 (s00, s01) and kb + 8 + 2tig, +1 (s10, s11)
+    float v0 = s00 * scale_log2, v1 = s01 * scale_log2, v2 = s10 * scale_log2, v3 = s11 * scale_log2;
+    v0 = (kb + 2 * tig < k_end) ? v0 : -INFINITY;
+    v1 = (kb + 2 * tig + 1 < k_end) ? v1 : -INFINITY;
+    v2 = (kb + 8 + 2 * tig < k_end) ? v2 : -INFINITY;
+    v3 = (kb + 8 + 2 * tig + 1 < k_end) ? v3 : -INFINITY;
+    float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(m_run, mx);
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+    const float alpha = ex2_approx(m_run - m_use);
+    const float p0 = ex2_approx(v0 - m_use), p1 = ex2_approx(v1 - m_use), p2 = ex2_approx(v2 - m_use),
+                p3 = ex2_approx(v3 - m_use);
+    l_run = l_run * alpha + ((p0 + p1) + (p2 + p3));
+    m_run = m_new;
+    const uint32_t pa0 = pack_bf16x2(p0, p1), pa2 = pack_bf16x2(p2, p3);  // P as A fragment (rows 8..15 zero)
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) {
+      o[n][0] *= alpha;
+      o[n][1] *= alpha;
+    }
+    cp_async_wait<1>();  // this lane's share of the current V block has landed ...
+    __syncwarp();        // ... and so has every other lane's (plus the direct stores of issue_v)
+    // ---- O += P V : B fragments through ldmatrix.trans (matrix rows = keys, cols = 8 d)
+    const uint32_t vs_base = smem_u32(&vstage[warp][it & 1][0]);
+#pragma unroll
+    for (int np = 0; np < HD / 16; ++np) {  // two 8-wide d chunks per ldmatrix.x4
+      const int mat = lane >> 3, r = lane & 7;
+      const int key = (mat & 1) * 8 + r;
+      const int c = np * 2 + (mat >> 1);
+      const uint32_t addr = vs_base + (key * HD + (((c & ~7) | ((c ^ key) & 7)) << 3)) * 2;
+      uint32_t b0, b1, b2, b3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                   : "r"(addr));
+      mma16816_top(o[np * 2][0], o[np * 2][1], z0, z1, pa0, pa2, b0, b1);
+      mma16816_top(o[np * 2 + 1][0], o[np * 2 + 1][1], z0, z1, pa0, pa2, b2, b3);
+    }
+    cur = nxt;
+  }
+  cp_async_wait<0>();
+  __syncwarp();  // every lane is done with the warp's ring: it now holds the warp's partial output rows
+  // ---- per-warp row statistics: combine the 4 key-column lanes of each head row
+  float m_w = fmaxf(m_run, __shfl_xor_sync(0xffffffffu, m_run, 1));
+  m_w = fmaxf(m_w, __shfl_xor_sync(0xffffffffu, m_w, 2));
+  const float fix = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_w);
+  float l_w = l_run * fix;
+  l_w += __shfl_xor_sync(0xffffffffu, l_w, 1);
+  l_w += __shfl_xor_sync(0xffffffffu, l_w, 2);
+  float (*so_w)[HD] = reinterpret_cast<float (*)[HD]>(&vstage[warp][0][0]);  // this warp's [8][HD] floats
+  if (g < GROUP) {
+    if (tig == 0) { s_m[warp][g] = m_w; s_l[warp][g] = l_w; }
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) {
+      so_w[g][n * 8 + 2 * tig] = o[n][0] * fix;
+      so_w[g][n * 8 + 2 * tig + 1] = o[n][1] * fix;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < GROUP * HD; idx += DEC_THREADS) {
+    const int gg = idx / HD, e = idx % HD;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) mm = fmaxf(mm, s_m[w][gg]);
+    float ll = 0.f, oo = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const float wgt = (s_m[w][gg] == -INFINITY) ? 0.f : ex2_approx(s_m[w][gg] - mm);
+      ll += s_l[w][gg] * wgt;
+      oo += reinterpret_cast<const float (*)[HD]>(&vstage[w][0][0])[gg][e] * wgt;
+    }
+    const int h = kvh * GROUP + gg;
+    const size_t pidx = (static_cast<size_t>(b) * hq + h) * splits + split;
+    o_part[pidx * HD + e] = oo;
+    if (e == 0) { ml_part[pidx * 2] = mm; ml_part[pidx * 2 + 1] = ll; }
+  }
+  if (tickets != nullptr) fused_combine_tail<HD, GROUP>(tickets, o_part, ml_part, out, ldo, b, kvh, hq, hkv, splits);
+}
+
 template <int HD>
 __global__ void decode_attn_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ ml_part,
                                            bf16* __restrict__ out, int ldo, int hq, int splits) {
@@ -486,8 +712,9 @@ static int decode_attn_impl(const void* qkv, int ldq, void* kcache, void* vcache
   bf16* kc_w = static_cast<bf16*>(kcache);
   bf16* vc_w = static_cast<bf16*>(vcache);
   const int group = hq / hkv;
-  if (rope && !(head_dim == 64 && (group == 4 || group == 2 || group == 1 || group == 8))) {
-    gar_set_error("gar_decode_attn_rope: fused RoPE needs head_dim 64 (got %d, group %d)", head_dim, group);
+  const bool wide_ok = head_dim == 128 && (group == 4 || group == 8 || group == 1);
+  if (rope && !wide_ok && !(head_dim == 64 && (group == 4 || group == 2 || group == 1 || group == 8))) {
+    gar_set_error("gar_decode_attn_rope: fused RoPE needs head_dim 64 or 128 (got %d, group %d)", head_dim, group);
     return GAR_ERR_SHAPE;
   }
   if (hq % hkv || splits < 1 || splits > 32) return GAR_ERR_ARG;
@@ -514,7 +741,22 @@ static int decode_attn_impl(const void* qkv, int ldq, void* kcache, void* vcache
                                 static_cast<float*>(ml_part_ws), tickets, static_cast<bf16*>(out), ldo,             \
                                 static_cast<const bf16*>(nullptr), static_cast<const bf16*>(nullptr)));             \
   } while (0)
-  if (head_dim == 64 && (rope || gar_global_option("decode_attn_mma")) && (group == 4 || group == 2 || group == 1 || group == 8)) {
+#define LAUNCH_WIDE_1(G_, R_)                                                                                       \
+  GAR_CUDA_CHECK(gar_launch(decode_attn_mma_wide_kernel<128, G_, R_>, grid, dim3(DEC_THREADS), 0, stream, true,     \
+                            dim3(1, 1, 1), static_cast<const bf16*>(qkv), ldq, kc_w, vc_w, pos_dev, slot_dev, hq,   \
+                            hkv, max_seq, splits, sl2, static_cast<float*>(o_part_ws),                              \
+                            static_cast<float*>(ml_part_ws), tickets, static_cast<bf16*>(out), ldo,                 \
+                            static_cast<const bf16*>(cos_t), static_cast<const bf16*>(sin_t)))
+#define LAUNCH_WIDE(G_)                                                                                             \
+  do {                                                                                                              \
+    if (rope) LAUNCH_WIDE_1(G_, true);                                                                              \
+    else LAUNCH_WIDE_1(G_, false);                                                                                  \
+  } while (0)
+  if (wide_ok && (rope || gar_global_option("decode_attn_mma"))) {
+    if (group == 4) LAUNCH_WIDE(4);
+    else if (group == 8) LAUNCH_WIDE(8);
+    else LAUNCH_WIDE(1);
+  } else if (head_dim == 64 && (rope || gar_global_option("decode_attn_mma")) && (group == 4 || group == 2 || group == 1 || group == 8)) {
     if (group == 4) LAUNCH_MMA(4);
     else if (group == 2) LAUNCH_MMA(2);
     else if (group == 1) LAUNCH_MMA(1);
@@ -529,6 +771,8 @@ static int decode_attn_impl(const void* qkv, int ldq, void* kcache, void* vcache
   }
 #undef LAUNCH_DEC
 #undef LAUNCH_MMA
+#undef LAUNCH_WIDE
+#undef LAUNCH_WIDE_1
   GAR_CUDA_CHECK(cudaGetLastError());
   if (tickets != nullptr) return GAR_OK;  // the split kernel's last CTA per (sequence, kv head) already combined
   dim3 cgrid(hq, batch);

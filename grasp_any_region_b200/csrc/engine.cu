@@ -236,7 +236,9 @@ int lm_head(gar_engine* e, const bf16* hrows, int ldh, int rows, bf16* logits, b
 int decode_splits(const gar_engine* e, int batch) {
   int splits = e->dec_splits;
   if (splits <= 0) {
-    splits = (3 * gar_num_sms()) / (batch * e->d.llm_kv_heads);
+    // resident CTAs per SM of the decode attention kernel: 3 at head_dim 64, 2 at head_dim 128 (204 registers)
+    const int per_sm = e->d.llm_head_dim >= 128 ? 2 : 3;
+    splits = (per_sm * gar_num_sms()) / (batch * e->d.llm_kv_heads);
     splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
   }
   return splits;
@@ -273,7 +275,7 @@ int decode_step_gemv(gar_engine* e, int batch, void* s) {
     }
     {
       ProfScope ps(e, s, PK_DECODE_ATTN, 0.0);
-      if (e->fuse_decode_rope && hd == 64) {
+      if (e->fuse_decode_rope && (hd == 64 || hd == 128)) {
         // RoPE of q and of the new K row, the KV append and the attention in one launch
         TRY(gar_decode_attn_rope(e->d_qkv, qkv_w, kc, vc, e->pos + e->slot_base, nullptr, batch, hq, hkv, hd, d.max_seq,
                                  splits, scale, cos_t, sin_t, e->o_part, e->ml_part, e->tickets, e->d_att, hq * hd, s));

@@ -55,6 +55,23 @@ def test_gemm_plain(M, N, K, block_n):
     assert mism < 0.02, f"{mism:.4f} of outputs differ from the fp32-accumulated reference by a bf16 ulp"
 
 
+@pytest.mark.parametrize("M,N,K,epi", [(4100, 1024, 4096, ops.EPI_BIAS_LS_RES),   # ViT fc2 (+ LayerScale residual)
+                                       (4672, 2048, 8192, ops.EPI_RES),           # Llama-3.2-1B down_proj (+ residual)
+                                       (2300, 4096, 14336, ops.EPI_RES),          # Llama-3.1-8B down_proj
+                                       (3000, 1536, 8960, ops.EPI_BIAS_LS_RES)])  # PE-G fc2
+def test_gemm_long_k_production_shapes(M, N, K, epi):
+    """The big-M tcgen05 GEMM at the longest reduction depths of the path (64..224 k-blocks through the TMA ring and
+    one TMEM accumulator): fp32-accumulated reference on the same bf16 inputs."""
+    a, b = rnd(M, K, scale=0.5, seed=11), rnd(N, K, scale=0.02, seed=12)
+    bias, gamma, res = rnd(N, scale=0.1, seed=13), rnd(N, scale=0.2, seed=14), rnd(M, N, seed=15)
+    out = ops.gemm(a, b, epi=epi, bias=bias, gamma=gamma, res=res)
+    torch.cuda.synchronize()
+    ref = gemm_ref(a, b, epi, bias, gamma, res)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 4e-2 * max(1.0, ref.abs().max().item()), err
+    assert (out.float() != ref).float().mean().item() < 0.03
+
+
 @pytest.mark.parametrize("epi", [ops.EPI_BIAS, ops.EPI_BIAS_GELU, ops.EPI_BIAS_LS_RES, ops.EPI_RES])
 @pytest.mark.parametrize("M,N,K", [(333, 512, 256), (1025, 1024, 1024), (4000, 2048, 512)])
 def test_gemm_epilogues(epi, M, N, K):
@@ -425,15 +442,16 @@ def test_decode_attention_fused_rope_matches_unfused():
         assert torch.equal(got, want)
 
 
-def test_decode_attention_long_context_and_poisoned_tail():
-    """Fused RoPE + append + decode attention at the bench's context (~4.7k keys, GAR-1B head layout, batch 8) against
+@pytest.mark.parametrize("hd", [64, 128])
+def test_decode_attention_long_context_and_poisoned_tail(hd):
+    """Fused RoPE + append + decode attention at the bench's context (~4.7k keys, GAR-1B / GAR-8B head layout, batch 8) against
     fp32 SDPA over the rotated cache; cache rows PAST every live length are poisoned with NaN (never-written memory)
     and must not reach the output; the appended rows must be bit-identical to the unfused RoPE + append kernel."""
     from grasp_any_region_b200.config import TextSpec
     from grasp_any_region_b200.rope import llama_cos_sin
 
-    B, hq, hkv, hd, max_seq, splits = 8, 32, 8, 64, 4864, 6
-    cos, sin = llama_cos_sin(TextSpec(), max_seq)
+    B, hq, hkv, max_seq, splits = 8, 32, 8, 4864, 6
+    cos, sin = llama_cos_sin(TextSpec(head_dim=hd), max_seq)
     cos, sin = cos.to(bf).to(DEV), sin.to(bf).to(DEV)
     qkv = rnd(B, (hq + 2 * hkv) * hd, seed=95)
     kc0, vc0 = rnd(B, hkv, max_seq, hd, seed=96), rnd(B, hkv, max_seq, hd, seed=97)

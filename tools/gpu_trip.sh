@@ -1,18 +1,11 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-run() {
-  timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-lib-baseline --no-e2e --no-profile "$@" 2>&1 | tail -1 > gpurun_out/ab.log
-  python - "$*" <<'PY'
-import json, sys
-try:
-    d = json.loads(open("gpurun_out/ab.log").read().strip().splitlines()[-1])
-    print(sys.argv[1] or "default", "| captions/s %.2f" % d["value"], "| decode ms/step %.4f" % d["phases"]["decode_ms_per_token_step"], "| enc ms/req %.2f" % d["phases"]["vit_assemble_prefill_ms_per_request"], d["clocks"]["sm_mhz"])
-except Exception as ex:
-    print(sys.argv[1], "FAILED", ex, open("gpurun_out/ab.log").read()[-400:])
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_engine.py -q -m gpu -x -k "decode or long_k or engine or eos" 2>&1 | tail -4 | tee gpurun_out/tests.log
+timeout 900 python -m pytest tests/test_gpu_fullsize.py -q -m gpu -x -k "8b" 2>&1 | tail -3 | tee -a gpurun_out/tests.log
+timeout 900 python bench.py --model gar-8b --batch 2 --new-tokens 256 --max-num-tiles 16 --steps 2 --warmup 3 --no-cpu-baseline --no-lib-baseline 2>&1 | tail -1 > gpurun_out/bench_8b.log
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/bench_8b.log").read().strip().splitlines()[-1])
+print("8B value", d["value"], "e2e", d["e2e"]["value"], d["clocks"]); print("phases", d["phases"])
 PY
-}
-run
-run --opt gemv_wide=0
-run
-run --opt gemv_wide=0
