@@ -70,9 +70,9 @@ def parse_args():
 
 def gemm_traffic_bytes():
     """Mean DRAM bytes (read+write) per tcgen05 GEMM launch of this same command, from the committed ncu pass
-    (profiles/r01_gemm_traffic.json; ncu cannot run inside the timed bench).  None if the file is absent."""
+    (profiles/r02_gemm_traffic.json; ncu cannot run inside the timed bench).  None if the file is absent."""
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_gemm_traffic.json")) as f:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_gemm_traffic.json")) as f:
             return json.load(f)["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         return None
