@@ -59,6 +59,75 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float one_plus_erf = x < 0.f ? erfc_abs : 2.0f - erfc_abs;
   return 0.5f * x * one_plus_erf;
 }
+// packed bf16 arithmetic with one round-to-nearest-even per op (sm_90+): exactly "fp32 op on the two bf16 inputs, then
+// one bf16 rounding" for products (exact in fp32) and sums (fp32 rounding of a bf16 + bf16 sum never changes its bf16
+// rounding) -- the reference's per-op rounding points at two elements per instruction
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+// gelu_erf_fast for two values at once on fp32x2 FMA-pipe instructions (same formula, constants and branch on the sign);
+// returns the bf16-rounded pair
+__device__ __forceinline__ uint32_t gelu_erf_fast_pack2(float x0, float x1) {
+  unsigned long long x2, a2, t2, p2, e2, r2;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "f"(fabsf(x0)), "f"(fabsf(x1)));
+  const float kp = 0.3275911f * 0.70710678118654752440f, kone = 1.0f;
+  unsigned long long kp2, one2, c2;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(kp2) : "f"(kp));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(one2) : "f"(kone));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t2) : "l"(a2), "l"(kp2), "l"(one2));  // 1 + p z, z = |x| / sqrt 2
+  float d0, d1, t0, t1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(t2));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(t2) : "f"(t0), "f"(t1));
+#define GAR_F2(dst, val) asm("mov.b64 %0, {%1, %1};" : "=l"(dst) : "f"(val))
+  GAR_F2(p2, 1.061405429f);
+  GAR_F2(c2, -1.453152027f);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(t2), "l"(p2), "l"(c2));
+  GAR_F2(c2, 1.421413741f);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(t2), "l"(p2), "l"(c2));
+  GAR_F2(c2, -0.284496736f);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(t2), "l"(p2), "l"(c2));
+  GAR_F2(c2, 0.254829592f);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(t2), "l"(p2), "l"(c2));
+  // exp(-z^2) = ex2(|x|^2 * (-log2(e) / 2))
+  GAR_F2(c2, -0.72134752044448170368f);
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(e2) : "l"(a2), "l"(a2));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(e2) : "l"(e2), "l"(c2));
+  float g0, g1, e0, e1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(g0), "=f"(g1) : "l"(e2));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(g0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(g1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(e2) : "f"(e0), "f"(e1));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p2) : "l"(p2), "l"(t2));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p2) : "l"(p2), "l"(e2));   // erfc(|x| / sqrt 2)
+  // 1 + erf(x / sqrt 2) = erfc for x < 0 (no 1 - erf cancellation in the tail), 2 - erfc otherwise
+  unsigned long long two2, q2;
+  GAR_F2(c2, -1.0f);
+  GAR_F2(two2, 2.0f);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(q2) : "l"(p2), "l"(c2), "l"(two2));
+  float n0, n1, q0, q1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(n0), "=f"(n1) : "l"(p2));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(q2));
+  q0 = x0 < 0.f ? n0 : q0;
+  q1 = x1 < 0.f ? n1 : q1;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(q2) : "f"(q0), "f"(q1));
+  GAR_F2(c2, 0.5f);
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(x2) : "l"(x2), "l"(c2));         // x / 2
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r2) : "l"(x2), "l"(q2));         // x/2 (1 + erf)
+#undef GAR_F2
+  float r0, r1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r2));
+  return pack_bf16x2(r0, r1);
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
 // single-instruction MUFU.EX2 / FMNMX3 (the softmax inner loops are issue-bound)

@@ -516,6 +516,7 @@ int gar_engine_vit_encode_patches(gar_engine* e, int T, int with_mask, void* s) 
   NEEDW(npw, "vit.norm_pre.w");
   NEEDW(npb, "vit.norm_pre.b");
   NEEDW(rope, "vit.rope");
+  NEEDW(rope_cm, "vit.rope_cm");
   const void* cls = e->npt ? W(e, "vit.cls") : nullptr;
   if (e->npt && !cls) return GAR_ERR_STATE;
   // the two k=s=14 convs as GEMMs: x = bf16(conv(px)) ; x = bf16(x + bf16(conv(mask)))
@@ -549,7 +550,7 @@ int gar_engine_vit_encode_patches(gar_engine* e, int T, int with_mask, void* s) 
     if (e->fuse_rope) {
       e->launches += 1;
       ProfScope ps(e, s, PK_GEMM, 2.0 * rows * 3.0 * dq * dv);
-      TRY(gar_gemm_bf16_rope2d(e->ln, dv, wqkv, dv, e->qkv_v, 3 * dq, rows, 3 * dq, dv, bqkv, rope, NT, e->npt, hdp,
+      TRY(gar_gemm_bf16_rope2d(e->ln, dv, wqkv, dv, e->qkv_v, 3 * dq, rows, 3 * dq, dv, bqkv, rope_cm, NT, e->npt, hdp,
                                2 * dq, s));
     } else {
       TRY(gemm(e, e->ln, dv, wqkv, dv, e->qkv_v, 3 * dq, rows, 3 * dq, dv, GAR_EPI_BIAS, bqkv, nullptr, nullptr, 0, s));

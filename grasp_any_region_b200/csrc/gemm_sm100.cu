@@ -46,7 +46,7 @@ struct EpiArgs {
   const bf16* res;
   int ldres;
   // EPI_BIAS_ROPE2D: PE-ViT interleaved-pair RoPE on columns < rope_cols of rows whose token index
-  // (row % ntok) is >= npt; table row = cat(sin[hd], cos[hd])
+  // (row % ntok) is >= npt; table in chunk-major layout [sin | cos][hd / 8][ntok - npt][8]
   const bf16* rope;
   int ntok, npt, hd, rope_cols;
 };
@@ -113,6 +113,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
+  // Register hand-over (per warpgroup): the control warpgroup (TMA, MMA, allocator, one idle warp) keeps 56 registers,
+  // the two epilogue warpgroups get 224 -- room for double-buffered TMEM loads and a whole tile's residual rows in
+  // flight.  The instruction sits at the top of each role branch so ptxas allocates the branch against its own budget.
+  if (warp < 4) setmaxnreg_dec<56>();
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
@@ -175,52 +179,99 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ----------------------------------
+    setmaxnreg_inc<224>();
     const int ew = warp - 4;           // 0..7
     const int quarter = warp & 3;      // TMEM lane quarter this warp may touch (warp id % 4)
     const int half = ew >> 2;          // which half of the tile's columns
     const int row = quarter * 32 + lane;
     constexpr int COLS_PER_HALF = BLOCK_N / 2;
     constexpr int CHUNKS = COLS_PER_HALF / C_CHUNK;
-    const uint32_t stage_c0 = smem_c + half * 2 * C_STAGE_BYTES;
-    const uint32_t bar_id = 1 + half;  // named barriers 1,2 (0 is __syncthreads)
-    const bool issuer = (quarter == 0 && lane == 0);
+    // staging: [half][2 buffers][128 rows x 64 B]; every warp owns the 32 rows of its TMEM lane quarter and stores them
+    // with its OWN TMA store (box 32 columns x 32 rows), so no warp ever waits for another one inside the epilogue
+    const uint32_t stage_c0 = smem_c + half * 2 * C_STAGE_BYTES + quarter * (C_STAGE_BYTES / 4);
+    const bool issuer = lane == 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     int cbuf = 0;
-    float gate[EPI == EPI_SWIGLU ? 32 : 1];  // EPI_SWIGLU: bf16-rounded gate chunk waiting for its up chunk
+    uint32_t gate[EPI == EPI_SWIGLU ? 16 : 1];  // EPI_SWIGLU: bf16-rounded gate chunk (packed pairs) waiting for its up chunk
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;  // n fastest: co-running CTAs share A rows, B stays in L2
       const int m_base = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;  // this CTA's 128 rows of the tile
       const int gm = m_base + row;
-      // residual rows are row-per-thread (strided) global loads: issue chunk c+1's while chunk c is processed,
-      // and chunk 0's before waiting for the accumulator, so their latency never sits on the epilogue path
-      uint4 rnext[4];
-      auto prefetch_res = [&](int c) {
-        if (EPI == EPI_BIAS_LS_RES || EPI == EPI_RES) {
-          const int gnp = n_blk * BLOCK_N + half * COLS_PER_HALF + c * C_CHUNK;
-          if (gm < M && gnp < N) {
-            const uint4* rp = reinterpret_cast<const uint4*>(ea.res + static_cast<size_t>(gm) * ea.ldres + gnp);
+      // Residual rows: requested for ALL chunks of the tile before waiting for the accumulator, with a coalesced
+      // mapping -- lane l fetches the 16-byte piece l%4 of rows 8j + l/4 (j < 4) of the warp's 32 x 64 B block, i.e.
+      // 8 rows x 64 contiguous bytes per load instruction instead of 32 rows x 16 bytes.  The pieces reach their
+      // row-per-thread owners through the warp's staging buffer just before it receives the C chunk.
+      constexpr bool HAS_RES = EPI == EPI_BIAS_LS_RES || EPI == EPI_RES;
+      uint4 rres[HAS_RES ? CHUNKS : 1][4];
+      if (HAS_RES) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) rnext[q] = rp[q];
+        for (int c = 0; c < CHUNKS; ++c) {
+          const int gnp = n_blk * BLOCK_N + half * COLS_PER_HALF + c * C_CHUNK;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rrow = m_base + quarter * 32 + 8 * j + (lane >> 2);
+            rres[c][j] = make_uint4(0, 0, 0, 0);
+            if (rrow < M && gnp < N)
+              rres[c][j] = *reinterpret_cast<const uint4*>(ea.res + static_cast<size_t>(rrow) * ea.ldres + gnp + 8 * (lane & 3));
+          }
+        }
+      }
+      // Column vectors (bias, LayerScale gamma) and RoPE table rows of chunk c+1 are requested while chunk c is
+      // processed (chunk 0: here, before waiting for the accumulator): with 230 KB of shared memory the L1 is a few KB,
+      // so each of these loads is an L2 round trip that must not sit between the TMEM load and the math.
+      constexpr bool HAS_BIAS = EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_LS_RES || EPI == EPI_BIAS_ROPE2D;
+      uint4 bnext[4], gnext[4], snext[4], cnext[4];
+      bool rope_next = false;
+      auto prefetch_side = [&](int c) {
+        const int gnp = n_blk * BLOCK_N + half * COLS_PER_HALF + c * C_CHUNK;
+        if (gnp >= N) return;
+        if (HAS_BIAS) {
+          const uint4* bp = reinterpret_cast<const uint4*>(ea.bias + gnp);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) bnext[q] = __ldg(bp + q);
+        }
+        if (EPI == EPI_BIAS_LS_RES) {
+          const uint4* gp = reinterpret_cast<const uint4*>(ea.gamma + gnp);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gnext[q] = __ldg(gp + q);
+        }
+        if (EPI == EPI_BIAS_ROPE2D) {
+          const int tok = gm % ea.ntok;
+          rope_next = gnp < ea.rope_cols && gm < M && tok >= ea.npt;
+          if (rope_next) {
+            // chunk-major table: [sin | cos][hd / 8][token][8] -- the 32 rows (consecutive tokens) of a warp read
+            // 512 contiguous bytes per load instead of 32 separate 16-byte pieces
+            const int nrt = ea.ntok - ea.npt, hc = ea.hd >> 3;
+            const uint4* tr = reinterpret_cast<const uint4*>(ea.rope) + static_cast<size_t>((gnp % ea.hd) >> 3) * nrt + (tok - ea.npt);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              snext[q] = __ldg(tr + static_cast<size_t>(q) * nrt);
+              cnext[q] = __ldg(tr + static_cast<size_t>(hc + q) * nrt);
+            }
           }
         }
       };
-      prefetch_res(0);
+      prefetch_side(0);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-#pragma unroll 1
+      // TMEM loads are double-buffered: chunk c+1 is requested before chunk c is processed
+      uint32_t rbuf[2][32];
+      const uint32_t tm_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + half * COLS_PER_HALF;
+      tmem_ld_32x32b_x32(tm_row, rbuf[0]);
+#pragma unroll
       for (int c = 0; c < CHUNKS; ++c) {
         const int col0 = half * COLS_PER_HALF + c * C_CHUNK;
         const int gn = n_blk * BLOCK_N + col0;
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + col0, r);
-        uint4 rcur[4];
-        if (EPI == EPI_BIAS_LS_RES || EPI == EPI_RES) {
+        uint32_t (&r)[32] = rbuf[c & 1];
+        const bool col_ok = gn < N;  // N % 32 == 0 is enforced on the host
+        uint4 bvec[4], gvec[4], rsin[4], rcos[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
-          if (c + 1 < CHUNKS) prefetch_res(c + 1);
-        }
+        for (int q = 0; q < 4; ++q) { bvec[q] = bnext[q]; gvec[q] = gnext[q]; rsin[q] = snext[q]; rcos[q] = cnext[q]; }
+        const bool do_rope = rope_next;
+        if (c + 1 < CHUNKS) prefetch_side(c + 1);
         tmem_ld_wait();
+        if (c + 1 < CHUNKS) tmem_ld_32x32b_x32(tm_row + (c + 1) * C_CHUNK, rbuf[(c + 1) & 1]);
         if (c == CHUNKS - 1) {
           // all of this warp's TMEM reads for the tile are done -> release the accumulator stage
           tc_fence_before();
@@ -230,17 +281,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             else mbar_arrive(tempty_bar(acc));
           }
         }
-        const bool col_ok = gn < N;  // N % 32 == 0 is enforced on the host
+        // Epilogue arithmetic on packed words.  The reference's rounding points are one bf16 rounding per torch op; a
+        // product or a sum of two bf16 values rounded once IS mul.rn.bf16x2 / add.rn.bf16x2 (the fp32 product of two
+        // bf16 values is exact, and an fp32 sum of two bf16 values rounds to the same bf16 as the exact sum), so the
+        // LayerScale multiply, the residual add and the RoPE products / sum run two elements per instruction with no
+        // unpacking; the GELU polynomial runs on fp32x2.
         uint32_t packed[16];
         if (col_ok) {
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_LS_RES || EPI == EPI_BIAS_ROPE2D) {
-            const uint4* bp = reinterpret_cast<const uint4*>(ea.bias + gn);
+          if (HAS_BIAS) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint4 b = __ldg(bp + q);
+              const uint4 b = bvec[q];
               const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -250,83 +304,90 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               }
             }
           }
-          // first rounding point: the Linear's bf16 output
+          // first rounding point: the Linear's bf16 output, as packed pairs
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = bf16r(v[i]);
+          for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
           if (EPI == EPI_SWIGLU) {
             // weight rows are interleaved in 32-row blocks [gate | up]: even chunks carry gate features,
             // the following odd chunk the matching up features: act = bf16(bf16(silu(g)) * u)
             if ((c & 1) == 0) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) gate[i] = v[i];
+              for (int i = 0; i < 16; ++i) gate[i] = packed[i];
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = bf16r(silu_f(gate[i])) * v[i];
+              for (int i = 0; i < 16; ++i) {
+                const float2 g = unpack_bf16x2(gate[i]);
+                packed[i] = mul_bf16x2(pack_bf16x2(silu_f(g.x), silu_f(g.y)), packed[i]);
+              }
             }
           }
           if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
+            for (int i = 0; i < 16; ++i) {
+              const float2 x = unpack_bf16x2(packed[i]);
+              packed[i] = gelu_erf_fast_pack2(x.x, x.y);
+            }
           }
           if (EPI == EPI_BIAS_ROPE2D) {
-            const int tok = gm % ea.ntok;
-            if (gn < ea.rope_cols && gm < M && tok >= ea.npt) {
-              const bf16* tr = ea.rope + static_cast<size_t>(tok - ea.npt) * 2 * ea.hd + (gn % ea.hd);
-              const uint4* sp = reinterpret_cast<const uint4*>(tr);
-              const uint4* cp = reinterpret_cast<const uint4*>(tr + ea.hd);
+            if (do_rope) {
+              // interleaved pairs (x0, x1): o0 = bf16(x0 c0) + bf16(-x1 s0), o1 = bf16(x1 c1) + bf16(x0 s1)
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const uint4 sv = __ldg(sp + q), cv = __ldg(cp + q);
-                const uint32_t sw4[4] = {sv.x, sv.y, sv.z, sv.w};
-                const uint32_t cw4[4] = {cv.x, cv.y, cv.z, cv.w};
+                const uint32_t sw4[4] = {rsin[q].x, rsin[q].y, rsin[q].z, rsin[q].w};
+                const uint32_t cw4[4] = {rcos[q].x, rcos[q].y, rcos[q].z, rcos[q].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const float2 sn = unpack_bf16x2(sw4[j]), cs = unpack_bf16x2(cw4[j]);
-                  const float x0 = v[q * 8 + j * 2], x1 = v[q * 8 + j * 2 + 1];
-                  v[q * 8 + j * 2] = bf16r(x0 * cs.x) + bf16r(-x1 * sn.x);
-                  v[q * 8 + j * 2 + 1] = bf16r(x1 * cs.y) + bf16r(x0 * sn.y);
+                  const uint32_t x = packed[q * 4 + j];
+                  const uint32_t xs = __byte_perm(x, x, 0x1032) ^ 0x00008000u;  // (-x1, x0)
+                  packed[q * 4 + j] = add_bf16x2(mul_bf16x2(x, cw4[j]), mul_bf16x2(xs, sw4[j]));
                 }
               }
             }
           }
           if (EPI == EPI_BIAS_LS_RES) {
-            const uint4* gp = reinterpret_cast<const uint4*>(ea.gamma + gn);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint4 g = __ldg(gp + q);
-              const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+              const uint32_t gw[4] = {gvec[q].x, gvec[q].y, gvec[q].z, gvec[q].w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2(gw[j]);
-                v[q * 8 + j * 2] = bf16r(v[q * 8 + j * 2] * f.x);
-                v[q * 8 + j * 2 + 1] = bf16r(v[q * 8 + j * 2 + 1] * f.y);
-              }
+              for (int j = 0; j < 4; ++j) packed[q * 4 + j] = mul_bf16x2(packed[q * 4 + j], gw[j]);
             }
           }
           if (EPI == EPI_BIAS_LS_RES || EPI == EPI_RES) {
-            if (gm < M) {
+            // exchange: coalesced pieces -> the free staging buffer (same swizzled row layout as the C chunk) -> rows
+            if (issuer) tma_store_wait_read<1>();
+            __syncwarp();
+            const uint32_t xbase = stage_c0 + cbuf * C_STAGE_BYTES;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 x = rcur[q];
-                const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
+            for (int j = 0; j < 4; ++j) {
+              const int xr = 8 * j + (lane >> 2);
+              const uint4 x = rres[HAS_RES ? c : 0][j];
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                               xbase + xr * 64 + ((static_cast<uint32_t>(lane & 3) ^ ((xr >> 1) & 3)) << 4)),
+                           "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w)
+                           : "memory");
+            }
+            __syncwarp();
+            uint4 xrow[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = unpack_bf16x2(xw[j]);
-                  v[q * 8 + j * 2] += f.x;
-                  v[q * 8 + j * 2 + 1] += f.y;
-                }
-              }
+            for (int q = 0; q < 4; ++q)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(xrow[q].x), "=r"(xrow[q].y), "=r"(xrow[q].z), "=r"(xrow[q].w)
+                           : "r"(xbase + lane * 64 + ((static_cast<uint32_t>(q) ^ ((lane >> 1) & 3)) << 4)));
+            __syncwarp();  // every lane has its row: the buffer may now receive the C chunk
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t xw[4] = {xrow[q].x, xrow[q].y, xrow[q].z, xrow[q].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) packed[q * 4 + j] = add_bf16x2(xw[j], packed[q * 4 + j]);
             }
           }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
         }
         if (EPI == EPI_SWIGLU && (c & 1) == 0) continue;  // nothing to store for a gate chunk
-        // staging buffer reuse: the TMA store issued two chunks ago must have finished reading smem
+        // staging buffer reuse: this warp's TMA store issued two chunks ago must have finished reading smem
         if (issuer) tma_store_wait_read<1>();
-        named_bar_sync(bar_id, 128);
+        __syncwarp();
         if (col_ok) {
-          const uint32_t rbase = stage_c0 + cbuf * C_STAGE_BYTES + row * 64;
+          const uint32_t rbase = stage_c0 + cbuf * C_STAGE_BYTES + lane * 64;
           const uint32_t sw = (row >> 1) & 3;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -337,10 +398,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
+        __syncwarp();
         if (issuer && col_ok) {
           const int gn_out = EPI == EPI_SWIGLU ? (gn - C_CHUNK) / 2 : gn;
-          tma_store_2d(&tmap_c, stage_c0 + cbuf * C_STAGE_BYTES, gn_out, m_base);
+          tma_store_2d(&tmap_c, stage_c0 + cbuf * C_STAGE_BYTES, gn_out, m_base + quarter * 32);
         }
         if (issuer) tma_store_commit();
         cbuf ^= 1;
@@ -439,7 +500,8 @@ static int gemm_impl(const void* A, int lda, const void* B, int ldb, void* Cout,
   int rc;
   if ((rc = gar_make_tmap_2d(&ta, A, K, M, lda, BLOCK_K, BLOCK_M, GAR_SW_128))) return rc;
   if ((rc = gar_make_tmap_2d(&tb, B, K, N, ldb, BLOCK_K, cta2 ? 128 : bn, GAR_SW_128))) return rc;
-  if ((rc = gar_make_tmap_2d(&tc, Cout, epi == EPI_SWIGLU ? N / 2 : N, M, ldc, C_CHUNK, BLOCK_M, GAR_SW_64))) return rc;
+  // C is stored warp by warp: box = 32 columns x the 32 rows of one TMEM lane quarter
+  if ((rc = gar_make_tmap_2d(&tc, Cout, epi == EPI_SWIGLU ? N / 2 : N, M, ldc, C_CHUNK, 32, GAR_SW_64))) return rc;
   EpiArgs ea{static_cast<const bf16*>(bias), static_cast<const bf16*>(gamma), static_cast<const bf16*>(res), ldres,
              static_cast<const bf16*>(rope), ntok, npt, hd, rope_cols};
   if (cta2) return dispatch_epi<256, true>(epi, ta, tb, tc, M, N, K, ea, stream);

@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from ._lib import GarModelDesc, check
 from .config import GARSpec
-from .rope import llama_cos_sin, vit_rope_table
+from .rope import llama_cos_sin, rope_table_chunk_major, vit_rope_table
 
 VT = "mllm.model.vision_tower.timm_model."
 PJ = "mllm.model.multi_modal_projector."
@@ -178,6 +178,7 @@ class Engine:
             rp[:, :hd], rp[:, hdp:hdp + hd] = sin, cos
             rope = rp
         self._set("vit.rope", rope)
+        self._set("vit.rope_cm", rope_table_chunk_major(rope, hdp))  # layout of the fused qkv-GEMM epilogue
         for i in range(v.depth):
             b = f"{VT}blocks.{i}."
             self._set(f"vit.{i}.ln1.w", sd[b + "norm1.weight"])

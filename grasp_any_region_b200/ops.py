@@ -42,7 +42,13 @@ def gemm(a, b, epi=EPI_NONE, bias=None, gamma=None, res=None, out=None, block_n=
     return out
 
 
-def gemm_rope2d(a, b, bias, rope, ntok, npt, hd, rope_cols):
+def gemm_rope2d(a, b, bias, rope, ntok, npt, hd, rope_cols, chunk_major=False):
+    """rope: the (ntok - npt, 2 * hd) cat(sin, cos) table (re-laid out chunk-major here), or, with chunk_major=True, the
+    output of rope.rope_table_chunk_major (what the engine uploads once)."""
+    if not chunk_major:
+        from .rope import rope_table_chunk_major
+
+        rope = rope_table_chunk_major(rope, hd)
     M, K = a.shape
     N = b.shape[0]
     out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)

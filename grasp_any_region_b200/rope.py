@@ -39,3 +39,10 @@ def llama_cos_sin(t: TextSpec, max_pos: int):
     inv = torch.where(mid, blend, scaled)
     ang = torch.arange(max_pos, dtype=torch.float32)[:, None] * inv[None, :]  # (max_pos, hd/2)
     return ang.cos(), ang.sin()
+
+
+def rope_table_chunk_major(table: torch.Tensor, hd: int) -> torch.Tensor:
+    """(n_tokens, 2 * hd) = cat(sin, cos)  ->  [sin | cos][hd / 8][n_tokens][8], the layout gar_gemm_bf16_rope2d reads
+    (include/gar_b200.h): consecutive tokens are contiguous for every 8-wide piece of the head dimension."""
+    n = table.shape[0]
+    return table.reshape(n, 2, hd // 8, 8).permute(1, 2, 0, 3).contiguous()

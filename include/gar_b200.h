@@ -56,7 +56,10 @@ int gar_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int l
                   const void* bias, const void* gamma, const void* res, int ldres, int block_n_hint, void* stream);
 
 /* Same GEMM with timm's apply_rot_embed_cat fused after the bias (PE-ViT qkv projection): columns < rope_cols of
- * rows with (row % ntok) >= npt are rotated with table row (row % ntok - npt) = cat(sin[hd], cos[hd]). */
+ * rows with (row % ntok) >= npt are rotated with the sin / cos values of token (row % ntok - npt).  `rope` is the
+ * CHUNK-MAJOR form of the (ntok - npt, 2 * hd) table cat(sin[hd], cos[hd]) that gar_vit_rope takes:
+ * rope[((k * hd / 8 + j) * (ntok - npt) + t) * 8 + i] = table[t][k * hd + 8 * j + i], k = 0 sin / 1 cos -- the 32 rows
+ * of an epilogue warp then read contiguous memory. */
 int gar_gemm_bf16_rope2d(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K,
                          const void* bias, const void* rope, int ntok, int npt, int hd, int rope_cols, void* stream);
 
