@@ -436,8 +436,12 @@ def main():
     def run_steps(batch_list, steps, gather=True):
         """`steps` batches through the public API (GARModel.generate_batch; --pipeline: generate_batches).
         gather=False for the rank-0-only diagnostic passes: a collective there would wait for ranks that never come."""
-        if args.pipeline:
-            toks = model.generate_batches([batch_list] * steps, max_new_tokens=NT, eos_token_id=None)
+        raw = "image_u8" in batch_list[0]
+        if args.pipeline or (raw and steps > 1):
+            # raw (uint8) requests: the next step's host -> device copies and device preprocessing run under the current
+            # step's decode (generate_batches(overlap="prepare")); every step's copies stay inside the timed region
+            toks = model.generate_batches([batch_list] * steps, max_new_tokens=NT, eos_token_id=None,
+                                          overlap="encode" if args.pipeline else "prepare")
             if world > 1 and gather:  # the path's one collective: all-gather of the decoded ids (north_star)
                 from grasp_any_region_b200.parallel import gather_tokens, pack_tokens
 
@@ -502,7 +506,9 @@ def main():
         e2e = {"value": world * B * args.steps / (ms_e / 1e3), "unit": "captions/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps,
                "inputs": ("uint8 image + uint8 region-id map from pinned host memory; resize / tiling / normalisation on "
-                          "the device inside the timed region" if args.e2e_inputs == "raw" else
+                          "the device inside the timed region; from the second step on, a step's copies and preprocessing "
+                          "run under the previous step's decode (GARModel.generate_batches(overlap='prepare'))"
+                          if args.e2e_inputs == "raw" else
                           "host-preprocessed bf16 tile tensors from pinned host memory")}
 
     # ---- phase split of one more step (events on the engine stream between the phases)

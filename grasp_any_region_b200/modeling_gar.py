@@ -269,15 +269,24 @@ class GARModel(_Base):
         if st & 2:
             raise AssertionError("each crop-token run must be 256 contiguous tokens")
 
-    def _stage(self, eng: Engine, slot0: int, requests: List[dict]) -> None:
+    def _prepare(self, eng: Engine, requests: List[dict]):
+        """Host -> device copies and (for raw uint8 requests) the device preprocessing of `requests` on the CURRENT stream;
+        returns the per-request tuples `_stage` consumes."""
+        return [self._prepare_raw_request(eng, r) if "image_u8" in r else
+                self._prepare_request(eng, r["pixel_values"], r.get("global_mask_values"), r["aspect_ratios"],
+                                      r["bboxes"], r["input_ids"]) for r in requests]
+
+    def _stage(self, eng: Engine, slot0: int, requests: List[dict], prepared=None, ready=None) -> None:
         """ViT -> assemble -> prefill of `requests` into KV slots slot0.. on the engine stream.  Consecutive requests
         of equal shape (tile count, prompt length) share one ViT pass and one prefill pass as far as the engine's
         arenas allow; the rest go one by one.  Each pass first runs the row plan and raises the reference's
-        exceptions (ValueError / KeyError / AssertionError) BEFORE any feature or logit of that pass is computed."""
-        prepared = [self._prepare_raw_request(eng, r) if "image_u8" in r else
-                    self._prepare_request(eng, r["pixel_values"], r.get("global_mask_values"), r["aspect_ratios"],
-                                          r["bboxes"], r["input_ids"]) for r in requests]
-        eng.stream.wait_stream(torch.cuda.current_stream(eng.device))
+        exceptions (ValueError / KeyError / AssertionError) BEFORE any feature or logit of that pass is computed.
+        prepared / ready: the output of `_prepare` made earlier on another stream and the event that marks it done."""
+        if prepared is None:
+            prepared = self._prepare(eng, requests)
+            eng.stream.wait_stream(torch.cuda.current_stream(eng.device))
+        else:
+            eng.stream.wait_event(ready)
         i = 0
         with torch.cuda.stream(eng.stream):
             while i < len(prepared):
@@ -431,8 +440,15 @@ class GARModel(_Base):
 
     @torch.no_grad()
     def generate_batches(self, batches: List[List[dict]], max_new_tokens: int = 128,
-                         eos_token_id=None) -> List[List[List[int]]]:
+                         eos_token_id=None, overlap: str = "encode") -> List[List[List[int]]]:
         """Throughput serving of a stream of request batches (B200 scheduler extension).
+
+        overlap="prepare": only the NEXT batch's host -> device copies and device preprocessing (uint8 image / id map ->
+        bf16 tiles) run under the current batch's decode, on their own stream from a helper thread; ViT, prefill and
+        decode of the batches stay back to back on the engine stream (one KV-slot group).  The copies and the
+        preprocessing launches are latency- and host-bound, the decode leaves the host idle: this hides them for free.
+
+        overlap="encode":
 
         Two KV-slot groups ping-pong: while group g decodes on the engine's decode stream, the next batch's
         ViT + assemble + prefill is enqueued (from a helper thread) on the encode stream into group 1-g.  The decode
@@ -445,6 +461,10 @@ class GARModel(_Base):
         eng = self.engine()
         if not batches:
             return []
+        if overlap == "prepare":
+            return self._generate_batches_prepare(eng, batches, max_new_tokens, eos_token_id, threading)
+        if overlap != "encode":
+            raise ValueError(f"overlap must be 'encode' or 'prepare', got {overlap!r}")
         G = max(len(b) for b in batches)
         if 2 * G > eng.max_batch:
             raise ValueError(f"pipelining needs engine max_batch >= 2 x batch ({2 * G}), got {eng.max_batch}")
@@ -462,6 +482,44 @@ class GARModel(_Base):
                 plain[0].wait_stream(eng.stream)
                 plain[1].wait_stream(eng.decode_stream)
             eng.stream, eng.decode_stream = plain
+
+    def _generate_batches_prepare(self, eng, batches, max_new_tokens, eos_token_id, threading):
+        dev = eng.device
+        if max(len(b) for b in batches) > eng.max_batch:
+            raise ValueError(f"batch larger than the engine's max_batch {eng.max_batch}")
+        prep = getattr(self, "_prep_stream", None)
+        if prep is None or prep.device != dev:
+            prep = self._prep_stream = torch.cuda.Stream(device=dev)
+
+        def prepare(bi: int):
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(prep):
+                prepared = self._prepare(eng, batches[bi])
+                ev = torch.cuda.Event()
+                ev.record(prep)
+            return prepared, ev
+
+        prep.wait_stream(torch.cuda.current_stream(dev))
+        out: List[List[List[int]]] = []
+        prepared, ev = prepare(0)
+        for i, batch in enumerate(batches):
+            self._stage(eng, 0, batch, prepared, ev)
+            box, th = {}, None
+            if i + 1 < len(batches):
+                def work(bi=i + 1):
+                    try:
+                        box["p"] = prepare(bi)
+                    except BaseException as ex:  # surfaced on the caller's thread
+                        box["err"] = ex
+                th = threading.Thread(target=work)
+                th.start()
+            out.append(eng.generate(len(batch), int(max_new_tokens), eos_token_id))
+            if th is not None:
+                th.join()
+                if "err" in box:
+                    raise box["err"]
+                prepared, ev = box["p"]
+        return out
 
     def _generate_batches(self, eng, batches, G, dev, max_new_tokens, eos_token_id, threading):
         timing = []  # (encode start, encode end, decode start, decode end) events per batch -> eng.pipeline_stats

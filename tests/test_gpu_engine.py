@@ -422,6 +422,9 @@ def test_raw_uint8_requests_match_preprocessed_requests():
     want = model.generate_batch(cooked, max_new_tokens=new_tokens)
     got = model.generate_batch(raws, max_new_tokens=new_tokens)
     assert got == want
+    # a stream of batches with the next batch's copies + device preprocessing under the current decode: same tokens
+    stream = model.generate_batches([raws, raws[::-1], raws], max_new_tokens=new_tokens, overlap="prepare")
+    assert stream == [want, want[::-1], want]
     raw_bytes = sum(r[k].numel() * r[k].element_size() for r in raws for k in ("image_u8", "idmap_u8", "input_ids"))
     cooked_bytes = sum(r[k].numel() * r[k].element_size() for r in cooked for k in ("pixel_values", "global_mask_values", "input_ids"))
     assert raw_bytes * 3 < cooked_bytes
