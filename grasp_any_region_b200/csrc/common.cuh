@@ -301,8 +301,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
   return r;
 }
+// Arrive on a (possibly remote) CTA's mbarrier, relaxed: a cluster-scope release compiles to MEMBAR.ALL.GPU + ERRBAR,
+// which made the GEMM epilogue's lane 0 wait for every prefetch load it had in flight each time it handed a TMEM
+// accumulator stage back (ncu: ~9 % of the epilogue's stall samples).  What the waiter needs there -- the epilogue's
+// TMEM reads being complete -- is ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync, not by a
+// generic-proxy release.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
