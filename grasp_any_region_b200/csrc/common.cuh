@@ -72,31 +72,31 @@ __device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
   asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
   return d;
 }
-// gelu_erf_fast for two values at once on fp32x2 FMA-pipe instructions (same formula, constants and branch on the sign);
-// returns the bf16-rounded pair
+// Exact-form (erf) GELU of two values on fp32x2 FMA-pipe instructions, branch-free:
+//   gelu(x) = x Phi(x) = max(x, 0) - |x| erfc(|x| / sqrt 2) / 2
+// (for x < 0 it is -|x| erfc/2 itself, so the tail keeps its relative accuracy; for x >= 0 a small term is subtracted
+// from x).  erfc by Abramowitz-Stegun 7.1.26 as in gelu_erf_fast, the factor 1/2 folded into the coefficients.  Returns
+// the bf16-rounded pair.
 __device__ __forceinline__ uint32_t gelu_erf_fast_pack2(float x0, float x1) {
-  unsigned long long x2, a2, t2, p2, e2, r2;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "f"(x0), "f"(x1));
+  unsigned long long a2, t2, p2, e2, c2, k2, one2;
+#define GAR_F2(dst, val) asm("mov.b64 %0, {%1, %1};" : "=l"(dst) : "f"(val))
   asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "f"(fabsf(x0)), "f"(fabsf(x1)));
-  const float kp = 0.3275911f * 0.70710678118654752440f, kone = 1.0f;
-  unsigned long long kp2, one2, c2;
-  asm("mov.b64 %0, {%1, %1};" : "=l"(kp2) : "f"(kp));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(one2) : "f"(kone));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t2) : "l"(a2), "l"(kp2), "l"(one2));  // 1 + p z, z = |x| / sqrt 2
+  GAR_F2(k2, 0.3275911f * 0.70710678118654752440f);
+  GAR_F2(one2, 1.0f);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t2) : "l"(a2), "l"(k2), "l"(one2));  // 1 + p z, z = |x| / sqrt 2
   float d0, d1, t0, t1;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(t2));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
   asm("mov.b64 %0, {%1, %2};" : "=l"(t2) : "f"(t0), "f"(t1));
-#define GAR_F2(dst, val) asm("mov.b64 %0, {%1, %1};" : "=l"(dst) : "f"(val))
-  GAR_F2(p2, 1.061405429f);
-  GAR_F2(c2, -1.453152027f);
+  GAR_F2(p2, 0.5f * 1.061405429f);
+  GAR_F2(c2, 0.5f * -1.453152027f);
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(t2), "l"(p2), "l"(c2));
-  GAR_F2(c2, 1.421413741f);
+  GAR_F2(c2, 0.5f * 1.421413741f);
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(t2), "l"(p2), "l"(c2));
-  GAR_F2(c2, -0.284496736f);
+  GAR_F2(c2, 0.5f * -0.284496736f);
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(t2), "l"(p2), "l"(c2));
-  GAR_F2(c2, 0.254829592f);
+  GAR_F2(c2, 0.5f * 0.254829592f);
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p2) : "l"(t2), "l"(p2), "l"(c2));
   // exp(-z^2) = ex2(|x|^2 * (-log2(e) / 2))
   GAR_F2(c2, -0.72134752044448170368f);
@@ -108,21 +108,12 @@ __device__ __forceinline__ uint32_t gelu_erf_fast_pack2(float x0, float x1) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(g1));
   asm("mov.b64 %0, {%1, %2};" : "=l"(e2) : "f"(e0), "f"(e1));
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p2) : "l"(p2), "l"(t2));
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p2) : "l"(p2), "l"(e2));   // erfc(|x| / sqrt 2)
-  // 1 + erf(x / sqrt 2) = erfc for x < 0 (no 1 - erf cancellation in the tail), 2 - erfc otherwise
-  unsigned long long two2, q2;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p2) : "l"(p2), "l"(e2));   // erfc(|x| / sqrt 2) / 2
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p2) : "l"(p2), "l"(a2));   // |x| erfc / 2
+  unsigned long long r2;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r2) : "f"(fmaxf(x0, 0.f)), "f"(fmaxf(x1, 0.f)));
   GAR_F2(c2, -1.0f);
-  GAR_F2(two2, 2.0f);
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(q2) : "l"(p2), "l"(c2), "l"(two2));
-  float n0, n1, q0, q1;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(n0), "=f"(n1) : "l"(p2));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(q2));
-  q0 = x0 < 0.f ? n0 : q0;
-  q1 = x1 < 0.f ? n1 : q1;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(q2) : "f"(q0), "f"(q1));
-  GAR_F2(c2, 0.5f);
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(x2) : "l"(x2), "l"(c2));         // x / 2
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r2) : "l"(x2), "l"(q2));         // x/2 (1 + erf)
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r2) : "l"(p2), "l"(c2), "l"(r2));  // max(x, 0) - |x| erfc / 2
 #undef GAR_F2
   float r0, r1;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r2));
