@@ -41,8 +41,13 @@ struct AttCfg {
   static constexpr int SMEM_Q = 0;
   static constexpr int SMEM_K = Q_BYTES;                      // 2 stages
   static constexpr int SMEM_V = SMEM_K + 2 * KV_BYTES;        // 2 stages: the load of V(j+1) no longer waits for PV(j)
-  static constexpr int SMEM_P = SMEM_V + 2 * KV_BYTES;        // BKV/64 sub-tiles [128 x 64]
-  static constexpr int SMEM_TOTAL = SMEM_P + (BKV / 64) * TILE_BYTES;
+  // P (the bf16 probabilities, A operand of the PV MMA) lives in TENSOR MEMORY next to S and O whenever the column
+  // budget allows (BKV/2 packed columns): the softmax warps tcgen05.st it and the MMA reads it from there, so the
+  // 32 KB smem write + 32 KB smem read per KV block (more than half of the kernel's shared-memory traffic) and the
+  // proxy fence disappear.  HD 64 / BKV 64 keeps P in smem (three CTAs x 256 columns would not fit 512).
+  static constexpr bool P_TMEM = !(HD == 64 && BKV == 64);
+  static constexpr int SMEM_P = SMEM_V + 2 * KV_BYTES;        // BKV/64 sub-tiles [128 x 64] (smem-P configurations)
+  static constexpr int SMEM_TOTAL = P_TMEM ? SMEM_P : SMEM_P + (BKV / 64) * TILE_BYTES;
   // no alignment slack: the dynamic segment is declared 1024-byte aligned (checked at run time), so two CTAs of the
   // HD 64 / BKV 128 configuration (112 KB each) still fit the SM's 228 KB
   static constexpr int SMEM_BYTES = SMEM_TOTAL;
@@ -52,8 +57,10 @@ struct AttCfg {
   static constexpr bool REALLOC = CTAS_PER_SM > 1;
   static constexpr int REG_CTRL = 48;
   static constexpr int REG_SOFTMAX = 2 * MAXREG - REG_CTRL;  // 112 / 208
-  static constexpr int TMEM_COLS = (BKV + HD) <= 128 ? 128 : 256;  // S: BKV columns, O: HD columns
+  static constexpr int TM_NEED = BKV + HD + (P_TMEM ? BKV / 2 : 0);  // S: BKV columns, O: HD columns, P: BKV/2
+  static constexpr int TMEM_COLS = TM_NEED <= 128 ? 128 : (TM_NEED <= 256 ? 256 : 512);
   static constexpr uint32_t TM_O = BKV;
+  static constexpr uint32_t TM_P = BKV + HD;
 };
 
 struct AttnParams {
@@ -126,8 +133,10 @@ __device__ __forceinline__ f32x2 exp2_poly2(f32x2 x2) {
   float j0, j1, p0, p1;
   upk2(j, j0, j1);
   upk2(pl, p0, p1);
-  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(j0) << 23));
-  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(j1) << 23));
+  // 2^n applied as ONE integer multiply-add on the exponent field (IMAD runs on the FMA pipe; a shift + add pair would
+  // cost two ALU-pipe slots, and the ALU pipe already carries the row max, the clamps and the bf16 packing)
+  p0 = __int_as_float(__float_as_int(j0) * (1 << 23) + __float_as_int(p0));
+  p1 = __int_as_float(__float_as_int(j1) * (1 << 23) + __float_as_int(p1));
   return pk2(p0, p1);
 }
 
@@ -135,9 +144,24 @@ __device__ __forceinline__ f32x2 exp2_poly2(f32x2 x2) {
 __host__ __device__ constexpr uint32_t poly_mask(int poly) { return poly == 0 ? 0x00u : (poly == 1 ? 0x11u : (poly == 2 ? 0x49u : 0x55u)); }
 
 // unmasked block: P = exp2(S * scale - m) -> bf16 -> swizzled smem; returns the row sum of the fp32 P values
-template <int NCOLS, int POLY>
+// destination of 8 packed columns (4 words) of P: swizzled smem (TM = false: rbase / sw as documented at the call) or,
+// TM = true, the caller's register array `out` -- the tensor-memory copy of P is written by the caller AFTER it has
+// waited for PV(j-1), so that wait hides behind the exponentials instead of in front of them
+template <bool TM, int NW>
+__device__ __forceinline__ void p_emit(int c, const uint32_t (&w)[4], uint32_t (&out)[NW], uint32_t rbase, uint32_t sw) {
+  if (TM) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[c * 4 + i] = w[i];
+  } else {
+    const uint32_t addr = rbase + (c >> 3) * TILE_BYTES + (((c & 7) ^ sw) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                 : "memory");
+  }
+}
+
+template <int NCOLS, int POLY, bool TM>
 __device__ __forceinline__ float exp_pack_store_fast(const uint32_t (&s)[NCOLS], float scale_log2, float neg_m,
-                                                     uint32_t rbase, uint32_t sw) {
+                                                     uint32_t rbase, uint32_t sw, uint32_t (&out)[TM ? NCOLS / 2 : 1]) {
   const f32x2 sc2 = pk2(scale_log2, scale_log2), nm2 = pk2(neg_m, neg_m);
   f32x2 rs2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
@@ -159,9 +183,7 @@ __device__ __forceinline__ float exp_pack_store_fast(const uint32_t (&s)[NCOLS],
       upk2(p2, p0, p1);
       w[i] = pack_bf16x2(p0, p1);
     }
-    const uint32_t addr = rbase + (c >> 3) * TILE_BYTES + (((c & 7) ^ sw) << 4);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                 : "memory");
+    p_emit<TM>(c, w, out, rbase, sw);
   }
   float a0, a1, b0, b1, c0, c1, d0, d1;
   upk2(rs2[0], a0, a1);
@@ -171,9 +193,10 @@ __device__ __forceinline__ float exp_pack_store_fast(const uint32_t (&s)[NCOLS],
   return ((a0 + a1) + (b0 + b1)) + ((c0 + c1) + (d0 + d1));
 }
 
-template <bool MASKED, int NCOLS>
+template <bool MASKED, int NCOLS, bool TM>
 __device__ __forceinline__ float exp_pack_store_n(const uint32_t (&s)[NCOLS], int kv0, int lim, float scale_log2,
-                                                  float neg_m, uint32_t rbase, uint32_t sw) {
+                                                  float neg_m, uint32_t rbase, uint32_t sw,
+                                                  uint32_t (&out)[TM ? NCOLS / 2 : 1]) {
   float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int c = 0; c < NCOLS / 8; ++c) {
@@ -189,9 +212,7 @@ __device__ __forceinline__ float exp_pack_store_n(const uint32_t (&s)[NCOLS], in
       rs4[i] += p0 + p1;
       w[i] = pack_bf16x2(p0, p1);
     }
-    const uint32_t addr = rbase + (c >> 3) * TILE_BYTES + (((c & 7) ^ sw) << 4);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                 : "memory");
+    p_emit<TM>(c, w, out, rbase, sw);
   }
   return (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
 }
@@ -324,8 +345,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           if (k < nk) {
-            const uint64_t pdesc = umma_desc_sw128(sbase + SMEM_P + (k >> 2) * TILE_BYTES, 0, 1024) + 2u * (k & 3);
-            umma_bf16_ss(tmem + TM_O, pdesc, vdesc + 128u * k, idesc_o, (j | k) != 0);
+            if constexpr (Cfg::P_TMEM) {
+              umma_bf16_ts(tmem + TM_O, tmem + Cfg::TM_P + 8u * k, vdesc + 128u * k, idesc_o, (j | k) != 0);
+            } else {
+              const uint64_t pdesc = umma_desc_sw128(sbase + SMEM_P + (k >> 2) * TILE_BYTES, 0, 1024) + 2u * (k & 3);
+              umma_bf16_ss(tmem + TM_O, pdesc, vdesc + 128u * k, idesc_o, (j | k) != 0);
+            }
           }
         }
         umma_commit(B_VEMPTY0 + 8 * (j & 1));
@@ -349,7 +374,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // barrier protocol in step (the ViT's 1025-token tiles leave a 1-row last query block), and a last KV block with
     // <= 32 live keys is handled on 32 score columns (and 2 of the BKV/16 PV MMAs) instead of BKV.
     const bool warp_live = q0 + quarter * 32 < p.q_len;
-    const uint32_t p_rbase = sbase + SMEM_P + (row >> 3) * 1024 + (row & 7) * 128;
+    const uint32_t p_rbase = Cfg::P_TMEM ? tmem + lane_addr + Cfg::TM_P : sbase + SMEM_P + (row >> 3) * 1024 + (row & 7) * 128;
     for (int j = 0; j < num_kvb; ++j) {
       TL_STAMP(0);
       mbar_wait(B_SFULL, j & 1);
@@ -386,28 +411,40 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const float alpha = bump ? ex2_approx(m_run - m_use) : 1.0f;
         TL_STAMP(3);
         // O and the P buffer are quiescent only once PV(j-1) has retired
-        if (j > 0) {
-          mbar_wait(B_PVDONE, (j - 1) & 1);
-          tc_fence_after();
-          TL_STAMP(4);
-          const bool any = __any_sync(0xffffffffu, alpha != 1.0f);
-          if (any) {
+        auto wait_pv_rescale = [&]() {
+          if (j > 0) {
+            mbar_wait(B_PVDONE, (j - 1) & 1);
+            tc_fence_after();
+            TL_STAMP(4);
+            const bool any = __any_sync(0xffffffffu, alpha != 1.0f);
+            if (any) {
 #pragma unroll
-            for (int c = 0; c < HD / 32; ++c) {
-              uint32_t o[32];
-              tmem_ld_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
-              tmem_ld_wait();
+              for (int c = 0; c < HD / 32; ++c) {
+                uint32_t o[32];
+                tmem_ld_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
+                tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
+              }
+              tmem_st_wait();
             }
-            tmem_st_wait();
           }
+        };
+        uint32_t pw[Cfg::P_TMEM ? NC / 2 : 1];
+        if constexpr (!Cfg::P_TMEM) wait_pv_rescale();  // smem P is written while it is computed
+        // P = exp2(S*scale - m) -> bf16.  Tensor-memory P: row r on lane r, two keys per 32-bit column (the A operand
+        // layout of the PV MMA); the packed words stay in registers until PV(j-1) has retired, so that wait hides
+        // behind the exponentials.  smem P (BKV 64): canonical K-major 128B-swizzled layout, row r, 16B chunk c at
+        // r*128 + ((c ^ (r&7))<<4)
+        const float rs = need_mask ? exp_pack_store_n<true, NC, Cfg::P_TMEM>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7, pw)
+                                   : exp_pack_store_fast<NC, POLY, Cfg::P_TMEM>(s, p.scale_log2, -m_use, p_rbase, row & 7, pw);
+        if constexpr (Cfg::P_TMEM) {
+          wait_pv_rescale();
+#pragma unroll
+          for (int c = 0; c < NC / 32; ++c)
+            tmem_st_32x32b_x16(p_rbase + 16 * c, *reinterpret_cast<uint32_t(*)[16]>(&pw[16 * c]));
         }
-        // P = exp2(S*scale - m) -> bf16 -> smem, canonical K-major 128B-swizzled layout:
-        // row r, 16B chunk c at r*128 + ((c ^ (r&7))<<4); two [128 x 64] sub-tiles
-        const float rs = need_mask ? exp_pack_store_n<true, NC>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, row & 7)
-                                   : exp_pack_store_fast<NC, POLY>(s, p.scale_log2, -m_use, p_rbase, row & 7);
         l_run = l_run * alpha + rs;
         m_run = m_new;
       };
@@ -418,7 +455,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         block(std::integral_constant<int, BKV>{}, need_mask);
       }
       TL_STAMP(5);
-      fence_proxy_async_smem();
+      if constexpr (Cfg::P_TMEM) tmem_st_wait();   // P (and a rescaled O) are in tensor memory
+      else fence_proxy_async_smem();               // P in smem must be visible to the async proxy
       tc_fence_before();
       mbar_arrive(B_PFULL);
       TL_STAMP(6);
