@@ -26,7 +26,7 @@ extern "C" int gar_copy_d2d(void* dst, const void* src, long long bytes, void* s
 static int g_pdl = 1;
 static int g_decode_attn_mma = 1;
 static int g_gemm_2cta = 1;
-static int g_attn_poly = 0;  // share of the softmax exponentials evaluated on the FMA pipe: 0 none (fastest measured), 1 2/8, 2 3/8, 3 4/8
+static int g_attn_poly = 1;  // share of the softmax exponentials evaluated on the FMA pipe: 0 none, 1 2/8 (fastest measured), 2 3/8, 3 4/8
 static int g_gemv_wide = 1;          // long-K decode GEMVs (down_proj) run 16 K-slices per CTA (A/B switch)
 static int g_gemv_norm_smem = 1;     // decode GEMV stages RMSNorm weights / statistics through shared memory (A/B switch)
 static int g_attn_bkv = 128;  // measured: 128 (2 CTAs/SM) beats 64 (3 CTAs/SM) on both ViT and prefill shapes
