@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgar_b200.so")
+# GAR_B200_LIB: load another build of the same C ABI (A/B runs of two library versions on one GPU box)
+LIB_PATH = os.environ.get("GAR_B200_LIB") or os.path.join(HERE, "libgar_b200.so")
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
