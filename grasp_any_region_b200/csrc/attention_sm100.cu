@@ -573,8 +573,9 @@ extern "C" int gar_attn_fwd(const void* q, long long q_row_stride, long long q_b
   p.timeline = g_attn_timeline;
 #define GAR_ATTN_ARGS q, q_row_stride, q_batch_stride, k, v, kv_row_stride, kv_batch_stride, kv_batches, o, o_row_stride, \
                       o_batch_stride, batch, heads, q_len, kv_rows_alloc, p, stream
-  const int poly = gar_global_option("attn_poly");  // exponentials on the FMA pipe: 0 none (default), 1 2/8, 2 3/8, 3 4/8
-  if (head_dim == 128) return poly == 0 ? launch_attn<128, 128, 0>(GAR_ATTN_ARGS) : launch_attn<128, 128, 2>(GAR_ATTN_ARGS);
+  const int poly = gar_global_option("attn_poly");  // exponentials on the FMA pipe: 0 none, 1 2/8 (default), 2 3/8, 3 4/8
+  // head_dim 128 has half the exponentials per MMA flop: the polynomial share only from attn_poly >= 2
+  if (head_dim == 128) return poly < 2 ? launch_attn<128, 128, 0>(GAR_ATTN_ARGS) : launch_attn<128, 128, 2>(GAR_ATTN_ARGS);
   if (gar_global_option("attn_bkv") == 128) {
     switch (poly) {
       case 0: return launch_attn<64, 128, 0>(GAR_ATTN_ARGS);
