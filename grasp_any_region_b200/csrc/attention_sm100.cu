@@ -17,6 +17,7 @@
 // Registers: the kernel launches at MAXREG per thread; the control warpgroup drops to 40 and the
 // softmax warpgroup (a whole 128-wide score row per thread lives in registers) takes the difference,
 // so the row-per-thread softmax compiles without local-memory spills.
+#include <mutex>
 #include <type_traits>
 
 #include "common.cuh"
@@ -505,6 +506,336 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant (default for the tensor-memory-P configurations).  The per-tile CTA above pays, for every
+// (sequence, head, query block): barrier init + TMEM allocation + a CTA-wide sync, a cold Q/K load before the first
+// S MMA (~2 300 cycles in which the softmax warpgroup only waits), and a finalize during which its MMA and TMA warps
+// idle -- together about a quarter of a ViT tile's 32 k cycles (profiles/r02_attn_timeline_ptmem.txt: 24 k of them
+// in the KV loop).  Here a CTA stays resident and walks tiles handed out by a device-side counter in the SAME order
+// the hardware would have launched them (query blocks of one (head, sequence) heaviest-first, heads next):
+//   * the TMA thread fetches the next tile index one tile ahead (atomicAdd), and as soon as the K/V ring has room
+//     loads the next tile's Q (second Q buffer) and first K/V blocks while the current tile is still in its KV loop;
+//   * the MMA thread issues S(0) of the next tile the moment the last S of the current one sits in the softmax
+//     warps' registers, so it runs under the current tile's last exponentials and its finalize;
+//   * the softmax warpgroup goes from one tile's finalize straight into the next tile's first block.
+// The K/V ring, the S / P / PV hand-offs and their parities simply keep counting KV blocks across tiles (`g`); the two
+// Q buffers double as the O staging tiles and are handed back to the TMA thread (QEMPTY) once the TMA store has
+// read them.  The tile index travels through shared memory next to the QFULL arrive (release) / wait (acquire).
+// The last CTA to retire resets the counter pair, so a launch needs no memset.
+template <int HD, int BKV>
+struct AttCfgP : AttCfg<HD, BKV> {
+  using Base = AttCfg<HD, BKV>;
+  static_assert(Base::P_TMEM, "persistent attention keeps P in tensor memory");
+  static constexpr int SMEM_Q = 0;                                   // 2 buffers
+  static constexpr int SMEM_K = 2 * Base::Q_BYTES;                   // 2 stages
+  static constexpr int SMEM_V = SMEM_K + 2 * Base::KV_BYTES;         // 2 stages
+  static constexpr int SMEM_BYTES = SMEM_V + 2 * Base::KV_BYTES;     // HD 64: 96 KB (2 CTAs/SM), HD 128: 192 KB
+  // the control threads carry the tile walk (tile index, coordinates, running block counter) on top of the per-tile
+  // kernel's state: 8 more registers for them keep the MMA issue loop free of local-memory traffic
+  static constexpr int REG_CTRL = 56;
+  static constexpr int REG_SOFTMAX = 2 * Base::MAXREG - REG_CTRL;   // 200
+};
+
+template <int HD, int BKV, int POLY>
+__global__ void __launch_bounds__(ATT_THREADS) __maxnreg__((AttCfg<HD, BKV>::MAXREG))
+attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                        const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+                        AttnParams p, int heads, int total_tiles, unsigned int* sched) {
+  using Cfg = AttCfgP<HD, BKV>;
+  constexpr int NSUB = Cfg::NSUB, SMEM_Q = Cfg::SMEM_Q, SMEM_K = Cfg::SMEM_K, SMEM_V = Cfg::SMEM_V;
+  constexpr int Q_BYTES = Cfg::Q_BYTES, KV_BYTES = Cfg::KV_BYTES, KV_TILE = Cfg::KV_TILE;
+  constexpr uint32_t TM_O = Cfg::TM_O;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[16];
+  __shared__ uint32_t tmem_ptr_sh;
+  __shared__ int tile_sh[2];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if (sbase & 1023u) __trap();
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t B_QFULL0 = bar0, B_QEMPTY0 = bar0 + 16, B_KFULL0 = bar0 + 32, B_KEMPTY0 = bar0 + 48,
+                 B_VFULL0 = bar0 + 64, B_VEMPTY0 = bar0 + 80, B_SFULL = bar0 + 96, B_PFULL = bar0 + 104,
+                 B_PVDONE = bar0 + 112, B_SCONS = bar0 + 120;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_qb = (p.q_len + BQ - 1) / BQ;
+  const int shift = p.kv_len - p.q_len;
+  // tile t -> (query block, head, sequence): query blocks fastest and heaviest (causal) first, as the per-tile grid
+  auto tile_coords = [&](int t, int& q0, int& h, int& b, int& kv_end) {
+    const int r = t / num_qb;
+    q0 = (num_qb - 1 - (t - r * num_qb)) * BQ;
+    b = r / heads;
+    h = r - b * heads;
+    kv_end = p.causal ? min(p.kv_len, q0 + BQ + shift) : p.kv_len;
+  };
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(B_QFULL0 + 8 * i, 1);
+      mbar_init(B_QEMPTY0 + 8 * i, 1);
+      mbar_init(B_KFULL0 + 8 * i, 1);
+      mbar_init(B_KEMPTY0 + 8 * i, 1);
+      mbar_init(B_VFULL0 + 8 * i, 1);
+      mbar_init(B_VEMPTY0 + 8 * i, 1);
+    }
+    mbar_init(B_SFULL, 1);
+    mbar_init(B_PFULL, 128);
+    mbar_init(B_PVDONE, 1);
+    mbar_init(B_SCONS, 128);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_o);
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&tmem_ptr_sh), Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&tmem_ptr_sh);
+  volatile int* tile_v = tile_sh;
+
+  if (warp < 4) {
+  if constexpr (Cfg::REALLOC) setmaxnreg_dec<Cfg::REG_CTRL>();
+  if (warp == 0) {
+    if (lane == 0) {
+      int t = blockIdx.x;  // the first tile of every CTA is static; the counter hands out the rest
+      uint32_t g = 0;      // KV blocks loaded so far: ring position and parity keep counting across tiles
+      for (int n = 0;; ++n) {
+        const int buf = n & 1;
+        // Q buffer `buf` last held tile n-2: its O tile must have left through the TMA store
+        if (n >= 2) mbar_wait(B_QEMPTY0 + 8 * buf, ((n >> 1) - 1) & 1);
+        tile_v[buf] = t;
+        if (t >= total_tiles) {
+          mbar_arrive(B_QFULL0 + 8 * buf);  // sentinel: the other roles leave their loops
+          break;
+        }
+        const int t_next = static_cast<int>(gridDim.x + atomicAdd(sched, 1u));  // needed only after this tile's loads
+        int q0, h, b, kv_end;
+        tile_coords(t, q0, h, b, kv_end);
+        const int num_kvb = (kv_end + BKV - 1) / BKV;
+        const int kvh = h / p.group;
+        const int kb_coord = b * p.kv_batch_mul + kvh * p.kv_batch_head_mul;
+        mbar_expect_tx(B_QFULL0 + 8 * buf, Q_BYTES);
+#pragma unroll
+        for (int u = 0; u < NSUB; ++u)
+          tma_load_3d(sbase + SMEM_Q + buf * Q_BYTES + u * TILE_BYTES, &tmap_q, p.q_col0 + h * p.q_head_cols + 64 * u, q0,
+                      b, B_QFULL0 + 8 * buf);
+        for (int j = 0; j < num_kvb; ++j, ++g) {
+          const uint32_t st = g & 1, par = ((g >> 1) & 1) ^ 1u;
+          mbar_wait(B_KEMPTY0 + 8 * st, par);
+          mbar_expect_tx(B_KFULL0 + 8 * st, KV_BYTES);
+#pragma unroll
+          for (int u = 0; u < NSUB; ++u)
+            tma_load_3d(sbase + SMEM_K + st * KV_BYTES + u * KV_TILE, &tmap_k, p.k_col0 + kvh * p.kv_head_cols + 64 * u,
+                        j * BKV, kb_coord, B_KFULL0 + 8 * st);
+          mbar_wait(B_VEMPTY0 + 8 * st, par);
+          mbar_expect_tx(B_VFULL0 + 8 * st, KV_BYTES);
+#pragma unroll
+          for (int u = 0; u < NSUB; ++u)
+            tma_load_3d(sbase + SMEM_V + st * KV_BYTES + u * KV_TILE, &tmap_v, p.v_col0 + kvh * p.kv_head_cols + 64 * u,
+                        j * BKV, kb_coord, B_VFULL0 + 8 * st);
+        }
+        t = t_next;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD, 0, 1);
+      uint32_t g = 0;  // KV blocks issued so far (all tiles)
+      for (int n = 0;; ++n) {
+        const int buf = n & 1;
+        mbar_wait(B_QFULL0 + 8 * buf, (n >> 1) & 1);
+        const int t = tile_v[buf];
+        if (t >= total_tiles) break;
+        int q0, h, b, kv_end;
+        tile_coords(t, q0, h, b, kv_end);
+        const int num_kvb = (kv_end + BKV - 1) / BKV;
+        const uint32_t qbase = sbase + SMEM_Q + buf * Q_BYTES;
+        auto issue_s = [&](uint32_t gj) {
+          const uint32_t st = gj & 1;
+          mbar_wait(B_KFULL0 + 8 * st, (gj >> 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) {
+            const uint64_t qdesc = umma_desc_sw128(qbase + (k >> 2) * TILE_BYTES, 0, 1024) + 2u * (k & 3);
+            const uint64_t kdesc = umma_desc_sw128(sbase + SMEM_K + st * KV_BYTES + (k >> 2) * KV_TILE, 0, 1024) + 2u * (k & 3);
+            umma_bf16_ss(tmem + TM_S, qdesc, kdesc, idesc_s, k != 0);
+          }
+          umma_commit(B_KEMPTY0 + 8 * st);
+          umma_commit(B_SFULL);
+        };
+        // the previous tile's last S must sit in the softmax warps' registers before TMEM S is overwritten
+        if (g > 0) mbar_wait(B_SCONS, (g - 1) & 1);
+        issue_s(g);
+        for (int j = 0; j < num_kvb; ++j) {
+          const uint32_t gj = g + j;
+          if (j + 1 < num_kvb) {
+            mbar_wait(B_SCONS, gj & 1);
+            issue_s(gj + 1);
+          }
+          mbar_wait(B_PFULL, gj & 1);  // P(j) in tensor memory, O rescaled (j == 0: the previous tile's O has been read out)
+          mbar_wait(B_VFULL0 + 8 * (gj & 1), (gj >> 1) & 1);
+          tc_fence_after();
+          const uint64_t vdesc = umma_desc_sw128(sbase + SMEM_V + (gj & 1) * KV_BYTES, KV_TILE, 1024);
+          const int nk = (BKV > 32 && kv_end - j * BKV <= 32) ? 2 : BKV / 16;
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {
+            if (k < nk) umma_bf16_ts(tmem + TM_O, tmem + Cfg::TM_P + 8u * k, vdesc + 128u * k, idesc_o, (j | k) != 0);
+          }
+          umma_commit(B_VEMPTY0 + 8 * (gj & 1));
+          umma_commit(B_PVDONE);
+        }
+        g += num_kvb;
+      }
+    }
+  }
+  } else {
+    if constexpr (Cfg::REALLOC) setmaxnreg_inc<Cfg::REG_SOFTMAX>();
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t p_rbase = tmem + lane_addr + Cfg::TM_P;
+    uint32_t g = 0;
+    for (int n = 0;; ++n) {
+      const int buf = n & 1;
+      mbar_wait(B_QFULL0 + 8 * buf, (n >> 1) & 1);
+      const int t = tile_v[buf];
+      if (t >= total_tiles) break;
+      int q0, h, b, kv_end;
+      tile_coords(t, q0, h, b, kv_end);
+      const int num_kvb = (kv_end + BKV - 1) / BKV;
+      const int q_pos = q0 + row + shift;
+      const bool warp_live = q0 + quarter * 32 < p.q_len;
+      const int lim = p.causal ? min(p.kv_len - 1, q_pos) : p.kv_len - 1;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < num_kvb; ++j) {
+        const uint32_t gj = g + j;
+        mbar_wait(B_SFULL, gj & 1);
+        tc_fence_after();
+        if (!warp_live) {
+          tc_fence_before();
+          mbar_arrive(B_SCONS);
+          if (j > 0) mbar_wait(B_PVDONE, (gj - 1) & 1);
+          mbar_arrive(B_PFULL);
+          continue;
+        }
+        const int kv0 = j * BKV;
+        auto block = [&](auto nc_tag, bool need_mask) {
+          constexpr int NC = decltype(nc_tag)::value;
+          uint32_t s[NC];
+#pragma unroll
+          for (int c = 0; c < NC / 32; ++c) {
+            uint32_t(&sc)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]);
+            tmem_ld_32x32b_x32(tmem + lane_addr + TM_S + c * 32, sc);
+          }
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(B_SCONS);
+          const float mx = need_mask ? row_max_n<true, NC>(s, kv0, lim) : row_max_n<false, NC>(s, kv0, lim);
+          const float m_cand = fmaxf(m_run, mx * p.scale_log2);
+          const bool bump = (m_cand - m_run) > 8.0f || m_run == -INFINITY;
+          const float m_new = bump ? m_cand : m_run;
+          const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+          const float alpha = bump ? ex2_approx(m_run - m_use) : 1.0f;
+          uint32_t pw[NC / 2];
+          const float rs = need_mask ? exp_pack_store_n<true, NC, true>(s, kv0, lim, p.scale_log2, -m_use, p_rbase, 0, pw)
+                                     : exp_pack_store_fast<NC, POLY, true>(s, p.scale_log2, -m_use, p_rbase, 0, pw);
+          if (j > 0) {  // O and the P columns are quiescent only once PV(j-1) has retired (j == 0: finalize waited)
+            mbar_wait(B_PVDONE, (gj - 1) & 1);
+            tc_fence_after();
+            const bool any = __any_sync(0xffffffffu, alpha != 1.0f);
+            if (any) {
+#pragma unroll
+              for (int c = 0; c < HD / 32; ++c) {
+                uint32_t o[32];
+                tmem_ld_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
+              }
+              tmem_st_wait();
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < NC / 32; ++c)
+            tmem_st_32x32b_x16(p_rbase + 16 * c, *reinterpret_cast<uint32_t(*)[16]>(&pw[16 * c]));
+          l_run = l_run * alpha + rs;
+          m_run = m_new;
+        };
+        if (BKV > 32 && kv_end - kv0 <= 32) {
+          block(std::integral_constant<int, 32>{}, true);
+        } else {
+          const bool need_mask = (kv0 + BKV > p.kv_len) || (p.causal && kv0 + BKV - 1 > q0 + shift);
+          block(std::integral_constant<int, BKV>{}, need_mask);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(B_PFULL);
+      }
+      g += num_kvb;
+      // ---- finalize: O / l -> bf16 -> this tile's Q buffer -> TMA store; S(0) of the next tile is already running ----
+      mbar_wait(B_PVDONE, (g - 1) & 1);
+      tc_fence_after();
+      const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+      const uint32_t rbase = sbase + SMEM_Q + buf * Q_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+      const uint32_t sw = row & 7;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        if (!warp_live) break;
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tmem + lane_addr + TM_O + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            w[i] = pack_bf16x2(__uint_as_float(o[q * 8 + 2 * i]) * inv_l, __uint_as_float(o[q * 8 + 2 * i + 1]) * inv_l);
+          const uint32_t addr = rbase + (c >> 1) * TILE_BYTES + ((static_cast<uint32_t>((c & 1) * 4 + q) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                       : "memory");
+        }
+      }
+      tc_fence_before();  // this thread's O reads are ordered before its next PFULL arrive lets PV(0) overwrite O
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (warp == 4 && lane == 0) {
+#pragma unroll
+        for (int u = 0; u < NSUB; ++u)
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmap_o)),
+                       "r"(sbase + SMEM_Q + buf * Q_BYTES + u * TILE_BYTES), "r"(p.o_col0 + h * p.q_head_cols + 64 * u),
+                       "r"(q0), "r"(b)
+                       : "memory");
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(B_QEMPTY0 + 8 * buf);  // the TMA thread may load tile n+2's Q into this buffer
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, Cfg::TMEM_COLS);
+  }
+  if (threadIdx.x == 0) {  // the TMA thread: its counter fetches precede this arrival
+    __threadfence();
+    if (atomicAdd(sched + 1, 1u) == gridDim.x - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
 }  // namespace
 
 static long long* g_attn_timeline = nullptr;
@@ -512,6 +843,24 @@ static long long* g_attn_timeline = nullptr;
 extern "C" int gar_attn_debug_timeline(void* dev_buf) {
   g_attn_timeline = static_cast<long long*>(dev_buf);
   return GAR_OK;
+}
+
+// Tile counters of the persistent kernel: {next tile, retired CTAs} pairs, zero at rest (the last CTA of a launch resets
+// its pair).  Launches rotate through 64 pairs so that two launches in flight on different streams never share one.
+static unsigned int* attn_sched_slot() {
+  static std::mutex mu;
+  static unsigned int* base = nullptr;
+  static unsigned int next = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  if (base == nullptr) {
+    if (cudaMalloc(&base, 64 * 2 * sizeof(unsigned int)) != cudaSuccess) {
+      gar_set_error("attention: cudaMalloc of the tile counters failed: %s", cudaGetErrorString(cudaGetLastError()));
+      base = nullptr;
+      return nullptr;
+    }
+    if (cudaMemset(base, 0, 64 * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+  }
+  return base + 2 * (next++ & 63u);
 }
 
 // Generic strided description (all in bf16 elements):
@@ -537,6 +886,25 @@ static int launch_attn(const void* q, long long q_row_stride, long long q_batch_
     GAR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<HD, BKV, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::SMEM_BYTES));
     attr_set = true;
+  }
+  if constexpr (Cfg::P_TMEM) {
+    if (gar_global_option("attn_persist") && p.timeline == nullptr) {
+      using CfgP = AttCfgP<HD, BKV>;
+      static bool attr_set_p = false;
+      if (!attr_set_p) {
+        GAR_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_persist_kernel<HD, BKV, POLY>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, CfgP::SMEM_BYTES));
+        attr_set_p = true;
+      }
+      unsigned int* sched = attn_sched_slot();
+      if (sched == nullptr) return GAR_ERR_CUDA;
+      const int total = ((q_len + BQ - 1) / BQ) * heads * batch;
+      const int resident = Cfg::CTAS_PER_SM * gar_grid_sms();
+      attn_fwd_persist_kernel<HD, BKV, POLY><<<dim3(total < resident ? total : resident), ATT_THREADS, CfgP::SMEM_BYTES,
+                                               stream>>>(tq, tk, tv, to, p, heads, total, sched);
+      GAR_CUDA_CHECK(cudaGetLastError());
+      return GAR_OK;
+    }
   }
   dim3 grid((q_len + BQ - 1) / BQ, heads, batch);
   attn_fwd_kernel<HD, BKV, POLY><<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);

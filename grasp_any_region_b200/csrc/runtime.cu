@@ -29,6 +29,7 @@ static int g_gemm_2cta = 1;
 static int g_attn_poly = 1;  // share of the softmax exponentials evaluated on the FMA pipe: 0 none, 1 2/8 (fastest measured), 2 3/8, 3 4/8
 static int g_gemv_wide = 1;          // long-K decode GEMVs (down_proj) run 16 K-slices per CTA (A/B switch)
 static int g_gemv_norm_smem = 1;     // decode GEMV stages RMSNorm weights / statistics through shared memory (A/B switch)
+static int g_attn_persist = 1;  // prefill / ViT attention as a persistent kernel with a device-side tile counter (A/B switch)
 static int g_attn_bkv = 128;  // measured: 128 (2 CTAs/SM) beats 64 (3 CTAs/SM) on both ViT and prefill shapes
 int gar_pdl_enabled() { return g_pdl; }
 void gar_set_pdl(int on) { g_pdl = on; }
@@ -37,6 +38,7 @@ int gar_global_option(const char* name) {
   if (!strcmp(name, "pdl")) return g_pdl;
   if (!strcmp(name, "attn_bkv")) return g_attn_bkv;
   if (!strcmp(name, "attn_poly")) return g_attn_poly;
+  if (!strcmp(name, "attn_persist")) return g_attn_persist;
   if (!strcmp(name, "gemm_2cta")) return g_gemm_2cta;
   if (!strcmp(name, "gemv_norm_smem")) return g_gemv_norm_smem;
   if (!strcmp(name, "gemv_wide")) return g_gemv_wide;
@@ -52,6 +54,7 @@ extern "C" int gar_set_global_option(const char* name, int value) {
   else if (!strcmp(name, "gemv_wide")) g_gemv_wide = value;
   else if (!strcmp(name, "attn_bkv") && (value == 64 || value == 128)) g_attn_bkv = value;
   else if (!strcmp(name, "attn_poly") && value >= 0 && value <= 3) g_attn_poly = value;
+  else if (!strcmp(name, "attn_persist")) g_attn_persist = value != 0;
   else {
     gar_set_error("gar_set_global_option: unknown option '%s'", name);
     return GAR_ERR_ARG;

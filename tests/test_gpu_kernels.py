@@ -355,13 +355,17 @@ def test_llama_rope_kv_and_swiglu_pool_argmax():
     assert nxt[2].item() == 5
 
 
-@pytest.fixture(params=[64, 128])
+# (keys per block, persistent): the BKV 64 configuration exists only as the per-tile kernel
+@pytest.fixture(params=[(64, 0), (128, 0), (128, 1)], ids=["bkv64", "bkv128-per-tile", "bkv128-persistent"])
 def attn_bkv(request):
     from grasp_any_region_b200 import _lib
 
-    _lib.check(_lib.load().gar_set_global_option(b"attn_bkv", request.param))
+    bkv, persist = request.param
+    _lib.check(_lib.load().gar_set_global_option(b"attn_bkv", bkv))
+    _lib.check(_lib.load().gar_set_global_option(b"attn_persist", persist))
     yield request.param
     _lib.check(_lib.load().gar_set_global_option(b"attn_bkv", 128))
+    _lib.check(_lib.load().gar_set_global_option(b"attn_persist", 1))
 
 
 @pytest.mark.parametrize("hd", [64, 128])
@@ -395,6 +399,36 @@ def test_attention_causal_gqa_cache_layout(S, hd, attn_bkv):
     ref = F.scaled_dot_product_attention(qq, kk, vv, is_causal=True)[0].transpose(0, 1).reshape(S, hq * hd)
     err = (out.float() - ref).abs().max().item()
     assert err <= 2e-2, err
+
+
+@pytest.mark.parametrize("hd", [64, 128])
+def test_attention_persistent_is_bit_identical_to_per_tile(hd):
+    """The persistent kernel walks the same tiles with the same arithmetic: outputs must be equal bit for bit, on the
+    ViT shape (many more tiles than resident CTAs, 1-row query tail, 1-key KV tail), on a batched causal GQA prefill
+    (tiles of 1..N blocks, heaviest first) and back to back on one stream (the tile counters reset themselves)."""
+    from grasp_any_region_b200 import _lib
+
+    lib = _lib.load()
+    T, ntok, heads = (40, 1025, 16) if hd == 64 else (12, 1025, 8)
+    qkv = rnd(T * ntok, 3 * heads * hd, seed=41)
+    S, hq, hkv, max_seq, nreq = 3000, 16, 4, 3072, 2  # 24 query blocks x 16 heads = 384 tiles per call > resident CTAs
+    q = rnd(nreq * S, (hq + 2 * hkv) * hd, seed=42)
+    kc, vc = rnd(nreq * hkv, max_seq, hd, seed=43), rnd(nreq * hkv, max_seq, hd, seed=44)
+    outs = {}
+    for persist in (0, 1):
+        _lib.check(lib.gar_set_global_option(b"attn_persist", persist))
+        a = [ops.attn_fwd_packed_qkv(qkv, T, ntok, heads, hd) for _ in range(3)]
+        c = [ops.attn_fwd_cache(q[i * S:(i + 1) * S], q.stride(0), kc[i * hkv:(i + 1) * hkv], vc[i * hkv:(i + 1) * hkv],
+                                hq, hkv, hd, S, max_seq) for i in range(nreq)]
+        torch.cuda.synchronize()
+        assert all(torch.equal(a[0], x) for x in a[1:])
+        outs[persist] = (a[0], torch.cat(c))
+    _lib.check(lib.gar_set_global_option(b"attn_persist", 1))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    qf, kf, vf = qkv.view(T, ntok, 3, heads, hd).permute(2, 0, 3, 1, 4)[:, :2].float()
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(2 * ntok, heads * hd)
+    assert (outs[1][0][:2 * ntok].float() - ref).abs().max().item() <= 2e-2
 
 
 @pytest.mark.parametrize("mma", [1, 0])
