@@ -64,6 +64,10 @@ def parse_args():
                     help="overlap decode of batch i with ViT+prefill of batch i+1 (pays off only for many steps)")
     ap.add_argument("--decode-sms", type=int, default=0,
                     help="with --pipeline: SMs of the decode partition (green contexts); 0 = no SM partitioning")
+    ap.add_argument("--decode-groups", type=int, default=3,
+                    help="consecutive steps whose decode loops run concurrently (GARModel.generate_batches(overlap='decode', "
+                         "ways=N): each step is still one batch of --batch requests through its own ViT / prefill / KV cache; "
+                         "1 = every step strictly after the previous one")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (pdl, skinny_gemm, decode_splits)")
     return ap.parse_args()
 
@@ -437,7 +441,17 @@ def main():
         """`steps` batches through the public API (GARModel.generate_batch; --pipeline: generate_batches).
         gather=False for the rank-0-only diagnostic passes: a collective there would wait for ranks that never come."""
         raw = "image_u8" in batch_list[0]
-        if args.pipeline or (raw and steps > 1):
+        if not args.pipeline and args.decode_groups > 1 and steps > 1:
+            # `decode_groups` consecutive steps: encodes back to back, decode loops concurrently (one engine twin per
+            # step in flight, shared weights); the next round's copies / device preprocessing under the current decode
+            toks = model.generate_batches([batch_list] * steps, max_new_tokens=NT, eos_token_id=None, overlap="decode",
+                                          ways=args.decode_groups)
+            if world > 1 and gather:  # the path's one collective: all-gather of the decoded ids (north_star)
+                from grasp_any_region_b200.parallel import gather_tokens, pack_tokens
+
+                for step_toks in toks:
+                    gather_tokens(pack_tokens(step_toks, B, NT, dev), world * B)
+        elif args.pipeline or (raw and steps > 1):
             # raw (uint8) requests: the next step's host -> device copies and device preprocessing run under the current
             # step's decode (generate_batches(overlap="prepare")); every step's copies stay inside the timed region
             toks = model.generate_batches([batch_list] * steps, max_new_tokens=NT, eos_token_id=None,
@@ -481,7 +495,8 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    step_resident(max(args.warmup, 2))  # >= 2 so both KV-slot groups capture their decode graph
+    # >= 2 so both KV-slot groups (--pipeline) / every engine twin (--decode-groups) capture their decode graph untimed
+    step_resident(max(args.warmup, 2, 1 if args.pipeline else args.decode_groups))
     note("warm-up done")
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -525,6 +540,30 @@ def main():
         enc, dec = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
         phases = {"vit_assemble_prefill_ms_per_request": enc / B, "decode_ms_total": dec,
                   "decode_ms_per_token_step": dec / max(1, NT - 1), "batch": B}
+        ways = args.decode_groups if (not args.pipeline and args.steps > 1) else 1
+        if ways > 1:
+            # the production decode: `ways` groups (one engine twin each) decoded concurrently, all encoded beforehand
+            import threading
+
+            engines = [eng] + eng.twins(ways - 1)
+            for e in engines:
+                model._stage(e, 0, reqs_dev)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(eng.stream)
+            ths = [threading.Thread(target=e.generate, args=(B, NT, None)) for e in engines[1:]]
+            for th in ths:
+                th.start()
+            eng.generate(B, NT, None)
+            for th in ths:
+                th.join()
+            for e in engines[1:]:
+                eng.stream.wait_stream(e.stream)
+            c1.record(eng.stream)
+            torch.cuda.synchronize()
+            cms = c0.elapsed_time(c1)
+            phases["decode_concurrent"] = {"groups": ways, "ms_total": cms, "ms_per_group": cms / ways,
+                                           "ms_per_token_step_per_group": cms / ways / max(1, NT - 1)}
 
     # ---- per-kernel-class timing of ONE more step (CUDA events around every launch of the class)
     roof, rooflines, stages = None, None, None
@@ -553,7 +592,10 @@ def main():
                                          + t.hidden_size * t.num_heads * t.head_dim
                                          + 3 * t.intermediate_size * t.hidden_size) + eng.vocab_padded * t.hidden_size)
         kv_bytes = 2.0 * 2 * t.num_kv_heads * t.head_dim * t.num_layers * B * (S + NT / 2.0)
-        d_ms = phases["decode_ms_per_token_step"]
+        d_alone = phases["decode_ms_per_token_step"]
+        conc = phases.get("decode_concurrent")
+        # production mode: `groups` decode chains in flight -> per group-step time = concurrent total / groups / steps
+        d_ms = conc["ms_per_token_step_per_group"] if conc else d_alone
         d_gbs = (w_bytes + kv_bytes) / (d_ms * 1e-3) / 1e9
         asm_gbs = s_by / (s_ms * 1e-3) / 1e9 if s_ms > 0 else 0.0
         rooflines = [
@@ -564,8 +606,14 @@ def main():
             {"bound": "hbm", "kernel": "decode step (CUDA graph: gemv_decode + decode_attn + argmax kernels)",
              "achieved": d_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": d_gbs / peaks["hbm"],
              "bytes_per_step": w_bytes + kv_bytes, "ms_per_launch": d_ms, "launches_per_step": NT - 1,
-             "share_of_step": phases["decode_ms_total"] / step_ms, "traffic": None,
-             "mode": "production (graph replay), from phases.decode_ms_per_token_step"},
+             "share_of_step": d_ms * (NT - 1) / step_ms, "traffic": None,
+             "alone": {"ms_per_launch": d_alone, "GB/s": (w_bytes + kv_bytes) / (d_alone * 1e-3) / 1e9,
+                       "frac": (w_bytes + kv_bytes) / (d_alone * 1e-3) / 1e9 / peaks["hbm"]},
+             "mode": (f"production (graph replay): {conc['groups']} independent groups of {B} sequences decoded concurrently, "
+                      "every group streams the weights and its own K/V once per step (bytes_per_step is ONE group's); "
+                      "ms_per_launch = concurrent total / groups / steps (phases.decode_concurrent); `alone` = one group "
+                      "by itself (phases.decode_ms_per_token_step)") if conc else
+                     "production (graph replay), from phases.decode_ms_per_token_step"},
             {"bound": "hbm", "kernel": "replay_rows + gather_rows (embed gather + image scatter + RoI replay; one call, "
                                        "the two grids side by side)",
              "achieved": asm_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": asm_gbs / peaks["hbm"],
@@ -612,6 +660,11 @@ def main():
                        "l2": "inputs+weights per step (3.2 GB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"dp{world} (independent requests per rank, one all-gather of token ids)",
                        "pipeline": bool(args.pipeline), "sm_partition": partition,
+                       "decode_groups": (f"{args.decode_groups}: the steps are taken {args.decode_groups} at a time -- encoded "
+                                         "back to back, then their decode loops run concurrently, each step's batch in its own "
+                                         "KV cache / workspaces / stream / CUDA graph (engine twins, one shared copy of the "
+                                         "weights); per-request tokens identical to the one-at-a-time run"
+                                         if (not args.pipeline and args.decode_groups > 1 and args.steps > 1) else 1),
                        "encode": "the B requests of a step share one ViT pass and one prefill pass (equal shapes); decode batched"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "rooflines": rooflines,
             "stages": stages, "phases": phases, "pipeline_stats": pipe_stats, "cpu_baseline": cpu, "gpu_lib_baseline": lib,

@@ -942,7 +942,7 @@ int gar_engine_set_option(gar_engine* e, const char* name, int value) {
   else if (n == "fuse_decode_rope") e->fuse_decode_rope = value;
   else if (n == "decode_splits" && value >= 0 && value <= 32) e->dec_splits = value;
   else if (n == "eos_poll_steps" && value >= 0) e->eos_poll_steps = value;
-  else if (n == "pdl" || n == "decode_attn_mma" || n == "attn_bkv" || n == "attn_poly" || n == "attn_persist" || n == "gemm_2cta" ||
+  else if (n == "pdl" || n == "decode_attn_mma" || n == "attn_bkv" || n == "attn_poly" || n == "attn_persist" || n == "gemm_group_kb" || n == "gemm_group_force" || n == "gemm_2cta" ||
            n == "gemv_norm_smem" || n == "gemv_wide") {
     if (gar_set_global_option(name, value)) return GAR_ERR_ARG;
   }

@@ -54,7 +54,7 @@ struct EpiArgs {
 template <int BLOCK_N, int EPI, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, EpiArgs ea) {
+                    const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K, int n_group, EpiArgs ea) {
   using C = Cfg<BLOCK_N, CTA2>;
   static_assert(!CTA2 || BLOCK_N == 256, "the CTA-pair kernel uses 256 x 256 tiles");
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
@@ -81,6 +81,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m * num_n;
   const int num_kb = K / BLOCK_K;
+  // Raster: column panels are walked in groups of `n_group`; inside a group n runs fastest, then m, so the CTAs in flight
+  // share a few row blocks of A and the group's panels of B (n_group x BLOCK_N x K x 2 bytes, sized by the host to stay
+  // L2-resident for all num_m row blocks); A is streamed once per group.  n_group >= num_n is the plain n-fastest order.
+  // (The SwiGLU gate/up weights are 67 MB: walked as one group they fell out of L2 between row blocks and were
+  // re-fetched from HBM ~25 times per launch -- 2.4 GB of DRAM traffic for 0.83 GB of operands.)
+  auto tile_mn = [&](int tile, int& m_blk, int& n_blk) {
+    const int per_group = num_m * n_group;
+    const int grp = tile / per_group, r = tile - grp * per_group;
+    const int ng = min(n_group, num_n - grp * n_group);
+    m_blk = r / ng;
+    n_blk = grp * n_group + (r - m_blk * ng);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -123,7 +135,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_blk = tile / num_n, n_blk = tile % num_n;  // n fastest: co-running CTAs share A rows, B stays in L2
+        int m_blk, n_blk;
+        tile_mn(tile, m_blk, n_blk);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_ab + stage * C::STAGE_BYTES;
@@ -195,7 +208,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int cbuf = 0;
     uint32_t gate[EPI == EPI_SWIGLU ? 16 : 1];  // EPI_SWIGLU: bf16-rounded gate chunk (packed pairs) waiting for its up chunk
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int m_blk = tile / num_n, n_blk = tile % num_n;  // n fastest: co-running CTAs share A rows, B stays in L2
+      int m_blk, n_blk;
+      tile_mn(tile, m_blk, n_blk);
       const int m_base = m_blk * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;  // this CTA's 128 rows of the tile
       const int gm = m_base + row;
       // Residual rows: requested for ALL chunks of the tile before waiting for the accumulator, with a coalesced
@@ -432,15 +446,39 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     attr_set = true;
   }
   const int tile_m = CTA2 ? 2 * BLOCK_M : BLOCK_M;
-  const int num_tiles = ((M + tile_m - 1) / tile_m) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = ((M + tile_m - 1) / tile_m) * num_n;
+  // Column panels per raster group.  With `fly` tiles in flight (one per CTA / CTA pair) and ng panels per group, the
+  // operands being read at any moment are fly/ng row blocks of A and ng panels of B; the walk stays L2-friendly while
+  // that working set fits a budget well inside the 126 MB L2 (default 40 MB: the output stream passes through the same
+  // cache and each L2 half keeps its own copy of shared lines).  The widest group that fits is taken (A is streamed
+  // once per group); when not even the narrowest working set fits (long K: ViT fc2, down_proj) the plain n-fastest
+  // walk is kept.  Measured with ncu on GAR-1B's SwiGLU GEMM (67 MB of weights): 2.14 -> 0.68 GB of DRAM reads per
+  // launch, 1.73 -> 1.60 ms; GAR-8B's (235 MB): 7.1 -> 1.5 GB, 1.73 -> 1.42 ms (profiles/r02_gemm_group_ncu.txt).
+  const int fly = CTA2 ? std::min(num_tiles, gar_grid_sms() / 2) : std::min(num_tiles, gar_grid_sms());
+  const double a_block = static_cast<double>(tile_m) * K * 2, b_panel = static_cast<double>(BLOCK_N) * K * 2;
+  const double budget = static_cast<double>(gar_global_option("gemm_group_kb")) * 1024.0;
+  int n_group = num_n;
+  const int forced = gar_global_option("gemm_group_force");  // test hook: panels per group
+  if (forced > 0) {
+    n_group = std::min(forced, num_n);
+  } else if (budget > 0) {
+    for (int groups = 1; groups <= num_n; ++groups) {
+      const int ng = (num_n + groups - 1) / groups;
+      if ((static_cast<double>(fly) / ng) * a_block + ng * b_panel <= budget) {
+        n_group = ng;
+        break;
+      }
+    }
+  }
   if (CTA2) {
     const int clusters = std::min(num_tiles, gar_grid_sms() / 2);
     GAR_CUDA_CHECK(gar_launch(kern, dim3(2 * clusters), dim3(NUM_THREADS), C::SMEM_BYTES, stream, false, dim3(2, 1, 1), ta,
-                              tb, tc, M, N, K, ea));
+                              tb, tc, M, N, K, n_group, ea));
     return GAR_OK;
   }
   const int grid = num_tiles < gar_grid_sms() ? num_tiles : gar_grid_sms();
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tc, M, N, K, ea);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tc, M, N, K, n_group, ea);
   GAR_CUDA_CHECK(cudaGetLastError());
   return GAR_OK;
 }

@@ -30,6 +30,8 @@ static int g_attn_poly = 1;  // share of the softmax exponentials evaluated on t
 static int g_gemv_wide = 1;          // long-K decode GEMVs (down_proj) run 16 K-slices per CTA (A/B switch)
 static int g_gemv_norm_smem = 1;     // decode GEMV stages RMSNorm weights / statistics through shared memory (A/B switch)
 static int g_attn_persist = 1;  // prefill / ViT attention as a persistent kernel with a device-side tile counter (A/B switch)
+static int g_gemm_group_kb = 40960;  // tcgen05 GEMM raster: L2 working-set budget (KB) that sizes the column-panel groups; 0 = one group
+static int g_gemm_group_force = 0;   // test hook: panels per raster group (0 = sized from gemm_group_kb)
 static int g_attn_bkv = 128;  // measured: 128 (2 CTAs/SM) beats 64 (3 CTAs/SM) on both ViT and prefill shapes
 int gar_pdl_enabled() { return g_pdl; }
 void gar_set_pdl(int on) { g_pdl = on; }
@@ -39,6 +41,8 @@ int gar_global_option(const char* name) {
   if (!strcmp(name, "attn_bkv")) return g_attn_bkv;
   if (!strcmp(name, "attn_poly")) return g_attn_poly;
   if (!strcmp(name, "attn_persist")) return g_attn_persist;
+  if (!strcmp(name, "gemm_group_kb")) return g_gemm_group_kb;
+  if (!strcmp(name, "gemm_group_force")) return g_gemm_group_force;
   if (!strcmp(name, "gemm_2cta")) return g_gemm_2cta;
   if (!strcmp(name, "gemv_norm_smem")) return g_gemv_norm_smem;
   if (!strcmp(name, "gemv_wide")) return g_gemv_wide;
@@ -55,6 +59,8 @@ extern "C" int gar_set_global_option(const char* name, int value) {
   else if (!strcmp(name, "attn_bkv") && (value == 64 || value == 128)) g_attn_bkv = value;
   else if (!strcmp(name, "attn_poly") && value >= 0 && value <= 3) g_attn_poly = value;
   else if (!strcmp(name, "attn_persist")) g_attn_persist = value != 0;
+  else if (!strcmp(name, "gemm_group_kb") && value >= 0) g_gemm_group_kb = value;
+  else if (!strcmp(name, "gemm_group_force") && value >= 0) g_gemm_group_force = value;
   else {
     gar_set_error("gar_set_global_option: unknown option '%s'", name);
     return GAR_ERR_ARG;

@@ -57,7 +57,9 @@ def roi_boxes_f32(spec: GARSpec, bboxes: Dict[str, Sequence[float]], ncw: int, n
 class Engine:
     def __init__(self, spec: GARSpec, state_dict: Dict[str, torch.Tensor], device: str = "cuda:0",
                  max_tiles: int = 17, max_seq: int = 6144, max_batch: int = 8, max_new_tokens: int = 128,
-                 max_prefill_rows: int = 0):
+                 max_prefill_rows: int = 0, share: Optional["Engine"] = None):
+        """share: another Engine of the same spec whose (already fused / padded) weight tensors this one points at
+        instead of building its own copies from `state_dict` -- see `twins`."""
         if not torch.cuda.is_available():
             raise _lib.GarError("grasp_any_region_b200 needs a CUDA device: there is no CPU fallback")
         self.lib = _lib.load()
@@ -95,7 +97,30 @@ class Engine:
         self.last_steps_run = 0
         self.replay_mode, self.crop_ids = REPLAY_MERGED, list(spec.crop_tokens_ids)
         self.trace = None  # debug: set to [] to collect (label, CUDA event) marks between the stage entry points
-        self._load_weights(state_dict)
+        self._caps = dict(max_tiles=max_tiles, max_seq=max_seq, max_batch=max_batch, max_new_tokens=max_new_tokens,
+                          max_prefill_rows=max_prefill_rows)
+        self._twins: List["Engine"] = []
+        self._options: Dict[str, int] = {}
+        self.decoded_once = False  # the first decode sets kernel attributes and captures the step graph
+        if share is not None:
+            for name, tensor in share._keep.items():  # same device tensors: one copy of the weights in HBM
+                self._keep[name] = tensor
+                check(self.lib.gar_engine_set_weight(self._h, name.encode(), C.c_void_p(tensor.data_ptr())),
+                      f"set_weight {name}")
+            for k, v in share._options.items():
+                self.set_option(k, v)
+            if share.replay_mode != REPLAY_MERGED or share.crop_ids != list(spec.crop_tokens_ids):
+                self.set_replay(share.replay_mode, share.crop_ids)
+        else:
+            self._load_weights(state_dict)
+
+    def twins(self, n: int) -> List["Engine"]:
+        """n more engines over the SAME weight tensors, each with its own workspaces, KV cache, streams and decode graph
+        (created on first use, then kept): independent request groups whose decode loops run concurrently
+        (GARModel.generate_batches(overlap="decode")).  Options and replay settings set on this engine follow."""
+        while len(self._twins) < n:
+            self._twins.append(Engine(self.spec, None, device=str(self.device), share=self, **self._caps))
+        return self._twins[:n]
 
     def enable_partition(self, decode_sms: int) -> bool:
         """Split the GPU's SMs into a decode partition (>= decode_sms, driver granularity) and an encode partition
@@ -126,6 +151,8 @@ class Engine:
         check(self.lib.gar_engine_set_replay(self._h, int(mode), None if crop_ids is None else arr,
                                              0 if crop_ids is None else len(ids)), "gar_engine_set_replay")
         self.replay_mode, self.crop_ids = int(mode), ids
+        for t in self._twins:
+            t.set_replay(mode, crop_ids)
 
     # ------------------------------------------------------------------ weights
     def _set(self, name: str, tensor: torch.Tensor):
@@ -351,6 +378,7 @@ class Engine:
         check(self.lib.gar_engine_generate_eos(self._h, slot0, batch, max_new_tokens, (C.c_int * max(1, len(eos)))(*eos),
                                                len(eos), buf, C.byref(steps), s), "gar_engine_generate")
         self.last_steps_run = steps.value
+        self.decoded_once = True
         out = []
         for b in range(batch):
             row = [buf[b * max_new_tokens + i] for i in range(max_new_tokens)]
@@ -363,10 +391,14 @@ class Engine:
         return st.value
 
     def launch_count(self) -> int:
-        return int(self.lib.gar_engine_launch_count(self._h))
+        return int(self.lib.gar_engine_launch_count(self._h)) + sum(t.launch_count() for t in self._twins)
 
     def set_option(self, name: str, value: int):
         check(self.lib.gar_engine_set_option(self._h, name.encode(), int(value)), "gar_engine_set_option")
+        self._options[name] = int(value)
+        self.decoded_once = False  # the C side dropped its decode graphs
+        for t in self._twins:
+            t.set_option(name, value)
 
     def profile(self, enable: bool):
         check(self.lib.gar_engine_profile(self._h, int(enable)), "gar_engine_profile")
@@ -380,6 +412,9 @@ class Engine:
         return {names[i]: (ms[i], work[i], cnt[i]) for i in range(n)}
 
     def close(self):
+        for t in getattr(self, "_twins", []):
+            t.close()
+        self._twins = []
         if getattr(self, "_h", None):
             self.lib.gar_engine_destroy(self._h)
             self._h = None

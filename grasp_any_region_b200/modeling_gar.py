@@ -440,8 +440,17 @@ class GARModel(_Base):
 
     @torch.no_grad()
     def generate_batches(self, batches: List[List[dict]], max_new_tokens: int = 128,
-                         eos_token_id=None, overlap: str = "encode") -> List[List[List[int]]]:
+                         eos_token_id=None, overlap: str = "encode", ways: int = 2) -> List[List[List[int]]]:
         """Throughput serving of a stream of request batches (B200 scheduler extension).
+
+        overlap="decode" (the bench's mode): `ways` consecutive batches are encoded back to back (ViT + assemble +
+        prefill, tensor-bound, each alone on the GPU) and then DECODED CONCURRENTLY -- every batch in its own engine
+        twin (own KV cache, workspaces, stream and step graph; one shared copy of the weights), driven by its own host
+        thread.  A decode step is a chain of ~80 dependent launches that reaches 0.58 of the HBM peak by itself; a
+        second and third independent chain fill its launch / drain gaps (measured on B200, 8 x 4.7k-token contexts:
+        0.98 ms per step alone, 0.78 with two groups in flight, 0.71 with three).  Nothing is shared between the
+        groups but read-only weights, so every request's tokens equal its batch-1 result.  The next round's host ->
+        device copies and device preprocessing run under the current round's decode as in overlap="prepare".
 
         overlap="prepare": only the NEXT batch's host -> device copies and device preprocessing (uint8 image / id map ->
         bf16 tiles) run under the current batch's decode, on their own stream from a helper thread; ViT, prefill and
@@ -463,8 +472,10 @@ class GARModel(_Base):
             return []
         if overlap == "prepare":
             return self._generate_batches_prepare(eng, batches, max_new_tokens, eos_token_id, threading)
+        if overlap == "decode":
+            return self._generate_batches_decode(eng, batches, max_new_tokens, eos_token_id, threading, int(ways))
         if overlap != "encode":
-            raise ValueError(f"overlap must be 'encode' or 'prepare', got {overlap!r}")
+            raise ValueError(f"overlap must be 'encode', 'prepare' or 'decode', got {overlap!r}")
         G = max(len(b) for b in batches)
         if 2 * G > eng.max_batch:
             raise ValueError(f"pipelining needs engine max_batch >= 2 x batch ({2 * G}), got {eng.max_batch}")
@@ -519,6 +530,81 @@ class GARModel(_Base):
                 if "err" in box:
                     raise box["err"]
                 prepared, ev = box["p"]
+        return out
+
+    def _generate_batches_decode(self, eng, batches, max_new_tokens, eos_token_id, threading, ways):
+        if ways < 1 or ways > 4:
+            raise ValueError(f"ways must be 1..4, got {ways}")
+        dev = eng.device
+        if max(len(b) for b in batches) > eng.max_batch:
+            raise ValueError(f"batch larger than the engine's max_batch {eng.max_batch}")
+        engines = [eng] + eng.twins(min(ways, len(batches)) - 1)
+        prep = getattr(self, "_prep_stream", None)
+        if prep is None or prep.device != dev:
+            prep = self._prep_stream = torch.cuda.Stream(device=dev)
+
+        def prepare(first: int, count: int):
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(prep):
+                prepared = [self._prepare(eng, batches[first + k]) for k in range(count)]
+                ev = torch.cuda.Event()
+                ev.record(prep)
+            return prepared, ev
+
+        def decode(e, n, box, k):
+            try:
+                torch.cuda.set_device(dev)
+                box[k] = e.generate(n, int(max_new_tokens), eos_token_id)
+            except BaseException as ex:  # surfaced on the caller's thread
+                box["err"] = ex
+
+        prep.wait_stream(torch.cuda.current_stream(dev))
+        out: List[List[List[int]]] = []
+        i = 0
+        count = min(ways, len(batches))
+        prepared, ev = prepare(0, count)
+        while i < len(batches):
+            # encodes back to back: each ViT / prefill pass owns the GPU (persistent tensor-core kernels), the first
+            # decode waits for the last encode so that all chains start together
+            for k in range(count):
+                if k > 0:
+                    engines[k].stream.wait_stream(engines[k - 1].stream)
+                self._stage(engines[k], 0, batches[i + k], prepared[k], ev)
+            for k in range(count - 1):
+                engines[k].stream.wait_stream(engines[count - 1].stream)
+            nxt = min(ways, len(batches) - (i + count))
+            pbox, pth = {}, None
+            if nxt > 0:
+                def work(first=i + count, c=nxt):
+                    try:
+                        pbox["p"] = prepare(first, c)
+                    except BaseException as ex:
+                        pbox["err"] = ex
+                pth = threading.Thread(target=work)
+                pth.start()
+            box = {}
+            # an engine's very first decode sets kernel attributes and captures its step graph: those run one by one
+            cold = [k for k in range(count) if not engines[k].decoded_once]
+            for k in cold:
+                decode(engines[k], len(batches[i + k]), box, k)
+            ths = [threading.Thread(target=decode, args=(engines[k], len(batches[i + k]), box, k))
+                   for k in range(1, count) if k not in cold]
+            for t in ths:
+                t.start()
+            if 0 not in cold:
+                decode(engines[0], len(batches[i]), box, 0)
+            for t in ths:
+                t.join()
+            if pth is not None:
+                pth.join()
+            for b in (box, pbox):
+                if "err" in b:
+                    raise b["err"]
+            out.extend(box[k] for k in range(count))
+            i += count
+            if nxt > 0:
+                prepared, ev = pbox["p"]
+                count = nxt
         return out
 
     def _generate_batches(self, eng, batches, G, dev, max_new_tokens, eos_token_id, threading):

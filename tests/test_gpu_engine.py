@@ -155,6 +155,44 @@ def test_pipelined_batches_match_sequential():
         print("green contexts unavailable:", getattr(eng, "partition_error", "?"))
 
 
+@pytest.mark.parametrize("ways", [2, 3])
+def test_concurrent_decode_groups_match_sequential(ways):
+    """generate_batches(overlap="decode"): `ways` consecutive batches are encoded back to back and decoded concurrently
+    in engine twins that share one copy of the weights (own KV cache / workspaces / stream / step graph, one host thread
+    each).  Every request must still produce exactly its batch-1 tokens -- odd batch counts, ragged batch sizes, stop
+    ids (a group that finishes early leaves the others running) and options set on the main engine included; the twins add no second copy of any weight."""
+    from grasp_any_region_b200 import GARConfig, GARModel
+
+    spec = gar_small()
+    oracle = build_oracle(spec, seed=0, dtype=torch.float32)
+    sd = {k: v.to(bf) for k, v in oracle.state_dict().items()}
+    model = GARModel(GARConfig.from_spec(spec))
+    model.load_state_dict(sd)
+    model = model.to(DEV)
+    reqs = [make_request(spec, seed=40 + i, n_masks=1 + i % 3, max_num_tiles=4, dtype=bf) for i in range(5)]
+    S = max(r["input_ids"].shape[1] for r in reqs)
+    new_tokens = 9
+    model.configure_engine(max_tiles=5, max_seq=S + 32, max_batch=2, max_new_tokens=new_tokens)
+    singles = [model.generate_batch([r], max_new_tokens=new_tokens)[0] for r in reqs]
+    order = [[0, 1], [2, 3], [4], [1, 0], [3], [2, 4], [0]]
+    batches = [[reqs[j] for j in b] for b in order]
+    want = [[singles[j] for j in b] for b in order]
+    for _ in range(2):  # second pass: warm twins, graphs replayed
+        assert model.generate_batches(batches, max_new_tokens=new_tokens, overlap="decode", ways=ways) == want
+    eng = model.engine()
+    assert len(eng._twins) == ways - 1
+    for t in eng._twins:
+        assert all(t._keep[k].data_ptr() == eng._keep[k].data_ptr() for k in eng._keep)
+    eos = singles[0][3]
+    cut = [[t[: t.index(eos) + 1] if eos in t else t for t in b] for b in want]
+    assert model.generate_batches(batches, max_new_tokens=new_tokens, eos_token_id=eos, overlap="decode", ways=ways) == cut
+    eng.set_option("eos_poll_steps", 2)  # follows to the twins (and drops every decode graph)
+    assert model.generate_batches(batches[:4], max_new_tokens=new_tokens, eos_token_id=[eos, 1], overlap="decode",
+                                  ways=ways) == [[t[: min([t.index(e) for e in (eos, 1) if e in t] + [len(t) - 1]) + 1]
+                                                  for t in b] for b in want[:4]]
+    assert [model.generate_batch([r], max_new_tokens=new_tokens)[0] for r in reqs] == singles
+
+
 def test_forward_loss_matches_oracle():
     """R10: GARModel.forward(data, mode="loss") -- teacher-forced LM loss over the assembled sequence
     (reference modeling_gar.py:74-246; replayed rows carry label -100)."""

@@ -114,6 +114,35 @@ def test_gemm_cta_pair_matches_single_cta(epi, M, N, K):
     assert torch.equal(one, two)
 
 
+@pytest.mark.parametrize("epi", [ops.EPI_NONE, ops.EPI_BIAS_LS_RES, ops.EPI_SWIGLU])
+@pytest.mark.parametrize("cta2", [0, 1])
+@pytest.mark.parametrize("M,N,K,panels", [(4097, 2048, 1024, 2),    # 8 (or 16 / 32 narrower) panels in groups of 2
+                                          (2300, 2816, 256, 3),     # 11 panels -> ragged last group
+                                          (17425, 1024, 512, 1),    # one panel per group
+                                          (1000, 3328, 512, 4)])    # 13 / 26 panels, ragged
+def test_gemm_grouped_raster_matches_plain_order(epi, cta2, M, N, K, panels):
+    """The raster only changes WHICH tile a CTA takes next (column panels in L2-sized groups): every output keeps its
+    accumulation order, so results are bit-identical to the single-group (n-fastest) walk -- ragged last groups, 64 /
+    128 / 256-wide tiles and the CTA-pair kernel included."""
+    from grasp_any_region_b200 import _lib
+
+    a, b = rnd(M, K, seed=90), rnd(N, K, scale=0.05, seed=91)
+    bias, gamma, res = rnd(N, scale=0.1, seed=92), rnd(N, scale=0.2, seed=93), rnd(M, N, seed=94)
+    lib = _lib.load()
+    _lib.check(lib.gar_set_global_option(b"gemm_2cta", cta2))
+    try:
+        _lib.check(lib.gar_set_global_option(b"gemm_group_kb", 0))
+        plain = ops.gemm(a, b, epi=epi, bias=bias, gamma=gamma, res=res)
+        _lib.check(lib.gar_set_global_option(b"gemm_group_force", panels))
+        grouped = ops.gemm(a, b, epi=epi, bias=bias, gamma=gamma, res=res)
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(lib.gar_set_global_option(b"gemm_group_force", 0))
+        _lib.check(lib.gar_set_global_option(b"gemm_group_kb", 40960))
+        _lib.check(lib.gar_set_global_option(b"gemm_2cta", 1))
+    assert torch.equal(plain, grouped)
+
+
 def test_gemm_inplace_residual():
     M, N, K = 700, 512, 512
     a, b, x = rnd(M, K, seed=8), rnd(N, K, scale=0.05, seed=9), rnd(M, N, seed=10)
