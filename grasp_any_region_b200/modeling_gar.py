@@ -545,11 +545,13 @@ class GARModel(_Base):
 
         def prepare(first: int, count: int):
             torch.cuda.set_device(dev)
+            prepared, evs = [], []
             with torch.cuda.stream(prep):
-                prepared = [self._prepare(eng, batches[first + k]) for k in range(count)]
-                ev = torch.cuda.Event()
-                ev.record(prep)
-            return prepared, ev
+                for k in range(count):  # one event per batch: the first encode starts while the later batches still copy
+                    prepared.append(self._prepare(eng, batches[first + k]))
+                    evs.append(torch.cuda.Event())
+                    evs[-1].record(prep)
+            return prepared, evs
 
         def decode(e, n, box, k):
             try:
@@ -569,7 +571,7 @@ class GARModel(_Base):
             for k in range(count):
                 if k > 0:
                     engines[k].stream.wait_stream(engines[k - 1].stream)
-                self._stage(engines[k], 0, batches[i + k], prepared[k], ev)
+                self._stage(engines[k], 0, batches[i + k], prepared[k], ev[k])
             for k in range(count - 1):
                 engines[k].stream.wait_stream(engines[count - 1].stream)
             nxt = min(ways, len(batches) - (i + count))

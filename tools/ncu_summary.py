@@ -52,14 +52,17 @@ def launch_list(path):
         print(f"{t:12.1f} {100*t/total:5.1f}% {c:6d} {t/c:9.1f}  {k[:100]}")
 
 
-def traffic(path, command):
-    """Mean DRAM bytes (read + write) and duration per launch, overall and per kernel variant (bench.py roofline.traffic)."""
+def traffic(path, command, only="gemm_bf16_tn"):
+    """Mean DRAM bytes (read + write) and duration per launch, overall and per kernel variant (bench.py roofline.traffic);
+    launches whose kernel name does not match `only` are skipped (the csv may hold the whole step)."""
     import json
 
     lines = open(path).readlines()
     start = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
     per_id = collections.OrderedDict()
     for r in csv.DictReader(lines[start:]):
+        if only and not re.search(only, r["Kernel Name"]):
+            continue
         d = per_id.setdefault(r["ID"], {"k": clean(r["Kernel Name"]), "bytes": 0.0, "us": 0.0})
         v = float(r["Metric Value"].replace(",", ""))
         u = r["Metric Unit"]
@@ -95,7 +98,7 @@ def full(path):
 
 
 if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[1] == "traffic":
-    traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")
+    traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "", sys.argv[4] if len(sys.argv) > 4 else "gemm_bf16_tn")
     sys.exit(0)
 
 if __name__ == "__main__":
