@@ -32,6 +32,7 @@ SIGNATURES = {
     "gar_set_global_option": (_i, [C.c_char_p, _i]),
     "gar_gemm_skinny_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "gar_gemm_bf16": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "gar_gemm_raster_probe": (_i, [_i, _i, _i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "gar_gemm_bf16_rope2d": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gar_gemv_decode": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _f, _vp,
                              C.POINTER(_i), _vp]),

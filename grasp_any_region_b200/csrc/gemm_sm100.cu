@@ -40,6 +40,39 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * C_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// Raster of the persistent tile walk: tile index -> (row block, column panel).  Column panels in groups of n_group
+// (the last group may be narrower), n fastest inside a group, then m, then the group.  Shared by the kernel and the
+// host-side probe (gar_gemm_raster_probe) the CPU tests use.
+__host__ __device__ __forceinline__ void raster_tile_mn(int tile, int num_m, int num_n, int n_group, int& m_blk, int& n_blk) {
+  const int per_group = num_m * n_group;
+  const int grp = tile / per_group, r = tile - grp * per_group;
+  const int rest = num_n - grp * n_group;
+  const int ng = n_group < rest ? n_group : rest;
+  m_blk = r / ng;
+  n_blk = grp * n_group + (r - m_blk * ng);
+}
+
+// Column panels per raster group.  With `fly` tiles in flight (one per CTA / CTA pair) and ng panels per group, the
+// operands being read at any moment are fly/ng row blocks of A and ng panels of B; the walk stays L2-friendly while
+// that working set fits a budget well inside the 126 MB L2 (default 40 MB: the output stream passes through the same
+// cache and each L2 half keeps its own copy of shared lines).  The widest group that fits is taken (A is streamed
+// once per group); when not even the narrowest working set fits (long K: ViT fc2, down_proj) the plain n-fastest
+// walk is kept.  Measured with ncu on GAR-1B's SwiGLU GEMM (67 MB of weights): 2.14 -> 0.68 GB of DRAM reads per
+// launch, 1.73 -> 1.60 ms; GAR-8B's (235 MB): 7.1 -> 1.5 GB, 1.73 -> 1.42 ms (profiles/r02_gemm_group_ncu.txt).
+static int raster_group_panels(int num_n, int fly, int tile_m, int block_n, int K) {
+  const double a_block = static_cast<double>(tile_m) * K * 2, b_panel = static_cast<double>(block_n) * K * 2;
+  const double budget = static_cast<double>(gar_global_option("gemm_group_kb")) * 1024.0;
+  const int forced = gar_global_option("gemm_group_force");  // test hook: panels per group
+  if (forced > 0) return std::min(forced, num_n);
+  if (budget > 0) {
+    for (int groups = 1; groups <= num_n; ++groups) {
+      const int ng = (num_n + groups - 1) / groups;
+      if ((static_cast<double>(fly) / ng) * a_block + ng * b_panel <= budget) return ng;
+    }
+  }
+  return num_n;
+}
+
 struct EpiArgs {
   const bf16* bias;
   const bf16* gamma;
@@ -86,13 +119,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // L2-resident for all num_m row blocks); A is streamed once per group.  n_group >= num_n is the plain n-fastest order.
   // (The SwiGLU gate/up weights are 67 MB: walked as one group they fell out of L2 between row blocks and were
   // re-fetched from HBM ~25 times per launch -- 2.4 GB of DRAM traffic for 0.83 GB of operands.)
-  auto tile_mn = [&](int tile, int& m_blk, int& n_blk) {
-    const int per_group = num_m * n_group;
-    const int grp = tile / per_group, r = tile - grp * per_group;
-    const int ng = min(n_group, num_n - grp * n_group);
-    m_blk = r / ng;
-    n_blk = grp * n_group + (r - m_blk * ng);
-  };
+  auto tile_mn = [&](int tile, int& m_blk, int& n_blk) { raster_tile_mn(tile, num_m, num_n, n_group, m_blk, n_blk); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -448,29 +475,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   const int tile_m = CTA2 ? 2 * BLOCK_M : BLOCK_M;
   const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = ((M + tile_m - 1) / tile_m) * num_n;
-  // Column panels per raster group.  With `fly` tiles in flight (one per CTA / CTA pair) and ng panels per group, the
-  // operands being read at any moment are fly/ng row blocks of A and ng panels of B; the walk stays L2-friendly while
-  // that working set fits a budget well inside the 126 MB L2 (default 40 MB: the output stream passes through the same
-  // cache and each L2 half keeps its own copy of shared lines).  The widest group that fits is taken (A is streamed
-  // once per group); when not even the narrowest working set fits (long K: ViT fc2, down_proj) the plain n-fastest
-  // walk is kept.  Measured with ncu on GAR-1B's SwiGLU GEMM (67 MB of weights): 2.14 -> 0.68 GB of DRAM reads per
-  // launch, 1.73 -> 1.60 ms; GAR-8B's (235 MB): 7.1 -> 1.5 GB, 1.73 -> 1.42 ms (profiles/r02_gemm_group_ncu.txt).
   const int fly = CTA2 ? std::min(num_tiles, gar_grid_sms() / 2) : std::min(num_tiles, gar_grid_sms());
-  const double a_block = static_cast<double>(tile_m) * K * 2, b_panel = static_cast<double>(BLOCK_N) * K * 2;
-  const double budget = static_cast<double>(gar_global_option("gemm_group_kb")) * 1024.0;
-  int n_group = num_n;
-  const int forced = gar_global_option("gemm_group_force");  // test hook: panels per group
-  if (forced > 0) {
-    n_group = std::min(forced, num_n);
-  } else if (budget > 0) {
-    for (int groups = 1; groups <= num_n; ++groups) {
-      const int ng = (num_n + groups - 1) / groups;
-      if ((static_cast<double>(fly) / ng) * a_block + ng * b_panel <= budget) {
-        n_group = ng;
-        break;
-      }
-    }
-  }
+  const int n_group = raster_group_panels(num_n, fly, tile_m, BLOCK_N, K);
   if (CTA2) {
     const int clusters = std::min(num_tiles, gar_grid_sms() / 2);
     GAR_CUDA_CHECK(gar_launch(kern, dim3(2 * clusters), dim3(NUM_THREADS), C::SMEM_BYTES, stream, false, dim3(2, 1, 1), ta,
@@ -546,6 +552,20 @@ static int gemm_impl(const void* A, int lda, const void* B, int ldb, void* Cout,
   if (bn == 256) return dispatch_epi<256>(epi, ta, tb, tc, M, N, K, ea, stream);
   if (bn == 128) return dispatch_epi<128>(epi, ta, tb, tc, M, N, K, ea, stream);
   return dispatch_epi<64>(epi, ta, tb, tc, M, N, K, ea, stream);
+}
+
+// Host-only view of the raster (no CUDA call): panels per group for a launch of this geometry and the (row block,
+// column panel) of `tile`; fly = tiles in flight (CTAs, or CTA pairs for 256-row tiles).
+extern "C" int gar_gemm_raster_probe(int M, int N, int K, int tile_m, int block_n, int fly, int tile, int* n_group,
+                                     int* m_blk, int* n_blk) {
+  if (M <= 0 || N <= 0 || K <= 0 || tile_m <= 0 || block_n <= 0 || fly <= 0 || !n_group) return GAR_ERR_ARG;
+  const int num_m = (M + tile_m - 1) / tile_m, num_n = (N + block_n - 1) / block_n;
+  *n_group = raster_group_panels(num_n, std::min(fly, num_m * num_n), tile_m, block_n, K);
+  if (m_blk && n_blk) {
+    if (tile < 0 || tile >= num_m * num_n) return GAR_ERR_ARG;
+    raster_tile_mn(tile, num_m, num_n, *n_group, *m_blk, *n_blk);
+  }
+  return GAR_OK;
 }
 
 extern "C" int gar_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* Cout, int ldc, int M, int N, int K,

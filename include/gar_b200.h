@@ -55,6 +55,13 @@ int gar_set_global_option(const char* name, int value);
 int gar_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int ldc, int M, int N, int K, int epi,
                   const void* bias, const void* gamma, const void* res, int ldres, int block_n_hint, void* stream);
 
+/* Host-only (no CUDA call): the tile walk gar_gemm_bf16 uses for a launch of this geometry -- tile_m x block_n output
+ * tiles (256-row tiles for the CTA-pair kernel), `fly` tiles in flight.  Column panels are walked in groups of
+ * *n_group panels sized to keep the operands in flight L2-resident (global option gemm_group_kb, default 40 MB of
+ * working set; 0 = one group); inside a group n runs fastest, then m.  If m_blk / n_blk are given, also maps `tile`. */
+int gar_gemm_raster_probe(int M, int N, int K, int tile_m, int block_n, int fly, int tile, int* n_group, int* m_blk,
+                          int* n_blk);
+
 /* Same GEMM with timm's apply_rot_embed_cat fused after the bias (PE-ViT qkv projection): columns < rope_cols of
  * rows with (row % ntok) >= npt are rotated with the sin / cos values of token (row % ntok - npt).  `rope` is the
  * CHUNK-MAJOR form of the (ntok - npt, 2 * hd) table cat(sin[hd], cos[hd]) that gar_vit_rope takes:

@@ -137,3 +137,44 @@ def test_checkpoint_round_trip_keeps_reference_key_layout(tmp_path):
     assert all(torch.equal(a[k], b[k]) for k in a)
     assert m2.config.prompt_numbers == 5 and m2.crop_tokens_ids == spec.crop_tokens_ids
     assert m2.lm_head.weight.shape == (spec.text.vocab_size, spec.text.hidden_size)
+
+
+def test_gemm_raster_groups_cover_every_tile_once(lib):
+    """Host-side view of the tcgen05 GEMM's tile walk (gar_gemm_raster_probe, no CUDA call): every (row block, column
+    panel) is visited exactly once, n runs fastest inside a group of panels, a ragged last group is handled, and the
+    L2 working-set rule picks the groups DESIGN.md quotes for the production shapes."""
+    import ctypes as C
+
+    def probe(M, N, K, tile_m, block_n, fly, tile=None):
+        ng, m, n = C.c_int(), C.c_int(), C.c_int()
+        rc = lib.gar_gemm_raster_probe(M, N, K, tile_m, block_n, fly, 0 if tile is None else tile, C.byref(ng),
+                                       None if tile is None else C.byref(m), None if tile is None else C.byref(n))
+        assert rc == 0
+        return ng.value, m.value, n.value
+
+    try:
+        # production shapes, CTA-pair kernel (256 x 256 tiles, 74 pairs in flight)
+        assert probe(37376, 16384, 2048, 256, 256, 74)[0] == 32    # GAR-1B gate/up: 64 panels of 1 MB -> 2 groups
+        assert probe(37376, 2048, 8192, 256, 256, 74)[0] == 8      # GAR-1B down: no working set fits -> one group
+        assert probe(139400, 4096, 1024, 256, 256, 74)[0] == 16    # ViT fc1: everything fits -> one group
+        assert probe(139400, 1024, 4096, 256, 256, 74)[0] == 4     # ViT fc2: long K -> one group
+        assert probe(9400, 28672, 4096, 256, 256, 74)[0] == 14     # GAR-8B gate/up: 112 panels of 2 MB -> 8 groups
+        assert lib.gar_set_global_option(b"gemm_group_kb", 0) == 0
+        assert probe(37376, 16384, 2048, 256, 256, 74)[0] == 64    # grouping off
+        for M, N, K, tm, bn, fly, force in [(2300, 2816, 256, 256, 256, 74, 3), (1000, 3328, 512, 128, 128, 148, 4),
+                                            (4097, 2048, 1024, 128, 64, 148, 5), (700, 512, 512, 128, 256, 148, 1)]:
+            assert lib.gar_set_global_option(b"gemm_group_force", force) == 0
+            num_m, num_n = -(-M // tm), -(-N // bn)
+            seen, prev = set(), None
+            for t in range(num_m * num_n):
+                ng, m, n = probe(M, N, K, tm, bn, fly, t)
+                assert ng == min(force, num_n) and 0 <= m < num_m and 0 <= n < num_n
+                seen.add((m, n))
+                if prev is not None and prev[1] // ng == n // ng and prev[0] == m:
+                    assert n == prev[1] + 1  # n fastest inside a group
+                prev = (m, n)
+            assert len(seen) == num_m * num_n
+    finally:
+        lib.gar_set_global_option(b"gemm_group_force", 0)
+        lib.gar_set_global_option(b"gemm_group_kb", 40960)
+
