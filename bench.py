@@ -82,6 +82,16 @@ def gemm_traffic_bytes():
         return None
 
 
+def kernel_traffic():
+    """Per-launch / per-step DRAM bytes of the attention kernel, the decode step and the assemble call, from the committed
+    ncu launch list of this same workload (profiles/r02_kernel_traffic.json); {} if the file is absent."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_kernel_traffic.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -601,15 +611,19 @@ def main():
         d_ms = conc["ms_per_token_step_per_group"] if conc else d_alone
         d_gbs = (w_bytes + kv_bytes) / (d_ms * 1e-3) / 1e9
         asm_gbs = s_by / (s_ms * 1e-3) / 1e9 if s_ms > 0 else 0.0
+        default_workload = (args.model, B, args.max_num_tiles, args.masks) == ("gar-1b", 8, 16, 1)
+        kt = kernel_traffic() if default_workload else {}
         rooflines = [
             roof,
-            {"bound": "tensor", "kernel": "attn_fwd_kernel (tcgen05, ViT + causal prefill)", "achieved": atf,
+            {"bound": "tensor", "kernel": "attn_fwd_persist_kernel (tcgen05, ViT + causal prefill)", "achieved": atf,
              "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": atf / peaks["tf_sustained"],
-             "launches_per_step": a_n, "ms_per_step": a_ms, "share_of_step": a_ms / step_ms, "traffic": None},
+             "launches_per_step": a_n, "ms_per_step": a_ms, "share_of_step": a_ms / step_ms,
+             "traffic": kt.get("attention", {}).get("dram_bytes_per_launch")},
             {"bound": "hbm", "kernel": "decode step (CUDA graph: gemv_decode + decode_attn + argmax kernels)",
              "achieved": d_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": d_gbs / peaks["hbm"],
              "bytes_per_step": w_bytes + kv_bytes, "ms_per_launch": d_ms, "launches_per_step": NT - 1,
-             "share_of_step": d_ms * (NT - 1) / step_ms, "traffic": None,
+             "share_of_step": d_ms * (NT - 1) / step_ms,
+             "traffic": kt.get("decode_step", {}).get("dram_bytes_per_step"),  # per decode step of ONE group, like bytes_per_step
              "alone": {"ms_per_launch": d_alone, "GB/s": (w_bytes + kv_bytes) / (d_alone * 1e-3) / 1e9,
                        "frac": (w_bytes + kv_bytes) / (d_alone * 1e-3) / 1e9 / peaks["hbm"]},
              "mode": (f"production (graph replay): {conc['groups']} independent groups of {B} sequences decoded concurrently, "
@@ -621,7 +635,7 @@ def main():
                                        "the two grids side by side)",
              "achieved": asm_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": asm_gbs / peaks["hbm"],
              "bytes_per_step": s_by, "ms_per_step": s_ms, "launches_per_step": s_n, "share_of_step": s_ms / step_ms,
-             "traffic": None,
+             "traffic": kt.get("assemble", {}).get("dram_bytes_per_call"),
              "note": "the row plan (plan_rows_kernel: ids only, no feature bytes) runs before the ViT so that a malformed "
                      f"prompt raises first; timed separately: {prof['plan'][0] * 1e3:.1f} us per step"},
         ]
