@@ -5,18 +5,21 @@
 // Same numerics contract as those kernels: S and the online softmax in fp32, P rounded to bf16 for
 // the PV product, fp32 O accumulation, one bf16 rounding of O / l at the end.
 //
-// One CTA = one (sequence, head, 128-query block); two CTAs co-reside per SM so one CTA's softmax
-// overlaps the other's MMAs.  Roles (256 threads = two warpgroups):
-//   warp 0     TMA producer: Q once, K double-buffered, V single-buffered (3-D tensor maps so rows
-//              past a sequence end are zero-filled on load and clipped on store)
+// A tile = one (sequence, head, 128-query block); two CTAs co-reside per SM (head_dim 64) so one CTA's softmax
+// overlaps the other's MMAs.  The default kernel is persistent (attn_fwd_persist_kernel below: resident CTAs walk tiles
+// handed out by a device-side counter); attn_fwd_kernel is the same tile code as one CTA per tile.  Roles (256 threads
+// = two warpgroups):
+//   warp 0     TMA producer: Q, K and V double-buffered (3-D tensor maps so rows past a sequence end are zero-filled
+//              on load and clipped on store)
 //   warp 1     MMA issuer : S = Q K^T  (128x128x64, both operands K-major, 128B swizzle)
-//                           O += P V   (128x64x128, P K-major from smem, V MN-major from smem)
+//                           O += P V   (128x64x128, P from TENSOR MEMORY (A operand), V MN-major from smem)
 //   warps 2-3  idle (they complete the control warpgroup so setmaxnreg can hand its registers over)
-//   warps 4-7  softmax    : tcgen05.ld S row-per-thread -> online softmax -> P (bf16) into swizzled
-//                           smem, rescale O in TMEM, final O/l -> smem -> TMA store
-// Registers: the kernel launches at MAXREG per thread; the control warpgroup drops to 40 and the
-// softmax warpgroup (a whole 128-wide score row per thread lives in registers) takes the difference,
-// so the row-per-thread softmax compiles without local-memory spills.
+//   warps 4-7  softmax    : tcgen05.ld S row-per-thread -> online softmax -> P (bf16) into tensor memory by tcgen05.st
+//                           (swizzled smem only in the BKV 64 configuration), rescale O in TMEM, final O/l -> smem ->
+//                           TMA store
+// Registers: the kernel launches at MAXREG per thread; the control warpgroup drops to 48 (56 in the persistent kernel)
+// and the softmax warpgroup (a whole 128-wide score row per thread lives in registers) takes the difference, so the
+// row-per-thread softmax compiles without local-memory spills.
 #include <mutex>
 #include <type_traits>
 
