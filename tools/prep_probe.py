@@ -1,3 +1,5 @@
+"""Cost of preparing a batch of raw (uint8) requests (host enqueue / GPU time) and end-to-end ms per step of
+generate_batches(overlap="decode") over raw requests for ways = 3 / 1 and 3 / 6 steps (warm allocator)."""
 import sys, time, torch
 sys.path.insert(0, ".")
 from grasp_any_region_b200 import GARConfig, GARModel
